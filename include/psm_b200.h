@@ -1,0 +1,213 @@
+/* psm_b200.h -- C-ABI of the B200-native pressure-surrogate hot path.
+ *
+ * Drop-in boundary for the per-timestep surrogate call that the reference makes through an
+ * embedded CPython interpreter.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference root):
+ *
+ *   FOAM = Thesis_Work/Chapter5/parallelized/DLPoissonSolver
+ *   PMP  = Thesis_Work/Chapter5/parallelized/test_case/python_module.py
+ *   SMC  = Improved_SM/deltaU_to_deltaP/source/pressureSM_deltas/SM_call.py
+ *   GRAD = Improved_SM/U_to_gradP/evaluation/Eval_dual_Dense_onlycil.py
+ *
+ * Conventions: plain pointers and sizes only; every function returns an int status
+ * (0 = PSM_OK, >0 informational, <0 error) and never throws; psm_last_error() gives the
+ * message of the last failure on a handle (or of the last failed psm_create when handle is
+ * NULL).  A handle owns all device state, is bound to one CUDA device and one stream, and is
+ * not thread-safe.  No allocation happens inside psm_predict*.
+ */
+#ifndef PSM_B200_H
+#define PSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSM_API_VERSION 1
+
+typedef struct psm_handle psm_handle;
+
+enum psm_status_code {
+    PSM_OK = 0,
+    PSM_SKIPPED = 1,          /* 'irrelevant' time step, SMC:407-415: p_out = p_prev            */
+    PSM_ERR_INVALID = -1,     /* bad argument                                                    */
+    PSM_ERR_CUDA = -2,        /* CUDA runtime failure (no device, out of memory, launch error)   */
+    PSM_ERR_GEOMETRY = -3,    /* grid on which the reference itself is undefined (p_i == 0, ...) */
+    PSM_ERR_STATE = -4,       /* call order (predict before init, ...)                           */
+    PSM_ERR_COMM = -5         /* NCCL failure in the multi-GPU path                              */
+};
+
+enum psm_variant_code {
+    PSM_DELTAU_TO_DELTAP = 0, /* SMC: right->left plan, 1 output channel, p = p_prev + delta_p   */
+    PSM_U_TO_GRADP = 1        /* GRAD: left->right plan, 2 output channels {dp/dx, dp/dy}        */
+};
+
+enum psm_standardization_code {
+    PSM_STD = 0,              /* (z - mean_in) / std_in ; r * std_out + mean_out   SMC:505-512,532-533 */
+    PSM_MAX_ABS = 1           /* z / max_abs_input_PCA ; r * max_abs_output_PCA    SMC:521-523, GRAD:525,531 */
+};
+
+/* Constants the reference hard-codes or takes from argparse (EP:89-98; PMP:195,303-304). */
+typedef struct psm_config {
+    int32_t variant;          /* psm_variant_code                                                */
+    int32_t device;           /* CUDA device ordinal                                             */
+    double  delta;            /* grid spacing, 5e-3                                              */
+    int32_t shape;            /* block edge S, 128 (only 128 is supported)                       */
+    int32_t overlap;          /* SMC `overlap` (32) or GRAD `avance` (96): shared columns of
+                                 neighbouring blocks; stride = shape - overlap                   */
+    int32_t input_cols;       /* 5: {Ux,Uy,Cx,Cy,p} as FOAM/PythonComm.H:2-9 fills it;
+                                 7: + {dUx,dUy} (deltaU_to_deltaP only).  With 5 columns the
+                                 deltaU variant keeps U(t-1) resident and forms dU on device.   */
+    int32_t additive;         /* deltaU variant: 1 -> p_out = p_prev + delta_p (SMC:644-645),
+                                 0 -> raw delta_p with p_prev fallback                           */
+    double  ref_bc;           /* outlet reference value, SMC:570 (0)                             */
+    double  skip_threshold;   /* SMC:410-411 (1e-4); <= 0 disables the skip rule                 */
+    double  near_wall_sdf;    /* PMP:492-494: cells with interpolated distance < this keep
+                                 p_prev (0.05 in PMP); <= 0 disables (PMS:430-432)               */
+    int32_t enable_timings;   /* 1 -> record per-stage CUDA events (psm_get_timings)             */
+    int32_t reserved;
+} psm_config;
+
+/* Artefacts the reference loads at import time (SMC:70-87,505-511; PMP:103-118,168-170).
+ * PCA matrices are in the reference's own layout: row = component, column index
+ * k = (ly*S + lx)*n_channels + c  (channel-last blocks flattened, SMC:491-492, GRAD:513-516). */
+typedef struct psm_params {
+    double  maxs[5];              /* max_abs_Ux, Uy, dist, p [, second output]   SMC:70-72, GRAD:49-52 */
+    int32_t pc_in;                /* kept input components  (SMC:87)                            */
+    int32_t pc_p;                 /* kept output components (SMC:86)                            */
+    int32_t n_out_channels;       /* 1 (deltaU_to_deltaP) or 2 (U_to_gradP)                     */
+    int32_t standardization;      /* psm_standardization_code                                   */
+    const double* pca_in_components;   /* [pc_in][S*S*3]                                        */
+    const double* pca_in_mean;         /* [S*S*3]                                               */
+    const double* pca_out_components;  /* [pc_p][S*S*n_out_channels]                            */
+    const double* pca_out_mean;        /* [S*S*n_out_channels]                                  */
+    const double* mean_in;  const double* std_in;    /* [pc_in]  (PSM_STD)                      */
+    const double* mean_out; const double* std_out;   /* [pc_p]   (PSM_STD)                      */
+    double  max_abs_input_PCA;    /* PSM_MAX_ABS                                                */
+    double  max_abs_output_PCA;
+    int32_t n_dense;              /* Dense layers incl. the linear output layer (4 for MLP_small, UTL:437-439) */
+    int32_t reserved;
+    const int32_t* layer_dims;    /* [n_dense+1]: pc_in, 512, 512, 512, pc_p                    */
+    const float* const* dense_kernels;  /* n_dense pointers, Keras layout [in][out] (NNS:24-33) */
+    const float* const* dense_biases;   /* n_dense pointers, [out]                              */
+} psm_params;
+
+/* Interpolation tables and raster built once per mesh (SMC:110-178; PMP:203-243).  The Python
+ * shim builds them with SciPy's Qhull -- the library the reference calls -- so they are
+ * bit-identical to the reference's; psm_init_with_tables copies them to the device. */
+typedef struct psm_tables {
+    int64_t n_cells;
+    int32_t grid_h, grid_w;       /* grid_shape_y, grid_shape_x  (SMC:148-149)                  */
+    const int32_t* vert;          /* [H*W][3] cell ids of the enclosing simplex   (UTL:40)      */
+    const double*  weights;       /* [H*W][3] barycentric weights                 (UTL:42-44)   */
+    const int32_t* vert_back;     /* [n_cells][3] grid-point ids (PMP:211); NULL -> grid output only */
+    const double*  weights_back;  /* [n_cells][3]                                               */
+    const int64_t* indices;       /* [H*W][2] (ii, jj) raster, (0,0) for invalid points (SMC:161-178) */
+    const double*  sdfunct;       /* [H][W] distance field, 0 outside the flow domain (SMC:163,175) */
+} psm_tables;
+
+/* Static geometry report (filled by psm_get_geometry). */
+typedef struct psm_geometry {
+    int32_t grid_h, grid_w, shape, overlap;
+    int32_t n_x, n_y, p_i, p_j;   /* SMC:461-462,213,216 / GRAD:479-480,277-278                 */
+    int32_t n_blocks, n_fields;
+    int64_t n_cells;
+    int32_t n_tasks;              /* masked strip means evaluated per step                      */
+    int32_t reserved;
+} psm_geometry;
+
+/* Device-resident intermediates that parity tests read back (psm_get_stage). */
+enum psm_stage_code {
+    PSM_STAGE_GRID = 0,       /* float [2][H][W]   scaled input channels 0,1 (SMC:430-444)       */
+    PSM_STAGE_XINPUT = 1,     /* float [B][pc_in]  standardised PCA coordinates (SMC:512)        */
+    PSM_STAGE_MLPOUT = 2,     /* float [B][pc_p]   de-standardised MLP output (SMC:533)          */
+    PSM_STAGE_BLOCKS = 3,     /* float [B][C][S][S] predicted blocks before correction (SMC:551) */
+    PSM_STAGE_OFFSETS = 4,    /* double [F][B]     per-block corrections BC_coor (SMC:243)       */
+    PSM_STAGE_FIELD = 5,      /* float [F][H][W]   assembled field(s) (SMC:350)                  */
+    PSM_STAGE_SCALARS = 6,    /* double [4]        U_max_norm, dU_max_norm, shift[0], shift[1]   */
+    PSM_STAGE_MEANS = 7       /* double [n_tasks]  masked strip means                            */
+};
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Replaces Py_Initialize + import python_module (FOAM/PythonComm_init.H:3-19).
+ * Fails with PSM_ERR_CUDA when no usable sm_100 device exists: there is no CPU fallback. */
+int psm_create(psm_handle** out, const psm_config* cfg);
+
+/* Replaces the module-level artefact loading (PMP:103-118,168-170; SMC:70-87). */
+int psm_load_params(psm_handle* h, const psm_params* params);
+
+/* Replaces init_func(array, top_boundary, obst_boundary) (PMP:172-247; FOAM/PythonComm_init.H:94)
+ * for callers that already hold the Qhull tables and raster (the Python shim). */
+int psm_init_with_tables(psm_handle* h, const psm_tables* tables);
+
+/* Idempotent; NULL is accepted. */
+int psm_destroy(psm_handle* h);
+
+/* ---- per time step --------------------------------------------------------------------- */
+
+/* Replaces py_func(array_in) (PMP:249-517; FOAM/PythonComm.H:24-35).
+ * cells : host, row-major double[n_cells][input_cols]
+ * p_out : host, double[n_cells] (deltaU_to_deltaP) or double[n_cells][2] (U_to_gradP)
+ * Both buffers stay owned by the caller.  Returns PSM_OK or PSM_SKIPPED. */
+int psm_predict(psm_handle* h, const double* cells, int64_t n_cells, double* p_out);
+
+/* Same with DEVICE pointers (caller already holds the fields on this GPU); asynchronous on
+ * the handle's stream unless `sync` is non-zero.  The status of an asynchronous call is
+ * reported by the next synchronous call or psm_synchronize. */
+int psm_predict_device(psm_handle* h, const double* d_cells, int64_t n_cells, double* d_p_out, int32_t sync);
+
+int psm_synchronize(psm_handle* h);
+
+/* Page-lock / unlock a caller buffer that lives for the whole run (FOAM/PythonComm_init.H:53
+ * allocates input_vals once), so that psm_predict copies at full PCIe speed. */
+int psm_register_host_buffer(void* ptr, int64_t bytes);
+int psm_unregister_host_buffer(void* ptr);
+
+/* ---- introspection (tests, tracing) ----------------------------------------------------- */
+
+const char* psm_last_error(const psm_handle* h);
+int psm_get_geometry(const psm_handle* h, psm_geometry* out);
+
+/* Block plan exactly as the reference loops produce it (SMC:464-479 / GRAD:486-500):
+ * origins int32[B][2] = (y0, x0), indices_list int32[B][2] = (idx_i, idx_j); either may be NULL. */
+int psm_get_plan(const psm_handle* h, int32_t* origins, int32_t* indices_list);
+
+/* Last-writer map of the placement step (SMC:332-348 / GRAD:345-356): int32[H][W] block id. */
+int psm_get_owner_map(const psm_handle* h, int32_t* owner);
+
+/* Device tables after the validity fold: vert int32[H*W][3], weights float[H*W][3]. */
+int psm_get_forward_table(const psm_handle* h, int32_t* vert, float* weights);
+
+/* Copy one device-resident intermediate of the LAST step to the host; n_bytes must match. */
+int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_bytes);
+
+/* Per-stage milliseconds of the last step (enable_timings=1).  Order: h2d, prep, gather,
+ * extract, pca_project, mlp, pca_inverse, strip_means, offsets, place, back_gather, d2h.
+ * Replaces the hand-rolled time.time() pairs of PMP:262-499. */
+#define PSM_N_TIMINGS 12
+int psm_get_timings(psm_handle* h, float* ms, int32_t n);
+
+/* Number of kernels launched by the last psm_predict* call. */
+int psm_get_launch_count(const psm_handle* h);
+
+/* ---- host-only plan compiler (no GPU needed; used by the CPU test-suite) ---------------- */
+
+/* Compile the static block/assembly plan for a grid and return its sizes.
+ * mask : uint8[H][W], 1 where the distance field is non-zero (SMC:224 `flow_bool`).
+ * Outputs may be NULL.  origins/indices_list int32[B][2]; owner int32[H][W];
+ * rec int32[F][B][4] = (task_a, task_b, parent_block, is_nan) of c_k = m[a] - (m[b] - c[parent]);
+ * tasks int32[n_tasks][8] = (src_block, mask_block, channel, y0, y1, x0, x1, count).        */
+int psm_plan_sizes(int32_t variant, int32_t grid_h, int32_t grid_w, int32_t shape, int32_t overlap,
+                   const uint8_t* mask, int32_t* n_blocks, int32_t* n_fields, int32_t* n_tasks);
+int psm_plan_compile(int32_t variant, int32_t grid_h, int32_t grid_w, int32_t shape, int32_t overlap,
+                     const uint8_t* mask, int32_t* origins, int32_t* indices_list, int32_t* owner,
+                     int32_t* rec, int32_t* tasks);
+
+int psm_api_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSM_B200_H */

@@ -18,6 +18,51 @@ def _mmean(vals, mask):
         return np.mean(vals[mask != 0])
 
 
+def _place_deltas(result, pf, idx_i, idx_j, n_x, n_y, shape, overlap, shape_x, shape_y, p_i):
+    """Placement step, SMC:332-348 (later blocks overwrite earlier ones)."""
+    st = shape - overlap
+    if [idx_i, idx_j] == [n_y + 1, 0]:
+        result[-p_i:shape_y, 0:shape] = pf[-p_i:]
+    elif idx_j == 0:
+        result[st * idx_i:st * idx_i + shape, 0:shape] = pf
+    elif idx_i == (n_y + 1):
+        jj = n_x - idx_j
+        result[-p_i:, shape_x - shape - jj * st:shape_x - jj * st] = pf[-p_i:]
+    else:
+        jj = n_x - idx_j
+        result[st * idx_i:st * idx_i + shape, shape_x - shape - jj * st:shape_x - jj * st] = pf
+
+
+def _place_gradp(result, pf, idx_i, idx_j, n_x, n_y, shape, avance, shape_y, izl):
+    """Placement step, GRAD:345-356."""
+    st = shape - avance
+    if [idx_i, idx_j] == [n_y + 1, n_x]:
+        result[0, (shape_y - st):shape_y, -izl:, 0] = pf[avance:shape, -izl:]
+    elif idx_j == n_x:
+        result[0, idx_i * st:idx_i * st + shape, -izl:, 0] = pf[:, -izl:]
+    elif idx_i == (n_y + 1):
+        result[0, (shape_y - st):shape_y, idx_j * st:shape + idx_j * st, 0] = pf[avance:shape, :]
+    else:
+        result[0, idx_i * st:idx_i * st + shape, idx_j * st:shape + idx_j * st, 0] = pf
+
+
+def owner_map(variant, indices_list, n_x, n_y, shape, overlap, shape_x, shape_y):
+    """Which block's value survives at every pixel: the placement step replayed with block ids."""
+    if variant == 'deltas':
+        result = np.full((shape_y, shape_x), -1.0)
+        p_i = shape_y - ((shape - overlap) * n_y + shape)
+        for k, (idx_i, idx_j) in enumerate(indices_list):
+            _place_deltas(result, np.full((shape, shape), float(k)), idx_i, idx_j, n_x, n_y, shape, overlap,
+                          shape_x, shape_y, p_i)
+        return result.astype(np.int64)
+    result = np.full((1, shape_y, shape_x, 1), -1.0)
+    p_j = (shape_x - shape) - n_x * (shape - overlap)
+    for k, (idx_i, idx_j) in enumerate(indices_list):
+        _place_gradp(result, np.full((shape, shape), float(k)), idx_i, idx_j, n_x, n_y, shape, overlap, shape_y,
+                     overlap - p_j)
+    return result[0, :, :, 0].astype(np.int64)
+
+
 def assemble_deltas(array, x_array, indices_list, n_x, n_y, shape, overlap, shape_x, shape_y,
                     Ref_BC=0.0, return_offsets=False):
     """SMC:182-350.  ``array`` [B,S,S] predicted blocks (NOT modified: a copy is corrected),
@@ -76,18 +121,7 @@ def assemble_deltas(array, x_array, indices_list, n_x, n_y, shape, overlap, shap
         offsets[k] = c
         old = pf
 
-        # placement, SMC:332-348
-        st = shape - overlap
-        if [idx_i, idx_j] == [n_y + 1, 0]:
-            result[-p_i:shape_y, 0:shape] = pf[-p_i:]
-        elif idx_j == 0:
-            result[st * idx_i:st * idx_i + shape, 0:shape] = pf
-        elif idx_i == (n_y + 1):
-            jj = n_x - idx_j
-            result[-p_i:, shape_x - shape - jj * st:shape_x - jj * st] = pf[-p_i:]
-        else:
-            jj = n_x - idx_j
-            result[st * idx_i:st * idx_i + shape, shape_x - shape - jj * st:shape_x - jj * st] = pf
+        _place_deltas(result, pf, idx_i, idx_j, n_x, n_y, shape, overlap, shape_x, shape_y, p_i)
 
     shift = np.mean(3 * result[:, -1] - result[:, -2]) / 3        # SMC:350
     result -= shift
@@ -163,16 +197,7 @@ def assemble_gradp(field, array, x_array, indices_list, n_x, n_y, shape, avance,
         offsets[k] = c
         old = pf
 
-        izl = intersect_zone_limit
-        st = shape - avance
-        if [idx_i, idx_j] == [n_y + 1, n_x]:                   # GRAD:345-356
-            result[0, (shape_y - st):shape_y, -izl:, 0] = pf[avance:shape, -izl:]
-        elif idx_j == n_x:
-            result[0, idx_i * st:idx_i * st + shape, -izl:, 0] = pf[:, -izl:]
-        elif idx_i == (n_y + 1):
-            result[0, (shape_y - st):shape_y, idx_j * st:shape + idx_j * st, 0] = pf[avance:shape, :]
-        else:
-            result[0, idx_i * st:idx_i * st + shape, idx_j * st:shape + idx_j * st, 0] = pf
+        _place_gradp(result, pf, idx_i, idx_j, n_x, n_y, shape, avance, shape_y, intersect_zone_limit)
 
     if field == 'dp_dx':                                        # GRAD:358-361
         shift = np.mean(3 * result[:, :, 0, :] - result[:, :, 1, :]) / 3

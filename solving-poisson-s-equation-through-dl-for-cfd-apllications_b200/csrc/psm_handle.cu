@@ -1,0 +1,653 @@
+// Handle, parameter/table upload and per-step orchestration behind the C-ABI (include/psm_b200.h).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/psm_b200.h"
+#include "psm_kernels.cuh"
+#include "psm_plan.h"
+
+using namespace psm;
+
+namespace {
+thread_local std::string g_create_error;
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline long long round_up_ll(long long v, long long m) { return (v + m - 1) / m * m; }
+}  // namespace
+
+struct psm_handle {
+    psm_config cfg{};
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool params_loaded = false, initialised = false;
+    std::vector<void*> allocs;
+
+    // ---- parameters -------------------------------------------------------------------------
+    int S = 128, C = 1, pc_in = 0, pc_p = 0, pc_in_pad = 0, pc_p_pad = 0, n_dense = 0, standardization = 0;
+    double maxs[5] = {1, 1, 1, 1, 1};
+    std::vector<int> dims, dims_pad;
+    float* d_comp_u = nullptr;        // [pc_in_pad][2*S*S]    input PCA, velocity channels, planar
+    float* d_comp_sdf = nullptr;      // [pc_in_pad][S*S]      input PCA, distance channel (init only)
+    std::vector<float> in_a, in_b;    // host: x = (z + zc) * a + b
+    float *d_in_a = nullptr, *d_in_b = nullptr;
+    std::vector<float*> d_W, d_bias;  // [out_pad][in_pad] (K-major), [out_pad]
+    float *d_out_s = nullptr, *d_out_m = nullptr;   // de-standardisation r' = r*s + m   [pc_p_pad]
+    float* d_comp_out_t = nullptr;    // [S*S*C][pc_p_pad]     output PCA transposed, planar rows (c, ly, lx)
+    float* d_pmean = nullptr;         // [S*S*C] planar
+
+    // ---- geometry / tables ----------------------------------------------------------------------
+    Plan plan;
+    long long n_cells = 0, G = 0, G_pad = 0;
+    int H = 0, W = 0, B = 0, B_pad = 0, F = 1;
+    bool have_back = false;
+    int32_t *d_fv[3] = {nullptr, nullptr, nullptr}; float* d_fw[3] = {nullptr, nullptr, nullptr};
+    int32_t *d_bv[3] = {nullptr, nullptr, nullptr}; float* d_bw[3] = {nullptr, nullptr, nullptr};
+    uint8_t* d_gmask = nullptr; uint16_t* d_owner = nullptr;
+    int32_t *d_by0 = nullptr, *d_bx0 = nullptr;
+    DevTask* d_tasks = nullptr; DevRec* d_rec = nullptr; int n_tasks = 0, rounds = 0;
+    float* d_zc = nullptr;            // [B_pad][pc_in_pad]
+
+    // ---- per-step buffers ---------------------------------------------------------------------------
+    double* d_cells = nullptr; double* d_out = nullptr; double* d_pprev = nullptr; double* d_uprev = nullptr;
+    float2* d_uv = nullptr; float* d_grid = nullptr; float* d_xu = nullptr; float* d_part = nullptr; int splits = 1;
+    float* d_xin = nullptr; float* d_act[2] = {nullptr, nullptr}; float* d_r = nullptr; float* d_blocks = nullptr;
+    double* d_means = nullptr; double* d_dbuf[2] = {nullptr, nullptr}; int32_t* d_pbuf[2] = {nullptr, nullptr};
+    double* d_offsets = nullptr; float* d_coff = nullptr; float* d_field = nullptr;
+    Scalars* d_sc = nullptr; Scalars* h_sc = nullptr;
+    int launches = 0;
+    cudaEvent_t ev[PSM_N_TIMINGS + 1] = {};
+    bool ev_valid = false;
+    bool last_host = false;
+};
+
+#define PSM_FAIL(h, code, ...)                                    \
+    do {                                                          \
+        char _b[512];                                             \
+        snprintf(_b, sizeof _b, __VA_ARGS__);                     \
+        (h)->err = _b;                                            \
+        return (code);                                            \
+    } while (0)
+
+#define CU(h, call)                                                                              \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) PSM_FAIL(h, PSM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+template <typename T>
+static int dalloc(psm_handle* h, T** p, size_t n, bool zero = true) {
+    void* q = nullptr;
+    size_t bytes = (n ? n : 1) * sizeof(T);
+    CU(h, cudaMalloc(&q, bytes));
+    h->allocs.push_back(q);
+    if (zero) CU(h, cudaMemsetAsync(q, 0, bytes, h->stream));
+    *p = static_cast<T*>(q);
+    return 0;
+}
+template <typename T>
+static int upload(psm_handle* h, T** p, const std::vector<T>& v) {
+    int rc = dalloc(h, p, v.size(), false);
+    if (rc) return rc;
+    CU(h, cudaMemcpy(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+#define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+
+extern "C" int psm_api_version(void) { return PSM_API_VERSION; }
+
+extern "C" const char* psm_last_error(const psm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int psm_create(psm_handle** out, const psm_config* cfg) {
+    if (!out || !cfg) { g_create_error = "psm_create: NULL argument"; return PSM_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->variant != PSM_DELTAU_TO_DELTAP && cfg->variant != PSM_U_TO_GRADP) { g_create_error = "unknown variant"; return PSM_ERR_INVALID; }
+    if (cfg->shape != 128) { g_create_error = "only shape == 128 is supported"; return PSM_ERR_INVALID; }
+    if (cfg->input_cols != 5 && !(cfg->input_cols == 7 && cfg->variant == PSM_DELTAU_TO_DELTAP)) {
+        g_create_error = "input_cols must be 5, or 7 for deltaU_to_deltaP"; return PSM_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
+        return PSM_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return PSM_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, cfg->device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return PSM_ERR_CUDA; }
+    if (prop.major != 10) {
+        g_create_error = "device is not sm_100 (Blackwell B200): kernels are built for sm_100a only";
+        return PSM_ERR_CUDA;
+    }
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return PSM_ERR_CUDA; }
+    psm_handle* h = new (std::nothrow) psm_handle();
+    if (!h) { g_create_error = "out of host memory"; return PSM_ERR_INVALID; }
+    h->cfg = *cfg;
+    h->S = cfg->shape;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e); delete h; return PSM_ERR_CUDA;
+    }
+    if (cudaMallocHost((void**)&h->h_sc, sizeof(Scalars)) != cudaSuccess) { g_create_error = "cudaMallocHost failed"; cudaStreamDestroy(h->stream); delete h; return PSM_ERR_CUDA; }
+    memset(h->h_sc, 0, sizeof(Scalars));
+    *out = h;
+    return PSM_OK;
+}
+
+extern "C" int psm_destroy(psm_handle* h) {
+    if (!h) return PSM_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->ev_valid) for (auto& e : h->ev) cudaEventDestroy(e);
+    if (h->h_sc) cudaFreeHost(h->h_sc);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int psm_load_params(psm_handle* h, const psm_params* p) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!p) PSM_FAIL(h, PSM_ERR_INVALID, "psm_load_params: NULL params");
+    if (h->params_loaded) PSM_FAIL(h, PSM_ERR_STATE, "parameters already loaded");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const int S = h->S, S2 = S * S;
+    const int C = p->n_out_channels;
+    if (C != (h->cfg.variant == PSM_U_TO_GRADP ? 2 : 1)) PSM_FAIL(h, PSM_ERR_INVALID, "n_out_channels does not match the variant");
+    if (p->pc_in < 1 || p->pc_p < 1 || p->n_dense < 1 || p->n_dense > 64) PSM_FAIL(h, PSM_ERR_INVALID, "bad pc_in/pc_p/n_dense");
+    if (!p->pca_in_components || !p->pca_in_mean || !p->pca_out_components || !p->pca_out_mean || !p->layer_dims ||
+        !p->dense_kernels || !p->dense_biases) PSM_FAIL(h, PSM_ERR_INVALID, "NULL parameter array");
+    if (p->layer_dims[0] != p->pc_in || p->layer_dims[p->n_dense] != p->pc_p) PSM_FAIL(h, PSM_ERR_INVALID, "layer_dims must start at pc_in and end at pc_p");
+    if (p->standardization == PSM_STD && (!p->mean_in || !p->std_in || !p->mean_out || !p->std_out)) PSM_FAIL(h, PSM_ERR_INVALID, "PSM_STD needs mean/std arrays");
+    h->C = C; h->F = C; h->pc_in = p->pc_in; h->pc_p = p->pc_p; h->n_dense = p->n_dense; h->standardization = p->standardization;
+    memcpy(h->maxs, p->maxs, sizeof h->maxs);
+    h->pc_in_pad = round_up(p->pc_in, 64);
+    h->pc_p_pad = round_up(p->pc_p, 64);
+    h->dims.assign(p->layer_dims, p->layer_dims + p->n_dense + 1);
+    h->dims_pad.resize(h->dims.size());
+    for (size_t i = 0; i < h->dims.size(); ++i) {
+        if (h->dims[i] < 1) PSM_FAIL(h, PSM_ERR_INVALID, "layer width < 1");
+        h->dims_pad[i] = round_up(h->dims[i], 64);
+    }
+    const int Kin = S2 * 3, Kout = S2 * C;
+
+    // input PCA: split the reference's channel-last columns k = p*3 + c into the two velocity planes
+    // (dynamic, K = 2*S*S) and the distance plane (static per mesh -> folded into zc at init).
+    {
+        std::vector<float> cu((size_t)h->pc_in_pad * 2 * S2, 0.f), cs((size_t)h->pc_in_pad * S2, 0.f);
+        std::vector<double> mconst(p->pc_in, 0.0);
+        for (int n = 0; n < p->pc_in; ++n) {
+            const double* row = p->pca_in_components + (size_t)n * Kin;
+            double acc = 0.0;
+            for (int q = 0; q < S2; ++q) {
+                cu[((size_t)n * 2 + 0) * S2 + q] = (float)row[q * 3 + 0];
+                cu[((size_t)n * 2 + 1) * S2 + q] = (float)row[q * 3 + 1];
+                cs[(size_t)n * S2 + q] = (float)row[q * 3 + 2];
+            }
+            for (int k = 0; k < Kin; ++k) acc += p->pca_in_mean[k] * row[k];      // mean_ . components_^T (PMP:349)
+            mconst[n] = acc;
+        }
+        TRY(upload(h, &h->d_comp_u, cu));
+        TRY(upload(h, &h->d_comp_sdf, cs));
+        h->in_a.assign(h->pc_in_pad, 0.f);
+        h->in_b.assign(h->pc_in_pad, 0.f);
+        for (int n = 0; n < p->pc_in; ++n) {
+            double a, m;
+            if (p->standardization == PSM_STD) { a = 1.0 / p->std_in[n]; m = p->mean_in[n]; }      // SMC:512
+            else { a = 1.0 / p->max_abs_input_PCA; m = 0.0; }                                      // SMC:523
+            h->in_a[n] = (float)a;
+            h->in_b[n] = (float)(-(mconst[n] + m) * a);
+        }
+        TRY(upload(h, &h->d_in_a, h->in_a));
+        TRY(upload(h, &h->d_in_b, h->in_b));
+    }
+    // Dense stack: Keras kernels [in][out] -> K-major [out_pad][in_pad], zero padded
+    for (int l = 0; l < p->n_dense; ++l) {
+        const int in = h->dims[l], out = h->dims[l + 1], in_p = h->dims_pad[l], out_p = h->dims_pad[l + 1];
+        if (!p->dense_kernels[l] || !p->dense_biases[l]) PSM_FAIL(h, PSM_ERR_INVALID, "NULL dense layer");
+        std::vector<float> w((size_t)out_p * in_p, 0.f), b(out_p, 0.f);
+        for (int i = 0; i < in; ++i)
+            for (int o = 0; o < out; ++o) w[(size_t)o * in_p + i] = p->dense_kernels[l][(size_t)i * out + o];
+        for (int o = 0; o < out; ++o) b[o] = p->dense_biases[l][o];
+        float *dw = nullptr, *db = nullptr;
+        TRY(upload(h, &dw, w));
+        TRY(upload(h, &db, b));
+        h->d_W.push_back(dw);
+        h->d_bias.push_back(db);
+    }
+    {   // de-standardisation (SMC:533 / 537)
+        std::vector<float> s(h->pc_p_pad, 0.f), m(h->pc_p_pad, 0.f);
+        for (int n = 0; n < p->pc_p; ++n) {
+            if (p->standardization == PSM_STD) { s[n] = (float)p->std_out[n]; m[n] = (float)p->mean_out[n]; }
+            else { s[n] = (float)p->max_abs_output_PCA; m[n] = 0.f; }
+        }
+        TRY(upload(h, &h->d_out_s, s));
+        TRY(upload(h, &h->d_out_m, m));
+    }
+    {   // output PCA transposed to K-major rows in planar pixel order q' = c*S2 + q  (reference k = q*C + c)
+        std::vector<float> ct((size_t)Kout * h->pc_p_pad, 0.f), pm(Kout, 0.f);
+        for (int n = 0; n < p->pc_p; ++n) {
+            const double* row = p->pca_out_components + (size_t)n * Kout;
+            for (int q = 0; q < S2; ++q)
+                for (int c = 0; c < C; ++c) ct[((size_t)c * S2 + q) * h->pc_p_pad + n] = (float)row[q * C + c];
+        }
+        for (int q = 0; q < S2; ++q)
+            for (int c = 0; c < C; ++c) pm[(size_t)c * S2 + q] = (float)p->pca_out_mean[q * C + c];
+        TRY(upload(h, &h->d_comp_out_t, ct));
+        TRY(upload(h, &h->d_pmean, pm));
+    }
+    h->params_loaded = true;
+    return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!t) PSM_FAIL(h, PSM_ERR_INVALID, "psm_init_with_tables: NULL tables");
+    if (!h->params_loaded) PSM_FAIL(h, PSM_ERR_STATE, "psm_load_params must be called before psm_init_with_tables");
+    if (h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "handle already initialised");
+    if (!t->vert || !t->weights || !t->indices || !t->sdfunct || t->n_cells < 3 || t->grid_h < 1 || t->grid_w < 1)
+        PSM_FAIL(h, PSM_ERR_INVALID, "bad tables");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const int H = t->grid_h, W = t->grid_w, S = h->S, S2 = S * S;
+    const long long G = (long long)H * W, N = t->n_cells;
+    h->H = H; h->W = W; h->G = G; h->n_cells = N;
+    h->G_pad = round_up_ll(G, 4);
+
+    // static flow mask: x_array[...,2] != 0 (SMC:224) <=> sdfunct != 0
+    std::vector<uint8_t> mask(G);
+    for (long long q = 0; q < G; ++q) mask[q] = (t->sdfunct[q] != 0.0) ? 1 : 0;
+    int rc = compile_plan(h->cfg.variant, H, W, S, h->cfg.overlap, mask.data(), h->plan);
+    if (rc) PSM_FAIL(h, rc, "%s", h->plan.error.c_str());
+    const Plan& P = h->plan;
+    h->B = P.B; h->B_pad = round_up(P.B, 128); h->F = P.F;
+    h->n_tasks = (int)P.tasks.size();
+    h->rounds = 0;
+    while ((1 << h->rounds) < P.max_depth + 1) ++h->rounds;
+
+    // ---- forward table with the validity fold (SMC:161-178,432-438; UTL:89) ------------------------
+    // grid[...][tuple(indices.T)] = interp : for duplicate targets the LAST source point wins, so
+    // pixel (0,0) receives the value of the last invalid point; untouched pixels stay 0.
+    {
+        std::vector<long long> src(G, -1);
+        for (long long m = 0; m < G; ++m) {
+            const long long ii = t->indices[2 * m], jj = t->indices[2 * m + 1];
+            if (ii < 0 || ii >= H || jj < 0 || jj >= W) PSM_FAIL(h, PSM_ERR_INVALID, "indices out of range at %lld", m);
+            src[ii * W + jj] = m;
+        }
+        std::vector<int32_t> v[3]; std::vector<float> w[3];
+        for (int j = 0; j < 3; ++j) { v[j].assign(h->G_pad, 0); w[j].assign(h->G_pad, 0.f); }
+        for (long long q = 0; q < G; ++q) {
+            const long long m = src[q];
+            if (m < 0) continue;
+            const double* wm = t->weights + 3 * m;
+            const bool neg = (wm[0] < 0) || (wm[1] < 0) || (wm[2] < 0);          // -> NaN (UTL:89) -> 0 (SMC:438)
+            for (int j = 0; j < 3; ++j) {
+                const int32_t vi = t->vert[3 * m + j];
+                if (vi < 0 || vi >= N) PSM_FAIL(h, PSM_ERR_INVALID, "vert out of range at %lld", m);
+                v[j][q] = vi;
+                w[j][q] = neg ? 0.f : (float)wm[j];
+            }
+        }
+        for (int j = 0; j < 3; ++j) { TRY(upload(h, &h->d_fv[j], v[j])); TRY(upload(h, &h->d_fw[j], w[j])); }
+    }
+    // ---- back table (PMP:481-496): vertex ids hop through `indices` (incl. the (0,0) quirk) ---------
+    h->have_back = (t->vert_back && t->weights_back);
+    if (h->have_back) {
+        std::vector<int32_t> v[3]; std::vector<float> w[3];
+        for (int j = 0; j < 3; ++j) { v[j].assign(N, 0); w[j].assign(N, 0.f); }
+        const bool near_wall = h->cfg.near_wall_sdf > 0.0;
+        for (long long c = 0; c < N; ++c) {
+            const double* wc = t->weights_back + 3 * c;
+            bool keep_prev = (wc[0] < 0) || (wc[1] < 0) || (wc[2] < 0);         // interpolate_fill -> NaN -> p_prev (PMP:496)
+            double sdf_mesh = 0.0;
+            for (int j = 0; j < 3; ++j) {
+                const long long g = t->vert_back[3 * c + j];
+                if (g < 0 || g >= G) PSM_FAIL(h, PSM_ERR_INVALID, "vert_back out of range at %lld", c);
+                sdf_mesh += t->sdfunct[g] * wc[j];                               // PMP:492 (flat take, no indices hop)
+                v[j][c] = (int32_t)(t->indices[2 * g] * W + t->indices[2 * g + 1]);
+                w[j][c] = (float)wc[j];
+            }
+            if (near_wall && !keep_prev && sdf_mesh < h->cfg.near_wall_sdf) keep_prev = true;   // PMP:494
+            if (keep_prev) v[0][c] = -1;
+        }
+        for (int j = 0; j < 3; ++j) { TRY(upload(h, &h->d_bv[j], v[j])); TRY(upload(h, &h->d_bw[j], w[j])); }
+    }
+    // ---- plan to device -----------------------------------------------------------------------------
+    TRY(upload(h, &h->d_gmask, mask));
+    {
+        std::vector<uint16_t> ow(G);
+        for (long long q = 0; q < G; ++q) ow[q] = (uint16_t)P.owner[q];
+        TRY(upload(h, &h->d_owner, ow));
+        std::vector<int32_t> by0(h->B_pad, 0), bx0(h->B_pad, 0);
+        for (int k = 0; k < P.B; ++k) { by0[k] = P.y0[k]; bx0[k] = P.x0[k]; }
+        TRY(upload(h, &h->d_by0, by0));
+        TRY(upload(h, &h->d_bx0, bx0));
+        std::vector<DevTask> tk(P.tasks.size());
+        for (size_t i = 0; i < tk.size(); ++i) {
+            const Task& s = P.tasks[i];
+            tk[i] = DevTask{s.src, s.msk, s.ch, s.y0, s.y1, s.x0, s.x1, s.count};
+        }
+        TRY(upload(h, &h->d_tasks, tk));
+        std::vector<DevRec> rc2(P.rec.size());
+        for (size_t i = 0; i < rc2.size(); ++i) rc2[i] = DevRec{P.rec[i].ta, P.rec[i].tb, P.rec[i].parent, P.rec[i].is_nan};
+        TRY(upload(h, &h->d_rec, rc2));
+    }
+    // ---- per-step buffers -------------------------------------------------------------------------------
+    const int ncol = h->cfg.input_cols;
+    const int Bp = h->B_pad;
+    int maxw = 0;
+    for (int d : h->dims_pad) maxw = d > maxw ? d : maxw;
+    TRY(dalloc(h, &h->d_cells, (size_t)N * ncol));
+    TRY(dalloc(h, &h->d_out, (size_t)N * h->F));
+    TRY(dalloc(h, &h->d_pprev, (size_t)N));
+    if (h->cfg.variant == PSM_DELTAU_TO_DELTAP && ncol == 5) TRY(dalloc(h, &h->d_uprev, (size_t)N * 2));
+    TRY(dalloc(h, &h->d_uv, (size_t)N));
+    TRY(dalloc(h, &h->d_grid, (size_t)h->G_pad * 2));
+    TRY(dalloc(h, &h->d_xu, (size_t)Bp * 2 * S2));
+    {
+        const int tiles = (Bp / 64) * (h->pc_in_pad / 64);
+        int sp = (4 * 148 + tiles - 1) / tiles;
+        if (sp > 64) sp = 64;
+        if (sp < 1) sp = 1;
+        h->splits = sp;
+    }
+    TRY(dalloc(h, &h->d_part, (size_t)h->splits * Bp * h->pc_in_pad));
+    TRY(dalloc(h, &h->d_xin, (size_t)Bp * h->pc_in_pad));
+    TRY(dalloc(h, &h->d_act[0], (size_t)Bp * maxw));
+    TRY(dalloc(h, &h->d_act[1], (size_t)Bp * maxw));
+    TRY(dalloc(h, &h->d_r, (size_t)Bp * h->pc_p_pad));
+    TRY(dalloc(h, &h->d_blocks, (size_t)Bp * h->C * S2));
+    TRY(dalloc(h, &h->d_means, (size_t)h->n_tasks));
+    for (int i = 0; i < 2; ++i) { TRY(dalloc(h, &h->d_dbuf[i], (size_t)h->F * h->B)); TRY(dalloc(h, &h->d_pbuf[i], (size_t)h->F * h->B)); }
+    TRY(dalloc(h, &h->d_offsets, (size_t)h->F * h->B));
+    TRY(dalloc(h, &h->d_coff, (size_t)h->F * h->B));
+    TRY(dalloc(h, &h->d_field, (size_t)h->F * G));
+    TRY(dalloc(h, &h->d_sc, 1));
+    TRY(dalloc(h, &h->d_zc, (size_t)Bp * h->pc_in_pad));
+
+    // ---- static distance-channel contribution per block: zc[b][n] = sum_p sdf_n[b,p] * comp[n][p*3+2] ----
+    // (grid[...,2] = sdfunct / max_abs_dist, SMC:434,443 -- constant for the mesh)
+    {
+        std::vector<float> sdfn(h->G_pad, 0.f);
+        for (long long q = 0; q < G; ++q) sdfn[q] = (float)(t->sdfunct[q] / h->maxs[2]);
+        float* d_sdfn = nullptr; float* d_sdfb = nullptr;
+        CU(h, cudaMalloc(&d_sdfn, (size_t)h->G_pad * sizeof(float)));
+        CU(h, cudaMalloc(&d_sdfb, (size_t)Bp * S2 * sizeof(float)));
+        CU(h, cudaMemsetAsync(d_sdfb, 0, (size_t)Bp * S2 * sizeof(float), h->stream));
+        CU(h, cudaMemcpyAsync(d_sdfn, sdfn.data(), (size_t)h->G_pad * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        ExtractArgs ea{d_sdfn, d_sdfn, h->d_by0, h->d_bx0, d_sdfb, h->B, W, S, 1};
+        launch_extract(ea, h->stream);
+        GemmArgs ga{};
+        ga.A = d_sdfb; ga.B = h->d_comp_sdf; ga.C = h->d_zc; ga.M = Bp; ga.N = h->pc_in_pad; ga.K = S2;
+        ga.lda = S2; ga.ldb = S2; ga.ldc = h->pc_in_pad; ga.splits = 1; ga.epi = EPI_PLAIN;
+        launch_sgemm(ga, h->stream);
+        CU(h, cudaStreamSynchronize(h->stream));
+        CU(h, cudaGetLastError());
+        cudaFree(d_sdfn); cudaFree(d_sdfb);
+    }
+    if (h->cfg.enable_timings) {
+        for (auto& e : h->ev) CU(h, cudaEventCreate(&e));
+        h->ev_valid = true;
+    }
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->initialised = true;
+    return PSM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One step on the device, input already in d_cells, output to d_out.
+static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
+    cudaStream_t s = h->stream;
+    const int S = h->S, S2 = S * S, Bp = h->B_pad;
+    const bool deltas = h->cfg.variant == PSM_DELTAU_TO_DELTAP;
+    const int mode = !deltas ? 0 : (h->cfg.input_cols == 7 ? 1 : 2);
+    int nl = 0, te = 1;
+    auto tick = [&]() { if (h->ev_valid) cudaEventRecord(h->ev[te], s); ++te; };
+
+    PrepArgs pa{d_cells, h->n_cells, h->cfg.input_cols, mode, h->d_uv, h->d_pprev, h->d_uprev, h->d_sc};
+    launch_prep(pa, s); ++nl;
+    ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], deltas ? h->maxs[3] : 1.0, deltas ? 1 : 0, h->cfg.skip_threshold, mode};
+    launch_scalars(sa, s); ++nl;
+    tick();   // prep
+    GatherArgs ga{h->d_fv[0], h->d_fv[1], h->d_fv[2], h->d_fw[0], h->d_fw[1], h->d_fw[2], h->d_uv,
+                  h->d_grid, h->d_grid + h->G_pad, h->G_pad / 4, h->d_sc};
+    launch_gather(ga, s); ++nl;
+    tick();   // gather
+    ExtractArgs ea{h->d_grid, h->d_grid + h->G_pad, h->d_by0, h->d_bx0, h->d_xu, h->B, h->W, S, 2};
+    launch_extract(ea, s); ++nl;
+    tick();   // extract
+    {
+        GemmArgs g{};
+        g.A = h->d_xu; g.B = h->d_comp_u; g.C = h->d_part; g.M = Bp; g.N = h->pc_in_pad; g.K = 2 * S2;
+        g.lda = 2 * S2; g.ldb = 2 * S2; g.ldc = h->pc_in_pad; g.splits = h->splits; g.epi = EPI_PARTIAL;
+        launch_sgemm(g, s); ++nl;
+        ReduceArgs r{h->d_part, h->splits, Bp, h->pc_in_pad, h->d_zc, h->d_in_a, h->d_in_b, h->d_xin};
+        launch_reduce_standardise(r, s); ++nl;
+    }
+    tick();   // pca_project
+    {
+        const float* in = h->d_xin;
+        for (int l = 0; l < h->n_dense; ++l) {
+            const bool last = (l == h->n_dense - 1);
+            GemmArgs g{};
+            g.A = in; g.B = h->d_W[l]; g.C = last ? h->d_r : h->d_act[l & 1];
+            g.M = Bp; g.N = h->dims_pad[l + 1]; g.K = h->dims_pad[l];
+            g.lda = g.K; g.ldb = g.K; g.ldc = g.N; g.splits = 1;
+            g.epi = last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU;
+            g.v0 = h->d_bias[l]; g.v1 = h->d_out_s; g.v2 = h->d_out_m;
+            launch_sgemm(g, s); ++nl;
+            in = g.C;
+        }
+    }
+    tick();   // mlp
+    {
+        GemmArgs g{};
+        g.A = h->d_r; g.B = h->d_comp_out_t; g.C = h->d_blocks; g.M = Bp; g.N = S2 * h->C; g.K = h->pc_p_pad;
+        g.lda = g.K; g.ldb = g.K; g.ldc = g.N; g.splits = 1; g.epi = EPI_PCA_INV; g.v0 = h->d_pmean; g.sc = h->d_sc;
+        launch_sgemm(g, s); ++nl;
+    }
+    tick();   // pca_inverse
+    MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->d_by0, h->d_bx0, h->C, S, h->W, h->d_means};
+    launch_means(ma, s); ++nl;
+    tick();   // strip_means
+    {
+        OffsetsArgs oa{};
+        oa.rec = h->d_rec; oa.B = h->B; oa.F = h->F; oa.rounds = h->rounds; oa.ref_bc = h->cfg.ref_bc; oa.means = h->d_means;
+        oa.dbuf0 = h->d_dbuf[0]; oa.dbuf1 = h->d_dbuf[1]; oa.pbuf0 = h->d_pbuf[0]; oa.pbuf1 = h->d_pbuf[1];
+        oa.offsets = h->d_offsets; oa.coff = h->d_coff; oa.blocks = h->d_blocks; oa.owner = h->d_owner;
+        oa.by0 = h->d_by0; oa.bx0 = h->d_bx0; oa.C = h->C; oa.S = S; oa.H = h->H; oa.W = h->W;
+        for (int f = 0; f < 2; ++f) { oa.shift_axis[f] = h->plan.shift_axis[f]; oa.shift_a[f] = h->plan.shift_a[f]; oa.shift_b[f] = h->plan.shift_b[f]; }
+        oa.sc = h->d_sc;
+        launch_offsets(oa, s); ++nl;
+    }
+    tick();   // offsets
+    PlaceArgs pl{h->d_blocks, h->d_owner, h->d_by0, h->d_bx0, h->d_coff, h->d_field, h->B, h->C, h->F, S, h->H, h->W};
+    launch_place(pl, s); ++nl;
+    tick();   // place
+    if (h->have_back && d_out) {
+        BackArgs ba{h->d_bv[0], h->d_bv[1], h->d_bv[2], h->d_bw[0], h->d_bw[1], h->d_bw[2], h->d_field, h->n_cells,
+                    h->G, h->d_pprev, d_out, h->F, h->cfg.additive, h->d_sc};
+        launch_back(ba, s); ++nl;
+    }
+    tick();   // back_gather
+    h->launches = nl;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) PSM_FAIL(h, PSM_ERR_CUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return PSM_OK;
+}
+
+static int finish(psm_handle* h) {
+    CU(h, cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return h->h_sc->skip ? PSM_SKIPPED : PSM_OK;
+}
+
+extern "C" int psm_predict(psm_handle* h, const double* cells, int64_t n_cells, double* p_out) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "psm_predict before psm_init_with_tables");
+    if (!cells || !p_out) PSM_FAIL(h, PSM_ERR_INVALID, "NULL buffer");
+    if (n_cells != h->n_cells) PSM_FAIL(h, PSM_ERR_INVALID, "n_cells %lld does not match the initialised mesh (%lld)", (long long)n_cells, h->n_cells);
+    if (!h->have_back) PSM_FAIL(h, PSM_ERR_STATE, "no grid->cell tables were given: use psm_predict_device(..., NULL, ...) + psm_get_stage(FIELD)");
+    CU(h, cudaSetDevice(h->cfg.device));
+    if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
+    CU(h, cudaMemcpyAsync(h->d_cells, cells, (size_t)n_cells * h->cfg.input_cols * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->ev_valid) cudaEventRecord(h->ev[11], h->stream);
+    h->last_host = true;
+    TRY(run_step(h, h->d_cells, h->d_out));
+    CU(h, cudaMemcpyAsync(p_out, h->d_out, (size_t)n_cells * h->F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
+    return finish(h);
+}
+
+extern "C" int psm_predict_device(psm_handle* h, const double* d_cells, int64_t n_cells, double* d_p_out, int32_t sync) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "psm_predict_device before psm_init_with_tables");
+    if (!d_cells) PSM_FAIL(h, PSM_ERR_INVALID, "NULL buffer");
+    if (n_cells != h->n_cells) PSM_FAIL(h, PSM_ERR_INVALID, "n_cells does not match the initialised mesh");
+    if (d_p_out && !h->have_back) PSM_FAIL(h, PSM_ERR_STATE, "no grid->cell tables were given");
+    CU(h, cudaSetDevice(h->cfg.device));
+    if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
+    h->last_host = false;
+    TRY(run_step(h, d_cells, d_p_out));
+    if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
+    if (sync) return finish(h);
+    return PSM_OK;
+}
+
+extern "C" int psm_synchronize(psm_handle* h) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "not initialised");
+    CU(h, cudaSetDevice(h->cfg.device));
+    return finish(h);
+}
+
+extern "C" int psm_register_host_buffer(void* ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) return PSM_ERR_INVALID;
+    return cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess ? PSM_OK : PSM_ERR_CUDA;
+}
+extern "C" int psm_unregister_host_buffer(void* ptr) {
+    if (!ptr) return PSM_ERR_INVALID;
+    return cudaHostUnregister(ptr) == cudaSuccess ? PSM_OK : PSM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int psm_get_geometry(const psm_handle* h, psm_geometry* g) {
+    if (!h || !g) return PSM_ERR_INVALID;
+    if (!h->initialised) return PSM_ERR_STATE;
+    const Plan& P = h->plan;
+    g->grid_h = P.H; g->grid_w = P.W; g->shape = P.S; g->overlap = P.ov; g->n_x = P.n_x; g->n_y = P.n_y;
+    g->p_i = P.p_i; g->p_j = P.p_j; g->n_blocks = P.B; g->n_fields = P.F; g->n_cells = h->n_cells;
+    g->n_tasks = (int32_t)P.tasks.size(); g->reserved = 0;
+    return PSM_OK;
+}
+
+extern "C" int psm_get_plan(const psm_handle* h, int32_t* origins, int32_t* indices_list) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!h->initialised) return PSM_ERR_STATE;
+    for (int k = 0; k < h->plan.B; ++k) {
+        if (origins) { origins[2 * k] = h->plan.y0[k]; origins[2 * k + 1] = h->plan.x0[k]; }
+        if (indices_list) { indices_list[2 * k] = h->plan.idx_i[k]; indices_list[2 * k + 1] = h->plan.idx_j[k]; }
+    }
+    return PSM_OK;
+}
+
+extern "C" int psm_get_owner_map(const psm_handle* h, int32_t* owner) {
+    if (!h || !owner) return PSM_ERR_INVALID;
+    if (!h->initialised) return PSM_ERR_STATE;
+    memcpy(owner, h->plan.owner.data(), h->plan.owner.size() * sizeof(int32_t));
+    return PSM_OK;
+}
+
+extern "C" int psm_get_forward_table(const psm_handle* hc, int32_t* vert, float* weights) {
+    psm_handle* h = const_cast<psm_handle*>(hc);
+    if (!h) return PSM_ERR_INVALID;
+    if (!h->initialised) return PSM_ERR_STATE;
+    CU(h, cudaSetDevice(h->cfg.device));
+    std::vector<int32_t> v(h->G); std::vector<float> w(h->G);
+    for (int j = 0; j < 3; ++j) {
+        CU(h, cudaMemcpy(v.data(), h->d_fv[j], h->G * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        CU(h, cudaMemcpy(w.data(), h->d_fw[j], h->G * sizeof(float), cudaMemcpyDeviceToHost));
+        for (long long q = 0; q < h->G; ++q) {
+            if (vert) vert[3 * q + j] = v[q];
+            if (weights) weights[3 * q + j] = w[q];
+        }
+    }
+    return PSM_OK;
+}
+
+extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_bytes) {
+    if (!h || !out) return PSM_ERR_INVALID;
+    if (!h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "not initialised");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    const int S2 = h->S * h->S;
+    auto need = [&](int64_t want) -> int {
+        if (n_bytes != want) PSM_FAIL(h, PSM_ERR_INVALID, "stage %d needs %lld bytes, got %lld", stage, (long long)want, (long long)n_bytes);
+        return 0;
+    };
+    switch (stage) {
+        case PSM_STAGE_GRID:
+            TRY(need((int64_t)2 * h->G * 4));
+            CU(h, cudaMemcpy(out, h->d_grid, h->G * 4, cudaMemcpyDeviceToHost));
+            CU(h, cudaMemcpy((char*)out + h->G * 4, h->d_grid + h->G_pad, h->G * 4, cudaMemcpyDeviceToHost));
+            return PSM_OK;
+        case PSM_STAGE_XINPUT:
+            TRY(need((int64_t)h->B * h->pc_in * 4));
+            CU(h, cudaMemcpy2D(out, (size_t)h->pc_in * 4, h->d_xin, (size_t)h->pc_in_pad * 4, (size_t)h->pc_in * 4, h->B, cudaMemcpyDeviceToHost));
+            return PSM_OK;
+        case PSM_STAGE_MLPOUT:
+            TRY(need((int64_t)h->B * h->pc_p * 4));
+            CU(h, cudaMemcpy2D(out, (size_t)h->pc_p * 4, h->d_r, (size_t)h->pc_p_pad * 4, (size_t)h->pc_p * 4, h->B, cudaMemcpyDeviceToHost));
+            return PSM_OK;
+        case PSM_STAGE_BLOCKS:
+            TRY(need((int64_t)h->B * h->C * S2 * 4));
+            CU(h, cudaMemcpy(out, h->d_blocks, (size_t)h->B * h->C * S2 * 4, cudaMemcpyDeviceToHost));
+            return PSM_OK;
+        case PSM_STAGE_OFFSETS:
+            TRY(need((int64_t)h->F * h->B * 8));
+            CU(h, cudaMemcpy(out, h->d_offsets, (size_t)h->F * h->B * 8, cudaMemcpyDeviceToHost));
+            return PSM_OK;
+        case PSM_STAGE_FIELD:
+            TRY(need((int64_t)h->F * h->G * 4));
+            CU(h, cudaMemcpy(out, h->d_field, (size_t)h->F * h->G * 4, cudaMemcpyDeviceToHost));
+            return PSM_OK;
+        case PSM_STAGE_SCALARS: {
+            TRY(need(4 * 8));
+            Scalars sc;
+            CU(h, cudaMemcpy(&sc, h->d_sc, sizeof sc, cudaMemcpyDeviceToHost));
+            double* o = (double*)out;
+            o[0] = sc.U_max_norm; o[1] = sc.dU_max_norm; o[2] = sc.shift[0]; o[3] = sc.shift[1];
+            return PSM_OK;
+        }
+        case PSM_STAGE_MEANS:
+            TRY(need((int64_t)h->n_tasks * 8));
+            CU(h, cudaMemcpy(out, h->d_means, (size_t)h->n_tasks * 8, cudaMemcpyDeviceToHost));
+            return PSM_OK;
+        default:
+            PSM_FAIL(h, PSM_ERR_INVALID, "unknown stage %d", stage);
+    }
+}
+
+extern "C" int psm_get_timings(psm_handle* h, float* ms, int32_t n) {
+    if (!h || !ms) return PSM_ERR_INVALID;
+    if (!h->ev_valid) PSM_FAIL(h, PSM_ERR_STATE, "timings were not enabled in psm_config");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    // events: ev[0] start, ev[11] after the H2D copy (host entry point only), ev[1..10] after
+    // prep .. back_gather, ev[12] end (after the D2H copy)
+    for (int i = 0; i < n && i < PSM_N_TIMINGS; ++i) ms[i] = 0.f;
+    float t = 0.f;
+    if (h->last_host && cudaEventElapsedTime(&t, h->ev[0], h->ev[11]) == cudaSuccess) ms[0] = t;
+    if (n > 1 && cudaEventElapsedTime(&t, h->ev[h->last_host ? 11 : 0], h->ev[1]) == cudaSuccess) ms[1] = t;
+    for (int i = 2; i <= 10 && i < n; ++i)
+        if (cudaEventElapsedTime(&t, h->ev[i - 1], h->ev[i]) == cudaSuccess) ms[i] = t;
+    if (n > 11 && cudaEventElapsedTime(&t, h->ev[10], h->ev[PSM_N_TIMINGS]) == cudaSuccess) ms[11] = t;
+    return PSM_OK;
+}
+
+extern "C" int psm_get_launch_count(const psm_handle* h) { return h ? h->launches : 0; }

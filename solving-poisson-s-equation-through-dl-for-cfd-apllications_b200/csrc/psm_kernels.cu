@@ -1,0 +1,399 @@
+// Hot-path kernels for sm_100a.  Reference lines each stage replaces are cited per kernel
+// (aliases as in include/psm_b200.h).  All HBM-bound kernels use 128-bit accesses over SoA
+// tables and grids sized in multiples of the SM count.
+#include "psm_kernels.cuh"
+
+#include <math_constants.h>
+
+namespace psm {
+
+static constexpr int kSMs = 148;
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0  prep: de-interleave the solver's double[n][ncol] rows, form the field to interpolate,
+//     running max of |U|^2 and |dU|^2.   PMP:267-273, SMC:386-405.
+//     The squares/sum are rounded separately (no FMA) so that U_max_norm is bit-identical to
+//     np.max(np.sqrt(np.square(Ux) + np.square(Uy))).
+__global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
+    double m_u = 0.0, m_d = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        const double* row = a.cells + i * a.ncol;
+        const double ux = row[0], uy = row[1];
+        a.p_prev[i] = row[4];
+        m_u = fmax(m_u, __dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)));
+        double fx, fy;
+        if (a.mode == 0) { fx = ux; fy = uy; }
+        else if (a.mode == 1) { fx = row[5]; fy = row[6]; }
+        else {
+            double2 prev = reinterpret_cast<double2*>(a.u_prev)[i];
+            fx = ux - prev.x; fy = uy - prev.y;
+            reinterpret_cast<double2*>(a.u_prev)[i] = make_double2(ux, uy);
+        }
+        if (a.mode != 0) m_d = fmax(m_d, __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)));
+        a.uv[i] = make_float2((float)fx, (float)fy);
+    }
+    m_u = warp_max(m_u);
+    m_d = warp_max(m_d);
+    __shared__ double s_u[8], s_d[8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_u[w] = m_u; s_d[w] = m_d; }
+    __syncthreads();
+    if (w == 0) {
+        m_u = (l < 8) ? s_u[l] : 0.0;
+        m_d = (l < 8) ? s_d[l] : 0.0;
+        m_u = warp_max(m_u);
+        m_d = warp_max(m_d);
+        if (l == 0) {   // non-negative doubles order like their bit patterns; NaN inputs are not ordered
+            atomicMax(&a.sc->umax2_bits, (unsigned long long)__double_as_longlong(m_u));
+            atomicMax(&a.sc->dumax2_bits, (unsigned long long)__double_as_longlong(m_d));
+        }
+    }
+}
+
+void launch_prep(const PrepArgs& a, cudaStream_t s) {
+    long long want = (a.n + 255) / 256;
+    int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
+    prep_kernel<<<blocks, 256, 0, s>>>(a);
+}
+
+// Scalars of the step (1 thread): U_max_norm, skip rule, scales; re-arms the running maxima.
+__global__ void scalars_kernel(ScalarArgs a) {
+    Scalars* sc = a.sc;
+    const double um = sqrt(__longlong_as_double((long long)sc->umax2_bits));
+    const double dm = sqrt(__longlong_as_double((long long)sc->dumax2_bits));
+    sc->U_max_norm = um;
+    sc->dU_max_norm = dm;
+    sc->in_scale[0] = (float)(1.0 / (um * a.max_abs_ux));
+    sc->in_scale[1] = (float)(1.0 / (um * a.max_abs_uy));
+    sc->out_scale = (float)(a.dimensionalise ? a.out_scale_base * um * um : a.out_scale_base);
+    int skip = 0;
+    if (a.mode != 0) {
+        if (a.skip_threshold > 0.0 && (dm / um) < a.skip_threshold) skip = 1;     // SMC:410-415
+        if (a.mode == 2 && !sc->have_prev) skip = 1;                              // no U(t-1) yet
+    }
+    sc->skip = skip;
+    sc->have_prev = 1;
+    sc->umax2_bits = 0ull;
+    sc->dumax2_bits = 0ull;
+}
+void launch_scalars(const ScalarArgs& a, cudaStream_t s) { scalars_kernel<<<1, 1, 0, s>>>(a); }
+
+// ------------------------------------------------------------------------------------------------
+// K1  cell -> grid gather.  UTL:88-89 (einsum over np.take), SMC:432-444 (scatter into the grid,
+//     NaN -> 0, max-abs scaling).  Validity, the negative-weight NaN rule and the (0,0) raster
+//     quirk are folded into the tables at init, so this is a pure weighted gather.
+__device__ __forceinline__ float2 ldg_f2(const float2* p) { return __ldg(p); }
+
+__global__ void __launch_bounds__(256) gather_kernel(GatherArgs a) {
+    const float s0 = a.sc->in_scale[0], s1 = a.sc->in_scale[1];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < a.n_pix4; g += stride) {
+        const int4 i0 = __ldcs(reinterpret_cast<const int4*>(a.v0) + g);
+        const int4 i1 = __ldcs(reinterpret_cast<const int4*>(a.v1) + g);
+        const int4 i2 = __ldcs(reinterpret_cast<const int4*>(a.v2) + g);
+        const float4 q0 = __ldcs(reinterpret_cast<const float4*>(a.w0) + g);
+        const float4 q1 = __ldcs(reinterpret_cast<const float4*>(a.w1) + g);
+        const float4 q2 = __ldcs(reinterpret_cast<const float4*>(a.w2) + g);
+        float2 a0 = ldg_f2(a.uv + i0.x), b0 = ldg_f2(a.uv + i1.x), c0 = ldg_f2(a.uv + i2.x);
+        float2 a1 = ldg_f2(a.uv + i0.y), b1 = ldg_f2(a.uv + i1.y), c1 = ldg_f2(a.uv + i2.y);
+        float2 a2 = ldg_f2(a.uv + i0.z), b2 = ldg_f2(a.uv + i1.z), c2 = ldg_f2(a.uv + i2.z);
+        float2 a3 = ldg_f2(a.uv + i0.w), b3 = ldg_f2(a.uv + i1.w), c3 = ldg_f2(a.uv + i2.w);
+        float4 ox, oy;
+        ox.x = (a0.x * q0.x + b0.x * q1.x + c0.x * q2.x) * s0;  oy.x = (a0.y * q0.x + b0.y * q1.x + c0.y * q2.x) * s1;
+        ox.y = (a1.x * q0.y + b1.x * q1.y + c1.x * q2.y) * s0;  oy.y = (a1.y * q0.y + b1.y * q1.y + c1.y * q2.y) * s1;
+        ox.z = (a2.x * q0.z + b2.x * q1.z + c2.x * q2.z) * s0;  oy.z = (a2.y * q0.z + b2.y * q1.z + c2.y * q2.z) * s1;
+        ox.w = (a3.x * q0.w + b3.x * q1.w + c3.x * q2.w) * s0;  oy.w = (a3.y * q0.w + b3.y * q1.w + c3.y * q2.w) * s1;
+        // grid[np.isnan(grid)] = 0  (SMC:438)
+        ox.x = (ox.x != ox.x) ? 0.f : ox.x; ox.y = (ox.y != ox.y) ? 0.f : ox.y;
+        ox.z = (ox.z != ox.z) ? 0.f : ox.z; ox.w = (ox.w != ox.w) ? 0.f : ox.w;
+        oy.x = (oy.x != oy.x) ? 0.f : oy.x; oy.y = (oy.y != oy.y) ? 0.f : oy.y;
+        oy.z = (oy.z != oy.z) ? 0.f : oy.z; oy.w = (oy.w != oy.w) ? 0.f : oy.w;
+        reinterpret_cast<float4*>(a.grid0)[g] = ox;
+        reinterpret_cast<float4*>(a.grid1)[g] = oy;
+    }
+}
+void launch_gather(const GatherArgs& a, cudaStream_t s) {
+    long long want = (a.n_pix4 + 255) / 256;
+    int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
+    gather_kernel<<<blocks, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  block extraction.  SMC:464-492: slices grid[y0:y0+S, x0:x0+S, 0:2] per plan entry; the
+//     operand is stored planar (c, ly, lx) -- the PCA matrix is permuted to match at init.
+__global__ void __launch_bounds__(256) extract_kernel(ExtractArgs a) {
+    // one warp per (block, channel, row): 128 floats = 32 lanes x 4
+    const int S = a.S;
+    const long long rows = (long long)a.B * a.nch * S;
+    const int lane = threadIdx.x & 31;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += wstride) {
+        const int ly = (int)(r % S);
+        const int c = (int)((r / S) % a.nch);
+        const int b = (int)(r / ((long long)a.nch * S));
+        const float* src = (c ? a.grid1 : a.grid0) + (long long)(a.by0[b] + ly) * a.W + a.bx0[b] + lane * 4;
+        float4 v = make_float4(src[0], src[1], src[2], src[3]);
+        reinterpret_cast<float4*>(a.xu + ((long long)b * a.nch + c) * S * S + (long long)ly * S)[lane] = v;
+    }
+}
+void launch_extract(const ExtractArgs& a, cudaStream_t s) {
+    long long rows = (long long)a.B * a.nch * a.S;
+    long long want = (rows + 7) / 8;
+    int blocks = (int)(want < (long long)kSMs * 8 ? want : kSMs * 8);
+    extract_kernel<<<blocks, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 GEMM (CUDA cores), C = A * B^T, 64x64x16 tiles, 4x4 register blocking.
+template <int EPI>
+__global__ void __launch_bounds__(256) sgemm_nt_kernel(GemmArgs a) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    int k_begin = 0, k_end = a.K;
+    if (EPI == EPI_PARTIAL) {
+        const int kper = ((a.K / BK + a.splits - 1) / a.splits) * BK;
+        k_begin = blockIdx.z * kper;
+        k_end = min(a.K, k_begin + kper);
+    }
+    const int lr = tid >> 2, lc = (tid & 3) * 4;      // loader: row lr (0..63), k offset lc
+    const float* Ap = a.A + (long long)(m0 + lr) * a.lda + lc;
+    const float* Bp = a.B + (long long)(n0 + lr) * a.ldb + lc;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        const float4 av = *reinterpret_cast<const float4*>(Ap + k0);
+        const float4 bv = *reinterpret_cast<const float4*>(Bp + k0);
+        As[lc + 0][lr] = av.x; As[lc + 1][lr] = av.y; As[lc + 2][lr] = av.z; As[lc + 3][lr] = av.w;
+        Bs[lc + 0][lr] = bv.x; Bs[lc + 1][lr] = bv.y; Bs[lc + 2][lr] = bv.z; Bs[lc + 3][lr] = bv.w;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            const float4 ra = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float4 rb = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            const float am[4] = {ra.x, ra.y, ra.z, ra.w};
+            const float bn[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(am[i], bn[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* Cp = a.C;
+    if (EPI == EPI_PARTIAL) Cp += (long long)blockIdx.z * a.M * a.ldc;
+    const int n = n0 + tx * 4;
+    float o_scale = 1.f;
+    if (EPI == EPI_PCA_INV) o_scale = a.sc->out_scale;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (EPI == EPI_BIAS_RELU) {
+            const float4 b = *reinterpret_cast<const float4*>(a.v0 + n);
+            o.x = fmaxf(o.x + b.x, 0.f); o.y = fmaxf(o.y + b.y, 0.f); o.z = fmaxf(o.z + b.z, 0.f); o.w = fmaxf(o.w + b.w, 0.f);
+        } else if (EPI == EPI_BIAS_AFFINE) {
+            const float4 b = *reinterpret_cast<const float4*>(a.v0 + n);
+            const float4 sc = *reinterpret_cast<const float4*>(a.v1 + n);
+            const float4 sh = *reinterpret_cast<const float4*>(a.v2 + n);
+            o.x = (o.x + b.x) * sc.x + sh.x; o.y = (o.y + b.y) * sc.y + sh.y;
+            o.z = (o.z + b.z) * sc.z + sh.z; o.w = (o.w + b.w) * sc.w + sh.w;
+        } else if (EPI == EPI_PCA_INV) {
+            const float4 b = *reinterpret_cast<const float4*>(a.v0 + n);
+            o.x = (o.x + b.x) * o_scale; o.y = (o.y + b.y) * o_scale; o.z = (o.z + b.z) * o_scale; o.w = (o.w + b.w) * o_scale;
+        }
+        *reinterpret_cast<float4*>(Cp + (long long)m * a.ldc + n) = o;
+    }
+}
+
+void launch_sgemm(const GemmArgs& a, cudaStream_t s) {
+    dim3 grid(a.N / 64, a.M / 64, a.epi == EPI_PARTIAL ? a.splits : 1);
+    switch (a.epi) {
+        case EPI_PARTIAL:     sgemm_nt_kernel<EPI_PARTIAL><<<grid, 256, 0, s>>>(a); break;
+        case EPI_BIAS_RELU:   sgemm_nt_kernel<EPI_BIAS_RELU><<<grid, 256, 0, s>>>(a); break;
+        case EPI_BIAS_AFFINE: sgemm_nt_kernel<EPI_BIAS_AFFINE><<<grid, 256, 0, s>>>(a); break;
+        case EPI_PCA_INV:     sgemm_nt_kernel<EPI_PCA_INV><<<grid, 256, 0, s>>>(a); break;
+        default:              sgemm_nt_kernel<EPI_PLAIN><<<grid, 256, 0, s>>>(a); break;
+    }
+}
+
+__global__ void __launch_bounds__(256) reduce_standardise_kernel(ReduceArgs a) {
+    const long long total = (long long)a.M * a.N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(i % a.N);
+        float sum = 0.f;
+        for (int sp = 0; sp < a.splits; ++sp) sum += a.part[(long long)sp * total + i];
+        a.x[i] = (sum + a.zc[i]) * a.a[n] + a.b[n];
+    }
+}
+void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {
+    long long total = (long long)a.M * a.N;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > kSMs * 4) blocks = kSMs * 4;
+    reduce_standardise_kernel<<<blocks, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6a  masked rectangle means.  Every np.mean(pred[rect][flow_bool[rect] != 0]) of SMC:233-316 /
+//      GRAD:300-340 on the UNCORRECTED blocks; FP64 accumulation.  One CTA per task.
+__global__ void __launch_bounds__(128) means_kernel(MeansArgs a) {
+    const DevTask t = a.tasks[blockIdx.x];
+    const int w = t.x1 - t.x0, h = t.y1 - t.y0;
+    const float* src = a.blocks + ((long long)t.src * a.C + t.ch) * a.S * a.S;
+    const uint8_t* msk = a.gmask + (long long)a.by0[t.msk] * a.W + a.bx0[t.msk];
+    double sum = 0.0;
+    for (int q = threadIdx.x; q < w * h; q += blockDim.x) {
+        const int y = t.y0 + q / w, x = t.x0 + q % w;
+        if (msk[(long long)y * a.W + x]) sum += (double)src[y * a.S + x];
+    }
+    sum = warp_sum(sum);
+    __shared__ double sm[4];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double tot = sm[0] + sm[1] + sm[2] + sm[3];
+        a.means[blockIdx.x] = (t.count > 0) ? tot / (double)t.count : CUDART_NAN;
+    }
+}
+void launch_means(const MeansArgs& a, cudaStream_t s) {
+    if (a.n_tasks > 0) means_kernel<<<a.n_tasks, 128, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6b  offsets.  c_k = m[a] - (m[b] - c[parent])  is a sum along the parent chain of
+//      d_k = m[a] - m[b] (roots: m[a] - Ref_BC), evaluated by pointer jumping in
+//      ceil(log2(depth)) rounds; then the global shift of SMC:350 / GRAD:358-361 through the
+//      owner map.  Single CTA: the whole problem is a few thousand scalars.
+__global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
+    const int n = a.B * a.F;
+    double* d_cur = a.dbuf0; double* d_nxt = a.dbuf1;
+    int32_t* p_cur = a.pbuf0; int32_t* p_nxt = a.pbuf1;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const DevRec r = a.rec[i];
+        const int f = i / a.B;
+        double d = a.means[r.ta] - (r.tb >= 0 ? a.means[r.tb] : a.ref_bc);
+        d_cur[i] = d;
+        p_cur[i] = (r.parent >= 0) ? f * a.B + r.parent : -1;
+    }
+    __syncthreads();
+    for (int round = 0; round < a.rounds; ++round) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int p = p_cur[i];
+            double d = d_cur[i];
+            int pn = -1;
+            if (p >= 0) { d += d_cur[p]; pn = p_cur[p]; }
+            d_nxt[i] = d; p_nxt[i] = pn;
+        }
+        __syncthreads();
+        double* td = d_cur; d_cur = d_nxt; d_nxt = td;
+        int32_t* tp = p_cur; p_cur = p_nxt; p_nxt = tp;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a.offsets[i] = d_cur[i];
+    __syncthreads();
+    __shared__ double red[32];
+    __shared__ double s_shift[2];
+    for (int f = 0; f < a.F; ++f) {
+        const int len = a.shift_axis[f] == 0 ? a.H : a.W;
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < len; i += blockDim.x) {
+            double v[2];
+#pragma unroll
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const int line = s2 == 0 ? a.shift_a[f] : a.shift_b[f];
+                const int y = a.shift_axis[f] == 0 ? i : line;
+                const int x = a.shift_axis[f] == 0 ? line : i;
+                const int o = a.owner[(long long)y * a.W + x];
+                const float pv = a.blocks[(((long long)o * a.C + f) * a.S + (y - a.by0[o])) * a.S + (x - a.bx0[o])];
+                v[s2] = (double)pv - a.offsets[f * a.B + o];
+            }
+            acc += 3.0 * v[0] - v[1];
+        }
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+            t = warp_sum(t);
+            if (threadIdx.x == 0) { s_shift[f] = t / (double)len / 3.0; a.sc->shift[f] = s_shift[f]; }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a.coff[i] = (float)(a.offsets[i] + s_shift[i / a.B]);
+}
+void launch_offsets(const OffsetsArgs& a, cudaStream_t s) { offsets_kernel<<<1, 1024, 0, s>>>(a); }
+
+// ------------------------------------------------------------------------------------------------
+// K7  placement.  SMC:332-348 / GRAD:345-356 as a gather through the last-writer map, with the
+//     block correction and the global shift subtracted on the fly.
+__global__ void __launch_bounds__(256) place_kernel(PlaceArgs a) {
+    const long long plane = (long long)a.H * a.W;
+    const long long total = plane * a.F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(i / plane);
+        const long long q = i - (long long)f * plane;
+        const int y = (int)(q / a.W), x = (int)(q - (long long)y * a.W);
+        const int o = a.owner[q];
+        const float v = a.blocks[(((long long)o * a.C + f) * a.S + (y - a.by0[o])) * a.S + (x - a.bx0[o])];
+        a.field[i] = v - a.coff[f * a.B + o];
+    }
+}
+void launch_place(const PlaceArgs& a, cudaStream_t s) {
+    long long total = (long long)a.H * a.W * a.F;
+    long long want = (total + 255) / 256;
+    int blocks = (int)(want < (long long)kSMs * 16 ? want : kSMs * 16);
+    place_kernel<<<blocks, 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8  grid -> cell gather.  PMP:481-496: result[indices] (folded into the vertex ids at init),
+//     interpolate_fill, previous-pressure fallback for NaN / near-wall cells; SMC:644-645
+//     (p = p_prev + delta_p) for the deltaU variant.
+__global__ void __launch_bounds__(256) back_kernel(BackArgs a) {
+    const int skip = a.sc->skip;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        const int i0 = __ldcs(a.v0 + i), i1 = __ldcs(a.v1 + i), i2 = __ldcs(a.v2 + i);
+        const float q0 = __ldcs(a.w0 + i), q1 = __ldcs(a.w1 + i), q2 = __ldcs(a.w2 + i);
+        if (a.n_fields == 1) {
+            const double pp = a.p_prev[i];
+            double out = pp;
+            if (i0 >= 0 && !skip) {
+                const float v = __ldg(a.field + i0) * q0 + __ldg(a.field + i1) * q1 + __ldg(a.field + i2) * q2;
+                if (v == v) out = a.additive ? pp + (double)v : (double)v;
+            }
+            a.out[i] = out;
+        } else {
+            double o0 = CUDART_NAN, o1 = CUDART_NAN;
+            if (i0 >= 0) {
+                const float* f1 = a.field + a.plane;
+                o0 = (double)(__ldg(a.field + i0) * q0 + __ldg(a.field + i1) * q1 + __ldg(a.field + i2) * q2);
+                o1 = (double)(__ldg(f1 + i0) * q0 + __ldg(f1 + i1) * q1 + __ldg(f1 + i2) * q2);
+            }
+            reinterpret_cast<double2*>(a.out)[i] = make_double2(o0, o1);
+        }
+    }
+}
+void launch_back(const BackArgs& a, cudaStream_t s) {
+    long long want = (a.n + 255) / 256;
+    int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
+    back_kernel<<<blocks, 256, 0, s>>>(a);
+}
+
+}  // namespace psm

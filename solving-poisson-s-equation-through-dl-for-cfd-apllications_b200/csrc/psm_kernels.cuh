@@ -1,0 +1,132 @@
+// Device-side data structures and kernel launchers of the surrogate hot path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace psm {
+
+// Per-step scalars kept on the device so that no host round-trip sits inside a step.
+struct Scalars {
+    unsigned long long umax2_bits;   // running max of Ux^2+Uy^2 (bit pattern of a non-negative double)
+    unsigned long long dumax2_bits;  // running max of dUx^2+dUy^2
+    double U_max_norm;               // SMC:404
+    double dU_max_norm;              // SMC:405
+    double shift[2];                 // global shift per field, SMC:350 / GRAD:358-361
+    float  in_scale[2];              // 1 / (U_max_norm * max_abs_U{x,y})        SMC:418-419,441-442
+    float  out_scale;                // max_abs_p * U_max_norm^2 (SMC:551) or 1 (GRAD:537-538)
+    int    skip;                     // 1: irrelevant time step (SMC:410-415) or no previous U yet
+    int    have_prev;                // 5-column deltaU mode: U(t-1) is resident
+    int    pad;
+};
+
+struct PrepArgs {
+    const double* cells;  // [n][ncol]
+    long long n;
+    int ncol;
+    int mode;             // 0: field = (col0, col1) [U_to_gradP]; 1: field = (col5, col6); 2: field = U - U_prev
+    float2* uv;           // [n] field to interpolate (not yet scaled)
+    double* p_prev;       // [n] column 4
+    double* u_prev;       // [n][2] (mode 2)
+    Scalars* sc;
+};
+void launch_prep(const PrepArgs& a, cudaStream_t s);
+
+struct ScalarArgs {
+    Scalars* sc;
+    double max_abs_ux, max_abs_uy, out_scale_base;  // out_scale = base * (dimensionalise ? U^2 : 1)
+    int dimensionalise;
+    double skip_threshold;
+    int mode;
+};
+void launch_scalars(const ScalarArgs& a, cudaStream_t s);
+
+// K1: cell -> grid barycentric gather over the folded tables (SoA, padded to a multiple of 4).
+struct GatherArgs {
+    const int32_t* v0; const int32_t* v1; const int32_t* v2;
+    const float* w0; const float* w1; const float* w2;
+    const float2* uv;
+    float* grid0; float* grid1;   // planes [H*W] (padded)
+    long long n_pix4;             // number of 4-pixel groups
+    const Scalars* sc;
+};
+void launch_gather(const GatherArgs& a, cudaStream_t s);
+
+// K2: overlapping block extraction into the K-major operand x_u[B_pad][2*S*S] (planar c, ly, lx).
+struct ExtractArgs {
+    const float* grid0; const float* grid1;   // channel planes [H*W]; nch == 1 uses grid0 only
+    const int32_t* by0; const int32_t* bx0;
+    float* xu; int B; int W; int S; int nch;
+};
+void launch_extract(const ExtractArgs& a, cudaStream_t s);
+
+// FP32 CUDA-core GEMM  C[M,N] = A[M,K] * B[N,K]^T  (both operands K-major), fused epilogues.
+// Used for init-time constant folding and as the debug cross-check of the tensor-core path.
+enum EpiKind { EPI_PARTIAL = 0, EPI_BIAS_RELU = 1, EPI_BIAS_AFFINE = 2, EPI_PCA_INV = 3, EPI_PLAIN = 4 };
+struct GemmArgs {
+    const float* A; const float* B; float* C;
+    int M, N, K;          // M % 64 == 0, N % 64 == 0, K % 16 == 0 (buffers are padded at init)
+    int lda, ldb, ldc;
+    int splits;           // EPI_PARTIAL: split-K factor, C holds [splits][M][N]
+    int epi;
+    const float* v0;      // bias[n] / pca mean[n]
+    const float* v1;      // scale[n]
+    const float* v2;      // shift[n]
+    const Scalars* sc;    // EPI_PCA_INV: out_scale
+};
+void launch_sgemm(const GemmArgs& a, cudaStream_t s);
+
+// Split-K reduction + per-block constant + standardisation (SMC:494,512).
+struct ReduceArgs {
+    const float* part; int splits; int M; int N;
+    const float* zc;      // [M][N] static sdf-channel contribution per block
+    const float* a; const float* b;   // x = (sum + zc) * a[n] + b[n]
+    float* x;
+};
+void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s);
+
+// K6a: masked rectangle means of the predicted blocks.
+struct DevTask { int32_t src, msk, ch, y0, y1, x0, x1, count; };
+struct MeansArgs {
+    const DevTask* tasks; int n_tasks;
+    const float* blocks;              // [B_pad][C][S][S]
+    const uint8_t* gmask;             // [H][W]
+    const int32_t* by0; const int32_t* bx0;
+    int C, S, W;
+    double* means;                    // [n_tasks]
+};
+void launch_means(const MeansArgs& a, cudaStream_t s);
+
+// K6b: offset recurrence (pointer jumping over the parent forest) + global shift.
+struct DevRec { int32_t ta, tb, parent, is_nan; };
+struct OffsetsArgs {
+    const DevRec* rec; int B; int F; int rounds; double ref_bc;
+    const double* means;
+    double* dbuf0; double* dbuf1; int32_t* pbuf0; int32_t* pbuf1;   // scratch [F*B]
+    double* offsets;                  // [F][B]  c_k
+    float* coff;                      // [F][B]  c_k + shift_f (consumed by the placement)
+    const float* blocks; const uint16_t* owner; const int32_t* by0; const int32_t* bx0;
+    int C, S, H, W;
+    int shift_axis[2], shift_a[2], shift_b[2];
+    Scalars* sc;
+};
+void launch_offsets(const OffsetsArgs& a, cudaStream_t s);
+
+// K7: placement through the owner map.
+struct PlaceArgs {
+    const float* blocks; const uint16_t* owner; const int32_t* by0; const int32_t* bx0;
+    const float* coff; float* field; int B, C, F, S, H, W;
+};
+void launch_place(const PlaceArgs& a, cudaStream_t s);
+
+// K8: grid -> cell gather, fallbacks (PMP:481-496).
+struct BackArgs {
+    const int32_t* v0; const int32_t* v1; const int32_t* v2;   // flat pixel ids, v0 < 0: keep p_prev
+    const float* w0; const float* w1; const float* w2;
+    const float* field; long long n; long long plane;           // plane = H*W
+    const double* p_prev; double* out;
+    int n_fields; int additive;
+    const Scalars* sc;
+};
+void launch_back(const BackArgs& a, cudaStream_t s);
+
+}  // namespace psm

@@ -1,0 +1,41 @@
+"""Build ``libpsm_b200.so`` in-tree with nvcc for sm_100a (``python -m psm_b200.build``).
+
+The built library lives next to this file (git-ignored, but it travels with the tree to the
+GPU box).  nvcc cross-compiles without a GPU.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(HERE), 'csrc')
+OUT = os.path.join(HERE, 'libpsm_b200.so')
+SOURCES = ['psm_plan.cpp', 'psm_kernels.cu', 'psm_handle.cu']
+HEADERS = ['psm_plan.h', 'psm_kernels.cuh', os.path.join('..', '..', 'include', 'psm_b200.h')]
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
+         '-Xcompiler', '-fPIC,-Wall,-Wno-unused-function', '-shared']
+
+
+def up_to_date():
+    if not os.path.exists(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(os.path.join(CSRC, f)) <= t for f in SOURCES + HEADERS)
+
+
+def build(force=False, verbose=False):
+    if not force and up_to_date():
+        return OUT
+    cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT] + SOURCES
+    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError('nvcc failed building libpsm_b200.so')
+    if verbose:
+        sys.stderr.write(r.stderr)
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,222 @@
+"""Python face of the C-ABI handle: ``PressureSurrogate``.
+
+Thin by design -- argument marshalling only.  All per-step arithmetic happens in the CUDA
+library behind ``psm_predict``; see ``python_module.py`` for the reference-named
+``init_func`` / ``py_func`` surface built on top of this class.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi as capi
+from . import tables as _tables
+
+_VARIANT_CODE = {'deltaU_to_deltaP': capi.PSM_DELTAU_TO_DELTAP, 'U_to_gradP': capi.PSM_U_TO_GRADP}
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def compile_plan(variant, H, W, mask, shape=128, overlap=32):
+    """Host-only plan compiler (no GPU): returns dict(origins, indices_list, owner, rec, tasks)."""
+    lib = capi.load()
+    mask = np.ascontiguousarray(mask, dtype=np.uint8)
+    assert mask.shape == (H, W)
+    nb, nf, nt = C.c_int32(), C.c_int32(), C.c_int32()
+    v = _VARIANT_CODE[variant]
+    rc = lib.psm_plan_sizes(v, H, W, shape, overlap, _ptr(mask, C.c_uint8), C.byref(nb), C.byref(nf), C.byref(nt))
+    if rc < 0:
+        raise capi.PsmError(rc, 'plan rejected (geometry on which the reference is undefined)')
+    B, F, T = nb.value, nf.value, nt.value
+    origins = np.zeros((B, 2), np.int32)
+    il = np.zeros((B, 2), np.int32)
+    owner = np.zeros((H, W), np.int32)
+    rec = np.zeros((F, B, 4), np.int32)
+    tasks = np.zeros((T, 8), np.int32)
+    rc = lib.psm_plan_compile(v, H, W, shape, overlap, _ptr(mask, C.c_uint8), _ptr(origins, C.c_int32),
+                              _ptr(il, C.c_int32), _ptr(owner, C.c_int32), _ptr(rec, C.c_int32), _ptr(tasks, C.c_int32))
+    if rc < 0:
+        raise capi.PsmError(rc, 'plan rejected')
+    return dict(origins=origins, indices_list=il, owner=owner, rec=rec, tasks=tasks, n_blocks=B, n_fields=F)
+
+
+class PressureSurrogate:
+    """One mesh, one GPU, one stream.  Mirrors the lifetime of the reference's module globals
+    (PMP:103-118 params, PMP:193 tables) behind an explicit handle."""
+
+    def __init__(self, variant='deltaU_to_deltaP', device=0, delta=5e-3, shape=128, overlap=None, input_cols=None,
+                 additive=True, ref_bc=0.0, skip_threshold=1e-4, near_wall_sdf=0.0, timings=False):
+        if variant not in _VARIANT_CODE:
+            raise ValueError('variant must be one of %s' % list(_VARIANT_CODE))
+        self.lib = capi.load()
+        self.variant = variant
+        if overlap is None:
+            overlap = 32 if variant == 'deltaU_to_deltaP' else 96       # EP:90 overlap_ratio 0.25 ; GRAD:708 avance
+        if input_cols is None:
+            input_cols = 7 if variant == 'deltaU_to_deltaP' else 5
+        self.input_cols = input_cols
+        self.n_fields = 1 if variant == 'deltaU_to_deltaP' else 2
+        self.delta = delta
+        cfg = capi.PsmConfig(variant=_VARIANT_CODE[variant], device=device, delta=delta, shape=shape, overlap=overlap,
+                             input_cols=input_cols, additive=int(additive), ref_bc=ref_bc,
+                             skip_threshold=skip_threshold, near_wall_sdf=near_wall_sdf,
+                             enable_timings=int(timings), reserved=0)
+        self._h = C.c_void_p()
+        rc = self.lib.psm_create(C.byref(self._h), C.byref(cfg))
+        if rc < 0:
+            raise capi.PsmError(rc, (self.lib.psm_last_error(None) or b'').decode())
+        self.n_cells = None
+        self._keep = []
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            self.lib.psm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        return capi.check(self._h, rc)
+
+    # ------------------------------------------------------------------ init
+    def load_params(self, p):
+        """``p``: dict as produced by ``psm_b200.synthetic.make_params`` / ``psm_b200.params.load_reference_dir``."""
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        P = capi.PsmParams()
+        maxs = list(np.asarray(p['maxs'], dtype=np.float64)) + [1.0] * 5
+        P.maxs = (C.c_double * 5)(*maxs[:5])
+        cin, cout = f64(p['pca_in_components']), f64(p['pca_out_components'])
+        min_, mout = f64(p['pca_in_mean']), f64(p['pca_out_mean'])
+        P.pc_in, P.pc_p = cin.shape[0], cout.shape[0]
+        P.n_out_channels = int(p.get('n_out_channels', 1))
+        keep = [cin, cout, min_, mout]
+        P.pca_in_components, P.pca_in_mean = _ptr(cin, C.c_double), _ptr(min_, C.c_double)
+        P.pca_out_components, P.pca_out_mean = _ptr(cout, C.c_double), _ptr(mout, C.c_double)
+        if p.get('standardization', 'std') == 'std':
+            P.standardization = capi.PSM_STD
+            for name in ('mean_in', 'std_in', 'mean_out', 'std_out'):
+                a = f64(p[name])
+                keep.append(a)
+                setattr(P, name, _ptr(a, C.c_double))
+        else:
+            P.standardization = capi.PSM_MAX_ABS
+            P.max_abs_input_PCA = float(p['max_abs_input_PCA'])
+            P.max_abs_output_PCA = float(p['max_abs_output_PCA'])
+        ws = [np.ascontiguousarray(w, dtype=np.float32) for w in p['mlp_weights']]
+        bs = [np.ascontiguousarray(b, dtype=np.float32) for b in p['mlp_biases']]
+        dims = np.ascontiguousarray([ws[0].shape[0]] + [w.shape[1] for w in ws], dtype=np.int32)
+        P.n_dense = len(ws)
+        P.layer_dims = _ptr(dims, C.c_int32)
+        wp = (capi.c_float_p * len(ws))(*[_ptr(w, C.c_float) for w in ws])
+        bp = (capi.c_float_p * len(bs))(*[_ptr(b, C.c_float) for b in bs])
+        P.dense_kernels, P.dense_biases = wp, bp
+        keep += ws + bs + [dims, wp, bp]
+        self._check(self.lib.psm_load_params(self._h, C.byref(P)))
+        self.pc_in, self.pc_p = P.pc_in, P.pc_p
+        return self
+
+    def init_tables(self, t):
+        """``t``: dict from ``psm_b200.tables.build_tables`` (PMP:172-247 equivalent)."""
+        T = capi.PsmTables()
+        T.n_cells, T.grid_h, T.grid_w = int(t['n_cells']), int(t['H']), int(t['W'])
+        vert = np.ascontiguousarray(t['vert'], dtype=np.int32)
+        wts = np.ascontiguousarray(t['weights'], dtype=np.float64)
+        ind = np.ascontiguousarray(t['indices'], dtype=np.int64)
+        sdf = np.ascontiguousarray(t['sdfunct'], dtype=np.float64).reshape(T.grid_h, T.grid_w)
+        T.vert, T.weights = _ptr(vert, C.c_int32), _ptr(wts, C.c_double)
+        T.indices, T.sdfunct = _ptr(ind, C.c_int64), _ptr(sdf, C.c_double)
+        keep = [vert, wts, ind, sdf]
+        if t.get('vert_back') is not None:
+            vb = np.ascontiguousarray(t['vert_back'], dtype=np.int32)
+            wb = np.ascontiguousarray(t['weights_back'], dtype=np.float64)
+            T.vert_back, T.weights_back = _ptr(vb, C.c_int32), _ptr(wb, C.c_double)
+            keep += [vb, wb]
+        self._check(self.lib.psm_init_with_tables(self._h, C.byref(T)))
+        self.n_cells, self.H, self.W = T.n_cells, T.grid_h, T.grid_w
+        g = self.geometry()
+        self.n_blocks = g['n_blocks']
+        return self
+
+    def init_from_mesh(self, cells_xy, top, obst, probe_values, back=True):
+        t = _tables.build_tables(cells_xy, top, obst, probe_values, variant=self.variant, delta=self.delta, back=back)
+        return self.init_tables(t)
+
+    # ------------------------------------------------------------------ per step
+    def predict(self, cells, out=None):
+        """``py_func`` body: host double[n][input_cols] -> host double[n] (or [n][2]).
+        Returns (out, status) with status PSM_OK or PSM_SKIPPED."""
+        cells = np.ascontiguousarray(cells, dtype=np.float64)
+        if cells.ndim != 2 or cells.shape[1] != self.input_cols:
+            raise ValueError('cells must be [n, %d]' % self.input_cols)
+        n = cells.shape[0]
+        if out is None:
+            out = np.empty(n if self.n_fields == 1 else (n, 2), dtype=np.float64)
+        rc = self._check(self.lib.psm_predict(self._h, cells.ctypes.data, n, out.ctypes.data))
+        return out, rc
+
+    def predict_device(self, d_cells_ptr, n_cells, d_out_ptr, sync=True):
+        """Device-pointer entry (ints from e.g. ``torch.Tensor.data_ptr()``); ``d_out_ptr`` may be 0."""
+        return self._check(self.lib.psm_predict_device(self._h, C.c_void_p(d_cells_ptr), n_cells,
+                                                       C.c_void_p(d_out_ptr) if d_out_ptr else None, int(sync)))
+
+    def synchronize(self):
+        return self._check(self.lib.psm_synchronize(self._h))
+
+    # ------------------------------------------------------------------ introspection
+    def geometry(self):
+        g = capi.PsmGeometry()
+        self._check(self.lib.psm_get_geometry(self._h, C.byref(g)))
+        return {k: getattr(g, k) for k, _ in g._fields_ if k != 'reserved'}
+
+    def plan(self):
+        B = self.geometry()['n_blocks']
+        o, il = np.zeros((B, 2), np.int32), np.zeros((B, 2), np.int32)
+        self._check(self.lib.psm_get_plan(self._h, _ptr(o, C.c_int32), _ptr(il, C.c_int32)))
+        return o, il
+
+    def owner_map(self):
+        ow = np.zeros((self.H, self.W), np.int32)
+        self._check(self.lib.psm_get_owner_map(self._h, _ptr(ow, C.c_int32)))
+        return ow
+
+    def forward_table(self):
+        v, w = np.zeros((self.H * self.W, 3), np.int32), np.zeros((self.H * self.W, 3), np.float32)
+        self._check(self.lib.psm_get_forward_table(self._h, _ptr(v, C.c_int32), _ptr(w, C.c_float)))
+        return v, w
+
+    def stage(self, name):
+        g = self.geometry()
+        B, F, S, Cn = g['n_blocks'], g['n_fields'], g['shape'], self.n_fields
+        spec = {
+            'grid': (capi.STAGE_GRID, (2, self.H, self.W), np.float32),
+            'x_input': (capi.STAGE_XINPUT, (B, self.pc_in), np.float32),
+            'mlp_out': (capi.STAGE_MLPOUT, (B, self.pc_p), np.float32),
+            'blocks': (capi.STAGE_BLOCKS, (B, Cn, S, S), np.float32),
+            'offsets': (capi.STAGE_OFFSETS, (F, B), np.float64),
+            'field': (capi.STAGE_FIELD, (F, self.H, self.W), np.float32),
+            'scalars': (capi.STAGE_SCALARS, (4,), np.float64),
+            'means': (capi.STAGE_MEANS, (g['n_tasks'],), np.float64),
+        }[name]
+        out = np.empty(spec[1], dtype=spec[2])
+        self._check(self.lib.psm_get_stage(self._h, spec[0], out.ctypes.data, out.nbytes))
+        return out
+
+    def timings(self):
+        ms = np.zeros(capi.N_TIMINGS, np.float32)
+        self._check(self.lib.psm_get_timings(self._h, _ptr(ms, C.c_float), capi.N_TIMINGS))
+        return dict(zip(capi.TIMING_NAMES, ms.tolist()))
+
+    def launch_count(self):
+        return int(self.lib.psm_get_launch_count(self._h))

@@ -1,0 +1,133 @@
+"""Host-side plan compiler (C++ in libpsm_b200.so, no GPU) against the oracle's literal loops."""
+import warnings
+
+import numpy as np
+import pytest
+
+import psm_b200
+from psm_b200 import _capi
+from oracle import assemble as oasm
+from oracle.pipeline import DeltasOracle, GradPOracle
+
+
+def oracle_plan(variant, H, W, ov):
+    o = (DeltasOracle(None, overlap=ov) if variant == 'deltaU_to_deltaP' else GradPOracle(None, avance=ov))
+    o.grid_shape_y, o.grid_shape_x = H, W
+    return o.block_plan()
+
+
+def disc_mask(H, W, cy, cx, r):
+    yy, xx = np.mgrid[0:H, 0:W]
+    return (((yy - cy) ** 2 + (xx - cx) ** 2) > r * r).astype(np.uint8)
+
+
+def eval_plan(plan, blocks, mask, ref_bc=0.0):
+    """NumPy evaluation of the compiled plan: task means -> sequential recurrence -> owner gather."""
+    B, F = plan['n_blocks'], plan['n_fields']
+    org = plan['origins']
+    means = np.zeros(len(plan['tasks']))
+    for t, (src, msk, ch, y0, y1, x0, x1, cnt) in enumerate(plan['tasks']):
+        m = mask[org[msk, 0] + y0:org[msk, 0] + y1, org[msk, 1] + x0:org[msk, 1] + x1] != 0
+        assert m.sum() == cnt
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", category=RuntimeWarning)
+            means[t] = np.mean(blocks[src, ch, y0:y1, x0:x1][m])
+    c = np.zeros((F, B))
+    for f in range(F):
+        for k in range(B):
+            ta, tb, par, is_nan = plan['rec'][f, k]
+            c[f, k] = means[ta] - ((means[tb] - c[f, par]) if tb >= 0 else ref_bc)
+            assert bool(is_nan) == bool(np.isnan(c[f, k]))
+    H, W = mask.shape
+    ow = plan['owner']
+    yy, xx = np.mgrid[0:H, 0:W]
+    fields = []
+    for f in range(F):
+        fields.append(blocks[ow, f, yy - org[ow, 0], xx - org[ow, 1]] - c[f][ow])
+    return c, fields
+
+
+SIZES = [(240, 330), (300, 420), (397, 998), (129, 130), (500, 700), (1000, 1000)]
+
+
+@pytest.mark.parametrize("H,W", SIZES)
+@pytest.mark.parametrize("variant,ov", [('deltaU_to_deltaP', 32), ('U_to_gradP', 96), ('deltaU_to_deltaP', 13)])
+def test_block_plan_and_owner_map_bit_exact(variant, ov, H, W):
+    st = 128 - ov
+    if (H - 128) % st == 0:
+        pytest.skip("reference undefined (p_i == 0)")
+    mask = np.ones((H, W), np.uint8)
+    plan = psm_b200.compile_plan(variant, H, W, mask, overlap=ov)
+    n_x, n_y, origins, il = oracle_plan(variant, H, W, ov)
+    np.testing.assert_array_equal(plan['origins'], np.array(origins, dtype=np.int32))
+    np.testing.assert_array_equal(plan['indices_list'], np.array(il, dtype=np.int32))
+    ow = oasm.owner_map('deltas' if variant == 'deltaU_to_deltaP' else 'grad', il, n_x, n_y, 128, ov, W, H)
+    np.testing.assert_array_equal(plan['owner'], ow)
+
+
+def test_rejects_geometries_where_the_reference_is_undefined():
+    mask = np.ones((224, 330), np.uint8)                   # (H - 128) % 96 == 0  ->  p_i == 0
+    with pytest.raises(_capi.PsmError) as e:
+        psm_b200.compile_plan('deltaU_to_deltaP', 224, 330, mask)
+    assert e.value.code == _capi.PSM_ERR_GEOMETRY
+    with pytest.raises(_capi.PsmError):                    # n_x == 0
+        psm_b200.compile_plan('deltaU_to_deltaP', 300, 128, np.ones((300, 128), np.uint8))
+    with pytest.raises(_capi.PsmError):                    # smaller than a block
+        psm_b200.compile_plan('deltaU_to_deltaP', 100, 330, np.ones((100, 330), np.uint8))
+
+
+CASES = [
+    ('deltaU_to_deltaP', 32, 240, 330, None),
+    ('deltaU_to_deltaP', 32, 300, 420, (150, 126, 20)),
+    ('deltaU_to_deltaP', 32, 240, 330, (112, 170, 70)),     # empty bottom strip -> NaN-fallback branch
+    ('deltaU_to_deltaP', 32, 240, 330, (112, 266, 75)),     # right-most column strip empty -> NaN chain
+    ('deltaU_to_deltaP', 32, 500, 700, (250, 210, 80)),
+    ('U_to_gradP', 96, 240, 340, None),
+    ('U_to_gradP', 96, 240, 340, (120, 102, 20)),
+    ('U_to_gradP', 96, 300, 421, (140, 200, 75)),
+]
+
+
+@pytest.mark.parametrize("variant,ov,H,W,disc", CASES)
+def test_closed_form_recurrence_equals_sequential_assembly(variant, ov, H, W, disc):
+    """c_k = m[a] - (m[b] - c[parent]) over the static plan reproduces SMC:221-350 / GRAD:282-361
+    (offsets, NaN pattern and assembled field) on random blocks."""
+    rng = np.random.default_rng(H * 1000 + W)
+    mask = np.ones((H, W), np.uint8) if disc is None else disc_mask(H, W, *disc)
+    plan = psm_b200.compile_plan(variant, H, W, mask, overlap=ov)
+    B, F = plan['n_blocks'], plan['n_fields']
+    blocks = rng.standard_normal((B, F, 128, 128))
+    n_x, n_y, origins, il = oracle_plan(variant, H, W, ov)
+    x_array = np.zeros((B, 128, 128, 3))
+    for k, (y0, x0) in enumerate(origins):
+        x_array[k, :, :, 2] = mask[y0:y0 + 128, x0:x0 + 128] * 0.37
+    c, fields = eval_plan(plan, blocks, mask)
+    for f in range(F):
+        if variant == 'deltaU_to_deltaP':
+            ref, offs, shift = oasm.assemble_deltas(blocks[:, 0], x_array, il, n_x, n_y, 128, ov, W, H, return_offsets=True)
+            mine = fields[0]
+            sh = np.mean(3 * mine[:, -1] - mine[:, -2]) / 3
+        else:
+            name = ('dp_dx', 'dp_dy')[f]
+            ref, offs, shift = oasm.assemble_gradp(name, blocks[:, f], x_array, il, n_x, n_y, 128, ov, W, H, return_offsets=True)
+            ref = ref[0, :, :, 0]
+            mine = fields[f]
+            sh = (np.mean(3 * mine[:, 0] - mine[:, 1]) / 3) if f == 0 else (np.mean(3 * mine[1, :] - mine[2, :]) / 3)
+        assert np.array_equal(np.isnan(offs), np.isnan(c[f]))
+        np.testing.assert_allclose(c[f], offs, rtol=0, atol=1e-12, equal_nan=True)
+        assert np.array_equal(np.isnan(ref), np.isnan(mine - sh))
+        np.testing.assert_allclose(mine - sh, ref, rtol=0, atol=1e-11, equal_nan=True)
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function include/psm_b200.h declares is exported by the built library."""
+    import os
+    import re
+    here = os.path.dirname(os.path.abspath(__file__))
+    hdr = open(os.path.join(here, '..', 'include', 'psm_b200.h')).read()
+    declared = set(re.findall(r'\b(psm_[a-z_0-9]+)\s*\(', hdr)) - {'psm_handle'}
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+    lib = _capi.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.psm_api_version() == 1
