@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""Benchmark of the pressure-surrogate hot path (BASELINE.json metric: mesh cells/s, ms per step).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload c2]
+
+One "step" = one per-timestep surrogate prediction (``py_func`` in the reference) over the whole
+synthetic mesh.  N=1 runs BASELINE.json configs[1]: deltaU_to_deltaP at ~1 M cells on a 1000x1000
+grid, random-init weights of the reference architecture (pc 128 -> 3x512 -> pc 128).
+  value    : cells/s with the solver's double[n][7] rows already resident in HBM (psm_predict_device),
+             timed with CUDA events on the handle's stream, L2 flushed between steps.
+  e2e      : cells/s through the public host-buffer API (psm_predict: pinned host rows in, host
+             pressures out, H2D + D2H inside the timed region).
+  roofline : dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference : the NumPy/SciPy oracle (the reference's own calls; TF Dense stack
+             replaced by float32 NumPy because TensorFlow is not installable here) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, 'solving-poisson-s-equation-through-dl-for-cfd-apllications_b200')
+for p in (PKG, REPO):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from psm_b200 import synthetic as syn, tables as ptables    # noqa: E402
+
+HBM_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(REPO, 'MEASURED_PEAKS.json')) as f:
+            return json.load(f), 'measured'
+    except Exception:
+        return {'hbm_gbs': HBM_FALLBACK_GBS}, 'fallback'
+
+
+def build_case(workload, variant, seed=0, back='closed_form'):
+    """Synthetic mesh + fields + parameters + once-per-mesh tables (init is not part of a step)."""
+    mesh = syn.make_mesh(seed=seed, **syn.CONFIGS[workload])
+    F = syn.make_fields(mesh, seed=seed)
+    deltas = variant == 'deltaU_to_deltaP'
+    params = syn.make_params(seed=seed, pc_in=128, pc_p=128, standardization='std' if deltas else 'max_abs',
+                             n_out_channels=1 if deltas else 2,
+                             maxs=syn.DEFAULT_MAXS if deltas else (1.0, 0.536, 0.999, 0.8, 0.7))
+    t0 = time.time()
+    tables = ptables.build_tables(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'], variant=variant, back=back)
+    return mesh, F, params, tables, time.time() - t0
+
+
+def stage_bytes(n_cells, G, B, C, pc_in, pc_p, ncol, S=128):
+    """Algorithmic bytes per step and stage (SURVEY.md section 8d / DESIGN.md): FP32 device storage,
+    f64 only at the ABI.  Overlap re-reads and L2-resident intermediates are NOT counted twice."""
+    S2 = S * S
+    return {
+        'prep': n_cells * (ncol * 8 + 8 + 8),                 # read rows, write float2 field + p_prev
+        'gather': G * (12 + 12 + 8) + 8 * n_cells,            # tables + 2 planes out + each cell value once
+        'extract': 8 * G + 4 * B * 2 * S2,                    # grid read once, operand written
+        'pca_project': 4 * B * 2 * S2 + 4 * 2 * S2 * pc_in + 4 * B * pc_in,
+        'mlp': 4 * (pc_in * 512 + 2 * 512 * 512 + 512 * pc_p) + 8 * B * pc_p,
+        'pca_inverse': 4 * pc_p * S2 * C + 4 * B * S2 * C,
+        'strip_means': 4 * B * S2 * C,
+        'offsets': 0,
+        'place': 4 * G * C + 4 * G * C + 2 * G,               # owner pixels read + field write + owner map
+        'back_gather': n_cells * (12 + 12 + 12 * C + 8 + 8 * C),
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def oracle_for(variant, params, mesh, F, tables):
+    from oracle.pipeline import DeltasOracle, GradPOracle, SurrogateParams
+    P = SurrogateParams(**{k: v for k, v in params.items() if k != 'shape'})
+    o = DeltasOracle(P) if variant == 'deltaU_to_deltaP' else GradPOracle(P)
+    o.compute_only_once(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'],
+                        tables=(tables['vert'], tables['weights'], tables['vert_back'], tables['weights_back']))
+    return o
+
+
+def oracle_step(o, variant, F):
+    if variant == 'deltaU_to_deltaP':
+        r = o.time_step(F['Ux'], F['Uy'], F['dUx'], F['dUy'])
+        p, _ = o.to_cells(r['field'], F['p_prev'])
+        return p
+    r = o.time_step(F['Ux'], F['Uy'])
+    return np.stack([o.to_cells(r['dp_dx']), o.to_cells(r['dp_dy'])], axis=1)
+
+
+def time_oracle(o, variant, F, steps, warmup):
+    for _ in range(warmup):
+        oracle_step(o, variant, F)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(o, variant, F)
+    return (time.perf_counter() - t0) / max(steps, 1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='native', choices=['native', 'reference'])
+    ap.add_argument('--workload', default=None, help='c1 | c2 | c5 | c4 | tiny (default: c2)')
+    ap.add_argument('--variant', default='deltaU_to_deltaP', choices=['deltaU_to_deltaP', 'U_to_gradP'])
+    ap.add_argument('--cpu-steps', type=int, default=5, help='oracle steps for the cpu_baseline leg')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    workload = args.workload or 'c2'
+    variant = args.variant
+    ncol = 7 if variant == 'deltaU_to_deltaP' else 5
+    cfg = {'workload': '%s: %s, synthetic flow-past-cylinder mesh %s, pc_in=pc_p=128, MLP 3x512, random-init'
+                       % (workload, variant, syn.CONFIGS[workload]),
+           'l2': 'flushed between timed steps (256 MiB write)', 'input_cols': ncol}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        import torch
+        torch.set_num_threads(os.cpu_count() or 1)
+        mesh, F, params, tables, t_init = build_case(workload, variant)
+        o = oracle_for(variant, params, mesh, F, tables)
+        steps, warm = min(args.steps, 10), min(args.warmup, 1)
+        sec = time_oracle(o, variant, F, steps, warm)
+        n = mesh['cells'].shape[0]
+        v = n / sec
+        line = {'impl': 'reference', 'metric': 'surrogate_cells_per_s', 'value': v, 'unit': 'cells/s',
+                'n_gpus': args.gpus, 'steps': steps, 'warmup': warm, 'ms_per_step': sec * 1e3,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64 (f32 MLP)',
+                'data': 'synthetic', 'config': cfg,
+                'cpu_baseline': {'value': v, 'unit': 'cells/s', 'cores': os.cpu_count(), 'kind': 'port',
+                                 'sample': '%d full steps of the NumPy/SciPy oracle on the same %d-cell mesh '
+                                           '(TF Dense stack replaced by float32 NumPy; init excluded)' % (steps, n)},
+                'e2e': {'value': v, 'unit': 'cells/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ native arm (B200)
+    import torch
+    import psm_b200
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl native needs a B200 (no CPU fallback exists)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    mesh, F, params, tables, t_init = build_case(workload, variant, seed=rank)
+    n = mesh['cells'].shape[0]
+    sm = psm_b200.PressureSurrogate(variant, device=local_rank, input_cols=ncol, timings=False)
+    sm.load_params(params)
+    sm.init_tables(tables)
+    geo = sm.geometry()
+    cells_np = syn.pack_cells(mesh, F, with_delta=(ncol == 7))
+    h_in = torch.from_numpy(cells_np).pin_memory()
+    h_out = torch.empty(n if sm.n_fields == 1 else (n, 2), dtype=torch.float64).pin_memory()
+    d_in = h_in.cuda()
+    d_out = torch.empty_like(h_out, device='cuda')
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    ext = torch.cuda.ExternalStream(sm.stream_ptr())
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_device(k, timed):
+        evs, tot = [], np.zeros(len(psm_b200._capi.TIMING_NAMES))
+        with torch.cuda.stream(ext):
+            for _ in range(k):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(ext)
+                sm.predict_device(d_in.data_ptr(), n, d_out.data_ptr(), sync=False)
+                e1.record(ext)
+                evs.append((e0, e1))
+                if timed:
+                    sm.synchronize()
+                    tm = sm.timings()
+                    tot += np.array([tm[k2] for k2 in psm_b200._capi.TIMING_NAMES])
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs), tot
+
+    run_device(max(args.warmup, 3), False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ms_total, _ = run_device(args.steps, False)
+    barrier()
+    launches = sm.launch_count() * args.steps
+    sm.set_timings(True)                       # per-stage breakdown in a separate pass (events cost a few us)
+    _, stage_ms = run_device(args.steps, True)
+    sm.set_timings(False)
+    # end to end through the host-buffer API
+    for _ in range(3):
+        sm.predict(h_in.numpy(), out=h_out.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sm.predict(h_in.numpy(), out=h_out.numpy())
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s = t.tolist()
+        nt = torch.tensor([float(n)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(nt)
+        n_total = nt.item()
+    else:
+        n_total = float(n)
+    ms_step = ms_total / args.steps
+    value = n_total / (ms_step * 1e-3)
+    e2e = n_total / (e2e_s / args.steps)
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        sb = stage_bytes(n, geo['grid_h'] * geo['grid_w'], geo['n_blocks'], sm.n_fields, sm.pc_in, sm.pc_p, ncol)
+        stage_avg = dict(zip(psm_b200._capi.TIMING_NAMES, (stage_ms / args.steps).tolist()))
+        stages = {k: {'ms': stage_avg[k], 'GBps': (sb[k] / (stage_avg[k] * 1e-3) / 1e9) if stage_avg.get(k, 0) > 0 else None}
+                  for k in sb}
+        hbm_stages = ['gather', 'back_gather', 'place', 'extract', 'prep']
+        dom = max(hbm_stages, key=lambda k: stage_avg[k])
+        ach = sb[dom] / (stage_avg[dom] * 1e-3) / 1e9
+        roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_launch': sb[dom]}
+        cpu = None
+        if not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            o = oracle_for(variant, params, mesh, F, tables)
+            sec = time_oracle(o, variant, F, args.cpu_steps, 1)
+            cpu = {'value': n / sec, 'unit': 'cells/s', 'cores': os.cpu_count(), 'kind': 'port',
+                   'sample': '%d full steps of the NumPy/SciPy oracle on the same %d-cell mesh (TF Dense stack '
+                             'replaced by float32 NumPy; init excluded)' % (args.cpu_steps, n), 'ms_per_step': sec * 1e3}
+        line = {'metric': 'surrogate_cells_per_s', 'value': value, 'unit': 'cells/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (f64 at the ABI and in the offset chain)',
+                'data': 'synthetic', 'config': cfg, 'clocks': clocks,
+                'e2e': {'value': e2e, 'unit': 'cells/s', 'h2d_bytes_per_step': int(n * ncol * 8),
+                        'd2h_bytes_per_step': int(n * sm.n_fields * 8), 'ms_per_step': e2e_s / args.steps * 1e3},
+                'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu, 'stages': stages,
+                'geometry': geo, 'init_tables_s': t_init, 'n_cells_total': n_total}
+        print(json.dumps(line))
+    sm.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -160,6 +160,10 @@ int psm_predict_device(psm_handle* h, const double* d_cells, int64_t n_cells, do
 
 int psm_synchronize(psm_handle* h);
 
+/* The CUDA stream (cudaStream_t) all work of this handle is launched on, so that a caller can
+ * order its own work or record its own events against it. */
+int psm_get_stream(const psm_handle* h, void** stream);
+
 /* Page-lock / unlock a caller buffer that lives for the whole run (FOAM/PythonComm_init.H:53
  * allocates input_vals once), so that psm_predict copies at full PCIe speed. */
 int psm_register_host_buffer(void* ptr, int64_t bytes);
@@ -188,6 +192,8 @@ int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_bytes);
  * Replaces the hand-rolled time.time() pairs of PMP:262-499. */
 #define PSM_N_TIMINGS 12
 int psm_get_timings(psm_handle* h, float* ms, int32_t n);
+/* Switch the per-stage events on/off at run time (they cost a few microseconds per step). */
+int psm_set_timings(psm_handle* h, int32_t on);
 
 /* Number of kernels launched by the last psm_predict* call. */
 int psm_get_launch_count(const psm_handle* h);

@@ -13,6 +13,8 @@
 
 using namespace psm;
 
+extern "C" int psm_set_timings(psm_handle* h, int32_t on);
+
 namespace {
 thread_local std::string g_create_error;
 
@@ -61,7 +63,7 @@ struct psm_handle {
     Scalars* d_sc = nullptr; Scalars* h_sc = nullptr;
     int launches = 0;
     cudaEvent_t ev[PSM_N_TIMINGS + 1] = {};
-    bool ev_valid = false;
+    bool ev_valid = false, ev_created = false;
     bool last_host = false;
 };
 
@@ -142,7 +144,7 @@ extern "C" int psm_destroy(psm_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->allocs) cudaFree(p);
-    if (h->ev_valid) for (auto& e : h->ev) cudaEventDestroy(e);
+    if (h->ev_created) for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -390,10 +392,7 @@ extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
         CU(h, cudaGetLastError());
         cudaFree(d_sdfn); cudaFree(d_sdfb);
     }
-    if (h->cfg.enable_timings) {
-        for (auto& e : h->ev) CU(h, cudaEventCreate(&e));
-        h->ev_valid = true;
-    }
+    if (h->cfg.enable_timings) TRY(psm_set_timings(h, 1));
     CU(h, cudaStreamSynchronize(h->stream));
     h->initialised = true;
     return PSM_OK;
@@ -526,6 +525,12 @@ extern "C" int psm_synchronize(psm_handle* h) {
     return finish(h);
 }
 
+extern "C" int psm_get_stream(const psm_handle* h, void** stream) {
+    if (!h || !stream) return PSM_ERR_INVALID;
+    *stream = (void*)h->stream;
+    return PSM_OK;
+}
+
 extern "C" int psm_register_host_buffer(void* ptr, int64_t bytes) {
     if (!ptr || bytes <= 0) return PSM_ERR_INVALID;
     return cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess ? PSM_OK : PSM_ERR_CUDA;
@@ -647,6 +652,17 @@ extern "C" int psm_get_timings(psm_handle* h, float* ms, int32_t n) {
     for (int i = 2; i <= 10 && i < n; ++i)
         if (cudaEventElapsedTime(&t, h->ev[i - 1], h->ev[i]) == cudaSuccess) ms[i] = t;
     if (n > 11 && cudaEventElapsedTime(&t, h->ev[10], h->ev[PSM_N_TIMINGS]) == cudaSuccess) ms[11] = t;
+    return PSM_OK;
+}
+
+extern "C" int psm_set_timings(psm_handle* h, int32_t on) {
+    if (!h) return PSM_ERR_INVALID;
+    CU(h, cudaSetDevice(h->cfg.device));
+    if (on && !h->ev_created) {
+        for (auto& e : h->ev) CU(h, cudaEventCreate(&e));
+        h->ev_created = true;
+    }
+    h->ev_valid = on != 0;
     return PSM_OK;
 }
 

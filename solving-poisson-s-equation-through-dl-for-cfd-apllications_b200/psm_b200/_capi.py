@@ -67,6 +67,7 @@ SYMBOLS = {
     'psm_predict': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'psm_predict_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
     'psm_synchronize': (C.c_int, [C.c_void_p]),
+    'psm_get_stream': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     'psm_register_host_buffer': (C.c_int, [C.c_void_p, C.c_int64]),
     'psm_unregister_host_buffer': (C.c_int, [C.c_void_p]),
     'psm_last_error': (C.c_char_p, [C.c_void_p]),
@@ -76,6 +77,7 @@ SYMBOLS = {
     'psm_get_forward_table': (C.c_int, [C.c_void_p, c_int32_p, c_float_p]),
     'psm_get_stage': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
     'psm_get_timings': (C.c_int, [C.c_void_p, c_float_p, C.c_int32]),
+    'psm_set_timings': (C.c_int, [C.c_void_p, C.c_int32]),
     'psm_get_launch_count': (C.c_int, [C.c_void_p]),
     'psm_plan_sizes': (C.c_int, [C.c_int32] * 5 + [c_uint8_p, c_int32_p, c_int32_p, c_int32_p]),
     'psm_plan_compile': (C.c_int, [C.c_int32] * 5 + [c_uint8_p] + [c_int32_p] * 5),

@@ -174,6 +174,12 @@ class PressureSurrogate:
     def synchronize(self):
         return self._check(self.lib.psm_synchronize(self._h))
 
+    def stream_ptr(self):
+        """cudaStream_t of the handle as an int (e.g. for ``torch.cuda.ExternalStream``)."""
+        st = C.c_void_p()
+        self._check(self.lib.psm_get_stream(self._h, C.byref(st)))
+        return st.value or 0
+
     # ------------------------------------------------------------------ introspection
     def geometry(self):
         g = capi.PsmGeometry()
@@ -217,6 +223,9 @@ class PressureSurrogate:
         ms = np.zeros(capi.N_TIMINGS, np.float32)
         self._check(self.lib.psm_get_timings(self._h, _ptr(ms, C.c_float), capi.N_TIMINGS))
         return dict(zip(capi.TIMING_NAMES, ms.tolist()))
+
+    def set_timings(self, on):
+        self._check(self.lib.psm_set_timings(self._h, int(on)))
 
     def launch_count(self):
         return int(self.lib.psm_get_launch_count(self._h))

@@ -33,6 +33,34 @@ def barycentric_tables(src_xy, dst_xy):
     return np.ascontiguousarray(vert, dtype=np.int32), np.ascontiguousarray(wts, dtype=np.float64)
 
 
+def regular_grid_back_tables(cells_xy, X0_row, Y0_col, W):
+    """Grid -> cell tables in closed form (no Qhull): the source points are the regular grid, so the
+    enclosing square is a floor() and the two triangles of a square follow a fixed diagonal
+    ((gi,gj)-(gi+1,gj+1)).  Every triangulation of a regular grid is Delaunay (co-circular corners),
+    so this is one of the valid answers; it is NOT the particular one Qhull's degenerate-input
+    handling picks for PMP:211, hence opt-in (``back='closed_form'``) for meshes where Qhull on
+    millions of grid points would take minutes.  Cells outside the grid hull get the same wrapped
+    'negative weight' marker the reference produces for them (-> previous-pressure fallback)."""
+    x0, y0 = X0_row[0], Y0_col[0]
+    dx = (X0_row[-1] - X0_row[0]) / (len(X0_row) - 1)
+    dy = (Y0_col[-1] - Y0_col[0]) / (len(Y0_col) - 1)
+    H = len(Y0_col)
+    fx = (cells_xy[:, 0] - x0) / dx
+    fy = (cells_xy[:, 1] - y0) / dy
+    outside = (fx < 0) | (fy < 0) | (fx > W - 1) | (fy > H - 1)
+    gj = np.clip(np.floor(fx).astype(np.int64), 0, W - 2)
+    gi = np.clip(np.floor(fy).astype(np.int64), 0, H - 2)
+    u, v = fx - gj, fy - gi
+    lower = u >= v                                   # triangle (0,0),(1,0),(1,1)  vs  (0,0),(1,1),(0,1)
+    p00, p10, p11, p01 = gi * W + gj, gi * W + gj + 1, (gi + 1) * W + gj + 1, (gi + 1) * W + gj
+    vert = np.where(lower[:, None], np.stack([p00, p10, p11], 1), np.stack([p00, p11, p01], 1)).astype(np.int32)
+    wl = np.stack([1 - u, u - v, v], 1)
+    wu = np.stack([1 - v, u, v - u], 1)
+    wts = np.where(lower[:, None], wl, wu)
+    wts[outside] = np.array([-1.0, 1.0, 1.0])
+    return np.ascontiguousarray(vert), np.ascontiguousarray(wts, dtype=np.float64)
+
+
 def _inside_convex(hull_pts, pts):
     inside = np.ones(pts.shape[0], dtype=bool)
     n = hull_pts.shape[0]
@@ -86,7 +114,9 @@ def build_tables(cells_xy, top, obst, probe_values, variant='deltaU_to_deltaP', 
     if precomputed is None:
         vert, weights = barycentric_tables(cells_xy, xy0)
         vert_back = weights_back = None
-        if back:
+        if back == 'closed_form':
+            vert_back, weights_back = regular_grid_back_tables(cells_xy, X0[:W], Y0[::W], W)
+        elif back:
             vert_back, weights_back = barycentric_tables(xy0, cells_xy)          # PMP:211
     else:
         vert, weights = precomputed[0], precomputed[1]
