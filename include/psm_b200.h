@@ -66,8 +66,16 @@ typedef struct psm_config {
     double  near_wall_sdf;    /* PMP:492-494: cells with interpolated distance < this keep
                                  p_prev (0.05 in PMP); <= 0 disables (PMS:430-432)               */
     int32_t enable_timings;   /* 1 -> record per-stage CUDA events (psm_get_timings)             */
-    int32_t reserved;
+    int32_t gemm_mode;        /* psm_gemm_mode_code; 0 (default) = tcgen05 3xTF32                */
 } psm_config;
+
+/* How the three dense contractions (PCA projection, Dense stack, PCA inverse) are evaluated.
+ * All modes are this library's own sm_100a kernels; 1 and 2 exist for cross-checking mode 0. */
+enum psm_gemm_mode_code {
+    PSM_GEMM_TC_3XTF32 = 0,   /* tcgen05.mma kind::tf32, hi/lo operand split: FP32-class accuracy  */
+    PSM_GEMM_TC_TF32 = 1,     /* tcgen05.mma kind::tf32, single pass (10-bit mantissa operands)    */
+    PSM_GEMM_FP32_SIMT = 2    /* CUDA-core FP32 FFMA kernel (debug cross-check)                   */
+};
 
 /* Artefacts the reference loads at import time (SMC:70-87,505-511; PMP:103-118,168-170).
  * PCA matrices are in the reference's own layout: row = component, column index
@@ -210,6 +218,11 @@ int psm_plan_sizes(int32_t variant, int32_t grid_h, int32_t grid_w, int32_t shap
 int psm_plan_compile(int32_t variant, int32_t grid_h, int32_t grid_w, int32_t shape, int32_t overlap,
                      const uint8_t* mask, int32_t* origins, int32_t* indices_list, int32_t* owner,
                      int32_t* rec, int32_t* tasks);
+
+/* Unit-test entry for the GEMM kernels: C[splits][M][N] (host) = A[M][K] * B[N][K]^T (host), split-K
+ * partials left unreduced.  mode = psm_gemm_mode_code.  M % 128 == 0, N % 64 == 0, K % 32 == 0. */
+int psm_debug_gemm(int32_t device, int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
+                   float* C, int32_t splits);
 
 int psm_api_version(void);
 

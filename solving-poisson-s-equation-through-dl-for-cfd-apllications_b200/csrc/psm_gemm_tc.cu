@@ -1,0 +1,312 @@
+// tcgen05 GEMM for the dense contractions of the surrogate (PCA projection, Dense stack, PCA
+// inverse):  C[M,N] = A[M,K] * B[N,K]^T, both operands K-major FP32 in global memory.
+//
+//   * TMA (cp.async.bulk.tensor, SWIZZLE_128B) stages 128 x 32 (A) and BN x 32 (B) FP32 tiles;
+//   * tcgen05.mma kind::tf32, M=128, N=BN, K=8 per instruction, FP32 accumulators in TMEM;
+//   * "3xTF32": four converter warps split every staged tile in place into hi = tf32(x) and
+//     lo = x - hi, and the issuing thread accumulates  hi*hi + hi*lo + lo*hi  -- FP32-class accuracy
+//     (the reference is float64 around a float32 Dense stack) at no extra HBM traffic; the kernels
+//     are HBM-bound, so the 3x tensor work is free;
+//   * the same four warps then run the epilogue: tcgen05.ld -> bias / ReLU / affine / PCA mean
+//     and re-dimensionalisation -> 128-bit stores.  Split-K partials go to a workspace.
+//
+// Warp roles (192 threads): 0 = TMA producer, 1 = TMEM allocator + MMA issuer, 2..5 = converters
+// and epilogue (TMEM lane quadrant = warp_idx % 4).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "psm_kernels.cuh"
+
+namespace psm {
+
+namespace {
+
+constexpr int BM = 128;           // UMMA_M
+constexpr int BK = 32;            // 32 fp32 = 128 B = one swizzle row
+constexpr int UMMA_K = 8;         // tf32
+constexpr int kThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+        : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4,
+// LBO = 1 (unused for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version 1, layout type 2.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32: c_format F32 (1) @4, a/b format TF32 (2) @7/@10,
+// K-major A and B, n_dim = N>>3 @17, m_dim = M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// dynamic shared memory: STAGES x [A_hi | A_lo | B_hi | B_lo] after manual 1024 B alignment, then barriers
+template <int BN> struct Cfg {
+    static constexpr int STAGES = (BN == 128) ? 3 : 4;
+    static constexpr int STAGE_BYTES = 2 * (BM + BN) * BK * 4;
+    static constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+}  // namespace
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcGemmArgs g) {
+    constexpr int STAGES = Cfg<BN>::STAGES;
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE = 2 * (A_BYTES + B_BYTES);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    // stage s: [A_hi | A_lo | B_hi | B_lo]
+    const uint32_t bars = base + STAGES * STAGE;                 // full[S], conv[S], empty[S], accum, tmem slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto conv_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (3 * STAGES);
+    const uint32_t tmem_slot = accum_bar + 8u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));   // generic pointer to the aligned base
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kb_total = g.K / BK;
+    const int kb_per = (kb_total + g.splits - 1) / g.splits;
+    const int kb0 = blockIdx.z * kb_per;
+    const int kb1 = min(kb_total, kb0 + kb_per);
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation: BN fp32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
+                const uint32_t st = base + s * STAGE;
+                tma_load_2d(st, &tmA, (kb0 + it) * BK, m0, full_bar(s));
+                tma_load_2d(st + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(BM, BN);
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(g.three_pass ? conv_bar(s) : full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * STAGE;
+                const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t ko = k * UMMA_K * 4;        // byte offset inside the 128 B swizzle row
+                    umma_tf32(tmem_base, make_smem_desc(a_hi + ko), make_smem_desc(b_hi + ko), idesc, (it | k) != 0);
+                    if (g.three_pass) {
+                        umma_tf32(tmem_base, make_smem_desc(a_hi + ko), make_smem_desc(b_lo + ko), idesc, 1);
+                        umma_tf32(tmem_base, make_smem_desc(a_lo + ko), make_smem_desc(b_hi + ko), idesc, 1);
+                    }
+                }
+                umma_commit(empty_bar(s));                     // frees the stage once these MMAs retire
+            }
+            umma_commit(accum_bar);                            // accumulator complete
+        }
+    } else {
+        // ===================== converters (3xTF32 split), then epilogue =====================
+        const int t = threadIdx.x - 64;                        // 0..127
+        if (g.three_pass) {
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                uint8_t* st = gen_base + s * STAGE;
+                float4* a_hi = reinterpret_cast<float4*>(st);
+                float4* a_lo = reinterpret_cast<float4*>(st + A_BYTES);
+                float4* b_hi = reinterpret_cast<float4*>(st + 2 * A_BYTES);
+                float4* b_lo = reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES);
+                auto split4 = [](float4 v, float4& hi, float4& lo) {
+                    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+                    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+                };
+#pragma unroll 4
+                for (int i = t; i < A_BYTES / 16; i += 128) {
+                    float4 hi, lo;
+                    split4(a_hi[i], hi, lo);
+                    a_hi[i] = hi; a_lo[i] = lo;
+                }
+#pragma unroll 4
+                for (int i = t; i < B_BYTES / 16; i += 128) {
+                    float4 hi, lo;
+                    split4(b_hi[i], hi, lo);
+                    b_hi[i] = hi; b_lo[i] = lo;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+                mbar_arrive(conv_bar(s));
+            }
+        }
+        // ---- epilogue: thread <-> accumulator row (TMEM lane), 16 columns per tcgen05.ld ----
+        if (nkb > 0) {
+            mbar_wait(accum_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int q = warp & 3;                                // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int m = m0 + row;
+        float* Cp = g.C + (g.epi == EPI_PARTIAL ? (size_t)blockIdx.z * g.M * g.ldc : 0) + (size_t)m * g.ldc + n0;
+        const float o_scale = (g.epi == EPI_PCA_INV) ? g.sc->out_scale : 1.f;
+        for (int c = 0; c < BN; c += 16) {
+            float v[16];
+            if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+            const int n = n0 + c;
+            if (g.epi == EPI_BIAS_RELU) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + __ldg(g.v0 + n + i), 0.f);
+            } else if (g.epi == EPI_BIAS_AFFINE) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = (v[i] + __ldg(g.v0 + n + i)) * __ldg(g.v1 + n + i) + __ldg(g.v2 + n + i);
+            } else if (g.epi == EPI_PCA_INV) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = (v[i] + __ldg(g.v0 + n + i)) * o_scale;
+            }
+            if (m < g.M) {
+#pragma unroll
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(Cp + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: tensor maps (driver entry point fetched through the runtime: no link-time libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_kmajor_map(TensorMap128* out, const float* ptr, int rows, int cols, int ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    static_assert(sizeof(TensorMap128) == sizeof(CUtensorMap), "tensor map size");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+int tc_gemm_bn(int N) { return (N % 128 == 0) ? 128 : 64; }
+
+int tc_gemm_prepare() {
+    cudaError_t e1 = cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_TOTAL);
+    cudaError_t e2 = cudaFuncSetAttribute(tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM_TOTAL);
+    return (e1 == cudaSuccess && e2 == cudaSuccess) ? 0 : -1;
+}
+
+void launch_tc_gemm(const TcGemm& t, cudaStream_t s) {
+    const int bn = tc_gemm_bn(t.args.N);
+    dim3 grid(t.args.N / bn, (t.args.M + BM - 1) / BM, t.args.splits);
+    const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(&t.mapA);
+    const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(&t.mapB);
+    if (bn == 128) tc_gemm_kernel<128><<<grid, kThreads, Cfg<128>::SMEM_TOTAL, s>>>(a, b, t.args);
+    else tc_gemm_kernel<64><<<grid, kThreads, Cfg<64>::SMEM_TOTAL, s>>>(a, b, t.args);
+}
+
+}  // namespace psm

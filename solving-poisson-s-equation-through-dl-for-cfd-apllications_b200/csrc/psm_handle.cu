@@ -61,6 +61,7 @@ struct psm_handle {
     double* d_means = nullptr; double* d_dbuf[2] = {nullptr, nullptr}; int32_t* d_pbuf[2] = {nullptr, nullptr};
     double* d_offsets = nullptr; float* d_coff = nullptr; float* d_field = nullptr;
     Scalars* d_sc = nullptr; Scalars* h_sc = nullptr;
+    TcGemm tc_proj{}, tc_inv{}; std::vector<TcGemm> tc_dense; int tc_splits = 1;   // tcgen05 path (gemm_mode 0/1)
     int launches = 0;
     cudaEvent_t ev[PSM_N_TIMINGS + 1] = {};
     bool ev_valid = false, ev_created = false;
@@ -109,6 +110,7 @@ extern "C" int psm_create(psm_handle** out, const psm_config* cfg) {
     *out = nullptr;
     if (cfg->variant != PSM_DELTAU_TO_DELTAP && cfg->variant != PSM_U_TO_GRADP) { g_create_error = "unknown variant"; return PSM_ERR_INVALID; }
     if (cfg->shape != 128) { g_create_error = "only shape == 128 is supported"; return PSM_ERR_INVALID; }
+    if (cfg->gemm_mode < 0 || cfg->gemm_mode > 2) { g_create_error = "unknown gemm_mode"; return PSM_ERR_INVALID; }
     if (cfg->input_cols != 5 && !(cfg->input_cols == 7 && cfg->variant == PSM_DELTAU_TO_DELTAP)) {
         g_create_error = "input_cols must be 5, or 7 for deltaU_to_deltaP"; return PSM_ERR_INVALID;
     }
@@ -357,8 +359,16 @@ extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
         if (sp > 64) sp = 64;
         if (sp < 1) sp = 1;
         h->splits = sp;
+        // tcgen05 path: one 128-row tile per CTA, split-K so that about one wave of CTAs streams the operands
+        const int kb_total = 2 * S2 / 32;
+        const int tc_tiles = (Bp / 128) * (h->pc_in_pad / tc_gemm_bn(h->pc_in_pad));
+        int ts = (148 + tc_tiles - 1) / tc_tiles;
+        if (ts > 128) ts = 128;
+        if (ts < 1) ts = 1;
+        const int per = (kb_total + ts - 1) / ts;
+        h->tc_splits = (kb_total + per - 1) / per;
     }
-    TRY(dalloc(h, &h->d_part, (size_t)h->splits * Bp * h->pc_in_pad));
+    TRY(dalloc(h, &h->d_part, (size_t)(h->splits > h->tc_splits ? h->splits : h->tc_splits) * Bp * h->pc_in_pad));
     TRY(dalloc(h, &h->d_xin, (size_t)Bp * h->pc_in_pad));
     TRY(dalloc(h, &h->d_act[0], (size_t)Bp * maxw));
     TRY(dalloc(h, &h->d_act[1], (size_t)Bp * maxw));
@@ -392,6 +402,31 @@ extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
         CU(h, cudaGetLastError());
         cudaFree(d_sdfn); cudaFree(d_sdfb);
     }
+    if (h->cfg.gemm_mode != PSM_GEMM_FP32_SIMT) {
+        // TMA tensor maps + argument blocks of the tcgen05 GEMMs (all pointers are fixed for the handle's life)
+        if (tc_gemm_prepare() != 0) PSM_FAIL(h, PSM_ERR_CUDA, "cannot opt in to %d B of shared memory for the tcgen05 GEMM", 197888);
+        const int three = (h->cfg.gemm_mode == PSM_GEMM_TC_3XTF32) ? 1 : 0;
+        auto mk = [&](TcGemm& g, const float* A, int a_rows, const float* Bm, int b_rows, int K, float* Cp, int ldc, int splits,
+                      int epi, const float* v0, const float* v1, const float* v2) -> int {
+            if (make_kmajor_map(&g.mapA, A, a_rows, K, K, 128) != 0 || make_kmajor_map(&g.mapB, Bm, b_rows, K, K, tc_gemm_bn(b_rows)) != 0)
+                PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+            g.args = TcGemmArgs{Cp, a_rows, b_rows, K, ldc, splits, epi, three, v0, v1, v2, h->d_sc};
+            return 0;
+        };
+        TRY(mk(h->tc_proj, h->d_xu, Bp, h->d_comp_u, h->pc_in_pad, 2 * S2, h->d_part, h->pc_in_pad, h->tc_splits, EPI_PARTIAL,
+               nullptr, nullptr, nullptr));
+        h->tc_dense.resize(h->n_dense);
+        const float* in = h->d_xin;
+        for (int l = 0; l < h->n_dense; ++l) {
+            const bool last = (l == h->n_dense - 1);
+            float* outp = last ? h->d_r : h->d_act[l & 1];
+            TRY(mk(h->tc_dense[l], in, Bp, h->d_W[l], h->dims_pad[l + 1], h->dims_pad[l], outp, h->dims_pad[l + 1], 1,
+                   last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU, h->d_bias[l], h->d_out_s, h->d_out_m));
+            in = outp;
+        }
+        TRY(mk(h->tc_inv, h->d_r, Bp, h->d_comp_out_t, S2 * h->C, h->pc_p_pad, h->d_blocks, S2 * h->C, 1, EPI_PCA_INV,
+               h->d_pmean, nullptr, nullptr));
+    }
     if (h->cfg.enable_timings) TRY(psm_set_timings(h, 1));
     CU(h, cudaStreamSynchronize(h->stream));
     h->initialised = true;
@@ -420,12 +455,17 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     ExtractArgs ea{h->d_grid, h->d_grid + h->G_pad, h->d_by0, h->d_bx0, h->d_xu, h->B, h->W, S, 2};
     launch_extract(ea, s); ++nl;
     tick();   // extract
+    const bool tc = h->cfg.gemm_mode != PSM_GEMM_FP32_SIMT;
     {
-        GemmArgs g{};
-        g.A = h->d_xu; g.B = h->d_comp_u; g.C = h->d_part; g.M = Bp; g.N = h->pc_in_pad; g.K = 2 * S2;
-        g.lda = 2 * S2; g.ldb = 2 * S2; g.ldc = h->pc_in_pad; g.splits = h->splits; g.epi = EPI_PARTIAL;
-        launch_sgemm(g, s); ++nl;
-        ReduceArgs r{h->d_part, h->splits, Bp, h->pc_in_pad, h->d_zc, h->d_in_a, h->d_in_b, h->d_xin};
+        if (tc) launch_tc_gemm(h->tc_proj, s);
+        else {
+            GemmArgs g{};
+            g.A = h->d_xu; g.B = h->d_comp_u; g.C = h->d_part; g.M = Bp; g.N = h->pc_in_pad; g.K = 2 * S2;
+            g.lda = 2 * S2; g.ldb = 2 * S2; g.ldc = h->pc_in_pad; g.splits = h->splits; g.epi = EPI_PARTIAL;
+            launch_sgemm(g, s);
+        }
+        ++nl;
+        ReduceArgs r{h->d_part, tc ? h->tc_splits : h->splits, Bp, h->pc_in_pad, h->d_zc, h->d_in_a, h->d_in_b, h->d_xin};
         launch_reduce_standardise(r, s); ++nl;
     }
     tick();   // pca_project
@@ -439,7 +479,9 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
             g.lda = g.K; g.ldb = g.K; g.ldc = g.N; g.splits = 1;
             g.epi = last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU;
             g.v0 = h->d_bias[l]; g.v1 = h->d_out_s; g.v2 = h->d_out_m;
-            launch_sgemm(g, s); ++nl;
+            if (tc) launch_tc_gemm(h->tc_dense[l], s);
+            else launch_sgemm(g, s);
+            ++nl;
             in = g.C;
         }
     }
@@ -448,7 +490,9 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         GemmArgs g{};
         g.A = h->d_r; g.B = h->d_comp_out_t; g.C = h->d_blocks; g.M = Bp; g.N = S2 * h->C; g.K = h->pc_p_pad;
         g.lda = g.K; g.ldb = g.K; g.ldc = g.N; g.splits = 1; g.epi = EPI_PCA_INV; g.v0 = h->d_pmean; g.sc = h->d_sc;
-        launch_sgemm(g, s); ++nl;
+        if (tc) launch_tc_gemm(h->tc_inv, s);
+        else launch_sgemm(g, s);
+        ++nl;
     }
     tick();   // pca_inverse
     MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->d_by0, h->d_bx0, h->C, S, h->W, h->d_means};
@@ -667,3 +711,40 @@ extern "C" int psm_set_timings(psm_handle* h, int32_t on) {
 }
 
 extern "C" int psm_get_launch_count(const psm_handle* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int psm_debug_gemm(int32_t device, int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
+                              float* C, int32_t splits) {
+    if (!A || !B || !C || M % 128 || N % 64 || K % 32 || splits < 1 || mode < 0 || mode > 2) return PSM_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return PSM_ERR_CUDA;
+    const int kb_total = K / 32;
+    const int per = (kb_total + splits - 1) / splits;
+    if ((kb_total + per - 1) / per != splits) return PSM_ERR_INVALID;     // every split must own >= 1 k-block
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    int rc = PSM_OK;
+    const size_t nA = (size_t)M * K, nB = (size_t)N * K, nC = (size_t)splits * M * N;
+    if (cudaMalloc(&dA, nA * 4) != cudaSuccess || cudaMalloc(&dB, nB * 4) != cudaSuccess || cudaMalloc(&dC, nC * 4) != cudaSuccess) rc = PSM_ERR_CUDA;
+    if (rc == PSM_OK) {
+        cudaMemcpy(dA, A, nA * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dB, B, nB * 4, cudaMemcpyHostToDevice);
+        cudaMemset(dC, 0xFF, nC * 4);                                     // NaN pattern: unwritten outputs are caught
+        if (mode == PSM_GEMM_FP32_SIMT) {
+            GemmArgs g{};
+            g.A = dA; g.B = dB; g.C = dC; g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldc = N; g.splits = splits;
+            g.epi = EPI_PARTIAL;
+            launch_sgemm(g, 0);
+        } else {
+            TcGemm t{};
+            if (tc_gemm_prepare() != 0 || make_kmajor_map(&t.mapA, dA, M, K, K, 128) != 0 ||
+                make_kmajor_map(&t.mapB, dB, N, K, K, tc_gemm_bn(N)) != 0) rc = PSM_ERR_CUDA;
+            else {
+                t.args = TcGemmArgs{dC, M, N, K, N, splits, EPI_PARTIAL, mode == PSM_GEMM_TC_3XTF32 ? 1 : 0, nullptr, nullptr, nullptr, nullptr};
+                launch_tc_gemm(t, 0);
+            }
+        }
+        if (rc == PSM_OK && (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess)) rc = PSM_ERR_CUDA;
+        if (rc == PSM_OK) cudaMemcpy(C, dC, nC * 4, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return rc;
+}

@@ -75,6 +75,22 @@ struct GemmArgs {
 };
 void launch_sgemm(const GemmArgs& a, cudaStream_t s);
 
+// tcgen05 / TMEM / TMA GEMM (psm_gemm_tc.cu): same contract as GemmArgs, operands described by
+// TMA tensor maps built once at init.  N % 64 == 0, K % 32 == 0, M % 128 == 0.
+struct alignas(64) TensorMap128 { unsigned char bytes[128]; };
+struct TcGemmArgs {
+    float* C; int M, N, K, ldc;
+    int splits, epi;
+    int three_pass;       // 1: hi/lo split (3xTF32, FP32-class accuracy), 0: single-pass TF32
+    const float* v0; const float* v1; const float* v2;
+    const Scalars* sc;
+};
+struct TcGemm { TensorMap128 mapA, mapB; TcGemmArgs args; };
+int make_kmajor_map(TensorMap128* out, const float* ptr, int rows, int cols, int ld, int box_rows);
+int tc_gemm_bn(int N);
+int tc_gemm_prepare();
+void launch_tc_gemm(const TcGemm& t, cudaStream_t s);
+
 // Split-K reduction + per-block constant + standardisation (SMC:494,512).
 struct ReduceArgs {
     const float* part; int splits; int M; int N;

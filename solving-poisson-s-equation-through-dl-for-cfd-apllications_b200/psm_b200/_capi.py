@@ -13,6 +13,7 @@ PSM_OK, PSM_SKIPPED = 0, 1
 PSM_ERR_INVALID, PSM_ERR_CUDA, PSM_ERR_GEOMETRY, PSM_ERR_STATE, PSM_ERR_COMM = -1, -2, -3, -4, -5
 PSM_DELTAU_TO_DELTAP, PSM_U_TO_GRADP = 0, 1
 PSM_STD, PSM_MAX_ABS = 0, 1
+GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_FP32_SIMT = 0, 1, 2
 (STAGE_GRID, STAGE_XINPUT, STAGE_MLPOUT, STAGE_BLOCKS, STAGE_OFFSETS, STAGE_FIELD, STAGE_SCALARS,
  STAGE_MEANS) = range(8)
 N_TIMINGS = 12
@@ -30,7 +31,7 @@ class PsmConfig(C.Structure):
     _fields_ = [('variant', C.c_int32), ('device', C.c_int32), ('delta', C.c_double), ('shape', C.c_int32),
                 ('overlap', C.c_int32), ('input_cols', C.c_int32), ('additive', C.c_int32),
                 ('ref_bc', C.c_double), ('skip_threshold', C.c_double), ('near_wall_sdf', C.c_double),
-                ('enable_timings', C.c_int32), ('reserved', C.c_int32)]
+                ('enable_timings', C.c_int32), ('gemm_mode', C.c_int32)]
 
 
 class PsmParams(C.Structure):
@@ -79,6 +80,7 @@ SYMBOLS = {
     'psm_get_timings': (C.c_int, [C.c_void_p, c_float_p, C.c_int32]),
     'psm_set_timings': (C.c_int, [C.c_void_p, C.c_int32]),
     'psm_get_launch_count': (C.c_int, [C.c_void_p]),
+    'psm_debug_gemm': (C.c_int, [C.c_int32] * 5 + [c_float_p, c_float_p, c_float_p, C.c_int32]),
     'psm_plan_sizes': (C.c_int, [C.c_int32] * 5 + [c_uint8_p, c_int32_p, c_int32_p, c_int32_p]),
     'psm_plan_compile': (C.c_int, [C.c_int32] * 5 + [c_uint8_p] + [c_int32_p] * 5),
 }

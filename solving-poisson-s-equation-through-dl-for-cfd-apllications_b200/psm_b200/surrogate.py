@@ -41,12 +41,26 @@ def compile_plan(variant, H, W, mask, shape=128, overlap=32):
     return dict(origins=origins, indices_list=il, owner=owner, rec=rec, tasks=tasks, n_blocks=B, n_fields=F)
 
 
+def debug_gemm(A, B, mode=0, splits=1, device=0):
+    """C[splits, M, N] = A[M, K] @ B[N, K].T on the GPU with one of the library's GEMM kernels (tests)."""
+    lib = capi.load()
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    B = np.ascontiguousarray(B, dtype=np.float32)
+    M, K = A.shape
+    N = B.shape[0]
+    Cc = np.empty((splits, M, N), dtype=np.float32)
+    rc = lib.psm_debug_gemm(device, mode, M, N, K, _ptr(A, C.c_float), _ptr(B, C.c_float), _ptr(Cc, C.c_float), splits)
+    if rc < 0:
+        raise capi.PsmError(rc, 'psm_debug_gemm failed')
+    return Cc
+
+
 class PressureSurrogate:
     """One mesh, one GPU, one stream.  Mirrors the lifetime of the reference's module globals
     (PMP:103-118 params, PMP:193 tables) behind an explicit handle."""
 
     def __init__(self, variant='deltaU_to_deltaP', device=0, delta=5e-3, shape=128, overlap=None, input_cols=None,
-                 additive=True, ref_bc=0.0, skip_threshold=1e-4, near_wall_sdf=0.0, timings=False):
+                 additive=True, ref_bc=0.0, skip_threshold=1e-4, near_wall_sdf=0.0, timings=False, gemm_mode=0):
         if variant not in _VARIANT_CODE:
             raise ValueError('variant must be one of %s' % list(_VARIANT_CODE))
         self.lib = capi.load()
@@ -61,7 +75,7 @@ class PressureSurrogate:
         cfg = capi.PsmConfig(variant=_VARIANT_CODE[variant], device=device, delta=delta, shape=shape, overlap=overlap,
                              input_cols=input_cols, additive=int(additive), ref_bc=ref_bc,
                              skip_threshold=skip_threshold, near_wall_sdf=near_wall_sdf,
-                             enable_timings=int(timings), reserved=0)
+                             enable_timings=int(timings), gemm_mode=int(gemm_mode))
         self._h = C.c_void_p()
         rc = self.lib.psm_create(C.byref(self._h), C.byref(cfg))
         if rc < 0:

@@ -232,6 +232,21 @@ def test_resident_previous_velocity_mode_and_skip_rule():
     b.close()
 
 
+@pytest.mark.parametrize("mode,tol", [(1, 2e-3), (2, 1e-4)])
+def test_gemm_modes_cross_check(deltas_case, mode, tol):
+    """Single-pass TF32 and the CUDA-core FP32 kernel against the default 3xTF32 tensor-core path."""
+    c = deltas_case
+    ref, _ = c.sm.predict(c.cells)
+    f_ref = c.sm.stage('field')[0]
+    with psm_b200.PressureSurrogate('deltaU_to_deltaP', gemm_mode=mode) as sm:
+        sm.load_params(c.params)
+        sm.init_tables(c.tables)
+        out, rc = sm.predict(c.cells)
+        assert rc == _capi.PSM_OK
+        assert rel_l2(sm.stage('field')[0], f_ref) < tol
+        assert rel_l2(out - c.F['p_prev'], ref - c.F['p_prev']) < tol
+
+
 def test_error_codes_not_crashes(deltas_case):
     c = deltas_case
     with pytest.raises(_capi.PsmError) as e:
