@@ -32,7 +32,7 @@ def test_gemm_matches_numpy(mode, M, N, K, splits):
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     assert not np.isnan(C).any()
     err = rel_l2(C, ref)
-    tol = {_capi.GEMM_TC_TF32: 2e-3, _capi.GEMM_TC_3XTF32: 3e-6, _capi.GEMM_FP32_SIMT: 3e-6}[mode]
+    tol = {_capi.GEMM_TC_TF32: 2e-3, _capi.GEMM_TC_3XTF32: 1.5e-5, _capi.GEMM_FP32_SIMT: 3e-6}[mode]
     assert err < tol, err
 
 
