@@ -52,6 +52,7 @@ struct psm_handle {
     uint8_t* d_gmask = nullptr; uint16_t* d_owner = nullptr;
     int32_t *d_by0 = nullptr, *d_bx0 = nullptr;
     DevTask* d_tasks = nullptr; DevRec* d_rec = nullptr; int n_tasks = 0, rounds = 0;
+    int2* d_rows = nullptr; int32_t* d_row_start = nullptr; double* d_row_sums = nullptr; int n_rows = 0;
     float* d_zc = nullptr;            // [B_pad][pc_in_pad]
 
     // ---- per-step buffers ---------------------------------------------------------------------------
@@ -66,6 +67,11 @@ struct psm_handle {
     cudaEvent_t ev[PSM_N_TIMINGS + 1] = {};
     bool ev_valid = false, ev_created = false;
     bool last_host = false;
+    // whole-step CUDA graphs, keyed by the caller's buffers (the solver passes the same ones every step,
+    // FOAM/PythonComm_init.H:53)
+    struct StepGraph { const void* in = nullptr; void* out = nullptr; cudaGraphExec_t exec = nullptr; };
+    StepGraph g_dev, g_host;
+    bool use_graphs = true;
 };
 
 #define PSM_FAIL(h, code, ...)                                    \
@@ -145,6 +151,8 @@ extern "C" int psm_destroy(psm_handle* h) {
     if (!h) return PSM_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->g_dev.exec) cudaGraphExecDestroy(h->g_dev.exec);
+    if (h->g_host.exec) cudaGraphExecDestroy(h->g_host.exec);
     for (void* p : h->allocs) cudaFree(p);
     if (h->ev_created) for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->h_sc) cudaFreeHost(h->h_sc);
@@ -337,6 +345,17 @@ extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
             tk[i] = DevTask{s.src, s.msk, s.ch, s.y0, s.y1, s.x0, s.x1, s.count};
         }
         TRY(upload(h, &h->d_tasks, tk));
+        std::vector<int2> rows;
+        std::vector<int32_t> row_start(tk.size() + 1, 0);
+        for (size_t i = 0; i < tk.size(); ++i) {
+            row_start[i] = (int32_t)rows.size();
+            for (int y = tk[i].y0; y < tk[i].y1; ++y) rows.push_back(make_int2((int)i, y));
+        }
+        row_start[tk.size()] = (int32_t)rows.size();
+        h->n_rows = (int)rows.size();
+        TRY(upload(h, &h->d_rows, rows));
+        TRY(upload(h, &h->d_row_start, row_start));
+        TRY(dalloc(h, &h->d_row_sums, rows.size()));
         std::vector<DevRec> rc2(P.rec.size());
         for (size_t i = 0; i < rc2.size(); ++i) rc2[i] = DevRec{P.rec[i].ta, P.rec[i].tb, P.rec[i].parent, P.rec[i].is_nan};
         TRY(upload(h, &h->d_rec, rc2));
@@ -495,8 +514,9 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         ++nl;
     }
     tick();   // pca_inverse
-    MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->d_by0, h->d_bx0, h->C, S, h->W, h->d_means};
-    launch_means(ma, s); ++nl;
+    MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->d_by0, h->d_bx0, h->C, S, h->W, h->d_means,
+                 h->d_rows, h->n_rows, h->d_row_start, h->d_row_sums};
+    launch_means(ma, s); nl += 2;
     tick();   // strip_means
     {
         OffsetsArgs oa{};
@@ -524,8 +544,53 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     return PSM_OK;
 }
 
-static int finish(psm_handle* h) {
+// Enqueue one step (optionally with the host copies around it) -- eagerly, or as a captured graph.
+static int enqueue_step(psm_handle* h, bool host, const double* in, double* out) {
+    if (host) {
+        CU(h, cudaMemcpyAsync(h->d_cells, in, (size_t)h->n_cells * h->cfg.input_cols * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (h->ev_valid) cudaEventRecord(h->ev[11], h->stream);
+        TRY(run_step(h, h->d_cells, h->d_out));
+        CU(h, cudaMemcpyAsync(out, h->d_out, (size_t)h->n_cells * h->F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        TRY(run_step(h, in, out));
+    }
     CU(h, cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
+    return PSM_OK;
+}
+
+static int submit_step(psm_handle* h, bool host, const double* in, double* out) {
+    h->last_host = host;
+    if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
+    if (!h->use_graphs || h->ev_valid) {             // per-stage events are recorded eagerly only
+        TRY(enqueue_step(h, host, in, out));
+    } else {
+        psm_handle::StepGraph& g = host ? h->g_host : h->g_dev;
+        if (!g.exec || g.in != in || g.out != out) {
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_step(h, host, in, out);
+            cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+            if (rc == PSM_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g.exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != PSM_OK || e != cudaSuccess) {
+                // e.g. a pageable host buffer that cannot be captured: same kernels, launched one by one
+                g.exec = nullptr;
+                cudaGetLastError();
+                h->use_graphs = false;
+                TRY(enqueue_step(h, host, in, out));
+                if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
+                return PSM_OK;
+            }
+            g.in = in; g.out = out;
+        }
+        CU(h, cudaGraphLaunch(g.exec, h->stream));
+    }
+    if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
+    return PSM_OK;
+}
+
+static int finish(psm_handle* h) {
     CU(h, cudaStreamSynchronize(h->stream));
     return h->h_sc->skip ? PSM_SKIPPED : PSM_OK;
 }
@@ -537,13 +602,7 @@ extern "C" int psm_predict(psm_handle* h, const double* cells, int64_t n_cells, 
     if (n_cells != h->n_cells) PSM_FAIL(h, PSM_ERR_INVALID, "n_cells %lld does not match the initialised mesh (%lld)", (long long)n_cells, h->n_cells);
     if (!h->have_back) PSM_FAIL(h, PSM_ERR_STATE, "no grid->cell tables were given: use psm_predict_device(..., NULL, ...) + psm_get_stage(FIELD)");
     CU(h, cudaSetDevice(h->cfg.device));
-    if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
-    CU(h, cudaMemcpyAsync(h->d_cells, cells, (size_t)n_cells * h->cfg.input_cols * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (h->ev_valid) cudaEventRecord(h->ev[11], h->stream);
-    h->last_host = true;
-    TRY(run_step(h, h->d_cells, h->d_out));
-    CU(h, cudaMemcpyAsync(p_out, h->d_out, (size_t)n_cells * h->F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
+    TRY(submit_step(h, true, cells, p_out));
     return finish(h);
 }
 
@@ -554,10 +613,7 @@ extern "C" int psm_predict_device(psm_handle* h, const double* d_cells, int64_t 
     if (n_cells != h->n_cells) PSM_FAIL(h, PSM_ERR_INVALID, "n_cells does not match the initialised mesh");
     if (d_p_out && !h->have_back) PSM_FAIL(h, PSM_ERR_STATE, "no grid->cell tables were given");
     CU(h, cudaSetDevice(h->cfg.device));
-    if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
-    h->last_host = false;
-    TRY(run_step(h, d_cells, d_p_out));
-    if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
+    TRY(submit_step(h, false, d_cells, d_p_out));
     if (sync) return finish(h);
     return PSM_OK;
 }

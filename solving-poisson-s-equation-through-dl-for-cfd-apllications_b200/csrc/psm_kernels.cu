@@ -235,46 +235,72 @@ void launch_sgemm(const GemmArgs& a, cudaStream_t s) {
     }
 }
 
+// 256 threads = 32 consecutive outputs x 8 split groups: every thread has splits/8 independent
+// coalesced loads in flight, then the 8 groups fold through shared memory in a fixed order.
 __global__ void __launch_bounds__(256) reduce_standardise_kernel(ReduceArgs a) {
     const long long total = (long long)a.M * a.N;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * 32 + ox;
+    float sum = 0.f;
+    if (i < total) {
+#pragma unroll 4
+        for (int sp = grp; sp < a.splits; sp += 8) sum += __ldcs(a.part + (long long)sp * total + i);
+    }
+    __shared__ float red[8][33];
+    red[grp][ox] = sum;
+    __syncthreads();
+    if (grp == 0 && i < total) {
+        float tot = red[0][ox];
+#pragma unroll
+        for (int g2 = 1; g2 < 8; ++g2) tot += red[g2][ox];
         const int n = (int)(i % a.N);
-        float sum = 0.f;
-        for (int sp = 0; sp < a.splits; ++sp) sum += a.part[(long long)sp * total + i];
-        a.x[i] = (sum + a.zc[i]) * a.a[n] + a.b[n];
+        a.x[i] = (tot + a.zc[i]) * a.a[n] + a.b[n];
     }
 }
 void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {
     long long total = (long long)a.M * a.N;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > kSMs * 4) blocks = kSMs * 4;
-    reduce_standardise_kernel<<<blocks, 256, 0, s>>>(a);
+    reduce_standardise_kernel<<<(unsigned)((total + 31) / 32), 256, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K6a  masked rectangle means.  Every np.mean(pred[rect][flow_bool[rect] != 0]) of SMC:233-316 /
 //      GRAD:300-340 on the UNCORRECTED blocks; FP64 accumulation.  One CTA per task.
-__global__ void __launch_bounds__(128) means_kernel(MeansArgs a) {
-    const DevTask t = a.tasks[blockIdx.x];
-    const int w = t.x1 - t.x0, h = t.y1 - t.y0;
-    const float* src = a.blocks + ((long long)t.src * a.C + t.ch) * a.S * a.S;
-    const uint8_t* msk = a.gmask + (long long)a.by0[t.msk] * a.W + a.bx0[t.msk];
+//      Two deterministic passes (no atomics): one warp per (task, row) writes a row partial, then one
+//      warp per task folds its rows -- rectangles range from 1 x 128 to 120 x 128 pixels, so the work
+//      is balanced per row, not per task.
+__global__ void __launch_bounds__(256) row_sums_kernel(MeansArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= a.n_rows) return;
+    const int2 ri = a.rows[r];                                   // (task, block-local y)
+    const DevTask t = a.tasks[ri.x];
+    const float* src = a.blocks + (((long long)t.src * a.C + t.ch) * a.S + ri.y) * a.S;
+    const uint8_t* msk = a.gmask + (long long)(a.by0[t.msk] + ri.y) * a.W + a.bx0[t.msk];
+    const float4 v = reinterpret_cast<const float4*>(src)[lane];  // the whole 128-pixel block row
+    const int x = lane * 4;
     double sum = 0.0;
-    for (int q = threadIdx.x; q < w * h; q += blockDim.x) {
-        const int y = t.y0 + q / w, x = t.x0 + q % w;
-        if (msk[(long long)y * a.W + x]) sum += (double)src[y * a.S + x];
-    }
+    if (x + 0 >= t.x0 && x + 0 < t.x1 && msk[x + 0]) sum += (double)v.x;
+    if (x + 1 >= t.x0 && x + 1 < t.x1 && msk[x + 1]) sum += (double)v.y;
+    if (x + 2 >= t.x0 && x + 2 < t.x1 && msk[x + 2]) sum += (double)v.z;
+    if (x + 3 >= t.x0 && x + 3 < t.x1 && msk[x + 3]) sum += (double)v.w;
     sum = warp_sum(sum);
-    __shared__ double sm[4];
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = sum;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const double tot = sm[0] + sm[1] + sm[2] + sm[3];
-        a.means[blockIdx.x] = (t.count > 0) ? tot / (double)t.count : CUDART_NAN;
-    }
+    if (lane == 0) a.row_sums[r] = sum;
+}
+__global__ void __launch_bounds__(256) task_means_kernel(MeansArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= a.n_tasks) return;
+    const int r0 = a.row_start[t], r1 = a.row_start[t + 1];
+    double sum = 0.0;
+    for (int r = r0 + lane; r < r1; r += 32) sum += a.row_sums[r];
+    sum = warp_sum(sum);
+    const int count = a.tasks[t].count;
+    if (lane == 0) a.means[t] = (count > 0) ? sum / (double)count : CUDART_NAN;
 }
 void launch_means(const MeansArgs& a, cudaStream_t s) {
-    if (a.n_tasks > 0) means_kernel<<<a.n_tasks, 128, 0, s>>>(a);
+    if (a.n_tasks <= 0) return;
+    row_sums_kernel<<<(a.n_rows + 7) / 8, 256, 0, s>>>(a);
+    task_means_kernel<<<(a.n_tasks + 7) / 8, 256, 0, s>>>(a);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -109,6 +109,9 @@ struct MeansArgs {
     const int32_t* by0; const int32_t* bx0;
     int C, S, W;
     double* means;                    // [n_tasks]
+    const int2* rows; int n_rows;     // (task, block-local y) of every rectangle row, grouped by task
+    const int32_t* row_start;         // [n_tasks + 1] first row of each task
+    double* row_sums;                 // [n_rows] scratch
 };
 void launch_means(const MeansArgs& a, cudaStream_t s);
 
