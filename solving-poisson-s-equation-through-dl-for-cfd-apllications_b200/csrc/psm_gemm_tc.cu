@@ -301,7 +301,7 @@ int tc_gemm_prepare() {
 }
 
 void launch_tc_gemm(const TcGemm& t, cudaStream_t s) {
-    const int bn = tc_gemm_bn(t.args.N);
+    const int bn = t.bn;
     dim3 grid(t.args.N / bn, (t.args.M + BM - 1) / BM, t.args.splits);
     const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(&t.mapA);
     const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(&t.mapB);

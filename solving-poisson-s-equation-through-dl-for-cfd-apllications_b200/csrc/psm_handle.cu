@@ -62,7 +62,8 @@ struct psm_handle {
     double* d_means = nullptr; double* d_dbuf[2] = {nullptr, nullptr}; int32_t* d_pbuf[2] = {nullptr, nullptr};
     double* d_offsets = nullptr; float* d_coff = nullptr; float* d_field = nullptr;
     Scalars* d_sc = nullptr; Scalars* h_sc = nullptr;
-    TcGemm tc_proj{}, tc_inv{}; std::vector<TcGemm> tc_dense; int tc_splits = 1;   // tcgen05 path (gemm_mode 0/1)
+    TcGemm tc_proj{}, tc_inv{}; std::vector<TcGemm> tc_dense; std::vector<int> dense_splits; int tc_splits = 1;
+    float* d_dpart = nullptr;       // split-K partials of the Dense layers   // tcgen05 path (gemm_mode 0/1)
     int launches = 0;
     cudaEvent_t ev[PSM_N_TIMINGS + 1] = {};
     bool ev_valid = false, ev_created = false;
@@ -426,25 +427,37 @@ extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
         if (tc_gemm_prepare() != 0) PSM_FAIL(h, PSM_ERR_CUDA, "cannot opt in to %d B of shared memory for the tcgen05 GEMM", 197888);
         const int three = (h->cfg.gemm_mode == PSM_GEMM_TC_3XTF32) ? 1 : 0;
         auto mk = [&](TcGemm& g, const float* A, int a_rows, const float* Bm, int b_rows, int K, float* Cp, int ldc, int splits,
-                      int epi, const float* v0, const float* v1, const float* v2) -> int {
-            if (make_kmajor_map(&g.mapA, A, a_rows, K, K, 128) != 0 || make_kmajor_map(&g.mapB, Bm, b_rows, K, K, tc_gemm_bn(b_rows)) != 0)
+                      int epi, const float* v0, const float* v1, const float* v2, int bn) -> int {
+            if (make_kmajor_map(&g.mapA, A, a_rows, K, K, 128) != 0 || make_kmajor_map(&g.mapB, Bm, b_rows, K, K, bn) != 0)
                 PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
             g.args = TcGemmArgs{Cp, a_rows, b_rows, K, ldc, splits, epi, three, v0, v1, v2, h->d_sc};
+            g.bn = bn;
             return 0;
         };
         TRY(mk(h->tc_proj, h->d_xu, Bp, h->d_comp_u, h->pc_in_pad, 2 * S2, h->d_part, h->pc_in_pad, h->tc_splits, EPI_PARTIAL,
-               nullptr, nullptr, nullptr));
+               nullptr, nullptr, nullptr, tc_gemm_bn(h->pc_in_pad)));
+        // Dense layers: the batch is only B blocks (one or a few 128-row tiles), so every layer is cut into
+        // 64-column tiles x split-K partials (each CTA streams <= ~100 KB), folded by the reduce kernel.
         h->tc_dense.resize(h->n_dense);
+        h->dense_splits.assign(h->n_dense, 1);
+        TRY(dalloc(h, &h->d_dpart, (size_t)8 * Bp * maxw));
         const float* in = h->d_xin;
         for (int l = 0; l < h->n_dense; ++l) {
             const bool last = (l == h->n_dense - 1);
             float* outp = last ? h->d_r : h->d_act[l & 1];
-            TRY(mk(h->tc_dense[l], in, Bp, h->d_W[l], h->dims_pad[l + 1], h->dims_pad[l], outp, h->dims_pad[l + 1], 1,
-                   last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU, h->d_bias[l], h->d_out_s, h->d_out_m));
+            const int kb = h->dims_pad[l] / 32;
+            const int tiles = (Bp / 128) * (h->dims_pad[l + 1] / 64);
+            int sp = (tiles >= 96) ? 1 : (kb >= 16 ? 4 : (kb >= 4 ? 2 : 1));
+            const int per = (kb + sp - 1) / sp;
+            sp = (kb + per - 1) / per;
+            h->dense_splits[l] = sp;
+            TRY(mk(h->tc_dense[l], in, Bp, h->d_W[l], h->dims_pad[l + 1], h->dims_pad[l], sp > 1 ? h->d_dpart : outp,
+                   h->dims_pad[l + 1], sp, sp > 1 ? EPI_PARTIAL : (last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU), h->d_bias[l],
+                   h->d_out_s, h->d_out_m, 64));
             in = outp;
         }
         TRY(mk(h->tc_inv, h->d_r, Bp, h->d_comp_out_t, S2 * h->C, h->pc_p_pad, h->d_blocks, S2 * h->C, 1, EPI_PCA_INV,
-               h->d_pmean, nullptr, nullptr));
+               h->d_pmean, nullptr, nullptr, 128));
     }
     if (h->cfg.enable_timings) TRY(psm_set_timings(h, 1));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -484,7 +497,8 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
             launch_sgemm(g, s);
         }
         ++nl;
-        ReduceArgs r{h->d_part, tc ? h->tc_splits : h->splits, Bp, h->pc_in_pad, h->d_zc, h->d_in_a, h->d_in_b, h->d_xin};
+        ReduceArgs r{h->d_part, tc ? h->tc_splits : h->splits, Bp, h->pc_in_pad, h->d_zc, h->d_in_a, h->d_in_b, h->d_xin,
+                     RED_STANDARDISE, nullptr};
         launch_reduce_standardise(r, s); ++nl;
     }
     tick();   // pca_project
@@ -498,8 +512,14 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
             g.lda = g.K; g.ldb = g.K; g.ldc = g.N; g.splits = 1;
             g.epi = last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU;
             g.v0 = h->d_bias[l]; g.v1 = h->d_out_s; g.v2 = h->d_out_m;
-            if (tc) launch_tc_gemm(h->tc_dense[l], s);
-            else launch_sgemm(g, s);
+            if (tc) {
+                launch_tc_gemm(h->tc_dense[l], s);
+                if (h->dense_splits[l] > 1) {
+                    ReduceArgs r{h->d_dpart, h->dense_splits[l], Bp, g.N, nullptr, h->d_out_s, h->d_out_m, g.C,
+                                 last ? RED_BIAS_AFFINE : RED_BIAS_RELU, h->d_bias[l]};
+                    launch_reduce_standardise(r, s); ++nl;
+                }
+            } else launch_sgemm(g, s);
             ++nl;
             in = g.C;
         }
@@ -795,6 +815,7 @@ extern "C" int psm_debug_gemm(int32_t device, int32_t mode, int32_t M, int32_t N
                 make_kmajor_map(&t.mapB, dB, N, K, K, tc_gemm_bn(N)) != 0) rc = PSM_ERR_CUDA;
             else {
                 t.args = TcGemmArgs{dC, M, N, K, N, splits, EPI_PARTIAL, mode == PSM_GEMM_TC_3XTF32 ? 1 : 0, nullptr, nullptr, nullptr, nullptr};
+                t.bn = tc_gemm_bn(N);
                 launch_tc_gemm(t, 0);
             }
         }

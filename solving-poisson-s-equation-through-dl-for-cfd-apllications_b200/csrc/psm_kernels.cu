@@ -254,7 +254,11 @@ __global__ void __launch_bounds__(256) reduce_standardise_kernel(ReduceArgs a) {
 #pragma unroll
         for (int g2 = 1; g2 < 8; ++g2) tot += red[g2][ox];
         const int n = (int)(i % a.N);
-        a.x[i] = (tot + a.zc[i]) * a.a[n] + a.b[n];
+        float o;
+        if (a.kind == RED_STANDARDISE) o = (tot + a.zc[i]) * a.a[n] + a.b[n];
+        else if (a.kind == RED_BIAS_RELU) o = fmaxf(tot + a.bias[n], 0.f);
+        else o = (tot + a.bias[n]) * a.a[n] + a.b[n];
+        a.x[i] = o;
     }
 }
 void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {

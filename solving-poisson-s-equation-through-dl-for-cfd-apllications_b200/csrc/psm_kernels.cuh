@@ -85,18 +85,22 @@ struct TcGemmArgs {
     const float* v0; const float* v1; const float* v2;
     const Scalars* sc;
 };
-struct TcGemm { TensorMap128 mapA, mapB; TcGemmArgs args; };
+struct TcGemm { TensorMap128 mapA, mapB; TcGemmArgs args; int bn; };   // bn: N tile (64 or 128) the B map was built for
 int make_kmajor_map(TensorMap128* out, const float* ptr, int rows, int cols, int ld, int box_rows);
 int tc_gemm_bn(int N);
 int tc_gemm_prepare();
 void launch_tc_gemm(const TcGemm& t, cudaStream_t s);
 
 // Split-K reduction + per-block constant + standardisation (SMC:494,512).
+// Also the split-K epilogue of the Dense layers: relu(sum + bias[n]) or (sum + bias[n]) * s[n] + m[n].
+enum ReduceKind { RED_STANDARDISE = 0, RED_BIAS_RELU = 1, RED_BIAS_AFFINE = 2 };
 struct ReduceArgs {
     const float* part; int splits; int M; int N;
-    const float* zc;      // [M][N] static sdf-channel contribution per block
-    const float* a; const float* b;   // x = (sum + zc) * a[n] + b[n]
+    const float* zc;      // RED_STANDARDISE: [M][N] static sdf-channel contribution per block
+    const float* a; const float* b;   // STANDARDISE: x = (sum + zc) * a[n] + b[n]; AFFINE: scale a[n], shift b[n]
     float* x;
+    int kind;
+    const float* bias;    // RED_BIAS_*: [N]
 };
 void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s);
 
