@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PSM_API_VERSION 1
+#define PSM_API_VERSION 2
 
 typedef struct psm_handle psm_handle;
 
@@ -115,17 +115,54 @@ typedef struct psm_tables {
     const double*  sdfunct;       /* [H][W] distance field, 0 outside the flow domain (SMC:163,175) */
 } psm_tables;
 
+/* One rank's share of a block-row partitioned mesh (multi-GPU, replaces the gather-to-root of
+ * PMP:179-185,258,501-511).  Built by psm_b200/shard.py (partition() from global tables, or band tables
+ * for meshes too large to triangulate on one host).  Tables are LOCAL and PRE-FOLDED:
+ *   - forward table rows cover pixel rows [row0,row1) only; invalid pixels have zero weights; the
+ *     (0,0)-pixel quirk (SMC:161,432) is already applied on the rank that holds pixel (0,0);
+ *   - cell ids are local: [0,n_owned) owned cells (the rows the caller passes to psm_predict, and the
+ *     cells it gets pressures for), [n_owned, n_owned+n_ghost) ghost cells received from their owners;
+ *   - back table ids are local field ids: (row-row0)*W+col for own pixels, n_pix_own+slot for ghost
+ *     pixels received from their owners; vert_back[c][0] = -1 keeps p_prev (PMP:492-496). */
+typedef struct psm_shard {
+    int32_t rank, world;
+    int32_t grid_h, grid_w;            /* GLOBAL grid                                                */
+    int32_t row0, row1;                /* pixel rows this rank gathers and places                    */
+    int32_t ext_rows;                  /* overlap rows [row1,row1+ext_rows) received from rank+1
+                                          before block extraction (the halo strip); 0 on the last   */
+    int32_t send_rows;                 /* rows [row0,row0+send_rows) sent to rank-1; 0 on rank 0     */
+    int32_t blk_row0, blk_row1;        /* block rows [blk_row0,blk_row1) of the global plan          */
+    int32_t reserved;
+    const uint8_t* mask_global;        /* [H][W] flow mask (sdfunct != 0) of the WHOLE grid          */
+    int64_t n_owned, n_ghost, n_ghost_pix;
+    const int32_t* vert;               /* [(row1-row0)*W][3]                                         */
+    const double*  weights;            /* [(row1-row0)*W][3]                                         */
+    const double*  sdfunct;            /* [row1-row0+ext_rows][W]                                    */
+    const int32_t* vert_back;          /* [n_owned][3] or NULL                                       */
+    const double*  weights_back;       /* [n_owned][3]                                               */
+    /* static sparse exchanges, CSR over peer ranks ([world+1] offsets) */
+    const int64_t* cell_send_ptr; const int32_t* cell_send_idx;   /* owned cell ids each peer needs   */
+    const int64_t* cell_recv_ptr;                                 /* ghost slots, grouped by owner    */
+    const int64_t* pix_send_ptr;  const int32_t* pix_send_idx;    /* own pixel ids each peer needs    */
+    const int64_t* pix_recv_ptr;                                  /* ghost pixel slots, by owner      */
+} psm_shard;
+
 /* Static geometry report (filled by psm_get_geometry). */
 typedef struct psm_geometry {
     int32_t grid_h, grid_w, shape, overlap;
     int32_t n_x, n_y, p_i, p_j;   /* SMC:461-462,213,216 / GRAD:479-480,277-278                 */
     int32_t n_blocks, n_fields;
     int64_t n_cells;
-    int32_t n_tasks;              /* masked strip means evaluated per step                      */
+    int32_t n_tasks;              /* masked strip means evaluated per step (whole mesh)         */
     int32_t reserved;
+    /* this rank's share (equal to the whole mesh on a single-GPU handle) */
+    int32_t row0, row1, ext_rows, first_block, n_local_blocks, world;
+    int64_t n_ghost_cells, n_ghost_pix;
 } psm_geometry;
 
 /* Device-resident intermediates that parity tests read back (psm_get_stage). */
+/* On a sharded handle H means this rank's rows (row1-row0, + ext_rows for GRID) and B its local
+ * blocks, except OFFSETS and MEANS which are global (every rank holds the same values). */
 enum psm_stage_code {
     PSM_STAGE_GRID = 0,       /* float [2][H][W]   scaled input channels 0,1 (SMC:430-444)       */
     PSM_STAGE_XINPUT = 1,     /* float [B][pc_in]  standardised PCA coordinates (SMC:512)        */
@@ -149,6 +186,25 @@ int psm_load_params(psm_handle* h, const psm_params* params);
 /* Replaces init_func(array, top_boundary, obst_boundary) (PMP:172-247; FOAM/PythonComm_init.H:94)
  * for callers that already hold the Qhull tables and raster (the Python shim). */
 int psm_init_with_tables(psm_handle* h, const psm_tables* tables);
+
+/* Same from a flat binary file written by `python -m psm_b200.tables_file` (or psm_save_tables), so that a
+ * C/C++ caller needs neither SciPy nor an interpreter at run time (INTEGRATION.md route B). */
+int psm_init_from_file(psm_handle* h, const char* path);
+int psm_load_params_file(psm_handle* h, const char* path);
+int psm_save_tables(const psm_tables* tables, const char* path);
+int psm_save_params(const psm_params* params, int32_t shape, const char* path);
+
+/* ---- multi-GPU: one process per GPU, block rows over ranks ------------- */
+
+#define PSM_UNIQUE_ID_BYTES 128
+/* Rank 0 creates the NCCL unique id; the caller ships the bytes to the other ranks with its own
+ * transport (MPI_Bcast / Pstream / torch.distributed) -- replaces MPI.COMM_WORLD of PMP:14-17. */
+int psm_comm_get_unique_id(void* id_out /* PSM_UNIQUE_ID_BYTES */);
+/* Collective over all ranks: creates the communicator the handle's step uses. */
+int psm_comm_init(psm_handle* h, const void* unique_id, int32_t rank, int32_t world);
+/* Collective: this rank's share of the mesh.  After it, psm_predict / psm_predict_device are
+ * collective calls: cells = this rank's n_owned rows, p_out = its n_owned pressures. */
+int psm_init_sharded(psm_handle* h, const psm_shard* shard);
 
 /* Idempotent; NULL is accepted. */
 int psm_destroy(psm_handle* h);
@@ -218,6 +274,13 @@ int psm_plan_sizes(int32_t variant, int32_t grid_h, int32_t grid_w, int32_t shap
 int psm_plan_compile(int32_t variant, int32_t grid_h, int32_t grid_w, int32_t shape, int32_t overlap,
                      const uint8_t* mask, int32_t* origins, int32_t* indices_list, int32_t* owner,
                      int32_t* rec, int32_t* tasks);
+
+/* Runs of the two global-shift lines (SMC:350 / GRAD:358-361) through the owner map:
+ * lines int32[n][8] = (field, block, y0, y1, x0, x1, coef, n_pixels), block-local rectangles; the shift of a
+ * field is sum(coef * (sum(raw block values over the run) - n_pixels * c[block])) / (3 * line length).
+ * `lines` may be NULL to query n_lines. */
+int psm_plan_shift_lines(int32_t variant, int32_t grid_h, int32_t grid_w, int32_t shape, int32_t overlap,
+                         const uint8_t* mask, int32_t* n_lines, int32_t* lines);
 
 /* Unit-test entry for the GEMM kernels: C[splits][M][N] (host) = A[M][K] * B[N][K]^T (host), split-K
  * partials left unreduced.  mode = psm_gemm_mode_code.  M % 128 == 0, N % 64 == 0, K % 32 == 0. */

@@ -1,8 +1,11 @@
 // Handle, parameter/table upload and per-step orchestration behind the C-ABI (include/psm_b200.h).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -20,6 +23,44 @@ thread_local std::string g_create_error;
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline long long round_up_ll(long long v, long long m) { return (v + m - 1) / m * m; }
+}  // namespace
+
+// NCCL is bound at run time (dlopen) so that single-GPU callers need no NCCL at all and a process that
+// already loaded one (e.g. the copy PyTorch bundles) shares it instead of loading a second.
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { error = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+        bool ok = true;
+        auto sym = [&](const char* n) { void* p = dlsym(lib, n); if (!p) { ok = false; error = std::string("missing NCCL symbol ") + n; } return p; };
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+        Send = (decltype(Send))sym("ncclSend");
+        Recv = (decltype(Recv))sym("ncclRecv");
+        GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+        if (!ok) { lib = nullptr; return false; }
+        return true;
+    }
+};
+NcclApi g_nccl;
 }  // namespace
 
 struct psm_handle {
@@ -43,15 +84,33 @@ struct psm_handle {
     float* d_pmean = nullptr;         // [S*S*C] planar
 
     // ---- geometry / tables ----------------------------------------------------------------------
-    Plan plan;
-    long long n_cells = 0, G = 0, G_pad = 0;
-    int H = 0, W = 0, B = 0, B_pad = 0, F = 1;
+    // Single-GPU handles are the world == 1 special case of a block-row shard: rows [row0,row1) of the
+    // global H x W grid are gathered and placed here, rows [row1,row1+ext_rows) arrive from rank+1,
+    // blocks [kb0,kb0+B) of the global plan are evaluated here.
+    Plan plan;                         // GLOBAL plan
+    long long n_cells = 0;             // owned cells (rows of psm_predict)
+    long long n_ghost = 0, n_ghost_pix = 0;
+    long long G = 0, G_pad = 0;        // own pixels (row1-row0)*W, padded to 4
+    long long grid_stride = 0;         // floats per grid plane (own + halo rows)
+    long long field_stride = 0;        // floats per field plane (own pixels + ghost pixels)
+    int H = 0, W = 0;                  // H = own rows (row1-row0); W global
+    int Hglob = 0, row0 = 0, row1 = 0, ext_rows = 0, send_rows = 0;
+    int B = 0, B_pad = 0, F = 1;       // B = local blocks
+    int Bg = 0, kb0 = 0;               // global block count, first global block of this rank
+    int rank = 0, world = 1;
     bool have_back = false;
+    ncclComm_t comm = nullptr;
+    std::vector<long long> cell_send_ptr, cell_recv_ptr, pix_send_ptr, pix_recv_ptr;
+    int32_t *d_cell_send_idx = nullptr, *d_pix_send_idx = nullptr;
+    float *d_cell_send = nullptr, *d_pix_send = nullptr;
+    double* d_means_loc = nullptr;     // world > 1: this rank's means, zero elsewhere (all-reduce source)
+    int n_tasks_glob = 0;              // means + shift-line sums of the whole mesh
+    DevShiftTerm* d_terms = nullptr; int term_start[3] = {0, 0, 0};
     int32_t *d_fv[3] = {nullptr, nullptr, nullptr}; float* d_fw[3] = {nullptr, nullptr, nullptr};
     int32_t *d_bv[3] = {nullptr, nullptr, nullptr}; float* d_bw[3] = {nullptr, nullptr, nullptr};
     uint8_t* d_gmask = nullptr; uint16_t* d_owner = nullptr;
     int32_t *d_by0 = nullptr, *d_bx0 = nullptr;
-    DevTask* d_tasks = nullptr; DevRec* d_rec = nullptr; int n_tasks = 0, rounds = 0;
+    DevTask* d_tasks = nullptr; DevRec* d_rec = nullptr; int n_tasks = 0 /* local */, rounds = 0;
     int2* d_rows = nullptr; int32_t* d_row_start = nullptr; double* d_row_sums = nullptr; int n_rows = 0;
     float* d_zc = nullptr;            // [B_pad][pc_in_pad]
 
@@ -154,6 +213,7 @@ extern "C" int psm_destroy(psm_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->g_dev.exec) cudaGraphExecDestroy(h->g_dev.exec);
     if (h->g_host.exec) cudaGraphExecDestroy(h->g_host.exec);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->ev_created) for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->h_sc) cudaFreeHost(h->h_sc);
@@ -258,94 +318,107 @@ extern "C" int psm_load_params(psm_handle* h, const psm_params* p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
-    if (!h) return PSM_ERR_INVALID;
-    if (!t) PSM_FAIL(h, PSM_ERR_INVALID, "psm_init_with_tables: NULL tables");
-    if (!h->params_loaded) PSM_FAIL(h, PSM_ERR_STATE, "psm_load_params must be called before psm_init_with_tables");
-    if (h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "handle already initialised");
-    if (!t->vert || !t->weights || !t->indices || !t->sdfunct || t->n_cells < 3 || t->grid_h < 1 || t->grid_w < 1)
-        PSM_FAIL(h, PSM_ERR_INVALID, "bad tables");
-    CU(h, cudaSetDevice(h->cfg.device));
-    const int H = t->grid_h, W = t->grid_w, S = h->S, S2 = S * S;
-    const long long G = (long long)H * W, N = t->n_cells;
-    h->H = H; h->W = W; h->G = G; h->n_cells = N;
-    h->G_pad = round_up_ll(G, 4);
+// Everything init needs about this rank's share, tables already folded and in local numbering.
+namespace {
+struct LocalInit {
+    int rank = 0, world = 1;
+    int H = 0, W = 0;                          // GLOBAL grid
+    int row0 = 0, row1 = 0, ext_rows = 0, send_rows = 0, blk_row0 = 0, blk_row1 = 0;
+    const uint8_t* mask_global = nullptr;      // [H][W]
+    long long n_owned = 0, n_ghost = 0, n_ghost_pix = 0;
+    std::vector<int32_t> fv[3]; std::vector<float> fw[3];      // [(row1-row0)*W]
+    const double* sdf_rows = nullptr;          // [row1-row0+ext_rows][W]
+    bool have_back = false;
+    std::vector<int32_t> bv[3]; std::vector<float> bw[3];      // [n_owned]
+    std::vector<long long> cell_send_ptr, cell_recv_ptr, pix_send_ptr, pix_recv_ptr;
+    std::vector<int32_t> cell_send_idx, pix_send_idx;
+};
+}  // namespace
 
-    // static flow mask: x_array[...,2] != 0 (SMC:224) <=> sdfunct != 0
-    std::vector<uint8_t> mask(G);
-    for (long long q = 0; q < G; ++q) mask[q] = (t->sdfunct[q] != 0.0) ? 1 : 0;
-    int rc = compile_plan(h->cfg.variant, H, W, S, h->cfg.overlap, mask.data(), h->plan);
+static int init_local(psm_handle* h, LocalInit& L) {
+    const int W = L.W, S = h->S, S2 = S * S;
+    h->Hglob = L.H; h->W = W; h->row0 = L.row0; h->row1 = L.row1; h->ext_rows = L.ext_rows; h->send_rows = L.send_rows;
+    h->H = L.row1 - L.row0;
+    h->rank = L.rank; h->world = L.world;
+    h->n_cells = L.n_owned; h->n_ghost = L.n_ghost; h->n_ghost_pix = L.n_ghost_pix;
+    const long long N = L.n_owned, Nall = L.n_owned + L.n_ghost;
+    const long long G = (long long)h->H * W;
+    const int Hl = h->H + L.ext_rows;
+    h->G = G; h->G_pad = round_up_ll(G, 4);
+    h->grid_stride = round_up_ll(std::max(h->G_pad, (long long)Hl * W), 4);
+    h->field_stride = round_up_ll(G + L.n_ghost_pix, 4);
+    h->have_back = L.have_back;
+
+    // ---- global plan, then this rank's slice ----------------------------------------------------------
+    int rc = compile_plan(h->cfg.variant, L.H, W, S, h->cfg.overlap, L.mask_global, h->plan);
     if (rc) PSM_FAIL(h, rc, "%s", h->plan.error.c_str());
     const Plan& P = h->plan;
-    h->B = P.B; h->B_pad = round_up(P.B, 128); h->F = P.F;
-    h->n_tasks = (int)P.tasks.size();
+    const int ncolb = P.n_x + 1;
+    if (L.blk_row1 < 0) L.blk_row1 = P.n_y + 2;
+    if (L.blk_row0 < 0 || L.blk_row1 > P.n_y + 2 || L.blk_row0 >= L.blk_row1) PSM_FAIL(h, PSM_ERR_INVALID, "bad block-row range [%d,%d)", L.blk_row0, L.blk_row1);
+    h->Bg = P.B; h->kb0 = L.blk_row0 * ncolb; h->B = (L.blk_row1 - L.blk_row0) * ncolb;
+    h->B_pad = round_up(h->B, 128); h->F = P.F;
+    const int kb0 = h->kb0, kb1 = h->kb0 + h->B;
     h->rounds = 0;
     while ((1 << h->rounds) < P.max_depth + 1) ++h->rounds;
+    for (int k = kb0; k < kb1; ++k)
+        if (P.y0[k] < L.row0 || P.y0[k] + S > L.row1 + L.ext_rows)
+            PSM_FAIL(h, PSM_ERR_GEOMETRY, "block %d (rows %d..%d) is outside this rank's rows [%d,%d)+%d", k, P.y0[k], P.y0[k] + S, L.row0, L.row1, L.ext_rows);
 
-    // ---- forward table with the validity fold (SMC:161-178,432-438; UTL:89) ------------------------
-    // grid[...][tuple(indices.T)] = interp : for duplicate targets the LAST source point wins, so
-    // pixel (0,0) receives the value of the last invalid point; untouched pixels stay 0.
-    {
-        std::vector<long long> src(G, -1);
-        for (long long m = 0; m < G; ++m) {
-            const long long ii = t->indices[2 * m], jj = t->indices[2 * m + 1];
-            if (ii < 0 || ii >= H || jj < 0 || jj >= W) PSM_FAIL(h, PSM_ERR_INVALID, "indices out of range at %lld", m);
-            src[ii * W + jj] = m;
-        }
-        std::vector<int32_t> v[3]; std::vector<float> w[3];
-        for (int j = 0; j < 3; ++j) { v[j].assign(h->G_pad, 0); w[j].assign(h->G_pad, 0.f); }
-        for (long long q = 0; q < G; ++q) {
-            const long long m = src[q];
-            if (m < 0) continue;
-            const double* wm = t->weights + 3 * m;
-            const bool neg = (wm[0] < 0) || (wm[1] < 0) || (wm[2] < 0);          // -> NaN (UTL:89) -> 0 (SMC:438)
-            for (int j = 0; j < 3; ++j) {
-                const int32_t vi = t->vert[3 * m + j];
-                if (vi < 0 || vi >= N) PSM_FAIL(h, PSM_ERR_INVALID, "vert out of range at %lld", m);
-                v[j][q] = vi;
-                w[j][q] = neg ? 0.f : (float)wm[j];
-            }
-        }
-        for (int j = 0; j < 3; ++j) { TRY(upload(h, &h->d_fv[j], v[j])); TRY(upload(h, &h->d_fw[j], w[j])); }
+    for (int j = 0; j < 3; ++j) {
+        L.fv[j].resize(h->G_pad, 0); L.fw[j].resize(h->G_pad, 0.f);
+        for (long long q = 0; q < G; ++q)
+            if (L.fv[j][q] < 0 || L.fv[j][q] >= Nall) PSM_FAIL(h, PSM_ERR_INVALID, "forward table: cell id out of range at pixel %lld", q);
+        TRY(upload(h, &h->d_fv[j], L.fv[j])); TRY(upload(h, &h->d_fw[j], L.fw[j]));
     }
-    // ---- back table (PMP:481-496): vertex ids hop through `indices` (incl. the (0,0) quirk) ---------
-    h->have_back = (t->vert_back && t->weights_back);
-    if (h->have_back) {
-        std::vector<int32_t> v[3]; std::vector<float> w[3];
-        for (int j = 0; j < 3; ++j) { v[j].assign(N, 0); w[j].assign(N, 0.f); }
-        const bool near_wall = h->cfg.near_wall_sdf > 0.0;
-        for (long long c = 0; c < N; ++c) {
-            const double* wc = t->weights_back + 3 * c;
-            bool keep_prev = (wc[0] < 0) || (wc[1] < 0) || (wc[2] < 0);         // interpolate_fill -> NaN -> p_prev (PMP:496)
-            double sdf_mesh = 0.0;
-            for (int j = 0; j < 3; ++j) {
-                const long long g = t->vert_back[3 * c + j];
-                if (g < 0 || g >= G) PSM_FAIL(h, PSM_ERR_INVALID, "vert_back out of range at %lld", c);
-                sdf_mesh += t->sdfunct[g] * wc[j];                               // PMP:492 (flat take, no indices hop)
-                v[j][c] = (int32_t)(t->indices[2 * g] * W + t->indices[2 * g + 1]);
-                w[j][c] = (float)wc[j];
-            }
-            if (near_wall && !keep_prev && sdf_mesh < h->cfg.near_wall_sdf) keep_prev = true;   // PMP:494
-            if (keep_prev) v[0][c] = -1;
+    if (L.have_back)
+        for (int j = 0; j < 3; ++j) {
+            for (long long c = 0; c < N; ++c)
+                if (L.bv[j][c] >= G + L.n_ghost_pix || (L.bv[j][c] < 0 && j > 0)) PSM_FAIL(h, PSM_ERR_INVALID, "back table: pixel id out of range at cell %lld", c);
+            TRY(upload(h, &h->d_bv[j], L.bv[j])); TRY(upload(h, &h->d_bw[j], L.bw[j]));
         }
-        for (int j = 0; j < 3; ++j) { TRY(upload(h, &h->d_bv[j], v[j])); TRY(upload(h, &h->d_bw[j], w[j])); }
-    }
+
     // ---- plan to device -----------------------------------------------------------------------------
-    TRY(upload(h, &h->d_gmask, mask));
     {
+        std::vector<uint8_t> mask(L.mask_global, L.mask_global + (size_t)L.H * W);
+        TRY(upload(h, &h->d_gmask, mask));
         std::vector<uint16_t> ow(G);
-        for (long long q = 0; q < G; ++q) ow[q] = (uint16_t)P.owner[q];
+        for (long long q = 0; q < G; ++q) {
+            const int o = P.owner[(size_t)L.row0 * W + q];
+            if (o < kb0 || o >= kb1) PSM_FAIL(h, PSM_ERR_GEOMETRY, "pixel row %lld is placed by block %d, outside this rank's blocks [%d,%d)", L.row0 + q / W, o, kb0, kb1);
+            ow[q] = (uint16_t)(o - kb0);
+        }
         TRY(upload(h, &h->d_owner, ow));
         std::vector<int32_t> by0(h->B_pad, 0), bx0(h->B_pad, 0);
-        for (int k = 0; k < P.B; ++k) { by0[k] = P.y0[k]; bx0[k] = P.x0[k]; }
+        for (int k = 0; k < h->B; ++k) { by0[k] = P.y0[kb0 + k] - L.row0; bx0[k] = P.x0[kb0 + k]; }
         TRY(upload(h, &h->d_by0, by0));
         TRY(upload(h, &h->d_bx0, bx0));
-        std::vector<DevTask> tk(P.tasks.size());
-        for (size_t i = 0; i < tk.size(); ++i) {
+        // tasks: masked means first, then the shift-line sums; a task is evaluated by the rank holding `src`
+        const int n_means = (int)P.tasks.size();
+        int n_lines = 0;
+        for (int f = 0; f < P.F; ++f) n_lines += (int)P.lines[f].size();
+        h->n_tasks_glob = n_means + n_lines;
+        std::vector<DevTask> tk;
+        for (int i = 0; i < n_means; ++i) {
             const Task& s = P.tasks[i];
-            tk[i] = DevTask{s.src, s.msk, s.ch, s.y0, s.y1, s.x0, s.x1, s.count};
+            if (s.src < kb0 || s.src >= kb1) continue;
+            tk.push_back(DevTask{s.src - kb0, 0, s.ch, s.y0, s.y1, s.x0, s.x1, s.count, P.y0[s.msk], P.x0[s.msk], i, 0});
         }
+        std::vector<DevShiftTerm> terms;
+        int slot = n_means;
+        for (int f = 0; f < P.F; ++f) {
+            h->term_start[f] = (int)terms.size();
+            for (const LineTask& s : P.lines[f]) {
+                terms.push_back(DevShiftTerm{slot, s.src, s.coef, s.n});
+                if (s.src >= kb0 && s.src < kb1)
+                    tk.push_back(DevTask{s.src - kb0, 1, s.ch, s.y0, s.y1, s.x0, s.x1, s.n, 0, 0, slot, 0});
+                ++slot;
+            }
+            h->term_start[f + 1] = (int)terms.size();
+        }
+        h->n_tasks = (int)tk.size();
         TRY(upload(h, &h->d_tasks, tk));
+        TRY(upload(h, &h->d_terms, terms));
         std::vector<int2> rows;
         std::vector<int32_t> row_start(tk.size() + 1, 0);
         for (size_t i = 0; i < tk.size(); ++i) {
@@ -361,6 +434,20 @@ extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
         for (size_t i = 0; i < rc2.size(); ++i) rc2[i] = DevRec{P.rec[i].ta, P.rec[i].tb, P.rec[i].parent, P.rec[i].is_nan};
         TRY(upload(h, &h->d_rec, rc2));
     }
+    // ---- exchange lists (world > 1) -------------------------------------------------------------------
+    if (L.world > 1) {
+        h->cell_send_ptr = L.cell_send_ptr; h->cell_recv_ptr = L.cell_recv_ptr;
+        h->pix_send_ptr = L.pix_send_ptr; h->pix_recv_ptr = L.pix_recv_ptr;
+        for (int32_t v : L.cell_send_idx) if (v < 0 || v >= N) PSM_FAIL(h, PSM_ERR_INVALID, "cell_send_idx out of range");
+        for (int32_t v : L.pix_send_idx) if (v < 0 || v >= G) PSM_FAIL(h, PSM_ERR_INVALID, "pix_send_idx out of range");
+        if (h->cell_recv_ptr[L.world] != L.n_ghost || h->pix_recv_ptr[L.world] != L.n_ghost_pix) PSM_FAIL(h, PSM_ERR_INVALID, "recv lists do not match the ghost counts");
+        TRY(upload(h, &h->d_cell_send_idx, L.cell_send_idx));
+        TRY(upload(h, &h->d_pix_send_idx, L.pix_send_idx));
+        TRY(dalloc(h, &h->d_cell_send, (size_t)L.cell_send_idx.size() * 2));
+        TRY(dalloc(h, &h->d_pix_send, (size_t)L.pix_send_idx.size() * h->F));
+        TRY(dalloc(h, &h->d_means_loc, (size_t)h->n_tasks_glob));
+        h->use_graphs = false;         // NCCL calls are enqueued eagerly between the kernels
+    }
     // ---- per-step buffers -------------------------------------------------------------------------------
     const int ncol = h->cfg.input_cols;
     const int Bp = h->B_pad;
@@ -370,8 +457,8 @@ extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
     TRY(dalloc(h, &h->d_out, (size_t)N * h->F));
     TRY(dalloc(h, &h->d_pprev, (size_t)N));
     if (h->cfg.variant == PSM_DELTAU_TO_DELTAP && ncol == 5) TRY(dalloc(h, &h->d_uprev, (size_t)N * 2));
-    TRY(dalloc(h, &h->d_uv, (size_t)N));
-    TRY(dalloc(h, &h->d_grid, (size_t)h->G_pad * 2));
+    TRY(dalloc(h, &h->d_uv, (size_t)Nall));
+    TRY(dalloc(h, &h->d_grid, (size_t)h->grid_stride * 2));
     TRY(dalloc(h, &h->d_xu, (size_t)Bp * 2 * S2));
     {
         const int tiles = (Bp / 64) * (h->pc_in_pad / 64);
@@ -394,24 +481,25 @@ extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
     TRY(dalloc(h, &h->d_act[1], (size_t)Bp * maxw));
     TRY(dalloc(h, &h->d_r, (size_t)Bp * h->pc_p_pad));
     TRY(dalloc(h, &h->d_blocks, (size_t)Bp * h->C * S2));
-    TRY(dalloc(h, &h->d_means, (size_t)h->n_tasks));
-    for (int i = 0; i < 2; ++i) { TRY(dalloc(h, &h->d_dbuf[i], (size_t)h->F * h->B)); TRY(dalloc(h, &h->d_pbuf[i], (size_t)h->F * h->B)); }
-    TRY(dalloc(h, &h->d_offsets, (size_t)h->F * h->B));
-    TRY(dalloc(h, &h->d_coff, (size_t)h->F * h->B));
-    TRY(dalloc(h, &h->d_field, (size_t)h->F * G));
+    TRY(dalloc(h, &h->d_means, (size_t)h->n_tasks_glob));
+    for (int i = 0; i < 2; ++i) { TRY(dalloc(h, &h->d_dbuf[i], (size_t)h->F * h->Bg)); TRY(dalloc(h, &h->d_pbuf[i], (size_t)h->F * h->Bg)); }
+    TRY(dalloc(h, &h->d_offsets, (size_t)h->F * h->Bg));
+    TRY(dalloc(h, &h->d_coff, (size_t)h->F * h->Bg));
+    TRY(dalloc(h, &h->d_field, (size_t)h->F * h->field_stride));
     TRY(dalloc(h, &h->d_sc, 1));
     TRY(dalloc(h, &h->d_zc, (size_t)Bp * h->pc_in_pad));
 
     // ---- static distance-channel contribution per block: zc[b][n] = sum_p sdf_n[b,p] * comp[n][p*3+2] ----
     // (grid[...,2] = sdfunct / max_abs_dist, SMC:434,443 -- constant for the mesh)
     {
-        std::vector<float> sdfn(h->G_pad, 0.f);
-        for (long long q = 0; q < G; ++q) sdfn[q] = (float)(t->sdfunct[q] / h->maxs[2]);
+        const size_t nl = (size_t)Hl * W;
+        std::vector<float> sdfn(nl, 0.f);
+        for (size_t q = 0; q < nl; ++q) sdfn[q] = (float)(L.sdf_rows[q] / h->maxs[2]);
         float* d_sdfn = nullptr; float* d_sdfb = nullptr;
-        CU(h, cudaMalloc(&d_sdfn, (size_t)h->G_pad * sizeof(float)));
+        CU(h, cudaMalloc(&d_sdfn, nl * sizeof(float)));
         CU(h, cudaMalloc(&d_sdfb, (size_t)Bp * S2 * sizeof(float)));
         CU(h, cudaMemsetAsync(d_sdfb, 0, (size_t)Bp * S2 * sizeof(float), h->stream));
-        CU(h, cudaMemcpyAsync(d_sdfn, sdfn.data(), (size_t)h->G_pad * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CU(h, cudaMemcpyAsync(d_sdfn, sdfn.data(), nl * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         ExtractArgs ea{d_sdfn, d_sdfn, h->d_by0, h->d_bx0, d_sdfb, h->B, W, S, 1};
         launch_extract(ea, h->stream);
         GemmArgs ga{};
@@ -465,26 +553,206 @@ extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
     return PSM_OK;
 }
 
+extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!t) PSM_FAIL(h, PSM_ERR_INVALID, "psm_init_with_tables: NULL tables");
+    if (!h->params_loaded) PSM_FAIL(h, PSM_ERR_STATE, "psm_load_params must be called before psm_init_with_tables");
+    if (h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "handle already initialised");
+    if (h->comm) PSM_FAIL(h, PSM_ERR_STATE, "a communicator is attached: use psm_init_sharded");
+    if (!t->vert || !t->weights || !t->indices || !t->sdfunct || t->n_cells < 3 || t->grid_h < 1 || t->grid_w < 1)
+        PSM_FAIL(h, PSM_ERR_INVALID, "bad tables");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const int H = t->grid_h, W = t->grid_w;
+    const long long G = (long long)H * W, N = t->n_cells;
+    LocalInit L;
+    L.H = H; L.W = W; L.row0 = 0; L.row1 = H; L.n_owned = N;
+    // static flow mask: x_array[...,2] != 0 (SMC:224) <=> sdfunct != 0
+    std::vector<uint8_t> mask(G);
+    for (long long q = 0; q < G; ++q) mask[q] = (t->sdfunct[q] != 0.0) ? 1 : 0;
+    L.mask_global = mask.data();
+    L.sdf_rows = t->sdfunct;
+    L.blk_row0 = 0; L.blk_row1 = -1;      // all block rows
+    // ---- forward table with the validity fold (SMC:161-178,432-438; UTL:89) ------------------------
+    // grid[...][tuple(indices.T)] = interp : for duplicate targets the LAST source point wins, so
+    // pixel (0,0) receives the value of the last invalid point; untouched pixels stay 0.
+    {
+        std::vector<long long> src(G, -1);
+        for (long long m = 0; m < G; ++m) {
+            const long long ii = t->indices[2 * m], jj = t->indices[2 * m + 1];
+            if (ii < 0 || ii >= H || jj < 0 || jj >= W) PSM_FAIL(h, PSM_ERR_INVALID, "indices out of range at %lld", m);
+            src[ii * W + jj] = m;
+        }
+        for (int j = 0; j < 3; ++j) { L.fv[j].assign(G, 0); L.fw[j].assign(G, 0.f); }
+        for (long long q = 0; q < G; ++q) {
+            const long long m = src[q];
+            if (m < 0) continue;
+            const double* wm = t->weights + 3 * m;
+            const bool neg = (wm[0] < 0) || (wm[1] < 0) || (wm[2] < 0);          // -> NaN (UTL:89) -> 0 (SMC:438)
+            for (int j = 0; j < 3; ++j) {
+                const int32_t vi = t->vert[3 * m + j];
+                if (vi < 0 || vi >= N) PSM_FAIL(h, PSM_ERR_INVALID, "vert out of range at %lld", m);
+                L.fv[j][q] = vi;
+                L.fw[j][q] = neg ? 0.f : (float)wm[j];
+            }
+        }
+    }
+    // ---- back table (PMP:481-496): vertex ids hop through `indices` (incl. the (0,0) quirk) ---------
+    L.have_back = (t->vert_back && t->weights_back);
+    if (L.have_back) {
+        for (int j = 0; j < 3; ++j) { L.bv[j].assign(N, 0); L.bw[j].assign(N, 0.f); }
+        const bool near_wall = h->cfg.near_wall_sdf > 0.0;
+        for (long long c = 0; c < N; ++c) {
+            const double* wc = t->weights_back + 3 * c;
+            bool keep_prev = (wc[0] < 0) || (wc[1] < 0) || (wc[2] < 0);         // interpolate_fill -> NaN -> p_prev (PMP:496)
+            double sdf_mesh = 0.0;
+            for (int j = 0; j < 3; ++j) {
+                const long long g = t->vert_back[3 * c + j];
+                if (g < 0 || g >= G) PSM_FAIL(h, PSM_ERR_INVALID, "vert_back out of range at %lld", c);
+                sdf_mesh += t->sdfunct[g] * wc[j];                               // PMP:492 (flat take, no indices hop)
+                L.bv[j][c] = (int32_t)(t->indices[2 * g] * W + t->indices[2 * g + 1]);
+                L.bw[j][c] = (float)wc[j];
+            }
+            if (near_wall && !keep_prev && sdf_mesh < h->cfg.near_wall_sdf) keep_prev = true;   // PMP:494
+            if (keep_prev) L.bv[0][c] = -1;
+        }
+    }
+    return init_local(h, L);
+}
+
+// Multi-GPU: this rank's pre-folded share (psm_b200/shard.py).
+extern "C" int psm_init_sharded(psm_handle* h, const psm_shard* s) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!s) PSM_FAIL(h, PSM_ERR_INVALID, "psm_init_sharded: NULL shard");
+    if (!h->params_loaded) PSM_FAIL(h, PSM_ERR_STATE, "psm_load_params must be called before psm_init_sharded");
+    if (h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "handle already initialised");
+    if (s->world < 1 || s->rank < 0 || s->rank >= s->world) PSM_FAIL(h, PSM_ERR_INVALID, "bad rank/world");
+    if (s->world > 1 && (!h->comm || h->world != s->world || h->rank != s->rank)) PSM_FAIL(h, PSM_ERR_STATE, "psm_comm_init(rank %d of %d) must precede psm_init_sharded", s->rank, s->world);
+    if (!s->vert || !s->weights || !s->sdfunct || !s->mask_global || s->n_owned < 1 || s->row0 < 0 || s->row1 <= s->row0 || s->row1 > s->grid_h ||
+        s->ext_rows < 0 || s->send_rows < 0 || s->row1 + s->ext_rows > s->grid_h)
+        PSM_FAIL(h, PSM_ERR_INVALID, "bad shard");
+    if (s->world > 1 && (!s->cell_send_ptr || !s->cell_recv_ptr || !s->pix_send_ptr || !s->pix_recv_ptr)) PSM_FAIL(h, PSM_ERR_INVALID, "missing exchange lists");
+    if ((s->rank == s->world - 1 && s->ext_rows) || (s->rank == 0 && s->send_rows)) PSM_FAIL(h, PSM_ERR_INVALID, "halo rows at the ends of the rank chain");
+    CU(h, cudaSetDevice(h->cfg.device));
+    LocalInit L;
+    L.rank = s->rank; L.world = s->world; L.H = s->grid_h; L.W = s->grid_w; L.row0 = s->row0; L.row1 = s->row1;
+    L.ext_rows = s->ext_rows; L.send_rows = s->send_rows; L.blk_row0 = s->blk_row0; L.blk_row1 = s->blk_row1;
+    L.mask_global = s->mask_global; L.n_owned = s->n_owned; L.n_ghost = s->n_ghost; L.n_ghost_pix = s->n_ghost_pix;
+    L.sdf_rows = s->sdfunct;
+    const long long G = (long long)(s->row1 - s->row0) * s->grid_w;
+    for (int j = 0; j < 3; ++j) {
+        L.fv[j].resize(G); L.fw[j].resize(G);
+        for (long long q = 0; q < G; ++q) { L.fv[j][q] = s->vert[3 * q + j]; L.fw[j][q] = (float)s->weights[3 * q + j]; }
+    }
+    L.have_back = (s->vert_back && s->weights_back);
+    if (L.have_back)
+        for (int j = 0; j < 3; ++j) {
+            L.bv[j].resize(s->n_owned); L.bw[j].resize(s->n_owned);
+            for (long long c = 0; c < s->n_owned; ++c) { L.bv[j][c] = s->vert_back[3 * c + j]; L.bw[j][c] = (float)s->weights_back[3 * c + j]; }
+        }
+    if (s->world > 1) {
+        const int Wd = s->world;
+        L.cell_send_ptr.assign(s->cell_send_ptr, s->cell_send_ptr + Wd + 1);
+        L.cell_recv_ptr.assign(s->cell_recv_ptr, s->cell_recv_ptr + Wd + 1);
+        L.pix_send_ptr.assign(s->pix_send_ptr, s->pix_send_ptr + Wd + 1);
+        L.pix_recv_ptr.assign(s->pix_recv_ptr, s->pix_recv_ptr + Wd + 1);
+        if (L.cell_send_ptr[Wd] > 0 && !s->cell_send_idx) PSM_FAIL(h, PSM_ERR_INVALID, "cell_send_idx is NULL");
+        if (L.pix_send_ptr[Wd] > 0 && !s->pix_send_idx) PSM_FAIL(h, PSM_ERR_INVALID, "pix_send_idx is NULL");
+        L.cell_send_idx.assign(s->cell_send_idx, s->cell_send_idx + L.cell_send_ptr[Wd]);
+        L.pix_send_idx.assign(s->pix_send_idx, s->pix_send_idx + L.pix_send_ptr[Wd]);
+    }
+    return init_local(h, L);
+}
+
+// ---- communicator --------------------------------------------------------------------------------------
+extern "C" int psm_comm_get_unique_id(void* id_out) {
+    if (!id_out) return PSM_ERR_INVALID;
+    static_assert(sizeof(ncclUniqueId) <= PSM_UNIQUE_ID_BYTES, "unique id size");
+    if (!g_nccl.load()) { g_create_error = g_nccl.error; return PSM_ERR_COMM; }
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r); return PSM_ERR_COMM; }
+    memset(id_out, 0, PSM_UNIQUE_ID_BYTES);
+    memcpy(id_out, &id, sizeof id);
+    return PSM_OK;
+}
+
+extern "C" int psm_comm_init(psm_handle* h, const void* unique_id, int32_t rank, int32_t world) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!unique_id || world < 1 || rank < 0 || rank >= world) PSM_FAIL(h, PSM_ERR_INVALID, "psm_comm_init: bad arguments");
+    if (h->initialised || h->comm) PSM_FAIL(h, PSM_ERR_STATE, "psm_comm_init must be called once, before psm_init_sharded");
+    if (!g_nccl.load()) PSM_FAIL(h, PSM_ERR_COMM, "%s", g_nccl.error.c_str());
+    CU(h, cudaSetDevice(h->cfg.device));
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, world, id, rank);
+    if (r != ncclSuccess) { h->comm = nullptr; PSM_FAIL(h, PSM_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(r)); }
+    h->rank = rank; h->world = world;
+    return PSM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // One step on the device, input already in d_cells, output to d_out.
+#define NC(h, call)                                                                                         \
+    do {                                                                                                    \
+        ncclResult_t _r = (call);                                                                           \
+        if (_r != ncclSuccess) PSM_FAIL(h, PSM_ERR_COMM, "%s: %s", #call, g_nccl.GetErrorString(_r));       \
+    } while (0)
+
+// Static sparse exchange: packed send buffer -> the ghost region of every peer (grouped send/recv).
+static int sparse_exchange(psm_handle* h, const float* sendbuf, const std::vector<long long>& sp, float* recvbuf,
+                           const std::vector<long long>& rp, int width) {
+    for (int p = 0; p < h->world; ++p) {
+        if (p == h->rank) continue;
+        const long long ns = sp[p + 1] - sp[p], nr = rp[p + 1] - rp[p];
+        if (ns > 0) NC(h, g_nccl.Send(sendbuf + sp[p] * width, (size_t)ns * width, ncclFloat, p, h->comm, h->stream));
+        if (nr > 0) NC(h, g_nccl.Recv(recvbuf + rp[p] * width, (size_t)nr * width, ncclFloat, p, h->comm, h->stream));
+    }
+    return PSM_OK;
+}
+
 static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     cudaStream_t s = h->stream;
     const int S = h->S, S2 = S * S, Bp = h->B_pad;
     const bool deltas = h->cfg.variant == PSM_DELTAU_TO_DELTAP;
+    const bool multi = h->world > 1;
     const int mode = !deltas ? 0 : (h->cfg.input_cols == 7 ? 1 : 2);
     int nl = 0, te = 1;
     auto tick = [&]() { if (h->ev_valid) cudaEventRecord(h->ev[te], s); ++te; };
 
     PrepArgs pa{d_cells, h->n_cells, h->cfg.input_cols, mode, h->d_uv, h->d_pprev, h->d_uprev, h->d_sc};
     launch_prep(pa, s); ++nl;
+    if (multi) {
+        // exchange 1: max|U|^2, max|dU|^2 over all ranks (non-negative doubles order like their bit patterns)
+        //             + the ghost cells other ranks' forward tables reference
+        const long long nsend = h->cell_send_ptr[h->world];
+        if (nsend > 0) { PackArgs pk{reinterpret_cast<const float*>(h->d_uv), h->d_cell_send_idx, h->d_cell_send, nsend, 2, 0}; launch_pack(pk, s); ++nl; }
+        NC(h, g_nccl.GroupStart());
+        NC(h, g_nccl.AllReduce(&h->d_sc->umax2_bits, &h->d_sc->umax2_bits, 2, ncclUint64, ncclMax, h->comm, s));
+        TRY(sparse_exchange(h, h->d_cell_send, h->cell_send_ptr, reinterpret_cast<float*>(h->d_uv + h->n_cells), h->cell_recv_ptr, 2));
+        NC(h, g_nccl.GroupEnd());
+    }
     ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], deltas ? h->maxs[3] : 1.0, deltas ? 1 : 0, h->cfg.skip_threshold, mode};
     launch_scalars(sa, s); ++nl;
     tick();   // prep
+    float* grid0 = h->d_grid; float* grid1 = h->d_grid + h->grid_stride;
     GatherArgs ga{h->d_fv[0], h->d_fv[1], h->d_fv[2], h->d_fw[0], h->d_fw[1], h->d_fw[2], h->d_uv,
-                  h->d_grid, h->d_grid + h->G_pad, h->G_pad / 4, h->d_sc};
+                  grid0, grid1, h->G_pad / 4, h->d_sc};
     launch_gather(ga, s); ++nl;
+    if (multi && (h->ext_rows || h->send_rows)) {
+        // exchange 2: the overlap strip -- the first rows of rank+1 complete this rank's last block row
+        NC(h, g_nccl.GroupStart());
+        if (h->send_rows) {
+            NC(h, g_nccl.Send(grid0, (size_t)h->send_rows * h->W, ncclFloat, h->rank - 1, h->comm, s));
+            NC(h, g_nccl.Send(grid1, (size_t)h->send_rows * h->W, ncclFloat, h->rank - 1, h->comm, s));
+        }
+        if (h->ext_rows) {
+            NC(h, g_nccl.Recv(grid0 + h->G, (size_t)h->ext_rows * h->W, ncclFloat, h->rank + 1, h->comm, s));
+            NC(h, g_nccl.Recv(grid1 + h->G, (size_t)h->ext_rows * h->W, ncclFloat, h->rank + 1, h->comm, s));
+        }
+        NC(h, g_nccl.GroupEnd());
+    }
     tick();   // gather
-    ExtractArgs ea{h->d_grid, h->d_grid + h->G_pad, h->d_by0, h->d_bx0, h->d_xu, h->B, h->W, S, 2};
+    ExtractArgs ea{grid0, grid1, h->d_by0, h->d_bx0, h->d_xu, h->B, h->W, S, 2};
     launch_extract(ea, s); ++nl;
     tick();   // extract
     const bool tc = h->cfg.gemm_mode != PSM_GEMM_FP32_SIMT;
@@ -534,27 +802,41 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         ++nl;
     }
     tick();   // pca_inverse
-    MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->d_by0, h->d_bx0, h->C, S, h->W, h->d_means,
+    MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->C, S, h->W, multi ? h->d_means_loc : h->d_means,
                  h->d_rows, h->n_rows, h->d_row_start, h->d_row_sums};
     launch_means(ma, s); nl += 2;
+    if (multi)   // exchange 3: every rank contributes its own slots (zero elsewhere) -> identical means everywhere
+        NC(h, g_nccl.AllReduce(h->d_means_loc, h->d_means, (size_t)h->n_tasks_glob, ncclDouble, ncclSum, h->comm, s));
     tick();   // strip_means
     {
         OffsetsArgs oa{};
-        oa.rec = h->d_rec; oa.B = h->B; oa.F = h->F; oa.rounds = h->rounds; oa.ref_bc = h->cfg.ref_bc; oa.means = h->d_means;
+        oa.rec = h->d_rec; oa.B = h->Bg; oa.F = h->F; oa.rounds = h->rounds; oa.ref_bc = h->cfg.ref_bc; oa.means = h->d_means;
         oa.dbuf0 = h->d_dbuf[0]; oa.dbuf1 = h->d_dbuf[1]; oa.pbuf0 = h->d_pbuf[0]; oa.pbuf1 = h->d_pbuf[1];
-        oa.offsets = h->d_offsets; oa.coff = h->d_coff; oa.blocks = h->d_blocks; oa.owner = h->d_owner;
-        oa.by0 = h->d_by0; oa.bx0 = h->d_bx0; oa.C = h->C; oa.S = S; oa.H = h->H; oa.W = h->W;
-        for (int f = 0; f < 2; ++f) { oa.shift_axis[f] = h->plan.shift_axis[f]; oa.shift_a[f] = h->plan.shift_a[f]; oa.shift_b[f] = h->plan.shift_b[f]; }
+        oa.offsets = h->d_offsets; oa.coff = h->d_coff; oa.terms = h->d_terms;
+        for (int f = 0; f < 3; ++f) oa.term_start[f] = h->term_start[f];
+        for (int f = 0; f < 2; ++f) oa.shift_len[f] = h->plan.shift_len[f];
         oa.sc = h->d_sc;
         launch_offsets(oa, s); ++nl;
     }
     tick();   // offsets
-    PlaceArgs pl{h->d_blocks, h->d_owner, h->d_by0, h->d_bx0, h->d_coff, h->d_field, h->B, h->C, h->F, S, h->H, h->W};
+    PlaceArgs pl{h->d_blocks, h->d_owner, h->d_by0, h->d_bx0, h->d_coff, h->d_field, h->Bg, h->kb0, h->C, h->F, S, h->H, h->W,
+                 h->field_stride};
     launch_place(pl, s); ++nl;
     tick();   // place
     if (h->have_back && d_out) {
+        if (multi) {
+            // exchange 4: the field pixels other ranks' grid->cell tables reference (rows next to a rank
+            //             boundary, and pixel (0,0) for the raster quirk of PMP:481)
+            const long long nsend = h->pix_send_ptr[h->world];
+            if (nsend > 0) { PackArgs pk{h->d_field, h->d_pix_send_idx, h->d_pix_send, nsend, h->F, h->field_stride}; launch_pack(pk, s); ++nl; }
+            NC(h, g_nccl.GroupStart());
+            for (int f = 0; f < h->F; ++f)
+                TRY(sparse_exchange(h, h->d_pix_send + (size_t)f * nsend, h->pix_send_ptr, h->d_field + (size_t)f * h->field_stride + h->G,
+                                    h->pix_recv_ptr, 1));
+            NC(h, g_nccl.GroupEnd());
+        }
         BackArgs ba{h->d_bv[0], h->d_bv[1], h->d_bv[2], h->d_bw[0], h->d_bw[1], h->d_bw[2], h->d_field, h->n_cells,
-                    h->G, h->d_pprev, d_out, h->F, h->cfg.additive, h->d_sc};
+                    h->field_stride, h->d_pprev, d_out, h->F, h->cfg.additive, h->d_sc};
         launch_back(ba, s); ++nl;
     }
     tick();   // back_gather
@@ -668,6 +950,8 @@ extern "C" int psm_get_geometry(const psm_handle* h, psm_geometry* g) {
     g->grid_h = P.H; g->grid_w = P.W; g->shape = P.S; g->overlap = P.ov; g->n_x = P.n_x; g->n_y = P.n_y;
     g->p_i = P.p_i; g->p_j = P.p_j; g->n_blocks = P.B; g->n_fields = P.F; g->n_cells = h->n_cells;
     g->n_tasks = (int32_t)P.tasks.size(); g->reserved = 0;
+    g->row0 = h->row0; g->row1 = h->row1; g->ext_rows = h->ext_rows; g->first_block = h->kb0; g->n_local_blocks = h->B;
+    g->world = h->world; g->n_ghost_cells = h->n_ghost; g->n_ghost_pix = h->n_ghost_pix;
     return PSM_OK;
 }
 
@@ -716,11 +1000,13 @@ extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_
         return 0;
     };
     switch (stage) {
-        case PSM_STAGE_GRID:
-            TRY(need((int64_t)2 * h->G * 4));
-            CU(h, cudaMemcpy(out, h->d_grid, h->G * 4, cudaMemcpyDeviceToHost));
-            CU(h, cudaMemcpy((char*)out + h->G * 4, h->d_grid + h->G_pad, h->G * 4, cudaMemcpyDeviceToHost));
+        case PSM_STAGE_GRID: {
+            const int64_t gl = (int64_t)(h->H + h->ext_rows) * h->W;
+            TRY(need(2 * gl * 4));
+            CU(h, cudaMemcpy(out, h->d_grid, gl * 4, cudaMemcpyDeviceToHost));
+            CU(h, cudaMemcpy((char*)out + gl * 4, h->d_grid + h->grid_stride, gl * 4, cudaMemcpyDeviceToHost));
             return PSM_OK;
+        }
         case PSM_STAGE_XINPUT:
             TRY(need((int64_t)h->B * h->pc_in * 4));
             CU(h, cudaMemcpy2D(out, (size_t)h->pc_in * 4, h->d_xin, (size_t)h->pc_in_pad * 4, (size_t)h->pc_in * 4, h->B, cudaMemcpyDeviceToHost));
@@ -734,12 +1020,12 @@ extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_
             CU(h, cudaMemcpy(out, h->d_blocks, (size_t)h->B * h->C * S2 * 4, cudaMemcpyDeviceToHost));
             return PSM_OK;
         case PSM_STAGE_OFFSETS:
-            TRY(need((int64_t)h->F * h->B * 8));
-            CU(h, cudaMemcpy(out, h->d_offsets, (size_t)h->F * h->B * 8, cudaMemcpyDeviceToHost));
+            TRY(need((int64_t)h->F * h->Bg * 8));
+            CU(h, cudaMemcpy(out, h->d_offsets, (size_t)h->F * h->Bg * 8, cudaMemcpyDeviceToHost));
             return PSM_OK;
         case PSM_STAGE_FIELD:
             TRY(need((int64_t)h->F * h->G * 4));
-            CU(h, cudaMemcpy(out, h->d_field, (size_t)h->F * h->G * 4, cudaMemcpyDeviceToHost));
+            CU(h, cudaMemcpy2D(out, (size_t)h->G * 4, h->d_field, (size_t)h->field_stride * 4, (size_t)h->G * 4, h->F, cudaMemcpyDeviceToHost));
             return PSM_OK;
         case PSM_STAGE_SCALARS: {
             TRY(need(4 * 8));
@@ -750,8 +1036,8 @@ extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_
             return PSM_OK;
         }
         case PSM_STAGE_MEANS:
-            TRY(need((int64_t)h->n_tasks * 8));
-            CU(h, cudaMemcpy(out, h->d_means, (size_t)h->n_tasks * 8, cudaMemcpyDeviceToHost));
+            TRY(need((int64_t)h->plan.tasks.size() * 8));
+            CU(h, cudaMemcpy(out, h->d_means, h->plan.tasks.size() * 8, cudaMemcpyDeviceToHost));
             return PSM_OK;
         default:
             PSM_FAIL(h, PSM_ERR_INVALID, "unknown stage %d", stage);

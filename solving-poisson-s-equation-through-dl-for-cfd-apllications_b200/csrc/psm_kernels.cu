@@ -268,9 +268,10 @@ void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------
 // K6a  masked rectangle means.  Every np.mean(pred[rect][flow_bool[rect] != 0]) of SMC:233-316 /
-//      GRAD:300-340 on the UNCORRECTED blocks; FP64 accumulation.  One CTA per task.
+//      GRAD:300-340 on the UNCORRECTED blocks, plus the plain line sums the global shift needs
+//      (SMC:350 / GRAD:358-361); FP64 accumulation.
 //      Two deterministic passes (no atomics): one warp per (task, row) writes a row partial, then one
-//      warp per task folds its rows -- rectangles range from 1 x 128 to 120 x 128 pixels, so the work
+//      warp per task folds its rows -- rectangles range from 1 x 1 to 120 x 128 pixels, so the work
 //      is balanced per row, not per task.
 __global__ void __launch_bounds__(256) row_sums_kernel(MeansArgs a) {
     const int lane = threadIdx.x & 31;
@@ -279,14 +280,19 @@ __global__ void __launch_bounds__(256) row_sums_kernel(MeansArgs a) {
     const int2 ri = a.rows[r];                                   // (task, block-local y)
     const DevTask t = a.tasks[ri.x];
     const float* src = a.blocks + (((long long)t.src * a.C + t.ch) * a.S + ri.y) * a.S;
-    const uint8_t* msk = a.gmask + (long long)(a.by0[t.msk] + ri.y) * a.W + a.bx0[t.msk];
     const float4 v = reinterpret_cast<const float4*>(src)[lane];  // the whole 128-pixel block row
     const int x = lane * 4;
+    bool m0 = x + 0 >= t.x0 && x + 0 < t.x1, m1 = x + 1 >= t.x0 && x + 1 < t.x1;
+    bool m2 = x + 2 >= t.x0 && x + 2 < t.x1, m3 = x + 3 >= t.x0 && x + 3 < t.x1;
+    if (t.kind == 0) {
+        const uint8_t* msk = a.gmask + (long long)(t.my0 + ri.y) * a.W + t.mx0;
+        m0 = m0 && msk[x + 0]; m1 = m1 && msk[x + 1]; m2 = m2 && msk[x + 2]; m3 = m3 && msk[x + 3];
+    }
     double sum = 0.0;
-    if (x + 0 >= t.x0 && x + 0 < t.x1 && msk[x + 0]) sum += (double)v.x;
-    if (x + 1 >= t.x0 && x + 1 < t.x1 && msk[x + 1]) sum += (double)v.y;
-    if (x + 2 >= t.x0 && x + 2 < t.x1 && msk[x + 2]) sum += (double)v.z;
-    if (x + 3 >= t.x0 && x + 3 < t.x1 && msk[x + 3]) sum += (double)v.w;
+    if (m0) sum += (double)v.x;
+    if (m1) sum += (double)v.y;
+    if (m2) sum += (double)v.z;
+    if (m3) sum += (double)v.w;
     sum = warp_sum(sum);
     if (lane == 0) a.row_sums[r] = sum;
 }
@@ -298,8 +304,8 @@ __global__ void __launch_bounds__(256) task_means_kernel(MeansArgs a) {
     double sum = 0.0;
     for (int r = r0 + lane; r < r1; r += 32) sum += a.row_sums[r];
     sum = warp_sum(sum);
-    const int count = a.tasks[t].count;
-    if (lane == 0) a.means[t] = (count > 0) ? sum / (double)count : CUDART_NAN;
+    const DevTask tk = a.tasks[t];
+    if (lane == 0) a.means[tk.out] = tk.kind ? sum : ((tk.count > 0) ? sum / (double)tk.count : CUDART_NAN);
 }
 void launch_means(const MeansArgs& a, cudaStream_t s) {
     if (a.n_tasks <= 0) return;
@@ -310,8 +316,9 @@ void launch_means(const MeansArgs& a, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------
 // K6b  offsets.  c_k = m[a] - (m[b] - c[parent])  is a sum along the parent chain of
 //      d_k = m[a] - m[b] (roots: m[a] - Ref_BC), evaluated by pointer jumping in
-//      ceil(log2(depth)) rounds; then the global shift of SMC:350 / GRAD:358-361 through the
-//      owner map.  Single CTA: the whole problem is a few thousand scalars.
+//      ceil(log2(depth)) rounds; then the global shift of SMC:350 / GRAD:358-361 from the per-run
+//      line sums.  Single CTA: the whole problem is a few thousand scalars.  In the multi-GPU path
+//      every rank evaluates this redundantly on the all-reduced means.
 __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
     const int n = a.B * a.F;
     double* d_cur = a.dbuf0; double* d_nxt = a.dbuf1;
@@ -341,20 +348,10 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
     __shared__ double red[32];
     __shared__ double s_shift[2];
     for (int f = 0; f < a.F; ++f) {
-        const int len = a.shift_axis[f] == 0 ? a.H : a.W;
         double acc = 0.0;
-        for (int i = threadIdx.x; i < len; i += blockDim.x) {
-            double v[2];
-#pragma unroll
-            for (int s2 = 0; s2 < 2; ++s2) {
-                const int line = s2 == 0 ? a.shift_a[f] : a.shift_b[f];
-                const int y = a.shift_axis[f] == 0 ? i : line;
-                const int x = a.shift_axis[f] == 0 ? line : i;
-                const int o = a.owner[(long long)y * a.W + x];
-                const float pv = a.blocks[(((long long)o * a.C + f) * a.S + (y - a.by0[o])) * a.S + (x - a.bx0[o])];
-                v[s2] = (double)pv - a.offsets[f * a.B + o];
-            }
-            acc += 3.0 * v[0] - v[1];
+        for (int i = a.term_start[f] + threadIdx.x; i < a.term_start[f + 1]; i += blockDim.x) {
+            const DevShiftTerm t = a.terms[i];
+            acc += (double)t.coef * (a.means[t.task] - (double)t.n * a.offsets[f * a.B + t.block]);
         }
         acc = warp_sum(acc);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -362,7 +359,7 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
         if (threadIdx.x < 32) {
             double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
             t = warp_sum(t);
-            if (threadIdx.x == 0) { s_shift[f] = t / (double)len / 3.0; a.sc->shift[f] = s_shift[f]; }
+            if (threadIdx.x == 0) { s_shift[f] = t / (double)a.shift_len[f] / 3.0; a.sc->shift[f] = s_shift[f]; }
         }
         __syncthreads();
     }
@@ -382,7 +379,7 @@ __global__ void __launch_bounds__(256) place_kernel(PlaceArgs a) {
         const int y = (int)(q / a.W), x = (int)(q - (long long)y * a.W);
         const int o = a.owner[q];
         const float v = a.blocks[(((long long)o * a.C + f) * a.S + (y - a.by0[o])) * a.S + (x - a.bx0[o])];
-        a.field[i] = v - a.coff[f * a.B + o];
+        a.field[(long long)f * a.plane_stride + q] = v - a.coff[f * a.B_glob + a.kb0 + o];
     }
 }
 void launch_place(const PlaceArgs& a, cudaStream_t s) {
@@ -424,6 +421,23 @@ void launch_back(const BackArgs& a, cudaStream_t s) {
     long long want = (a.n + 255) / 256;
     int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
     back_kernel<<<blocks, 256, 0, s>>>(a);
+}
+
+// Static sparse exchange (multi-GPU): contiguous send buffer from an index list.
+__global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
+    const long long total = a.n * a.width;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i / a.width; const int c = (int)(i - e * a.width);
+        // src_stride == 0: interleaved records of `width` floats (dst interleaved too);
+        // otherwise `width` planes src_stride apart (dst planar: [width][n])
+        if (a.src_stride) a.dst[(long long)c * a.n + e] = a.src[(long long)c * a.src_stride + a.idx[e]];
+        else a.dst[i] = a.src[(long long)a.idx[e] * a.width + c];
+    }
+}
+void launch_pack(const PackArgs& a, cudaStream_t s) {
+    if (a.n <= 0) return;
+    long long want = (a.n * a.width + 255) / 256;
+    pack_kernel<<<(int)(want < 1184 ? want : 1184), 256, 0, s>>>(a);
 }
 
 }  // namespace psm

@@ -104,40 +104,49 @@ struct ReduceArgs {
 };
 void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s);
 
-// K6a: masked rectangle means of the predicted blocks.
-struct DevTask { int32_t src, msk, ch, y0, y1, x0, x1, count; };
+// K6a: masked rectangle means (and the plain line sums of the global shift) of the predicted blocks.
+struct DevTask {
+    int32_t src;                      // LOCAL block the values come from
+    int32_t kind;                     // 0: masked mean, 1: plain sum (shift-line run)
+    int32_t ch, y0, y1, x0, x1;       // channel, block-local rectangle
+    int32_t count;                    // mask pixels in the rectangle (0 -> NaN mean)
+    int32_t my0, mx0;                 // GLOBAL grid origin of the block whose flow mask applies
+    int32_t out;                      // slot in the GLOBAL means array
+    int32_t pad;
+};
 struct MeansArgs {
-    const DevTask* tasks; int n_tasks;
-    const float* blocks;              // [B_pad][C][S][S]
-    const uint8_t* gmask;             // [H][W]
-    const int32_t* by0; const int32_t* bx0;
+    const DevTask* tasks; int n_tasks;        // tasks evaluated by this rank
+    const float* blocks;              // [B_loc_pad][C][S][S]
+    const uint8_t* gmask;             // GLOBAL [H][W]
     int C, S, W;
-    double* means;                    // [n_tasks]
-    const int2* rows; int n_rows;     // (task, block-local y) of every rectangle row, grouped by task
+    double* means;                    // GLOBAL slots (this rank writes only its own)
+    const int2* rows; int n_rows;     // (local task, block-local y) of every rectangle row, grouped by task
     const int32_t* row_start;         // [n_tasks + 1] first row of each task
     double* row_sums;                 // [n_rows] scratch
 };
 void launch_means(const MeansArgs& a, cudaStream_t s);
 
-// K6b: offset recurrence (pointer jumping over the parent forest) + global shift.
+// K6b: offset recurrence (pointer jumping over the parent forest) + global shift from the line sums.
 struct DevRec { int32_t ta, tb, parent, is_nan; };
+struct DevShiftTerm { int32_t task, block, coef, n; };     // coef * (means[task] - n * c[block])
 struct OffsetsArgs {
     const DevRec* rec; int B; int F; int rounds; double ref_bc;
     const double* means;
     double* dbuf0; double* dbuf1; int32_t* pbuf0; int32_t* pbuf1;   // scratch [F*B]
     double* offsets;                  // [F][B]  c_k
     float* coff;                      // [F][B]  c_k + shift_f (consumed by the placement)
-    const float* blocks; const uint16_t* owner; const int32_t* by0; const int32_t* bx0;
-    int C, S, H, W;
-    int shift_axis[2], shift_a[2], shift_b[2];
+    const DevShiftTerm* terms; int term_start[3]; int shift_len[2];
     Scalars* sc;
 };
 void launch_offsets(const OffsetsArgs& a, cudaStream_t s);
 
 // K7: placement through the owner map.
 struct PlaceArgs {
-    const float* blocks; const uint16_t* owner; const int32_t* by0; const int32_t* bx0;
-    const float* coff; float* field; int B, C, F, S, H, W;
+    const float* blocks; const uint16_t* owner; const int32_t* by0; const int32_t* bx0;   // LOCAL blocks / rows
+    const float* coff;                // GLOBAL [F][B_glob]
+    float* field;                     // [F][plane_stride]
+    int B_glob, kb0, C, F, S, H, W;   // H = local rows placed; kb0 = first global block of this rank
+    long long plane_stride;
 };
 void launch_place(const PlaceArgs& a, cudaStream_t s);
 
@@ -151,5 +160,9 @@ struct BackArgs {
     const Scalars* sc;
 };
 void launch_back(const BackArgs& a, cudaStream_t s);
+
+// Static sparse exchange (multi-GPU): dst[i] = src[idx[i]] for the elements other ranks need.
+struct PackArgs { const float* src; const int32_t* idx; float* dst; long long n; int width; long long src_stride; };
+void launch_pack(const PackArgs& a, cudaStream_t s);
 
 }  // namespace psm

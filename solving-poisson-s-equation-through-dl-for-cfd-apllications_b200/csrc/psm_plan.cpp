@@ -193,6 +193,29 @@ int compile_plan(int variant, int H, int W, int S, int ov, const uint8_t* mask, 
         P.shift_axis[0] = 0; P.shift_a[0] = 0; P.shift_b[0] = 1;                            // GRAD:359
         P.shift_axis[1] = 1; P.shift_a[1] = 1; P.shift_b[1] = 2;                            // GRAD:361
     }
+    // result -= mean(3*line_a - line_b)/3 through the owner map, as per-block runs: the placed value is
+    // raw - c[owner], so every run contributes coef * (sum(raw) - n * c[owner]).
+    for (int f = 0; f < P.F; ++f) {
+        const int axis = P.shift_axis[f];
+        const int len = axis == 0 ? H : W;
+        P.shift_len[f] = len;
+        for (int s2 = 0; s2 < 2; ++s2) {
+            const int line = s2 == 0 ? P.shift_a[f] : P.shift_b[f];
+            const int coef = s2 == 0 ? 3 : -1;
+            int i = 0;
+            while (i < len) {
+                const int o = P.owner[axis == 0 ? (size_t)i * W + line : (size_t)line * W + i];
+                int e = i + 1;
+                while (e < len && P.owner[axis == 0 ? (size_t)e * W + line : (size_t)line * W + e] == o) ++e;
+                LineTask t{};
+                t.src = o; t.ch = f; t.coef = coef; t.n = e - i;
+                if (axis == 0) { t.y0 = i - P.y0[o]; t.y1 = e - P.y0[o]; t.x0 = line - P.x0[o]; t.x1 = t.x0 + 1; }
+                else           { t.x0 = i - P.x0[o]; t.x1 = e - P.x0[o]; t.y0 = line - P.y0[o]; t.y1 = t.y0 + 1; }
+                P.lines[f].push_back(t);
+                i = e;
+            }
+        }
+    }
     return 0;
 }
 
@@ -230,5 +253,25 @@ extern "C" int psm_plan_compile(int32_t variant, int32_t grid_h, int32_t grid_w,
         int32_t* o = tasks + 8 * q;
         o[0] = t.src; o[1] = t.msk; o[2] = t.ch; o[3] = t.y0; o[4] = t.y1; o[5] = t.x0; o[6] = t.x1; o[7] = t.count;
     }
+    return 0;
+}
+
+// Shift-line runs (SMC:350 / GRAD:358-361 through the owner map): int32[n][8] =
+// (field, block, y0, y1, x0, x1, coef, n_pixels); `lines` may be NULL to query the count.
+extern "C" int psm_plan_shift_lines(int32_t variant, int32_t grid_h, int32_t grid_w, int32_t shape, int32_t overlap,
+                                    const uint8_t* mask, int32_t* n_lines, int32_t* lines) {
+    psm::Plan P;
+    int rc = psm::compile_plan(variant, grid_h, grid_w, shape, overlap, mask, P);
+    if (rc != 0) return rc;
+    int n = 0;
+    for (int f = 0; f < P.F; ++f)
+        for (const psm::LineTask& t : P.lines[f]) {
+            if (lines) {
+                int32_t* o = lines + 8 * n;
+                o[0] = f; o[1] = t.src; o[2] = t.y0; o[3] = t.y1; o[4] = t.x0; o[5] = t.x1; o[6] = t.coef; o[7] = t.n;
+            }
+            ++n;
+        }
+    if (n_lines) *n_lines = n;
     return 0;
 }

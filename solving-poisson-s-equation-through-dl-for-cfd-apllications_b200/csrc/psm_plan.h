@@ -23,6 +23,14 @@ struct Task {
     int32_t count;               // mask pixels in the rectangle (0 -> mean is NaN)
 };
 
+// One maximal run of a shift line (SMC:350 / GRAD:358-361) owned by a single block: the plain sum of the
+// UNCORRECTED block values over `rect` enters the global shift as  coef * (sum - n * c[block]).
+struct LineTask {
+    int32_t src, ch;             // block, channel (= field)
+    int32_t y0, y1, x0, x1;      // block-local rectangle (one pixel wide or high)
+    int32_t coef, n;             // +3 (line a) or -1 (line b); number of pixels
+};
+
 struct Rec {
     int32_t ta, tb, parent;      // c_k = m[ta] - (tb >= 0 ? m[tb] - c[parent] : ref_bc)
     int32_t is_nan;              // statically known NaN
@@ -38,6 +46,8 @@ struct Plan {
     std::vector<Rec> rec;                            // [F*B]
     int shift_axis[2] = {0, 0};                      // 0: two columns (mean over rows); 1: two rows
     int shift_a[2] = {0, 0}, shift_b[2] = {0, 0};    // result -= mean(3*line_a - line_b)/3
+    std::vector<LineTask> lines[2];                  // per field: runs of the two shift lines through the owner map
+    int shift_len[2] = {0, 0};                       // pixels per shift line (H or W)
     int max_depth = 0;                               // longest parent chain
     std::string error;
 };

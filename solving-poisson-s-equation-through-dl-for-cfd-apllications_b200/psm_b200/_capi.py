@@ -16,6 +16,7 @@ PSM_STD, PSM_MAX_ABS = 0, 1
 GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_FP32_SIMT = 0, 1, 2
 (STAGE_GRID, STAGE_XINPUT, STAGE_MLPOUT, STAGE_BLOCKS, STAGE_OFFSETS, STAGE_FIELD, STAGE_SCALARS,
  STAGE_MEANS) = range(8)
+UNIQUE_ID_BYTES = 128
 N_TIMINGS = 12
 TIMING_NAMES = ('h2d', 'prep', 'gather', 'extract', 'pca_project', 'mlp', 'pca_inverse', 'strip_means',
                 'offsets', 'place', 'back_gather', 'd2h')
@@ -55,7 +56,22 @@ class PsmGeometry(C.Structure):
     _fields_ = [('grid_h', C.c_int32), ('grid_w', C.c_int32), ('shape', C.c_int32), ('overlap', C.c_int32),
                 ('n_x', C.c_int32), ('n_y', C.c_int32), ('p_i', C.c_int32), ('p_j', C.c_int32),
                 ('n_blocks', C.c_int32), ('n_fields', C.c_int32), ('n_cells', C.c_int64),
-                ('n_tasks', C.c_int32), ('reserved', C.c_int32)]
+                ('n_tasks', C.c_int32), ('reserved', C.c_int32),
+                ('row0', C.c_int32), ('row1', C.c_int32), ('ext_rows', C.c_int32), ('first_block', C.c_int32),
+                ('n_local_blocks', C.c_int32), ('world', C.c_int32),
+                ('n_ghost_cells', C.c_int64), ('n_ghost_pix', C.c_int64)]
+
+
+class PsmShard(C.Structure):
+    _fields_ = [('rank', C.c_int32), ('world', C.c_int32), ('grid_h', C.c_int32), ('grid_w', C.c_int32),
+                ('row0', C.c_int32), ('row1', C.c_int32), ('ext_rows', C.c_int32), ('send_rows', C.c_int32),
+                ('blk_row0', C.c_int32), ('blk_row1', C.c_int32), ('reserved', C.c_int32),
+                ('mask_global', c_uint8_p),
+                ('n_owned', C.c_int64), ('n_ghost', C.c_int64), ('n_ghost_pix', C.c_int64),
+                ('vert', c_int32_p), ('weights', c_double_p), ('sdfunct', c_double_p),
+                ('vert_back', c_int32_p), ('weights_back', c_double_p),
+                ('cell_send_ptr', c_int64_p), ('cell_send_idx', c_int32_p), ('cell_recv_ptr', c_int64_p),
+                ('pix_send_ptr', c_int64_p), ('pix_send_idx', c_int32_p), ('pix_recv_ptr', c_int64_p)]
 
 
 # every symbol include/psm_b200.h declares: name -> (restype, argtypes)
@@ -64,6 +80,13 @@ SYMBOLS = {
     'psm_create': (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(PsmConfig)]),
     'psm_load_params': (C.c_int, [C.c_void_p, C.POINTER(PsmParams)]),
     'psm_init_with_tables': (C.c_int, [C.c_void_p, C.POINTER(PsmTables)]),
+    'psm_init_sharded': (C.c_int, [C.c_void_p, C.POINTER(PsmShard)]),
+    'psm_comm_get_unique_id': (C.c_int, [C.c_void_p]),
+    'psm_comm_init': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    'psm_init_from_file': (C.c_int, [C.c_void_p, C.c_char_p]),
+    'psm_load_params_file': (C.c_int, [C.c_void_p, C.c_char_p]),
+    'psm_save_tables': (C.c_int, [C.POINTER(PsmTables), C.c_char_p]),
+    'psm_save_params': (C.c_int, [C.POINTER(PsmParams), C.c_int32, C.c_char_p]),
     'psm_destroy': (C.c_int, [C.c_void_p]),
     'psm_predict': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'psm_predict_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
@@ -83,6 +106,7 @@ SYMBOLS = {
     'psm_debug_gemm': (C.c_int, [C.c_int32] * 5 + [c_float_p, c_float_p, c_float_p, C.c_int32]),
     'psm_plan_sizes': (C.c_int, [C.c_int32] * 5 + [c_uint8_p, c_int32_p, c_int32_p, c_int32_p]),
     'psm_plan_compile': (C.c_int, [C.c_int32] * 5 + [c_uint8_p] + [c_int32_p] * 5),
+    'psm_plan_shift_lines': (C.c_int, [C.c_int32] * 5 + [c_uint8_p, c_int32_p, c_int32_p]),
 }
 
 _lib = None

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), 'csrc')
 OUT = os.path.join(HERE, 'libpsm_b200.so')
-SOURCES = ['psm_plan.cpp', 'psm_kernels.cu', 'psm_gemm_tc.cu', 'psm_handle.cu']
+SOURCES = ['psm_plan.cpp', 'psm_files.cpp', 'psm_kernels.cu', 'psm_gemm_tc.cu', 'psm_handle.cu']
 HEADERS = ['psm_plan.h', 'psm_kernels.cuh', os.path.join('..', '..', 'include', 'psm_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',

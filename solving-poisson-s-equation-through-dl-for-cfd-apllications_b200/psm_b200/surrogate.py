@@ -38,7 +38,11 @@ def compile_plan(variant, H, W, mask, shape=128, overlap=32):
                               _ptr(il, C.c_int32), _ptr(owner, C.c_int32), _ptr(rec, C.c_int32), _ptr(tasks, C.c_int32))
     if rc < 0:
         raise capi.PsmError(rc, 'plan rejected')
-    return dict(origins=origins, indices_list=il, owner=owner, rec=rec, tasks=tasks, n_blocks=B, n_fields=F)
+    nl = C.c_int32()
+    lib.psm_plan_shift_lines(v, H, W, shape, overlap, _ptr(mask, C.c_uint8), C.byref(nl), None)
+    lines = np.zeros((nl.value, 8), np.int32)
+    lib.psm_plan_shift_lines(v, H, W, shape, overlap, _ptr(mask, C.c_uint8), C.byref(nl), _ptr(lines, C.c_int32))
+    return dict(origins=origins, indices_list=il, owner=owner, rec=rec, tasks=tasks, lines=lines, n_blocks=B, n_fields=F)
 
 
 def debug_gemm(A, B, mode=0, splits=1, device=0):
@@ -163,6 +167,54 @@ class PressureSurrogate:
         self.n_blocks = g['n_blocks']
         return self
 
+    # ------------------------------------------------------------------ multi-GPU
+    @staticmethod
+    def unique_id():
+        """Rank 0: the NCCL unique id (bytes) to ship to the other ranks (MPI_Bcast, torch.distributed ...)."""
+        buf = C.create_string_buffer(capi.UNIQUE_ID_BYTES)
+        rc = capi.load().psm_comm_get_unique_id(buf)
+        if rc < 0:
+            raise capi.PsmError(rc, (capi.load().psm_last_error(None) or b'').decode())
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        """Collective: attach this handle to the communicator of ``world`` ranks (before ``init_shard``)."""
+        buf = C.create_string_buffer(bytes(unique_id), capi.UNIQUE_ID_BYTES)
+        self._check(self.lib.psm_comm_init(self._h, buf, int(rank), int(world)))
+        return self
+
+    def init_shard(self, sh):
+        """``sh``: one dict of ``psm_b200.shard.partition`` -- this rank's block rows (PMP:179-185 replaced)."""
+        T = capi.PsmShard()
+        T.rank, T.world, T.grid_h, T.grid_w = int(sh['rank']), int(sh['world']), int(sh['H']), int(sh['W'])
+        T.row0, T.row1, T.ext_rows, T.send_rows = int(sh['row0']), int(sh['row1']), int(sh['ext_rows']), int(sh['send_rows'])
+        T.blk_row0, T.blk_row1 = int(sh['blk_row0']), int(sh['blk_row1'])
+        T.n_owned, T.n_ghost, T.n_ghost_pix = int(sh['n_owned']), int(sh['n_ghost']), int(sh['n_ghost_pix'])
+        keep = []
+
+        def arr(name, dtype, ctype):
+            a = sh.get(name)
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=dtype)
+            keep.append(a)
+            return _ptr(a, ctype)
+        T.mask_global = arr('mask_global', np.uint8, C.c_uint8)
+        T.vert, T.weights = arr('vert', np.int32, C.c_int32), arr('weights', np.float64, C.c_double)
+        T.sdfunct = arr('sdfunct', np.float64, C.c_double)
+        T.vert_back, T.weights_back = arr('vert_back', np.int32, C.c_int32), arr('weights_back', np.float64, C.c_double)
+        T.cell_send_ptr, T.cell_recv_ptr = arr('cell_send_ptr', np.int64, C.c_int64), arr('cell_recv_ptr', np.int64, C.c_int64)
+        T.pix_send_ptr, T.pix_recv_ptr = arr('pix_send_ptr', np.int64, C.c_int64), arr('pix_recv_ptr', np.int64, C.c_int64)
+        T.cell_send_idx, T.pix_send_idx = arr('cell_send_idx', np.int32, C.c_int32), arr('pix_send_idx', np.int32, C.c_int32)
+        self._check(self.lib.psm_init_sharded(self._h, C.byref(T)))
+        self.n_cells, self.W = T.n_owned, T.grid_w
+        self.H = T.row1 - T.row0
+        self.H_ext = self.H + T.ext_rows
+        self.H_global = T.grid_h
+        g = self.geometry()
+        self.n_blocks = g['n_blocks']
+        return self
+
     def init_from_mesh(self, cells_xy, top, obst, probe_values, back=True):
         t = _tables.build_tables(cells_xy, top, obst, probe_values, variant=self.variant, delta=self.delta, back=back)
         return self.init_tables(t)
@@ -207,7 +259,7 @@ class PressureSurrogate:
         return o, il
 
     def owner_map(self):
-        ow = np.zeros((self.H, self.W), np.int32)
+        ow = np.zeros((getattr(self, 'H_global', self.H), self.W), np.int32)
         self._check(self.lib.psm_get_owner_map(self._h, _ptr(ow, C.c_int32)))
         return ow
 
@@ -218,13 +270,13 @@ class PressureSurrogate:
 
     def stage(self, name):
         g = self.geometry()
-        B, F, S, Cn = g['n_blocks'], g['n_fields'], g['shape'], self.n_fields
+        Bg, B, F, S, Cn = g['n_blocks'], g['n_local_blocks'], g['n_fields'], g['shape'], self.n_fields
         spec = {
-            'grid': (capi.STAGE_GRID, (2, self.H, self.W), np.float32),
+            'grid': (capi.STAGE_GRID, (2, getattr(self, 'H_ext', self.H), self.W), np.float32),
             'x_input': (capi.STAGE_XINPUT, (B, self.pc_in), np.float32),
             'mlp_out': (capi.STAGE_MLPOUT, (B, self.pc_p), np.float32),
             'blocks': (capi.STAGE_BLOCKS, (B, Cn, S, S), np.float32),
-            'offsets': (capi.STAGE_OFFSETS, (F, B), np.float64),
+            'offsets': (capi.STAGE_OFFSETS, (F, Bg), np.float64),
             'field': (capi.STAGE_FIELD, (F, self.H, self.W), np.float32),
             'scalars': (capi.STAGE_SCALARS, (4,), np.float64),
             'means': (capi.STAGE_MEANS, (g['n_tasks'],), np.float64),

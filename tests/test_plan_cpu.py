@@ -117,6 +117,17 @@ def test_closed_form_recurrence_equals_sequential_assembly(variant, ov, H, W, di
         np.testing.assert_allclose(c[f], offs, rtol=0, atol=1e-12, equal_nan=True)
         assert np.array_equal(np.isnan(ref), np.isnan(mine - sh))
         np.testing.assert_allclose(mine - sh, ref, rtol=0, atol=1e-11, equal_nan=True)
+        # the shift as the kernels evaluate it: per-block runs of the two lines (psm_plan_shift_lines)
+        acc, npx = 0.0, 0
+        for (lf, blk, y0, y1, x0, x1, coef, n) in plan['lines']:
+            if lf != f:
+                continue
+            assert (y1 - y0) * (x1 - x0) == n
+            acc += coef * (blocks[blk, f, y0:y1, x0:x1].sum() - n * c[f][blk])
+            npx += n
+        L = H if (variant == 'deltaU_to_deltaP' or f == 0) else W
+        assert npx == 2 * L
+        np.testing.assert_allclose(acc / L / 3, sh, rtol=0, atol=1e-11, equal_nan=True)
 
 
 def test_library_exports_every_declared_symbol():
@@ -130,4 +141,4 @@ def test_library_exports_every_declared_symbol():
     lib = _capi.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.psm_api_version() == 1
+    assert lib.psm_api_version() == 2
