@@ -56,6 +56,41 @@ def build_case(workload, variant, seed=0, back='closed_form'):
     return mesh, F, params, tables, time.time() - t0
 
 
+def sharded_grid_rows(world, variant):
+    """Weak scaling: ~1 M cells (1000 grid rows x 1000 columns) per GPU, stacked in y.  Rows are nudged so
+    that (H - 128) is not a multiple of the stride -- the reference is undefined there."""
+    stride = 96 if variant == 'deltaU_to_deltaP' else 32
+    H = 1000 * world
+    while (H - 128) % stride == 0:
+        H += 8
+    return H
+
+
+def build_sharded_case(world, rank, variant, dist, mesh_kw=None, seed=0):
+    """One rank's share of the N-GPU workload, built band-locally (psm_b200.shard.band_phase1..3): every
+    rank triangulates only the cells around its own block rows; the two small global facts travel by
+    all_gather_object.  Returns (mesh, fields, params, shard, seconds)."""
+    from psm_b200 import shard as pshard
+    if mesh_kw is None:
+        H = sharded_grid_rows(world, variant)
+        mesh_kw = dict(H=H, W=1000, nx=1000, ny=H, R=0.4)
+    mesh = syn.make_mesh(seed=seed, **mesh_kw)
+    F = syn.make_fields(mesh, seed=seed)
+    deltas = variant == 'deltaU_to_deltaP'
+    params = syn.make_params(seed=seed, pc_in=128, pc_p=128, standardization='std' if deltas else 'max_abs',
+                             n_out_channels=1 if deltas else 2,
+                             maxs=syn.DEFAULT_MAXS if deltas else (1.0, 0.536, 0.999, 0.8, 0.7))
+    t0 = time.time()
+    L, s1 = pshard.band_phase1(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'], rank, world, variant=variant)
+    all1 = [None] * world
+    dist.all_gather_object(all1, s1)
+    L, s2 = pshard.band_phase2(L, all1)
+    all2 = [None] * world
+    dist.all_gather_object(all2, s2)
+    sh = pshard.band_phase3(L, all2)
+    return mesh, F, params, sh, time.time() - t0
+
+
 def stage_bytes(n_cells, G, B, C, pc_in, pc_p, ncol, S=128):
     """Algorithmic bytes per step and stage (SURVEY.md section 8d / DESIGN.md): FP32 device storage,
     f64 only at the ABI.  Overlap re-reads and L2-resident intermediates are NOT counted twice."""
@@ -163,9 +198,23 @@ def main():
     workload = args.workload or 'c2'
     variant = args.variant
     ncol = 7 if variant == 'deltaU_to_deltaP' else 5
-    cfg = {'workload': '%s: %s, synthetic flow-past-cylinder mesh %s, pc_in=pc_p=128, MLP 3x512, random-init'
-                       % (workload, variant, syn.CONFIGS[workload]),
-           'l2': 'flushed between timed steps (256 MiB write)', 'input_cols': ncol}
+    scaling = 'weak'
+    sharded_kw = None
+    if world > 1 and args.impl == 'native' and args.workload:
+        # a FIXED domain (e.g. c4 = BASELINE.json configs[3], 16 M cells) cut over the ranks: strong scaling
+        scaling, sharded_kw = 'strong', dict(syn.CONFIGS[workload])
+        cfg = {'workload': '%s: %s, synthetic mesh %s sharded by block rows over %d B200, NCCL halo / ghost / strip-mean '
+                           'exchanges, pc_in=pc_p=128, MLP 3x512, random-init' % (workload, variant, sharded_kw, world),
+               'l2': 'flushed between timed steps (256 MiB write)', 'input_cols': ncol}
+    elif world > 1 and args.impl == 'native':
+        Hs = sharded_grid_rows(world, variant)
+        cfg = {'workload': 'c2 x %d: %s, %d x 1000 grid (~1 M cells per GPU) sharded by block rows over %d B200, NCCL halo / '
+                           'ghost / strip-mean exchanges, pc_in=pc_p=128, MLP 3x512, random-init' % (world, variant, Hs, world),
+               'l2': 'flushed between timed steps (256 MiB write)', 'input_cols': ncol}
+    else:
+        cfg = {'workload': '%s: %s, synthetic flow-past-cylinder mesh %s, pc_in=pc_p=128, MLP 3x512, random-init'
+                           % (workload, variant, syn.CONFIGS[workload]),
+               'l2': 'flushed between timed steps (256 MiB write)', 'input_cols': ncol}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == 'reference':
@@ -199,13 +248,25 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    mesh, F, params, tables, t_init = build_case(workload, variant, seed=rank)
-    n = mesh['cells'].shape[0]
     sm = psm_b200.PressureSurrogate(variant, device=local_rank, input_cols=ncol, timings=False)
-    sm.load_params(params)
-    sm.init_tables(tables)
+    if world > 1:
+        # ONE domain sharded by block rows (BASELINE.json configs[3] shape, sized for weak scaling)
+        mesh, F, params, sh, t_init = build_sharded_case(world, rank, variant, dist, sharded_kw)
+        ids = [psm_b200.PressureSurrogate.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sm.load_params(params)
+        sm.comm_init(ids[0], rank, world)
+        sm.init_shard(sh)
+        n = sh['n_owned']
+        cells_np = np.ascontiguousarray(syn.pack_cells(mesh, F, with_delta=(ncol == 7))[sh['owned_ids']])
+        tables = None
+    else:
+        mesh, F, params, tables, t_init = build_case(workload, variant)
+        n = mesh['cells'].shape[0]
+        sm.load_params(params)
+        sm.init_tables(tables)
+        cells_np = syn.pack_cells(mesh, F, with_delta=(ncol == 7))
     geo = sm.geometry()
-    cells_np = syn.pack_cells(mesh, F, with_delta=(ncol == 7))
     h_in = torch.from_numpy(cells_np).pin_memory()
     h_out = torch.empty(n if sm.n_fields == 1 else (n, 2), dtype=torch.float64).pin_memory()
     d_in = h_in.cuda()
@@ -271,7 +332,7 @@ def main():
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        sb = stage_bytes(n, geo['grid_h'] * geo['grid_w'], geo['n_blocks'], sm.n_fields, sm.pc_in, sm.pc_p, ncol)
+        sb = stage_bytes(n, (geo['row1'] - geo['row0']) * geo['grid_w'], geo['n_local_blocks'], sm.n_fields, sm.pc_in, sm.pc_p, ncol)
         stage_avg = dict(zip(psm_b200._capi.TIMING_NAMES, (stage_ms / args.steps).tolist()))
         stages = {k: {'ms': stage_avg[k], 'GBps': (sb[k] / (stage_avg[k] * 1e-3) / 1e9) if stage_avg.get(k, 0) > 0 else None}
                   for k in sb}
@@ -282,7 +343,7 @@ def main():
                 'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': sb[dom]}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:
             torch.set_num_threads(os.cpu_count() or 1)
             o = oracle_for(variant, params, mesh, F, tables)
             sec = time_oracle(o, variant, F, args.cpu_steps, 1)
@@ -291,7 +352,7 @@ def main():
                              'replaced by float32 NumPy; init excluded)' % (args.cpu_steps, n), 'ms_per_step': sec * 1e3}
         line = {'metric': 'surrogate_cells_per_s', 'value': value, 'unit': 'cells/s', 'n_gpus': world,
                 'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (f64 at the ABI and in the offset chain)',
+                'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32 (f64 at the ABI and in the offset chain)',
                 'data': 'synthetic', 'config': cfg, 'clocks': clocks,
                 'e2e': {'value': e2e, 'unit': 'cells/s', 'h2d_bytes_per_step': int(n * ncol * 8),
                         'd2h_bytes_per_step': int(n * sm.n_fields * 8), 'ms_per_step': e2e_s / args.steps * 1e3},

@@ -132,12 +132,15 @@ typedef struct psm_shard {
                                           before block extraction (the halo strip); 0 on the last   */
     int32_t send_rows;                 /* rows [row0,row0+send_rows) sent to rank-1; 0 on rank 0     */
     int32_t blk_row0, blk_row1;        /* block rows [blk_row0,blk_row1) of the global plan          */
-    int32_t reserved;
+    int32_t local_ext_rows;            /* overlap rows [row1,row1+local_ext_rows) this rank gathers ITSELF
+                                          (the forward table covers them; their cells arrive as ghost
+                                          cells) -- the halo strip travels in cell space; use either this
+                                          or ext_rows                                                  */
     const uint8_t* mask_global;        /* [H][W] flow mask (sdfunct != 0) of the WHOLE grid          */
     int64_t n_owned, n_ghost, n_ghost_pix;
-    const int32_t* vert;               /* [(row1-row0)*W][3]                                         */
-    const double*  weights;            /* [(row1-row0)*W][3]                                         */
-    const double*  sdfunct;            /* [row1-row0+ext_rows][W]                                    */
+    const int32_t* vert;               /* [(row1-row0+local_ext_rows)*W][3]                          */
+    const double*  weights;            /* [(row1-row0+local_ext_rows)*W][3]                          */
+    const double*  sdfunct;            /* [row1-row0+local_ext_rows+ext_rows][W]                     */
     const int32_t* vert_back;          /* [n_owned][3] or NULL                                       */
     const double*  weights_back;       /* [n_owned][3]                                               */
     /* static sparse exchanges, CSR over peer ranks ([world+1] offsets) */
@@ -162,7 +165,7 @@ typedef struct psm_geometry {
 
 /* Device-resident intermediates that parity tests read back (psm_get_stage). */
 /* On a sharded handle H means this rank's rows (row1-row0, + ext_rows for GRID) and B its local
- * blocks, except OFFSETS and MEANS which are global (every rank holds the same values). */
+ * blocks (GRID additionally holds the overlap rows below), except OFFSETS and MEANS which are global. */
 enum psm_stage_code {
     PSM_STAGE_GRID = 0,       /* float [2][H][W]   scaled input channels 0,1 (SMC:430-444)       */
     PSM_STAGE_XINPUT = 1,     /* float [B][pc_in]  standardised PCA coordinates (SMC:512)        */

@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -90,7 +91,9 @@ struct psm_handle {
     Plan plan;                         // GLOBAL plan
     long long n_cells = 0;             // owned cells (rows of psm_predict)
     long long n_ghost = 0, n_ghost_pix = 0;
-    long long G = 0, G_pad = 0;        // own pixels (row1-row0)*W, padded to 4
+    long long G = 0;                   // pixels placed here, (row1-row0)*W
+    long long Gg = 0, G_pad = 0;       // pixels gathered here (+ local overlap rows), padded to 4
+    int local_ext = 0;
     long long grid_stride = 0;         // floats per grid plane (own + halo rows)
     long long field_stride = 0;        // floats per field plane (own pixels + ghost pixels)
     int H = 0, W = 0;                  // H = own rows (row1-row0); W global
@@ -132,6 +135,7 @@ struct psm_handle {
     struct StepGraph { const void* in = nullptr; void* out = nullptr; cudaGraphExec_t exec = nullptr; };
     StepGraph g_dev, g_host;
     bool use_graphs = true;
+    int eager_steps = 0;
 };
 
 #define PSM_FAIL(h, code, ...)                                    \
@@ -198,6 +202,7 @@ extern "C" int psm_create(psm_handle** out, const psm_config* cfg) {
     if (!h) { g_create_error = "out of host memory"; return PSM_ERR_INVALID; }
     h->cfg = *cfg;
     h->S = cfg->shape;
+    if (const char* e = getenv("PSM_NO_GRAPHS")) h->use_graphs = !(e[0] == '1');
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e); delete h; return PSM_ERR_CUDA;
     }
@@ -323,11 +328,11 @@ namespace {
 struct LocalInit {
     int rank = 0, world = 1;
     int H = 0, W = 0;                          // GLOBAL grid
-    int row0 = 0, row1 = 0, ext_rows = 0, send_rows = 0, blk_row0 = 0, blk_row1 = 0;
+    int row0 = 0, row1 = 0, ext_rows = 0, send_rows = 0, blk_row0 = 0, blk_row1 = 0, local_ext = 0;
     const uint8_t* mask_global = nullptr;      // [H][W]
     long long n_owned = 0, n_ghost = 0, n_ghost_pix = 0;
-    std::vector<int32_t> fv[3]; std::vector<float> fw[3];      // [(row1-row0)*W]
-    const double* sdf_rows = nullptr;          // [row1-row0+ext_rows][W]
+    std::vector<int32_t> fv[3]; std::vector<float> fw[3];      // [(row1-row0+local_ext)*W]
+    const double* sdf_rows = nullptr;          // [row1-row0+local_ext+ext_rows][W]
     bool have_back = false;
     std::vector<int32_t> bv[3]; std::vector<float> bw[3];      // [n_owned]
     std::vector<long long> cell_send_ptr, cell_recv_ptr, pix_send_ptr, pix_recv_ptr;
@@ -342,9 +347,11 @@ static int init_local(psm_handle* h, LocalInit& L) {
     h->rank = L.rank; h->world = L.world;
     h->n_cells = L.n_owned; h->n_ghost = L.n_ghost; h->n_ghost_pix = L.n_ghost_pix;
     const long long N = L.n_owned, Nall = L.n_owned + L.n_ghost;
-    const long long G = (long long)h->H * W;
-    const int Hl = h->H + L.ext_rows;
-    h->G = G; h->G_pad = round_up_ll(G, 4);
+    const long long G = (long long)h->H * W;                        // pixels placed here
+    const long long Gg = (long long)(h->H + L.local_ext) * W;       // pixels gathered here
+    const int Hl = h->H + L.local_ext + L.ext_rows;                 // rows the local blocks are cut from
+    h->local_ext = L.local_ext;
+    h->G = G; h->Gg = Gg; h->G_pad = round_up_ll(Gg, 4);
     h->grid_stride = round_up_ll(std::max(h->G_pad, (long long)Hl * W), 4);
     h->field_stride = round_up_ll(G + L.n_ghost_pix, 4);
     h->have_back = L.have_back;
@@ -362,12 +369,12 @@ static int init_local(psm_handle* h, LocalInit& L) {
     h->rounds = 0;
     while ((1 << h->rounds) < P.max_depth + 1) ++h->rounds;
     for (int k = kb0; k < kb1; ++k)
-        if (P.y0[k] < L.row0 || P.y0[k] + S > L.row1 + L.ext_rows)
-            PSM_FAIL(h, PSM_ERR_GEOMETRY, "block %d (rows %d..%d) is outside this rank's rows [%d,%d)+%d", k, P.y0[k], P.y0[k] + S, L.row0, L.row1, L.ext_rows);
+        if (P.y0[k] < L.row0 || P.y0[k] + S > L.row1 + L.local_ext + L.ext_rows)
+            PSM_FAIL(h, PSM_ERR_GEOMETRY, "block %d (rows %d..%d) is outside this rank's rows [%d,%d)+%d", k, P.y0[k], P.y0[k] + S, L.row0, L.row1, L.local_ext + L.ext_rows);
 
     for (int j = 0; j < 3; ++j) {
         L.fv[j].resize(h->G_pad, 0); L.fw[j].resize(h->G_pad, 0.f);
-        for (long long q = 0; q < G; ++q)
+        for (long long q = 0; q < Gg; ++q)
             if (L.fv[j][q] < 0 || L.fv[j][q] >= Nall) PSM_FAIL(h, PSM_ERR_INVALID, "forward table: cell id out of range at pixel %lld", q);
         TRY(upload(h, &h->d_fv[j], L.fv[j])); TRY(upload(h, &h->d_fw[j], L.fw[j]));
     }
@@ -446,7 +453,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
         TRY(dalloc(h, &h->d_cell_send, (size_t)L.cell_send_idx.size() * 2));
         TRY(dalloc(h, &h->d_pix_send, (size_t)L.pix_send_idx.size() * h->F));
         TRY(dalloc(h, &h->d_means_loc, (size_t)h->n_tasks_glob));
-        h->use_graphs = false;         // NCCL calls are enqueued eagerly between the kernels
+        h->eager_steps = 2;            // NCCL sets its connections up lazily: the first steps run uncaptured
     }
     // ---- per-step buffers -------------------------------------------------------------------------------
     const int ncol = h->cfg.input_cols;
@@ -628,7 +635,7 @@ extern "C" int psm_init_sharded(psm_handle* h, const psm_shard* s) {
     if (s->world < 1 || s->rank < 0 || s->rank >= s->world) PSM_FAIL(h, PSM_ERR_INVALID, "bad rank/world");
     if (s->world > 1 && (!h->comm || h->world != s->world || h->rank != s->rank)) PSM_FAIL(h, PSM_ERR_STATE, "psm_comm_init(rank %d of %d) must precede psm_init_sharded", s->rank, s->world);
     if (!s->vert || !s->weights || !s->sdfunct || !s->mask_global || s->n_owned < 1 || s->row0 < 0 || s->row1 <= s->row0 || s->row1 > s->grid_h ||
-        s->ext_rows < 0 || s->send_rows < 0 || s->row1 + s->ext_rows > s->grid_h)
+        s->ext_rows < 0 || s->send_rows < 0 || s->local_ext_rows < 0 || s->row1 + s->ext_rows + s->local_ext_rows > s->grid_h)
         PSM_FAIL(h, PSM_ERR_INVALID, "bad shard");
     if (s->world > 1 && (!s->cell_send_ptr || !s->cell_recv_ptr || !s->pix_send_ptr || !s->pix_recv_ptr)) PSM_FAIL(h, PSM_ERR_INVALID, "missing exchange lists");
     if ((s->rank == s->world - 1 && s->ext_rows) || (s->rank == 0 && s->send_rows)) PSM_FAIL(h, PSM_ERR_INVALID, "halo rows at the ends of the rank chain");
@@ -636,9 +643,10 @@ extern "C" int psm_init_sharded(psm_handle* h, const psm_shard* s) {
     LocalInit L;
     L.rank = s->rank; L.world = s->world; L.H = s->grid_h; L.W = s->grid_w; L.row0 = s->row0; L.row1 = s->row1;
     L.ext_rows = s->ext_rows; L.send_rows = s->send_rows; L.blk_row0 = s->blk_row0; L.blk_row1 = s->blk_row1;
+    L.local_ext = s->local_ext_rows;
     L.mask_global = s->mask_global; L.n_owned = s->n_owned; L.n_ghost = s->n_ghost; L.n_ghost_pix = s->n_ghost_pix;
     L.sdf_rows = s->sdfunct;
-    const long long G = (long long)(s->row1 - s->row0) * s->grid_w;
+    const long long G = (long long)(s->row1 - s->row0 + s->local_ext_rows) * s->grid_w;
     for (int j = 0; j < 3; ++j) {
         L.fv[j].resize(G); L.fw[j].resize(G);
         for (long long q = 0; q < G; ++q) { L.fv[j][q] = s->vert[3 * q + j]; L.fw[j][q] = (float)s->weights[3 * q + j]; }
@@ -746,8 +754,8 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
             NC(h, g_nccl.Send(grid1, (size_t)h->send_rows * h->W, ncclFloat, h->rank - 1, h->comm, s));
         }
         if (h->ext_rows) {
-            NC(h, g_nccl.Recv(grid0 + h->G, (size_t)h->ext_rows * h->W, ncclFloat, h->rank + 1, h->comm, s));
-            NC(h, g_nccl.Recv(grid1 + h->G, (size_t)h->ext_rows * h->W, ncclFloat, h->rank + 1, h->comm, s));
+            NC(h, g_nccl.Recv(grid0 + h->Gg, (size_t)h->ext_rows * h->W, ncclFloat, h->rank + 1, h->comm, s));
+            NC(h, g_nccl.Recv(grid1 + h->Gg, (size_t)h->ext_rows * h->W, ncclFloat, h->rank + 1, h->comm, s));
         }
         NC(h, g_nccl.GroupEnd());
     }
@@ -863,7 +871,8 @@ static int enqueue_step(psm_handle* h, bool host, const double* in, double* out)
 static int submit_step(psm_handle* h, bool host, const double* in, double* out) {
     h->last_host = host;
     if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
-    if (!h->use_graphs || h->ev_valid) {             // per-stage events are recorded eagerly only
+    if (!h->use_graphs || h->ev_valid || h->eager_steps > 0) {   // per-stage events are recorded eagerly only
+        if (h->eager_steps > 0) --h->eager_steps;
         TRY(enqueue_step(h, host, in, out));
     } else {
         psm_handle::StepGraph& g = host ? h->g_host : h->g_dev;
@@ -950,7 +959,7 @@ extern "C" int psm_get_geometry(const psm_handle* h, psm_geometry* g) {
     g->grid_h = P.H; g->grid_w = P.W; g->shape = P.S; g->overlap = P.ov; g->n_x = P.n_x; g->n_y = P.n_y;
     g->p_i = P.p_i; g->p_j = P.p_j; g->n_blocks = P.B; g->n_fields = P.F; g->n_cells = h->n_cells;
     g->n_tasks = (int32_t)P.tasks.size(); g->reserved = 0;
-    g->row0 = h->row0; g->row1 = h->row1; g->ext_rows = h->ext_rows; g->first_block = h->kb0; g->n_local_blocks = h->B;
+    g->row0 = h->row0; g->row1 = h->row1; g->ext_rows = h->ext_rows + h->local_ext; g->first_block = h->kb0; g->n_local_blocks = h->B;
     g->world = h->world; g->n_ghost_cells = h->n_ghost; g->n_ghost_pix = h->n_ghost_pix;
     return PSM_OK;
 }
@@ -1001,7 +1010,7 @@ extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_
     };
     switch (stage) {
         case PSM_STAGE_GRID: {
-            const int64_t gl = (int64_t)(h->H + h->ext_rows) * h->W;
+            const int64_t gl = (int64_t)(h->H + h->local_ext + h->ext_rows) * h->W;
             TRY(need(2 * gl * 4));
             CU(h, cudaMemcpy(out, h->d_grid, gl * 4, cudaMemcpyDeviceToHost));
             CU(h, cudaMemcpy((char*)out + gl * 4, h->d_grid + h->grid_stride, gl * 4, cudaMemcpyDeviceToHost));

@@ -65,7 +65,7 @@ class PsmGeometry(C.Structure):
 class PsmShard(C.Structure):
     _fields_ = [('rank', C.c_int32), ('world', C.c_int32), ('grid_h', C.c_int32), ('grid_w', C.c_int32),
                 ('row0', C.c_int32), ('row1', C.c_int32), ('ext_rows', C.c_int32), ('send_rows', C.c_int32),
-                ('blk_row0', C.c_int32), ('blk_row1', C.c_int32), ('reserved', C.c_int32),
+                ('blk_row0', C.c_int32), ('blk_row1', C.c_int32), ('local_ext_rows', C.c_int32),
                 ('mask_global', c_uint8_p),
                 ('n_owned', C.c_int64), ('n_ghost', C.c_int64), ('n_ghost_pix', C.c_int64),
                 ('vert', c_int32_p), ('weights', c_double_p), ('sdfunct', c_double_p),

@@ -189,6 +189,7 @@ class PressureSurrogate:
         T.rank, T.world, T.grid_h, T.grid_w = int(sh['rank']), int(sh['world']), int(sh['H']), int(sh['W'])
         T.row0, T.row1, T.ext_rows, T.send_rows = int(sh['row0']), int(sh['row1']), int(sh['ext_rows']), int(sh['send_rows'])
         T.blk_row0, T.blk_row1 = int(sh['blk_row0']), int(sh['blk_row1'])
+        T.local_ext_rows = int(sh.get('local_ext_rows', 0))
         T.n_owned, T.n_ghost, T.n_ghost_pix = int(sh['n_owned']), int(sh['n_ghost']), int(sh['n_ghost_pix'])
         keep = []
 
@@ -209,7 +210,7 @@ class PressureSurrogate:
         self._check(self.lib.psm_init_sharded(self._h, C.byref(T)))
         self.n_cells, self.W = T.n_owned, T.grid_w
         self.H = T.row1 - T.row0
-        self.H_ext = self.H + T.ext_rows
+        self.H_ext = self.H + T.ext_rows + T.local_ext_rows
         self.H_global = T.grid_h
         g = self.geometry()
         self.n_blocks = g['n_blocks']

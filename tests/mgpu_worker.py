@@ -36,6 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--variant', default='deltaU_to_deltaP')
     ap.add_argument('--near-wall', type=float, default=0.0)
+    ap.add_argument('--halo', default='cells', choices=['cells', 'grid'])
     args = ap.parse_args()
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', rank))
@@ -49,7 +50,7 @@ def main():
                              n_out_channels=1 if deltas else 2,
                              maxs=syn.DEFAULT_MAXS if deltas else (1.0, 0.536, 0.999, 0.8, 0.7))
     tables = ptables.build_tables(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'], variant=variant)
-    shards = pshard.partition(tables, mesh['cells'], world, variant=variant, near_wall_sdf=args.near_wall)
+    shards = pshard.partition(tables, mesh['cells'], world, variant=variant, near_wall_sdf=args.near_wall, halo=args.halo)
     sh = shards[rank]
     cells = syn.pack_cells(mesh, F, with_delta=deltas)
 
@@ -60,7 +61,7 @@ def main():
     sm.comm_init(ids[0], rank, world)
     sm.init_shard(sh)
     out = None
-    for _ in range(3):                          # repeated steps: the exchange buffers are reused
+    for _ in range(5):                          # repeated steps: eager first, then the captured graph
         out, rc = sm.predict(cells[sh['owned_ids']])
     offsets = sm.stage('offsets')
     field = sm.stage('field')

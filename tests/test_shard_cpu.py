@@ -68,17 +68,18 @@ def test_block_row_split_rejects_too_many_ranks():
 def test_partition_is_a_relabelling_of_the_global_tables(variant, world):
     mesh, F, params, t = make_case(variant)
     H, W = t['H'], t['W']
-    shards = pshard.partition(t, mesh['cells'], world, variant=variant)
+    shards = pshard.partition(t, mesh['cells'], world, variant=variant, halo='grid' if world == 3 else 'cells')
     fv, fw = pshard.fold_forward_table(t['vert'], t['weights'], t['indices'], H, W)
     bv, keep = pshard.hop_back_table(t['vert_back'], t['weights_back'], t['indices'], t['sdfunct'], W)
     owned_all = np.concatenate([s['owned_ids'] for s in shards])
     assert np.array_equal(np.sort(owned_all), np.arange(t['n_cells']))          # every cell owned exactly once
     for s in shards:
         q0, q1 = s['row0'] * W, s['row1'] * W
+        qg = q1 + s['local_ext_rows'] * W
         l2g = np.concatenate([s['owned_ids'], s['ghost_ids']])
         live = np.any(s['weights'] != 0, axis=1)
-        assert np.array_equal(l2g[s['vert']][live], fv[q0:q1][live])
-        assert np.array_equal(s['weights'], fw[q0:q1])
+        assert np.array_equal(l2g[s['vert']][live], fv[q0:qg][live])
+        assert np.array_equal(s['weights'], fw[q0:qg])
         pix_l2g = np.concatenate([np.arange(q0, q1), s['ghost_pix']])
         k = keep[s['owned_ids']]
         assert np.array_equal(s['vert_back'][:, 0] < 0, k)
@@ -114,7 +115,7 @@ def _exchange(send_arrays, recv_counts, width, rank, world):
     return np.concatenate([np.asarray(b) for b in recv])
 
 
-def _rank_step(rank, world, port, variant, q):
+def _rank_step(rank, world, port, variant, q, halo='cells'):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -123,7 +124,7 @@ def _rank_step(rank, world, port, variant, q):
         mesh, F, params, t = make_case(variant)
         ov = 32 if deltas else 96
         P = oracle_params(params)
-        sh = pshard.partition(t, mesh['cells'], world, variant=variant)[rank]
+        sh = pshard.partition(t, mesh['cells'], world, variant=variant, halo=halo)[rank]
         H, W, S = sh['H'], sh['W'], 128
         own = sh['owned_ids']
         # ---- exchange 1: max|U|^2 and ghost cells -------------------------------------------------
@@ -138,7 +139,7 @@ def _rank_step(rank, world, port, variant, q):
         uv = np.concatenate([fld, ghosts]) / U_max_norm
         # ---- gather own rows, then exchange 2: the overlap strip --------------------------------------
         r0, r1, ext = sh['row0'], sh['row1'], sh['ext_rows']
-        g = np.einsum('qjc,qj->qc', uv[sh['vert']], sh['weights']).reshape(r1 - r0, W, 2)
+        g = np.einsum('qjc,qj->qc', uv[sh['vert']], sh['weights']).reshape(r1 - r0 + sh['local_ext_rows'], W, 2)
         g = np.nan_to_num(g, nan=0.0) / np.array([P.maxs[0], P.maxs[1]])
         reqs = []
         if sh['send_rows']:
@@ -229,12 +230,13 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("variant,world", [('deltaU_to_deltaP', 2), ('U_to_gradP', 2), ('deltaU_to_deltaP', 3)])
-def test_sharded_step_over_gloo_equals_unsharded_oracle(variant, world):
+@pytest.mark.parametrize("variant,world,halo", [('deltaU_to_deltaP', 2, 'cells'), ('U_to_gradP', 2, 'cells'),
+                                                ('deltaU_to_deltaP', 3, 'grid')])
+def test_sharded_step_over_gloo_equals_unsharded_oracle(variant, world, halo):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_step, args=(r, world, port, variant, q)) for r in range(world)]
+    procs = [ctx.Process(target=_rank_step, args=(r, world, port, variant, q, halo)) for r in range(world)]
     for p in procs:
         p.start()
     gathered = q.get(timeout=600)
@@ -264,3 +266,36 @@ def test_sharded_step_over_gloo_equals_unsharded_oracle(variant, world):
     np.testing.assert_allclose(fld, ref_f, rtol=0, atol=2e-5 * scale)       # float32 Dense stack on both sides
     assert np.array_equal(np.isnan(full), np.isnan(ref))
     np.testing.assert_allclose(full, ref, rtol=0, atol=2e-5 * scale, equal_nan=True)
+
+
+@pytest.mark.parametrize("variant,world", [('deltaU_to_deltaP', 2), ('deltaU_to_deltaP', 3), ('U_to_gradP', 2)])
+def test_band_local_shards_equal_partition_of_global_tables(variant, world):
+    """Triangulating only a band of cells per rank gives the same shard as cutting the global tables
+    (same simplices; Qhull may list a simplex's vertices in another order, so entries are compared
+    after sorting by cell id; weights to round-off)."""
+    deltas = variant == 'deltaU_to_deltaP'
+    mesh = syn.make_mesh(seed=5, **MESHES[variant])
+    F = syn.make_fields(mesh, seed=5)
+    t = ptables.build_tables(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'], variant=variant, back='closed_form')
+    ref = pshard.partition(t, mesh['cells'], world, variant=variant, near_wall_sdf=0.05 if deltas else 0.0)
+    got = pshard.build_band_shards_serial(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'], world, variant=variant,
+                                          near_wall_sdf=0.05 if deltas else 0.0)
+
+    def canon(v, w):
+        o = np.argsort(v, axis=1, kind='stable')
+        return np.take_along_axis(v, o, 1), np.take_along_axis(w, o, 1)
+    for a, b in zip(ref, got):
+        for k in ('rank', 'world', 'H', 'W', 'row0', 'row1', 'ext_rows', 'send_rows', 'blk_row0', 'blk_row1', 'n_owned',
+                  'n_ghost', 'n_ghost_pix', 'local_ext_rows'):
+            assert a[k] == b[k], k
+        for k in ('mask_global', 'owned_ids', 'ghost_ids', 'ghost_pix', 'cell_send_ptr', 'cell_send_idx', 'cell_recv_ptr',
+                  'pix_send_ptr', 'pix_send_idx', 'pix_recv_ptr', 'vert_back'):
+            assert np.array_equal(a[k], b[k]), k
+        np.testing.assert_allclose(a['sdfunct'], b['sdfunct'], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(a['weights_back'], b['weights_back'], rtol=0, atol=0)
+        va, wa = canon(a['vert'], a['weights'])
+        vb, wb = canon(b['vert'], b['weights'])
+        live = np.any(wa != 0, axis=1)
+        assert np.array_equal(live, np.any(wb != 0, axis=1))
+        assert np.array_equal(va[live], vb[live])
+        np.testing.assert_allclose(wa, wb, rtol=0, atol=1e-11)
