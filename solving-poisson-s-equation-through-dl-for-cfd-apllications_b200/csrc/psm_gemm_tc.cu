@@ -261,6 +261,197 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dense layer (NNS:24-33) as ONE launch: cluster split-K with an on-chip reduction.
+// The batch is only B blocks (one or a few 128-row tiles), so a layer is latency-bound: it is cut into
+// 64-column tiles x KS K-slices, the KS CTAs of a tile form a thread-block cluster, every CTA runs the
+// TMA -> 3xTF32 split -> tcgen05.mma pipeline over its K-slice, parks its partial accumulator in its
+// own shared memory, and after a cluster barrier CTA z folds rows [z*128/KS, (z+1)*128/KS) of all KS
+// partials through distributed shared memory (fixed order: deterministic), applies bias + ReLU (or
+// bias + de-standardisation, SMC:533) and stores coalesced rows.  No partials in HBM, no reduce kernel.
+namespace {
+constexpr int D_BN = 64;
+constexpr int D_STAGES = 2;
+constexpr int D_A_BYTES = BM * BK * 4, D_B_BYTES = D_BN * BK * 4, D_STAGE = 2 * (D_A_BYTES + D_B_BYTES);
+constexpr int D_PARK = BM * (D_BN + 1) * 4;            // partial accumulator, row stride 65 floats (bank-conflict free)
+constexpr int D_SMEM = D_STAGES * D_STAGE + D_PARK + 1024 + 256;
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(uint32_t local_addr, uint32_t cta) {
+    uint32_t remote; float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+    return v;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcGemmArgs g) {
+    constexpr int BN = D_BN, STAGES = D_STAGES, A_BYTES = D_A_BYTES, B_BYTES = D_B_BYTES, STAGE = D_STAGE;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t park = base + STAGES * STAGE;
+    const uint32_t bars = park + D_PARK;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto conv_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (3 * STAGES);
+    const uint32_t tmem_slot = accum_bar + 8u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KS = gridDim.z;                                    // cluster = (1,1,KS): rank in cluster = blockIdx.z
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kb_total = g.K / BK;
+    const int kb_per = (kb_total + KS - 1) / KS;
+    const int kb0 = blockIdx.z * kb_per;
+    const int kb1 = min(kb_total, kb0 + kb_per);
+    const int nkb = max(kb1 - kb0, 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1);
+                mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
+                const uint32_t st = base + s * STAGE;
+                tma_load_2d(st, &tmA, (kb0 + it) * BK, m0, full_bar(s));
+                tma_load_2d(st + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(s));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(BM, BN);
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(g.three_pass ? conv_bar(s) : full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * STAGE;
+                const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t ko = k * UMMA_K * 4;
+                    umma_tf32(tmem_base, make_smem_desc(a_hi + ko), make_smem_desc(b_hi + ko), idesc, (it | k) != 0);
+                    if (g.three_pass) {
+                        umma_tf32(tmem_base, make_smem_desc(a_hi + ko), make_smem_desc(b_lo + ko), idesc, 1);
+                        umma_tf32(tmem_base, make_smem_desc(a_lo + ko), make_smem_desc(b_hi + ko), idesc, 1);
+                    }
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    } else {
+        const int t = threadIdx.x - 64;
+        if (g.three_pass) {
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                uint8_t* st = gen_base + s * STAGE;
+                float4* a_hi = reinterpret_cast<float4*>(st);
+                float4* a_lo = reinterpret_cast<float4*>(st + A_BYTES);
+                float4* b_hi = reinterpret_cast<float4*>(st + 2 * A_BYTES);
+                float4* b_lo = reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES);
+                auto split4 = [](float4 v, float4& hi, float4& lo) {
+                    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+                    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+                };
+#pragma unroll 4
+                for (int j = t; j < A_BYTES / 16; j += 128) { float4 hi, lo; split4(a_hi[j], hi, lo); a_hi[j] = hi; a_lo[j] = lo; }
+#pragma unroll 4
+                for (int j = t; j < B_BYTES / 16; j += 128) { float4 hi, lo; split4(b_hi[j], hi, lo); b_hi[j] = hi; b_lo[j] = lo; }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(conv_bar(s));
+            }
+        }
+        // park the partial accumulator: thread <-> row (TMEM lane), row stride 65 floats
+        if (nkb > 0) {
+            mbar_wait(accum_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        float* prow = reinterpret_cast<float*>(gen_base + (park - base)) + row * (BN + 1);
+        for (int c = 0; c < BN; c += 16) {
+            float v[16];
+            if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) prow[c + i] = v[i];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                          // all KS partials are parked
+    {
+        // CTA z folds rows [z*rows_per, ...) of the tile: 192 threads, one (row, column) per thread per pass
+        const int rows_per = BM / KS;
+        const int r_lo = blockIdx.z * rows_per;
+        for (int e = threadIdx.x; e < rows_per * BN; e += kThreads) {
+            const int r = r_lo + e / BN, c = e % BN;
+            const uint32_t addr = park + (uint32_t)(r * (BN + 1) + c) * 4u;
+            float acc = 0.f;
+            for (int z = 0; z < KS; ++z) acc += ld_dsmem(addr, (uint32_t)z);
+            const int n = n0 + c, m = m0 + r;
+            float o;
+            if (g.epi == EPI_BIAS_RELU) o = fmaxf(acc + __ldg(g.v0 + n), 0.f);
+            else o = (acc + __ldg(g.v0 + n)) * __ldg(g.v1 + n) + __ldg(g.v2 + n);
+            if (m < g.M) g.C[(size_t)m * g.ldc + n] = o;
+        }
+    }
+    cluster_sync_all();                                          // nobody leaves while its shared memory is being read
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+int dense_cluster_prepare() {
+    return cudaFuncSetAttribute(dense_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D_SMEM) == cudaSuccess ? 0 : -1;
+}
+
+// t.args.splits = KS (1, 2, 4 or 8: the cluster size along z); epi = EPI_BIAS_RELU or EPI_BIAS_AFFINE
+int launch_dense_cluster(const TcGemm& t, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(t.args.N / D_BN, (t.args.M + BM - 1) / BM, t.args.splits);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = D_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = t.args.splits;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(&t.mapA);
+    const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(&t.mapB);
+    return cudaLaunchKernelEx(&cfg, dense_cluster_kernel, a, b, t.args) == cudaSuccess ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side: tensor maps (driver entry point fetched through the runtime: no link-time libcuda).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

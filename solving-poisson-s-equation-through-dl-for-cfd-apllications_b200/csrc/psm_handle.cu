@@ -126,6 +126,7 @@ struct psm_handle {
     Scalars* d_sc = nullptr; Scalars* h_sc = nullptr;
     TcGemm tc_proj{}, tc_inv{}; std::vector<TcGemm> tc_dense; std::vector<int> dense_splits; int tc_splits = 1;
     float* d_dpart = nullptr;       // split-K partials of the Dense layers   // tcgen05 path (gemm_mode 0/1)
+    bool dense_cluster = true;      // Dense layers: cluster split-K with on-chip reduction (one launch per layer)
     int launches = 0;
     cudaEvent_t ev[PSM_N_TIMINGS + 1] = {};
     bool ev_valid = false, ev_created = false;
@@ -243,13 +244,14 @@ extern "C" int psm_load_params(psm_handle* h, const psm_params* p) {
     if (p->standardization == PSM_STD && (!p->mean_in || !p->std_in || !p->mean_out || !p->std_out)) PSM_FAIL(h, PSM_ERR_INVALID, "PSM_STD needs mean/std arrays");
     h->C = C; h->F = C; h->pc_in = p->pc_in; h->pc_p = p->pc_p; h->n_dense = p->n_dense; h->standardization = p->standardization;
     memcpy(h->maxs, p->maxs, sizeof h->maxs);
-    h->pc_in_pad = round_up(p->pc_in, 64);
-    h->pc_p_pad = round_up(p->pc_p, 64);
+    // widths are padded to 128: the fused Dense kernel gives each of the 8 CTAs of a cluster N/8 (>= 16) columns
+    h->pc_in_pad = round_up(p->pc_in, 128);
+    h->pc_p_pad = round_up(p->pc_p, 128);
     h->dims.assign(p->layer_dims, p->layer_dims + p->n_dense + 1);
     h->dims_pad.resize(h->dims.size());
     for (size_t i = 0; i < h->dims.size(); ++i) {
         if (h->dims[i] < 1) PSM_FAIL(h, PSM_ERR_INVALID, "layer width < 1");
-        h->dims_pad[i] = round_up(h->dims[i], 64);
+        h->dims_pad[i] = round_up(h->dims[i], 128);
     }
     const int Kin = S2 * 3, Kout = S2 * C;
 
@@ -535,6 +537,8 @@ static int init_local(psm_handle* h, LocalInit& L) {
         // 64-column tiles x split-K partials (each CTA streams <= ~100 KB), folded by the reduce kernel.
         h->tc_dense.resize(h->n_dense);
         h->dense_splits.assign(h->n_dense, 1);
+        h->dense_cluster = !getenv("PSM_NO_DENSE_CLUSTER");
+        if (h->dense_cluster && dense_cluster_prepare() != 0) PSM_FAIL(h, PSM_ERR_CUDA, "cannot opt in to the shared memory of the Dense cluster kernel");
         TRY(dalloc(h, &h->d_dpart, (size_t)8 * Bp * maxw));
         const float* in = h->d_xin;
         for (int l = 0; l < h->n_dense; ++l) {
@@ -542,6 +546,16 @@ static int init_local(psm_handle* h, LocalInit& L) {
             float* outp = last ? h->d_r : h->d_act[l & 1];
             const int kb = h->dims_pad[l] / 32;
             const int tiles = (Bp / 128) * (h->dims_pad[l + 1] / 64);
+            if (h->dense_cluster) {
+                // K-slices per tile = cluster size: as many as keep the grid within ~2 waves, at most one k-block each
+                int ks = 8;
+                while (ks > 1 && (ks > kb || tiles * ks > 2 * 148)) ks >>= 1;
+                h->dense_splits[l] = ks;
+                TRY(mk(h->tc_dense[l], in, Bp, h->d_W[l], h->dims_pad[l + 1], h->dims_pad[l], outp, h->dims_pad[l + 1], ks,
+                       last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU, h->d_bias[l], h->d_out_s, h->d_out_m, 64));
+                in = outp;
+                continue;
+            }
             int sp = (tiles >= 96) ? 1 : (kb >= 16 ? 4 : (kb >= 4 ? 2 : 1));
             const int per = (kb + sp - 1) / sp;
             sp = (kb + per - 1) / per;
@@ -778,7 +792,12 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         launch_reduce_standardise(r, s); ++nl;
     }
     tick();   // pca_project
-    {
+    if (tc && h->dense_cluster) {
+        for (int l = 0; l < h->n_dense; ++l) {
+            if (launch_dense_cluster(h->tc_dense[l], s) != 0) PSM_FAIL(h, PSM_ERR_CUDA, "Dense cluster launch: %s", cudaGetErrorString(cudaGetLastError()));
+            ++nl;
+        }
+    } else {
         const float* in = h->d_xin;
         for (int l = 0; l < h->n_dense; ++l) {
             const bool last = (l == h->n_dense - 1);

@@ -91,6 +91,11 @@ int tc_gemm_bn(int N);
 int tc_gemm_prepare();
 void launch_tc_gemm(const TcGemm& t, cudaStream_t s);
 
+// Dense layer in one launch: cluster split-K + distributed-shared-memory reduction + fused epilogue
+// (psm_gemm_tc.cu).  t.args.splits = cluster size along K (1, 2, 4 or 8); N % 64 == 0.
+int dense_cluster_prepare();
+int launch_dense_cluster(const TcGemm& t, cudaStream_t s);
+
 // Split-K reduction + per-block constant + standardisation (SMC:494,512).
 // Also the split-K epilogue of the Dense layers: relu(sum + bias[n]) or (sum + bias[n]) * s[n] + m[n].
 enum ReduceKind { RED_STANDARDISE = 0, RED_BIAS_RELU = 1, RED_BIAS_AFFINE = 2 };

@@ -266,3 +266,26 @@ def test_linearity_of_assembly_in_block_constants(deltas_case):
     o1, _ = c.sm.predict(c.cells)
     o2, _ = c.sm.predict(c.cells)
     np.testing.assert_array_equal(o1, o2)
+
+
+def test_cluster_dense_layers_equal_split_k_gemms_on_several_batch_tiles(monkeypatch):
+    """The cluster split-K Dense kernel (DSMEM reduction, fused epilogue) against the split-K GEMM + reduce kernels
+    and the oracle, on a mesh with more than 128 blocks (two 128-row batch tiles => two clusters)."""
+    c = Case('U_to_gradP', dict(H=500, W=420, nx=150, ny=180, R=0.1), seed=9, pc_in=45, pc_p=48)
+    try:
+        assert c.sm.geometry()['n_blocks'] > 128
+        c.sm.predict(c.cells)
+        fused = c.sm.stage('mlp_out')
+        monkeypatch.setenv('PSM_NO_DENSE_CLUSTER', '1')
+        with psm_b200.PressureSurrogate('U_to_gradP') as sm:
+            sm.load_params(c.params)
+            sm.init_tables(c.tables)
+            sm.predict(c.cells)
+            layered = sm.stage('mlp_out')
+        r = c.oracle.time_step(c.F['Ux'], c.F['Uy'])
+        P = c.oracle.params
+        want = r['mlp_out'] * P.max_abs_output_PCA
+        assert rel_l2(fused, layered) < 2e-5
+        assert rel_l2(fused, want) < 1e-4
+    finally:
+        c.sm.close()
