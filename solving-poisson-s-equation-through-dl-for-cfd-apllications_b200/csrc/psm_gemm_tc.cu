@@ -123,6 +123,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_slot = accum_bar + 8u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));   // generic pointer to the aligned base
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int kb_total = g.K / BK;
@@ -144,6 +145,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+    pdl_wait();                                                  // barriers + TMEM are set up while the previous kernel drains
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -301,6 +303,7 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const uint32_t tmem_slot = accum_bar + 8u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KS = gridDim.z;                                    // cluster = (1,1,KS): rank in cluster = blockIdx.z
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -323,6 +326,7 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+    pdl_wait();                                                  // barriers + TMEM are set up while the previous kernel drains
 
     if (warp == 0) {
         if (lane == 0) {
@@ -442,10 +446,12 @@ int launch_dense_cluster(const TcGemm& t, cudaStream_t s) {
     cfg.blockDim = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = D_SMEM;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = t.args.splits;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(&t.mapA);
     const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(&t.mapB);
     return cudaLaunchKernelEx(&cfg, dense_cluster_kernel, a, b, t.args) == cudaSuccess ? 0 : -1;
@@ -496,8 +502,8 @@ void launch_tc_gemm(const TcGemm& t, cudaStream_t s) {
     dim3 grid(t.args.N / bn, (t.args.M + BM - 1) / BM, t.args.splits);
     const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(&t.mapA);
     const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(&t.mapB);
-    if (bn == 128) tc_gemm_kernel<128><<<grid, kThreads, Cfg<128>::SMEM_TOTAL, s>>>(a, b, t.args);
-    else tc_gemm_kernel<64><<<grid, kThreads, Cfg<64>::SMEM_TOTAL, s>>>(a, b, t.args);
+    if (bn == 128) launch_k(tc_gemm_kernel<128>, grid, dim3(kThreads), Cfg<128>::SMEM_TOTAL, s, a, b, t.args);
+    else launch_k(tc_gemm_kernel<64>, grid, dim3(kThreads), Cfg<64>::SMEM_TOTAL, s, a, b, t.args);
 }
 
 }  // namespace psm

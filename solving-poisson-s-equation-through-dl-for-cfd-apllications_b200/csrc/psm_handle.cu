@@ -123,7 +123,8 @@ struct psm_handle {
     float* d_xin = nullptr; float* d_act[2] = {nullptr, nullptr}; float* d_r = nullptr; float* d_blocks = nullptr;
     double* d_means = nullptr; double* d_dbuf[2] = {nullptr, nullptr}; int32_t* d_pbuf[2] = {nullptr, nullptr};
     double* d_offsets = nullptr; float* d_coff = nullptr; float* d_field = nullptr;
-    Scalars* d_sc = nullptr; Scalars* h_sc = nullptr;
+    Scalars* d_sc = nullptr; Scalars* h_sc = nullptr;   // h_sc: mapped pinned host memory, only .skip is written by the device
+    int* d_host_skip = nullptr;
     TcGemm tc_proj{}, tc_inv{}; std::vector<TcGemm> tc_dense; std::vector<int> dense_splits; int tc_splits = 1;
     float* d_dpart = nullptr;       // split-K partials of the Dense layers   // tcgen05 path (gemm_mode 0/1)
     bool dense_cluster = true;      // Dense layers: cluster split-K with on-chip reduction (one launch per layer)
@@ -133,8 +134,9 @@ struct psm_handle {
     bool last_host = false;
     // whole-step CUDA graphs, keyed by the caller's buffers (the solver passes the same ones every step,
     // FOAM/PythonComm_init.H:53)
-    struct StepGraph { const void* in = nullptr; void* out = nullptr; cudaGraphExec_t exec = nullptr; };
-    StepGraph g_dev, g_host;
+    struct StepGraph { const void* in = nullptr; void* out = nullptr; bool host = false, timed = false; cudaGraphExec_t exec = nullptr; unsigned long long used = 0; };
+    StepGraph graphs[4];             // small LRU: a solver alternates between at most a few buffer pairs
+    unsigned long long graph_clock = 0;
     bool use_graphs = true;
     int eager_steps = 0;
 };
@@ -207,8 +209,13 @@ extern "C" int psm_create(psm_handle** out, const psm_config* cfg) {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e); delete h; return PSM_ERR_CUDA;
     }
-    if (cudaMallocHost((void**)&h->h_sc, sizeof(Scalars)) != cudaSuccess) { g_create_error = "cudaMallocHost failed"; cudaStreamDestroy(h->stream); delete h; return PSM_ERR_CUDA; }
+    if (cudaHostAlloc((void**)&h->h_sc, sizeof(Scalars), cudaHostAllocMapped) != cudaSuccess) { g_create_error = "cudaMallocHost failed"; cudaStreamDestroy(h->stream); delete h; return PSM_ERR_CUDA; }
     memset(h->h_sc, 0, sizeof(Scalars));
+    {
+        void* dp = nullptr;
+        if (cudaHostGetDevicePointer(&dp, &h->h_sc->skip, 0) != cudaSuccess) { g_create_error = "cudaHostGetDevicePointer failed"; cudaFreeHost(h->h_sc); cudaStreamDestroy(h->stream); delete h; return PSM_ERR_CUDA; }
+        h->d_host_skip = static_cast<int*>(dp);
+    }
     *out = h;
     return PSM_OK;
 }
@@ -217,8 +224,7 @@ extern "C" int psm_destroy(psm_handle* h) {
     if (!h) return PSM_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->g_dev.exec) cudaGraphExecDestroy(h->g_dev.exec);
-    if (h->g_host.exec) cudaGraphExecDestroy(h->g_host.exec);
+    for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->ev_created) for (auto& e : h->ev) cudaEventDestroy(e);
@@ -754,11 +760,10 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         NC(h, g_nccl.GroupEnd());
     }
     ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], deltas ? h->maxs[3] : 1.0, deltas ? 1 : 0, h->cfg.skip_threshold, mode};
-    launch_scalars(sa, s); ++nl;
     tick();   // prep
     float* grid0 = h->d_grid; float* grid1 = h->d_grid + h->grid_stride;
     GatherArgs ga{h->d_fv[0], h->d_fv[1], h->d_fv[2], h->d_fw[0], h->d_fw[1], h->d_fw[2], h->d_uv,
-                  grid0, grid1, h->G_pad / 4, h->d_sc};
+                  grid0, grid1, h->G_pad / 4, sa};
     launch_gather(ga, s); ++nl;
     if (multi && (h->ext_rows || h->send_rows)) {
         // exchange 2: the overlap strip -- the first rows of rank+1 complete this rank's last block row
@@ -831,7 +836,7 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     tick();   // pca_inverse
     MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->C, S, h->W, multi ? h->d_means_loc : h->d_means,
                  h->d_rows, h->n_rows, h->d_row_start, h->d_row_sums};
-    launch_means(ma, s); nl += 2;
+    launch_means(ma, s, multi); nl += multi ? 2 : 1;
     if (multi)   // exchange 3: every rank contributes its own slots (zero elsewhere) -> identical means everywhere
         NC(h, g_nccl.AllReduce(h->d_means_loc, h->d_means, (size_t)h->n_tasks_glob, ncclDouble, ncclSum, h->comm, s));
     tick();   // strip_means
@@ -843,6 +848,9 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         for (int f = 0; f < 3; ++f) oa.term_start[f] = h->term_start[f];
         for (int f = 0; f < 2; ++f) oa.shift_len[f] = h->plan.shift_len[f];
         oa.sc = h->d_sc;
+        oa.tasks = h->d_tasks; oa.n_fold_tasks = multi ? 0 : h->n_tasks; oa.row_start = h->d_row_start; oa.row_sums = h->d_row_sums;
+        oa.means_out = h->d_means;
+        oa.host_skip = h->d_host_skip;
         launch_offsets(oa, s); ++nl;
     }
     tick();   // offsets
@@ -883,38 +891,42 @@ static int enqueue_step(psm_handle* h, bool host, const double* in, double* out)
     } else {
         TRY(run_step(h, in, out));
     }
-    CU(h, cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost, h->stream));
-    return PSM_OK;
+    return PSM_OK;     // the step's status word reaches the host through mapped memory (offsets_kernel)
 }
 
 static int submit_step(psm_handle* h, bool host, const double* in, double* out) {
     h->last_host = host;
     if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
-    if (!h->use_graphs || h->ev_valid || h->eager_steps > 0) {   // per-stage events are recorded eagerly only
+    if (!h->use_graphs || h->ev_valid || h->eager_steps > 0) {   // per-stage events: eager launches (event nodes of a graph carry no usable timestamps)
         if (h->eager_steps > 0) --h->eager_steps;
         TRY(enqueue_step(h, host, in, out));
     } else {
-        psm_handle::StepGraph& g = host ? h->g_host : h->g_dev;
-        if (!g.exec || g.in != in || g.out != out) {
-            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        psm_handle::StepGraph* g = nullptr;
+        for (auto& c : h->graphs)
+            if (c.exec && c.in == in && c.out == out && c.host == host && c.timed == h->ev_valid) g = &c;
+        if (!g) {
+            g = &h->graphs[0];
+            for (auto& c : h->graphs) if (!c.exec) { g = &c; break; } else if (c.used < g->used) g = &c;
+            if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
             cudaGraph_t graph = nullptr;
             CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
             int rc = enqueue_step(h, host, in, out);
             cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
-            if (rc == PSM_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g.exec, graph, 0);
+            if (rc == PSM_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, graph, 0);
             if (graph) cudaGraphDestroy(graph);
             if (rc != PSM_OK || e != cudaSuccess) {
                 // e.g. a pageable host buffer that cannot be captured: same kernels, launched one by one
-                g.exec = nullptr;
+                g->exec = nullptr;
                 cudaGetLastError();
                 h->use_graphs = false;
                 TRY(enqueue_step(h, host, in, out));
                 if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
                 return PSM_OK;
             }
-            g.in = in; g.out = out;
+            g->in = in; g->out = out; g->host = host; g->timed = h->ev_valid;
         }
-        CU(h, cudaGraphLaunch(g.exec, h->stream));
+        g->used = ++h->graph_clock;
+        CU(h, cudaGraphLaunch(g->exec, h->stream));
     }
     if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
     return PSM_OK;

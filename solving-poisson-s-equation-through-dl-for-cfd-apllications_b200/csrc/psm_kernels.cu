@@ -5,9 +5,16 @@
 
 #include <math_constants.h>
 
+#include <cstdlib>
+
 namespace psm {
 
 static constexpr int kSMs = 148;
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("PSM_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
 
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
@@ -25,24 +32,31 @@ __device__ __forceinline__ double warp_sum(double v) {
 //     running max of |U|^2 and |dU|^2.   PMP:267-273, SMC:386-405.
 //     The squares/sum are rounded separately (no FMA) so that U_max_norm is bit-identical to
 //     np.max(np.sqrt(np.square(Ux) + np.square(Uy))).
+template <int MODE, int NCOL>
 __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
+    pdl_enter();
+    const double* __restrict__ cells = a.cells;
+    double* __restrict__ p_prev = a.p_prev;
+    float2* __restrict__ uv = a.uv;
+    double2* __restrict__ u_prev = reinterpret_cast<double2*>(a.u_prev);
     double m_u = 0.0, m_d = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
-        const double* row = a.cells + i * a.ncol;
-        const double ux = row[0], uy = row[1];
-        a.p_prev[i] = row[4];
-        m_u = fmax(m_u, __dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)));
+        const double* row = cells + i * NCOL;
+        // all loads of the row first (independent), then the arithmetic
+        const double ux = __ldcs(row + 0), uy = __ldcs(row + 1), pp = __ldcs(row + 4);
         double fx, fy;
-        if (a.mode == 0) { fx = ux; fy = uy; }
-        else if (a.mode == 1) { fx = row[5]; fy = row[6]; }
+        if (MODE == 0) { fx = ux; fy = uy; }
+        else if (MODE == 1) { fx = __ldcs(row + 5); fy = __ldcs(row + 6); }
         else {
-            double2 prev = reinterpret_cast<double2*>(a.u_prev)[i];
+            const double2 prev = u_prev[i];
             fx = ux - prev.x; fy = uy - prev.y;
-            reinterpret_cast<double2*>(a.u_prev)[i] = make_double2(ux, uy);
+            u_prev[i] = make_double2(ux, uy);
         }
-        if (a.mode != 0) m_d = fmax(m_d, __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)));
-        a.uv[i] = make_float2((float)fx, (float)fy);
+        p_prev[i] = pp;
+        m_u = fmax(m_u, __dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)));
+        if (MODE != 0) m_d = fmax(m_d, __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)));
+        uv[i] = make_float2((float)fx, (float)fy);
     }
     m_u = warp_max(m_u);
     m_d = warp_max(m_d);
@@ -65,30 +79,10 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
 void launch_prep(const PrepArgs& a, cudaStream_t s) {
     long long want = (a.n + 255) / 256;
     int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
-    prep_kernel<<<blocks, 256, 0, s>>>(a);
+    if (a.mode == 0) launch_k(prep_kernel<0, 5>, dim3(blocks), dim3(256), 0, s, a);
+    else if (a.mode == 1) launch_k(prep_kernel<1, 7>, dim3(blocks), dim3(256), 0, s, a);
+    else launch_k(prep_kernel<2, 5>, dim3(blocks), dim3(256), 0, s, a);
 }
-
-// Scalars of the step (1 thread): U_max_norm, skip rule, scales; re-arms the running maxima.
-__global__ void scalars_kernel(ScalarArgs a) {
-    Scalars* sc = a.sc;
-    const double um = sqrt(__longlong_as_double((long long)sc->umax2_bits));
-    const double dm = sqrt(__longlong_as_double((long long)sc->dumax2_bits));
-    sc->U_max_norm = um;
-    sc->dU_max_norm = dm;
-    sc->in_scale[0] = (float)(1.0 / (um * a.max_abs_ux));
-    sc->in_scale[1] = (float)(1.0 / (um * a.max_abs_uy));
-    sc->out_scale = (float)(a.dimensionalise ? a.out_scale_base * um * um : a.out_scale_base);
-    int skip = 0;
-    if (a.mode != 0) {
-        if (a.skip_threshold > 0.0 && (dm / um) < a.skip_threshold) skip = 1;     // SMC:410-415
-        if (a.mode == 2 && !sc->have_prev) skip = 1;                              // no U(t-1) yet
-    }
-    sc->skip = skip;
-    sc->have_prev = 1;
-    sc->umax2_bits = 0ull;
-    sc->dumax2_bits = 0ull;
-}
-void launch_scalars(const ScalarArgs& a, cudaStream_t s) { scalars_kernel<<<1, 1, 0, s>>>(a); }
 
 // ------------------------------------------------------------------------------------------------
 // K1  cell -> grid gather.  UTL:88-89 (einsum over np.take), SMC:432-444 (scatter into the grid,
@@ -96,8 +90,29 @@ void launch_scalars(const ScalarArgs& a, cudaStream_t s) { scalars_kernel<<<1, 1
 //     quirk are folded into the tables at init, so this is a pure weighted gather.
 __device__ __forceinline__ float2 ldg_f2(const float2* p) { return __ldg(p); }
 
+// The step's scalars come straight from the running maxima of prep (all-reduced over ranks in the multi-GPU
+// path): every thread derives the two input scales itself; thread 0 publishes U_max_norm, the output scale
+// and the skip rule (SMC:404-419,551) for the later kernels.  The maxima are re-armed by offsets_kernel.
 __global__ void __launch_bounds__(256) gather_kernel(GatherArgs a) {
-    const float s0 = a.sc->in_scale[0], s1 = a.sc->in_scale[1];
+    pdl_enter();
+    Scalars* sc = a.sa.sc;
+    const double um = sqrt(__longlong_as_double((long long)sc->umax2_bits));
+    const float s0 = (float)(1.0 / (um * a.sa.max_abs_ux)), s1 = (float)(1.0 / (um * a.sa.max_abs_uy));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double dm = sqrt(__longlong_as_double((long long)sc->dumax2_bits));
+        sc->U_max_norm = um;
+        sc->dU_max_norm = dm;
+        sc->in_scale[0] = s0;
+        sc->in_scale[1] = s1;
+        sc->out_scale = (float)(a.sa.dimensionalise ? a.sa.out_scale_base * um * um : a.sa.out_scale_base);
+        int skip = 0;
+        if (a.sa.mode != 0) {
+            if (a.sa.skip_threshold > 0.0 && (dm / um) < a.sa.skip_threshold) skip = 1;     // SMC:410-415
+            if (a.sa.mode == 2 && !sc->have_prev) skip = 1;                                // no U(t-1) yet
+        }
+        sc->skip = skip;
+        sc->have_prev = 1;
+    }
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < a.n_pix4; g += stride) {
         const int4 i0 = __ldcs(reinterpret_cast<const int4*>(a.v0) + g);
@@ -127,13 +142,14 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs a) {
 void launch_gather(const GatherArgs& a, cudaStream_t s) {
     long long want = (a.n_pix4 + 255) / 256;
     int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
-    gather_kernel<<<blocks, 256, 0, s>>>(a);
+    launch_k(gather_kernel, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2  block extraction.  SMC:464-492: slices grid[y0:y0+S, x0:x0+S, 0:2] per plan entry; the
 //     operand is stored planar (c, ly, lx) -- the PCA matrix is permuted to match at init.
 __global__ void __launch_bounds__(256) extract_kernel(ExtractArgs a) {
+    pdl_enter();
     // one warp per (block, channel, row): 128 floats = 32 lanes x 4
     const int S = a.S;
     const long long rows = (long long)a.B * a.nch * S;
@@ -152,13 +168,14 @@ void launch_extract(const ExtractArgs& a, cudaStream_t s) {
     long long rows = (long long)a.B * a.nch * a.S;
     long long want = (rows + 7) / 8;
     int blocks = (int)(want < (long long)kSMs * 8 ? want : kSMs * 8);
-    extract_kernel<<<blocks, 256, 0, s>>>(a);
+    launch_k(extract_kernel, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
 // FP32 GEMM (CUDA cores), C = A * B^T, 64x64x16 tiles, 4x4 register blocking.
 template <int EPI>
 __global__ void __launch_bounds__(256) sgemm_nt_kernel(GemmArgs a) {
+    pdl_enter();
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -227,17 +244,18 @@ __global__ void __launch_bounds__(256) sgemm_nt_kernel(GemmArgs a) {
 void launch_sgemm(const GemmArgs& a, cudaStream_t s) {
     dim3 grid(a.N / 64, a.M / 64, a.epi == EPI_PARTIAL ? a.splits : 1);
     switch (a.epi) {
-        case EPI_PARTIAL:     sgemm_nt_kernel<EPI_PARTIAL><<<grid, 256, 0, s>>>(a); break;
-        case EPI_BIAS_RELU:   sgemm_nt_kernel<EPI_BIAS_RELU><<<grid, 256, 0, s>>>(a); break;
-        case EPI_BIAS_AFFINE: sgemm_nt_kernel<EPI_BIAS_AFFINE><<<grid, 256, 0, s>>>(a); break;
-        case EPI_PCA_INV:     sgemm_nt_kernel<EPI_PCA_INV><<<grid, 256, 0, s>>>(a); break;
-        default:              sgemm_nt_kernel<EPI_PLAIN><<<grid, 256, 0, s>>>(a); break;
+        case EPI_PARTIAL:     launch_k(sgemm_nt_kernel<EPI_PARTIAL>, grid, dim3(256), 0, s, a); break;
+        case EPI_BIAS_RELU:   launch_k(sgemm_nt_kernel<EPI_BIAS_RELU>, grid, dim3(256), 0, s, a); break;
+        case EPI_BIAS_AFFINE: launch_k(sgemm_nt_kernel<EPI_BIAS_AFFINE>, grid, dim3(256), 0, s, a); break;
+        case EPI_PCA_INV:     launch_k(sgemm_nt_kernel<EPI_PCA_INV>, grid, dim3(256), 0, s, a); break;
+        default:              launch_k(sgemm_nt_kernel<EPI_PLAIN>, grid, dim3(256), 0, s, a); break;
     }
 }
 
 // 256 threads = 32 consecutive outputs x 8 split groups: every thread has splits/8 independent
 // coalesced loads in flight, then the 8 groups fold through shared memory in a fixed order.
 __global__ void __launch_bounds__(256) reduce_standardise_kernel(ReduceArgs a) {
+    pdl_enter();
     const long long total = (long long)a.M * a.N;
     const int ox = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const long long i = (long long)blockIdx.x * 32 + ox;
@@ -263,7 +281,7 @@ __global__ void __launch_bounds__(256) reduce_standardise_kernel(ReduceArgs a) {
 }
 void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {
     long long total = (long long)a.M * a.N;
-    reduce_standardise_kernel<<<(unsigned)((total + 31) / 32), 256, 0, s>>>(a);
+    launch_k(reduce_standardise_kernel, dim3((unsigned)((total + 31) / 32)), dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -274,6 +292,7 @@ void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {
 //      warp per task folds its rows -- rectangles range from 1 x 1 to 120 x 128 pixels, so the work
 //      is balanced per row, not per task.
 __global__ void __launch_bounds__(256) row_sums_kernel(MeansArgs a) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (r >= a.n_rows) return;
@@ -297,6 +316,7 @@ __global__ void __launch_bounds__(256) row_sums_kernel(MeansArgs a) {
     if (lane == 0) a.row_sums[r] = sum;
 }
 __global__ void __launch_bounds__(256) task_means_kernel(MeansArgs a) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= a.n_tasks) return;
@@ -307,10 +327,10 @@ __global__ void __launch_bounds__(256) task_means_kernel(MeansArgs a) {
     const DevTask tk = a.tasks[t];
     if (lane == 0) a.means[tk.out] = tk.kind ? sum : ((tk.count > 0) ? sum / (double)tk.count : CUDART_NAN);
 }
-void launch_means(const MeansArgs& a, cudaStream_t s) {
+void launch_means(const MeansArgs& a, cudaStream_t s, bool fold_rows_here) {
     if (a.n_tasks <= 0) return;
-    row_sums_kernel<<<(a.n_rows + 7) / 8, 256, 0, s>>>(a);
-    task_means_kernel<<<(a.n_tasks + 7) / 8, 256, 0, s>>>(a);
+    launch_k(row_sums_kernel, dim3((a.n_rows + 7) / 8), dim3(256), 0, s, a);
+    if (fold_rows_here) launch_k(task_means_kernel, dim3((a.n_tasks + 7) / 8), dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -320,6 +340,19 @@ void launch_means(const MeansArgs& a, cudaStream_t s) {
 //      line sums.  Single CTA: the whole problem is a few thousand scalars.  In the multi-GPU path
 //      every rank evaluates this redundantly on the all-reduced means.
 __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
+    pdl_enter();
+    if (a.n_fold_tasks > 0) {      // fold the row partials of every task (one warp per task), FP64, fixed order
+        const int lane = threadIdx.x & 31;
+        for (int t = threadIdx.x >> 5; t < a.n_fold_tasks; t += blockDim.x >> 5) {
+            const int r0 = a.row_start[t], r1 = a.row_start[t + 1];
+            double sum = 0.0;
+            for (int r = r0 + lane; r < r1; r += 32) sum += a.row_sums[r];
+            sum = warp_sum(sum);
+            const DevTask tk = a.tasks[t];
+            if (lane == 0) a.means_out[tk.out] = tk.kind ? sum : ((tk.count > 0) ? sum / (double)tk.count : CUDART_NAN);
+        }
+        __syncthreads();
+    }
     const int n = a.B * a.F;
     double* d_cur = a.dbuf0; double* d_nxt = a.dbuf1;
     int32_t* p_cur = a.pbuf0; int32_t* p_nxt = a.pbuf1;
@@ -364,16 +397,56 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
         __syncthreads();
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) a.coff[i] = (float)(a.offsets[i] + s_shift[i / a.B]);
+    if (threadIdx.x == 0) {
+        a.sc->umax2_bits = 0ull; a.sc->dumax2_bits = 0ull;      // re-arm the running maxima of prep
+        if (a.host_skip) { *reinterpret_cast<volatile int*>(a.host_skip) = a.sc->skip; __threadfence_system(); }
+    }
 }
-void launch_offsets(const OffsetsArgs& a, cudaStream_t s) { offsets_kernel<<<1, 1024, 0, s>>>(a); }
+void launch_offsets(const OffsetsArgs& a, cudaStream_t s) { launch_k(offsets_kernel, dim3(1), dim3(1024), 0, s, a); }
 
 // ------------------------------------------------------------------------------------------------
 // K7  placement.  SMC:332-348 / GRAD:345-356 as a gather through the last-writer map, with the
 //     block correction and the global shift subtracted on the fly.
 __global__ void __launch_bounds__(256) place_kernel(PlaceArgs a) {
+    pdl_enter();
+    // 4 consecutive pixels of a row per thread (W % 4 == 0 fast path): one 8-byte owner load, and when the
+    // four pixels share their owner and the block column is 16-byte aligned, one 128-bit block load
+    const int W4 = a.W >> 2;
+    const long long groups = (long long)a.H * W4;
+    const long long total = groups * a.F;
+    if ((a.W & 3) == 0) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+            const int f = (int)(i / groups);
+            const long long g = i - (long long)f * groups;
+            const int y = (int)(g / W4), x = (int)(g - (long long)y * W4) << 2;
+            const long long q = (long long)y * a.W + x;
+            const ushort4 o4 = *reinterpret_cast<const ushort4*>(a.owner + q);
+            float4 out;
+            const int o = o4.x;
+            const int lx = x - a.bx0[o];
+            const float* brow = a.blocks + (((long long)o * a.C + f) * a.S + (y - a.by0[o])) * a.S;
+            if (o4.y == o && o4.z == o && o4.w == o && (lx & 3) == 0) {
+                const float4 v = *reinterpret_cast<const float4*>(brow + lx);
+                const float c = a.coff[f * a.B_glob + a.kb0 + o];
+                out = make_float4(v.x - c, v.y - c, v.z - c, v.w - c);
+            } else {
+                const int os[4] = {o4.x, o4.y, o4.z, o4.w};
+                float r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ok = os[k];
+                    r[k] = a.blocks[(((long long)ok * a.C + f) * a.S + (y - a.by0[ok])) * a.S + (x + k - a.bx0[ok])] -
+                           a.coff[f * a.B_glob + a.kb0 + ok];
+                }
+                out = make_float4(r[0], r[1], r[2], r[3]);
+            }
+            *reinterpret_cast<float4*>(a.field + (long long)f * a.plane_stride + q) = out;
+        }
+        return;
+    }
     const long long plane = (long long)a.H * a.W;
-    const long long total = plane * a.F;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long tot1 = plane * a.F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot1; i += (long long)gridDim.x * blockDim.x) {
         const int f = (int)(i / plane);
         const long long q = i - (long long)f * plane;
         const int y = (int)(q / a.W), x = (int)(q - (long long)y * a.W);
@@ -383,10 +456,10 @@ __global__ void __launch_bounds__(256) place_kernel(PlaceArgs a) {
     }
 }
 void launch_place(const PlaceArgs& a, cudaStream_t s) {
-    long long total = (long long)a.H * a.W * a.F;
+    long long total = (long long)a.H * a.W * a.F / (((a.W & 3) == 0) ? 4 : 1);
     long long want = (total + 255) / 256;
-    int blocks = (int)(want < (long long)kSMs * 16 ? want : kSMs * 16);
-    place_kernel<<<blocks, 256, 0, s>>>(a);
+    int blocks = (int)(want < (long long)kSMs * 8 ? want : kSMs * 8);
+    launch_k(place_kernel, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -394,6 +467,7 @@ void launch_place(const PlaceArgs& a, cudaStream_t s) {
 //     interpolate_fill, previous-pressure fallback for NaN / near-wall cells; SMC:644-645
 //     (p = p_prev + delta_p) for the deltaU variant.
 __global__ void __launch_bounds__(256) back_kernel(BackArgs a) {
+    pdl_enter();
     const int skip = a.sc->skip;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
         const int i0 = __ldcs(a.v0 + i), i1 = __ldcs(a.v1 + i), i2 = __ldcs(a.v2 + i);
@@ -420,11 +494,12 @@ __global__ void __launch_bounds__(256) back_kernel(BackArgs a) {
 void launch_back(const BackArgs& a, cudaStream_t s) {
     long long want = (a.n + 255) / 256;
     int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
-    back_kernel<<<blocks, 256, 0, s>>>(a);
+    launch_k(back_kernel, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // Static sparse exchange (multi-GPU): contiguous send buffer from an index list.
 __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
+    pdl_enter();
     const long long total = a.n * a.width;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long e = i / a.width; const int c = (int)(i - e * a.width);
@@ -437,7 +512,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
 void launch_pack(const PackArgs& a, cudaStream_t s) {
     if (a.n <= 0) return;
     long long want = (a.n * a.width + 255) / 256;
-    pack_kernel<<<(int)(want < 1184 ? want : 1184), 256, 0, s>>>(a);
+    launch_k(pack_kernel, dim3((int)(want < 1184 ? want : 1184)), dim3(256), 0, s, a);
 }
 
 }  // namespace psm

@@ -5,6 +5,26 @@
 
 namespace psm {
 
+// Programmatic dependent launch: every kernel of the step is launched with the programmatic-serialisation
+// attribute and starts with pdl_enter(): its CTAs may become resident while the previous kernel drains
+// (launch latency and prologue overlap), and touch memory only after the previous kernel has completed.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
+#endif
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // Per-step scalars kept on the device so that no host round-trip sits inside a step.
 struct Scalars {
     unsigned long long umax2_bits;   // running max of Ux^2+Uy^2 (bit pattern of a non-negative double)
@@ -38,7 +58,6 @@ struct ScalarArgs {
     double skip_threshold;
     int mode;
 };
-void launch_scalars(const ScalarArgs& a, cudaStream_t s);
 
 // K1: cell -> grid barycentric gather over the folded tables (SoA, padded to a multiple of 4).
 struct GatherArgs {
@@ -47,7 +66,7 @@ struct GatherArgs {
     const float2* uv;
     float* grid0; float* grid1;   // planes [H*W] (padded)
     long long n_pix4;             // number of 4-pixel groups
-    const Scalars* sc;
+    ScalarArgs sa;                // thread 0 also publishes the step's scalars (U_max_norm, scales, skip rule)
 };
 void launch_gather(const GatherArgs& a, cudaStream_t s);
 
@@ -129,7 +148,7 @@ struct MeansArgs {
     const int32_t* row_start;         // [n_tasks + 1] first row of each task
     double* row_sums;                 // [n_rows] scratch
 };
-void launch_means(const MeansArgs& a, cudaStream_t s);
+void launch_means(const MeansArgs& a, cudaStream_t s, bool fold_rows_here);
 
 // K6b: offset recurrence (pointer jumping over the parent forest) + global shift from the line sums.
 struct DevRec { int32_t ta, tb, parent, is_nan; };
@@ -142,6 +161,9 @@ struct OffsetsArgs {
     float* coff;                      // [F][B]  c_k + shift_f (consumed by the placement)
     const DevShiftTerm* terms; int term_start[3]; int shift_len[2];
     Scalars* sc;
+    int* host_skip;                   // mapped pinned host word: the step's status without a copy node
+    // single-GPU: the row partials are folded into means here (multi-GPU does it before the all-reduce)
+    const DevTask* tasks; int n_fold_tasks; const int32_t* row_start; const double* row_sums; double* means_out;
 };
 void launch_offsets(const OffsetsArgs& a, cudaStream_t s);
 
