@@ -113,6 +113,7 @@ struct psm_handle {
     int32_t *d_bv[3] = {nullptr, nullptr, nullptr}; float* d_bw[3] = {nullptr, nullptr, nullptr};
     uint8_t* d_gmask = nullptr; uint16_t* d_owner = nullptr;
     int32_t *d_by0 = nullptr, *d_bx0 = nullptr;
+    CoverEntry *d_rowcov = nullptr, *d_colcov = nullptr; bool fused_extract = false;   // gather writes the block operand itself
     DevTask* d_tasks = nullptr; DevRec* d_rec = nullptr; int n_tasks = 0 /* local */, rounds = 0;
     int2* d_rows = nullptr; int32_t* d_row_start = nullptr; double* d_row_sums = nullptr; int n_rows = 0;
     float* d_zc = nullptr;            // [B_pad][pc_in_pad]
@@ -408,6 +409,28 @@ static int init_local(psm_handle* h, LocalInit& L) {
         for (int k = 0; k < h->B; ++k) { by0[k] = P.y0[kb0 + k] - L.row0; bx0[k] = P.x0[kb0 + k]; }
         TRY(upload(h, &h->d_by0, by0));
         TRY(upload(h, &h->d_bx0, bx0));
+        {   // which block rows / block columns cover a pixel row / a 4-pixel column group (fused gather + extraction)
+            const int nrows_g = h->H + L.local_ext, nbr = L.blk_row1 - L.blk_row0;
+            bool ok = (W % 4 == 0) && L.ext_rows == 0 && !getenv("PSM_NO_FUSED_EXTRACT");
+            for (int j = 0; j < ncolb && ok; ++j) ok = (bx0[j] % 4 == 0);
+            std::vector<CoverEntry> rcv(nrows_g), ccv(W / 4 + 1);
+            for (int y = 0; y < nrows_g && ok; ++y) {
+                CoverEntry ce{}; 
+                for (int r = 0; r < nbr; ++r) {
+                    const int y0 = by0[r * ncolb];
+                    if (y >= y0 && y < y0 + S) { if (ce.n >= 7) { ok = false; break; } ce.idx[ce.n++] = (int16_t)r; }
+                }
+                rcv[y] = ce;
+            }
+            for (int xg = 0; xg < W / 4 && ok; ++xg) {
+                CoverEntry ce{};
+                for (int j = 0; j < ncolb; ++j)
+                    if (xg * 4 >= bx0[j] && xg * 4 < bx0[j] + S) { if (ce.n >= 7) { ok = false; break; } ce.idx[ce.n++] = (int16_t)j; }
+                ccv[xg] = ce;
+            }
+            h->fused_extract = ok;
+            if (ok) { TRY(upload(h, &h->d_rowcov, rcv)); TRY(upload(h, &h->d_colcov, ccv)); }
+        }
         // tasks: masked means first, then the shift-line sums; a task is evaluated by the rank holding `src`
         const int n_means = (int)P.tasks.size();
         int n_lines = 0;
@@ -764,7 +787,12 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     float* grid0 = h->d_grid; float* grid1 = h->d_grid + h->grid_stride;
     GatherArgs ga{h->d_fv[0], h->d_fv[1], h->d_fv[2], h->d_fw[0], h->d_fw[1], h->d_fw[2], h->d_uv,
                   grid0, grid1, h->G_pad / 4, sa};
-    launch_gather(ga, s); ++nl;
+    if (h->fused_extract) {
+        GatherExtractArgs ge{ga, h->d_rowcov, h->d_colcov, h->d_by0, h->d_bx0, h->d_xu, h->W / 4, h->plan.n_x + 1, S};
+        launch_gather_extract(ge, s); ++nl;
+    } else {
+        launch_gather(ga, s); ++nl;
+    }
     if (multi && (h->ext_rows || h->send_rows)) {
         // exchange 2: the overlap strip -- the first rows of rank+1 complete this rank's last block row
         NC(h, g_nccl.GroupStart());
@@ -779,8 +807,10 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         NC(h, g_nccl.GroupEnd());
     }
     tick();   // gather
-    ExtractArgs ea{grid0, grid1, h->d_by0, h->d_bx0, h->d_xu, h->B, h->W, S, 2};
-    launch_extract(ea, s); ++nl;
+    if (!h->fused_extract) {
+        ExtractArgs ea{grid0, grid1, h->d_by0, h->d_bx0, h->d_xu, h->B, h->W, S, 2};
+        launch_extract(ea, s); ++nl;
+    }
     tick();   // extract
     const bool tc = h->cfg.gemm_mode != PSM_GEMM_FP32_SIMT;
     {
@@ -836,7 +866,7 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     tick();   // pca_inverse
     MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->C, S, h->W, multi ? h->d_means_loc : h->d_means,
                  h->d_rows, h->n_rows, h->d_row_start, h->d_row_sums};
-    launch_means(ma, s, multi); nl += multi ? 2 : 1;
+    launch_means(ma, s, true); nl += 2;
     if (multi)   // exchange 3: every rank contributes its own slots (zero elsewhere) -> identical means everywhere
         NC(h, g_nccl.AllReduce(h->d_means_loc, h->d_means, (size_t)h->n_tasks_glob, ncclDouble, ncclSum, h->comm, s));
     tick();   // strip_means
@@ -848,7 +878,7 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         for (int f = 0; f < 3; ++f) oa.term_start[f] = h->term_start[f];
         for (int f = 0; f < 2; ++f) oa.shift_len[f] = h->plan.shift_len[f];
         oa.sc = h->d_sc;
-        oa.tasks = h->d_tasks; oa.n_fold_tasks = multi ? 0 : h->n_tasks; oa.row_start = h->d_row_start; oa.row_sums = h->d_row_sums;
+        oa.tasks = h->d_tasks; oa.n_fold_tasks = 0;    // a single CTA folding all tasks is slower than task_means_kernel (measured) oa.row_start = h->d_row_start; oa.row_sums = h->d_row_sums;
         oa.means_out = h->d_means;
         oa.host_skip = h->d_host_skip;
         launch_offsets(oa, s); ++nl;

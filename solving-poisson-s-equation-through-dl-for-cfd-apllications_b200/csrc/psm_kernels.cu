@@ -10,6 +10,7 @@
 namespace psm {
 
 static constexpr int kSMs = 148;
+static constexpr int kOffsetsSmemMax = 8192;      // F*B scalars whose recurrence runs in shared memory (192 KB)
 
 bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("PSM_NO_PDL"); return !(e && e[0] == '1'); }();
@@ -143,6 +144,75 @@ void launch_gather(const GatherArgs& a, cudaStream_t s) {
     long long want = (a.n_pix4 + 255) / 256;
     int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
     launch_k(gather_kernel, dim3(blocks), dim3(256), 0, s, a);
+}
+
+// K1+K2 fused (see psm_kernels.cuh): identical arithmetic to gather_kernel, then one 128-bit store per
+// covering block and channel.
+__global__ void __launch_bounds__(256) gather_extract_kernel(GatherExtractArgs e) {
+    pdl_enter();
+    const GatherArgs& a = e.g;
+    Scalars* sc = a.sa.sc;
+    const double um = sqrt(__longlong_as_double((long long)sc->umax2_bits));
+    const float s0 = (float)(1.0 / (um * a.sa.max_abs_ux)), s1 = (float)(1.0 / (um * a.sa.max_abs_uy));
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double dm = sqrt(__longlong_as_double((long long)sc->dumax2_bits));
+        sc->U_max_norm = um;
+        sc->dU_max_norm = dm;
+        sc->in_scale[0] = s0;
+        sc->in_scale[1] = s1;
+        sc->out_scale = (float)(a.sa.dimensionalise ? a.sa.out_scale_base * um * um : a.sa.out_scale_base);
+        int skip = 0;
+        if (a.sa.mode != 0) {
+            if (a.sa.skip_threshold > 0.0 && (dm / um) < a.sa.skip_threshold) skip = 1;     // SMC:410-415
+            if (a.sa.mode == 2 && !sc->have_prev) skip = 1;                                // no U(t-1) yet
+        }
+        sc->skip = skip;
+        sc->have_prev = 1;
+    }
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const int S2 = e.S * e.S;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < a.n_pix4; g += stride) {
+        const int4 i0 = __ldcs(reinterpret_cast<const int4*>(a.v0) + g);
+        const int4 i1 = __ldcs(reinterpret_cast<const int4*>(a.v1) + g);
+        const int4 i2 = __ldcs(reinterpret_cast<const int4*>(a.v2) + g);
+        const float4 q0 = __ldcs(reinterpret_cast<const float4*>(a.w0) + g);
+        const float4 q1 = __ldcs(reinterpret_cast<const float4*>(a.w1) + g);
+        const float4 q2 = __ldcs(reinterpret_cast<const float4*>(a.w2) + g);
+        float2 a0 = ldg_f2(a.uv + i0.x), b0 = ldg_f2(a.uv + i1.x), c0 = ldg_f2(a.uv + i2.x);
+        float2 a1 = ldg_f2(a.uv + i0.y), b1 = ldg_f2(a.uv + i1.y), c1 = ldg_f2(a.uv + i2.y);
+        float2 a2 = ldg_f2(a.uv + i0.z), b2 = ldg_f2(a.uv + i1.z), c2 = ldg_f2(a.uv + i2.z);
+        float2 a3 = ldg_f2(a.uv + i0.w), b3 = ldg_f2(a.uv + i1.w), c3 = ldg_f2(a.uv + i2.w);
+        float4 ox, oy;
+        ox.x = (a0.x * q0.x + b0.x * q1.x + c0.x * q2.x) * s0;  oy.x = (a0.y * q0.x + b0.y * q1.x + c0.y * q2.x) * s1;
+        ox.y = (a1.x * q0.y + b1.x * q1.y + c1.x * q2.y) * s0;  oy.y = (a1.y * q0.y + b1.y * q1.y + c1.y * q2.y) * s1;
+        ox.z = (a2.x * q0.z + b2.x * q1.z + c2.x * q2.z) * s0;  oy.z = (a2.y * q0.z + b2.y * q1.z + c2.y * q2.z) * s1;
+        ox.w = (a3.x * q0.w + b3.x * q1.w + c3.x * q2.w) * s0;  oy.w = (a3.y * q0.w + b3.y * q1.w + c3.y * q2.w) * s1;
+        ox.x = (ox.x != ox.x) ? 0.f : ox.x; ox.y = (ox.y != ox.y) ? 0.f : ox.y;
+        ox.z = (ox.z != ox.z) ? 0.f : ox.z; ox.w = (ox.w != ox.w) ? 0.f : ox.w;
+        oy.x = (oy.x != oy.x) ? 0.f : oy.x; oy.y = (oy.y != oy.y) ? 0.f : oy.y;
+        oy.z = (oy.z != oy.z) ? 0.f : oy.z; oy.w = (oy.w != oy.w) ? 0.f : oy.w;
+        reinterpret_cast<float4*>(a.grid0)[g] = ox;
+        reinterpret_cast<float4*>(a.grid1)[g] = oy;
+        const int y = (int)(g / e.W4), xg = (int)(g - (long long)y * e.W4);
+        const CoverEntry rc = e.rowcov[y];
+        const CoverEntry cc = e.colcov[xg];
+        const int x = xg << 2;
+        for (int r = 0; r < rc.n; ++r) {
+            const int b_row = rc.idx[r] * e.ncolb;
+            const int ly = y - e.by0[b_row];
+            for (int c = 0; c < cc.n; ++c) {
+                const int b = b_row + cc.idx[c];
+                float* dst = e.xu + ((long long)b * 2) * S2 + ly * e.S + (x - e.bx0[b]);
+                *reinterpret_cast<float4*>(dst) = ox;
+                *reinterpret_cast<float4*>(dst + S2) = oy;
+            }
+        }
+    }
+}
+void launch_gather_extract(const GatherExtractArgs& a, cudaStream_t s) {
+    long long want = (a.g.n_pix4 + 255) / 256;
+    int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
+    launch_k(gather_extract_kernel, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -354,8 +424,13 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
         __syncthreads();
     }
     const int n = a.B * a.F;
-    double* d_cur = a.dbuf0; double* d_nxt = a.dbuf1;
-    int32_t* p_cur = a.pbuf0; int32_t* p_nxt = a.pbuf1;
+    // pointer jumping in shared memory when the forest fits (n <= kOffsetsSmemMax), else in the global scratch
+    extern __shared__ unsigned char off_smem[];
+    const bool in_smem = n <= kOffsetsSmemMax;
+    double* d_cur = in_smem ? reinterpret_cast<double*>(off_smem) : a.dbuf0;
+    double* d_nxt = in_smem ? d_cur + n : a.dbuf1;
+    int32_t* p_cur = in_smem ? reinterpret_cast<int32_t*>(d_nxt + n) : a.pbuf0;
+    int32_t* p_nxt = in_smem ? p_cur + n : a.pbuf1;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const DevRec r = a.rec[i];
         const int f = i / a.B;
@@ -402,7 +477,13 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
         if (a.host_skip) { *reinterpret_cast<volatile int*>(a.host_skip) = a.sc->skip; __threadfence_system(); }
     }
 }
-void launch_offsets(const OffsetsArgs& a, cudaStream_t s) { launch_k(offsets_kernel, dim3(1), dim3(1024), 0, s, a); }
+void launch_offsets(const OffsetsArgs& a, cudaStream_t s) {
+    const int n = a.B * a.F;
+    const size_t smem = n <= kOffsetsSmemMax ? (size_t)n * 24 : 0;
+    static bool opted = false;
+    if (!opted) { cudaFuncSetAttribute(offsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOffsetsSmemMax * 24); opted = true; }
+    launch_k(offsets_kernel, dim3(1), dim3(1024), smem, s, a);
+}
 
 // ------------------------------------------------------------------------------------------------
 // K7  placement.  SMC:332-348 / GRAD:345-356 as a gather through the last-writer map, with the

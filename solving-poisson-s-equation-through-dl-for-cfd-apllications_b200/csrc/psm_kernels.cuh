@@ -70,6 +70,19 @@ struct GatherArgs {
 };
 void launch_gather(const GatherArgs& a, cudaStream_t s);
 
+// K1+K2 fused: the gathered 4-pixel group goes straight into every overlapping block's operand row
+// (SMC:464-492), so the grid is never re-read.  Needs W % 4 == 0 and block columns on multiples of 4.
+// rowcov[y] / colcov[x/4]: {count, up to 7 covering block rows / block columns}.
+struct CoverEntry { int16_t n; int16_t idx[7]; };
+struct GatherExtractArgs {
+    GatherArgs g;
+    const CoverEntry* rowcov;     // [rows gathered]   idx = local block row
+    const CoverEntry* colcov;     // [W/4]             idx = block position within its row
+    const int32_t* by0; const int32_t* bx0;
+    float* xu; int W4; int ncolb; int S;
+};
+void launch_gather_extract(const GatherExtractArgs& a, cudaStream_t s);
+
 // K2: overlapping block extraction into the K-major operand x_u[B_pad][2*S*S] (planar c, ly, lx).
 struct ExtractArgs {
     const float* grid0; const float* grid1;   // channel planes [H*W]; nch == 1 uses grid0 only

@@ -289,3 +289,18 @@ def test_cluster_dense_layers_equal_split_k_gemms_on_several_batch_tiles(monkeyp
         assert rel_l2(fused, want) < 1e-4
     finally:
         c.sm.close()
+
+
+def test_fused_gather_extraction_is_bit_identical_to_the_two_kernel_path(deltas_case, monkeypatch):
+    """gather_extract_kernel writes the block operand itself; the separate extract kernel re-reads the grid.
+    Same arithmetic, so every downstream stage must agree bit for bit."""
+    c = deltas_case
+    c.sm.predict(c.cells)
+    fused = {k: c.sm.stage(k) for k in ('grid', 'x_input', 'blocks', 'field')}
+    monkeypatch.setenv('PSM_NO_FUSED_EXTRACT', '1')
+    with psm_b200.PressureSurrogate('deltaU_to_deltaP') as sm:
+        sm.load_params(c.params)
+        sm.init_tables(c.tables)
+        sm.predict(c.cells)
+        for k, v in fused.items():
+            np.testing.assert_array_equal(sm.stage(k), v, err_msg=k)
