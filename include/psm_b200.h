@@ -157,7 +157,8 @@ typedef struct psm_geometry {
     int32_t n_blocks, n_fields;
     int64_t n_cells;
     int32_t n_tasks;              /* masked strip means evaluated per step (whole mesh)         */
-    int32_t reserved;
+    int32_t peer_memory_exchange; /* multi-GPU: 1 = exchanges pushed over cudaIpc-mapped peer memory
+                                     (NVLink), 0 = NCCL send/recv + all-reduce (PSM_COMM=nccl)        */
     /* this rank's share (equal to the whole mesh on a single-GPU handle) */
     int32_t row0, row1, ext_rows, first_block, n_local_blocks, world;
     int64_t n_ghost_cells, n_ghost_pix;

@@ -35,6 +35,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -52,6 +53,7 @@ struct NcclApi {
         CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
         CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy");
         AllReduce = (decltype(AllReduce))sym("ncclAllReduce");
+        AllGather = (decltype(AllGather))sym("ncclAllGather");
         Send = (decltype(Send))sym("ncclSend");
         Recv = (decltype(Recv))sym("ncclRecv");
         GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
@@ -107,6 +109,10 @@ struct psm_handle {
     int32_t *d_cell_send_idx = nullptr, *d_pix_send_idx = nullptr;
     float *d_cell_send = nullptr, *d_pix_send = nullptr;
     double* d_means_loc = nullptr;     // world > 1: this rank's means, zero elsewhere (all-reduce source)
+    // peer-memory exchange (default for world > 1; NCCL send/recv + all-reduce is the fallback, PSM_COMM=nccl)
+    bool p2p = false;
+    P2PArgs* d_p2p = nullptr; PeerMail* d_mail = nullptr;
+    std::vector<void*> ipc_opened;
     int n_tasks_glob = 0;              // means + shift-line sums of the whole mesh
     DevShiftTerm* d_terms = nullptr; int term_start[3] = {0, 0, 0};
     int32_t *d_fv[3] = {nullptr, nullptr, nullptr}; float* d_fw[3] = {nullptr, nullptr, nullptr};
@@ -174,6 +180,12 @@ static int upload(psm_handle* h, T** p, const std::vector<T>& v) {
     return 0;
 }
 #define TRY(x) do { int _rc = (x); if (_rc) return _rc; } while (0)
+#define NC(h, call)                                                                                         \
+    do {                                                                                                    \
+        ncclResult_t _r = (call);                                                                           \
+        if (_r != ncclSuccess) PSM_FAIL(h, PSM_ERR_COMM, "%s: %s", #call, g_nccl.GetErrorString(_r));       \
+    } while (0)
+
 
 extern "C" int psm_api_version(void) { return PSM_API_VERSION; }
 
@@ -226,6 +238,7 @@ extern "C" int psm_destroy(psm_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (void* p : h->allocs) cudaFree(p);
     if (h->ev_created) for (auto& e : h->ev) cudaEventDestroy(e);
@@ -348,6 +361,83 @@ struct LocalInit {
     std::vector<int32_t> cell_send_idx, pix_send_idx;
 };
 }  // namespace
+
+// Map every peer's exchange buffers (cudaIpc over NVLink) and build the push tables.  Collective.  Falls back
+// to the NCCL exchange when any rank cannot map a peer, when PSM_COMM=nccl, or in the grid-row halo mode.
+static int setup_p2p(psm_handle* h) {
+    struct PeerInfo {
+        cudaIpcMemHandle_t uv, field, means, mail;
+        long long n_owned, G, field_stride;
+        long long cell_recv_ptr[kMaxPeers + 1], pix_recv_ptr[kMaxPeers + 1];
+        int ok;
+    };
+    const int Wd = h->world, me = h->rank;
+    const char* mode = getenv("PSM_COMM");
+    int want = (Wd <= kMaxPeers) && h->ext_rows == 0 && h->send_rows == 0 && !(mode && std::string(mode) == "nccl");
+    TRY(dalloc(h, &h->d_mail, 1));
+    PeerInfo mine{};
+    mine.ok = want;
+    if (want) {
+        if (cudaIpcGetMemHandle(&mine.uv, h->d_uv) != cudaSuccess || cudaIpcGetMemHandle(&mine.field, h->d_field) != cudaSuccess ||
+            cudaIpcGetMemHandle(&mine.means, h->d_means) != cudaSuccess || cudaIpcGetMemHandle(&mine.mail, h->d_mail) != cudaSuccess) {
+            mine.ok = 0; cudaGetLastError();
+        }
+    }
+    mine.n_owned = h->n_cells; mine.G = h->G; mine.field_stride = h->field_stride;
+    for (int p = 0; p <= Wd && p <= kMaxPeers; ++p) { mine.cell_recv_ptr[p] = h->cell_recv_ptr[p]; mine.pix_recv_ptr[p] = h->pix_recv_ptr[p]; }
+    // all-gather the descriptors (bytes) through NCCL
+    PeerInfo* d_all = nullptr;
+    CU(h, cudaMalloc(&d_all, sizeof(PeerInfo) * Wd));
+    CU(h, cudaMemcpyAsync(d_all + me, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    NC(h, g_nccl.AllGather(d_all + me, d_all, sizeof(PeerInfo), ncclChar, h->comm, h->stream));
+    std::vector<PeerInfo> all(Wd);
+    CU(h, cudaMemcpyAsync(all.data(), d_all, sizeof(PeerInfo) * Wd, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    bool ok = true;
+    for (int p = 0; p < Wd; ++p) ok = ok && all[p].ok;
+    P2PArgs pa{};
+    pa.rank = me; pa.world = Wd; pa.sc = h->d_sc;
+    if (ok) {
+        for (int p = 0; p < Wd && ok; ++p) {
+            void *uv = h->d_uv, *field = h->d_field, *means = h->d_means, *mail = h->d_mail;
+            if (p != me) {
+                auto open = [&](void** out, cudaIpcMemHandle_t hd) {
+                    if (cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
+                    h->ipc_opened.push_back(*out);
+                    return true;
+                };
+                ok = open(&uv, all[p].uv) && open(&field, all[p].field) && open(&means, all[p].means) && open(&mail, all[p].mail);
+                if (!ok) break;
+            }
+            pa.mail[p] = static_cast<PeerMail*>(mail);
+            pa.means[p] = static_cast<double*>(means);
+            pa.uv_ghost[p] = static_cast<float2*>(uv) + all[p].n_owned + all[p].cell_recv_ptr[me];
+            pa.field_ghost[p] = static_cast<float*>(field) + all[p].G + all[p].pix_recv_ptr[me];
+            pa.field_stride[p] = all[p].field_stride;
+        }
+    }
+    // every rank must take the same path: agree through one more tiny all-gather
+    int* d_flag = nullptr;
+    CU(h, cudaMalloc(&d_flag, sizeof(int) * Wd));
+    int okv = ok ? 1 : 0;
+    CU(h, cudaMemcpyAsync(d_flag + me, &okv, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NC(h, g_nccl.AllGather(d_flag + me, d_flag, sizeof(int), ncclChar, h->comm, h->stream));
+    std::vector<int> flags(Wd);
+    CU(h, cudaMemcpyAsync(flags.data(), d_flag, sizeof(int) * Wd, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_all); cudaFree(d_flag);
+    for (int p = 0; p < Wd; ++p) ok = ok && flags[p];
+    h->p2p = ok;
+    if (!ok) return PSM_OK;                       // NCCL exchange
+    for (int p = 0; p <= Wd; ++p) { pa.cell_send_ptr[p] = h->cell_send_ptr[p]; pa.pix_send_ptr[p] = h->pix_send_ptr[p]; }
+    for (int p = Wd + 1; p <= kMaxPeers; ++p) { pa.cell_send_ptr[p] = pa.cell_send_ptr[Wd]; pa.pix_send_ptr[p] = pa.pix_send_ptr[Wd]; }
+    pa.pix_recv_mask = 0;
+    for (int p = 0; p < Wd; ++p) if (h->pix_recv_ptr[p + 1] > h->pix_recv_ptr[p]) pa.pix_recv_mask |= 1u << p;
+    std::vector<P2PArgs> v(1, pa);
+    TRY(upload(h, &h->d_p2p, v));
+    h->eager_steps = 0;                           // nothing lazy left on the step's path: capture from the first step
+    return PSM_OK;
+}
 
 static int init_local(psm_handle* h, LocalInit& L) {
     const int W = L.W, S = h->S, S2 = S * S;
@@ -597,6 +687,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
         TRY(mk(h->tc_inv, h->d_r, Bp, h->d_comp_out_t, S2 * h->C, h->pc_p_pad, h->d_blocks, S2 * h->C, 1, EPI_PCA_INV,
                h->d_pmean, nullptr, nullptr, 128));
     }
+    if (L.world > 1) TRY(setup_p2p(h));
     if (h->cfg.enable_timings) TRY(psm_set_timings(h, 1));
     CU(h, cudaStreamSynchronize(h->stream));
     h->initialised = true;
@@ -743,12 +834,6 @@ extern "C" int psm_comm_init(psm_handle* h, const void* unique_id, int32_t rank,
 
 // ------------------------------------------------------------------------------------------------
 // One step on the device, input already in d_cells, output to d_out.
-#define NC(h, call)                                                                                         \
-    do {                                                                                                    \
-        ncclResult_t _r = (call);                                                                           \
-        if (_r != ncclSuccess) PSM_FAIL(h, PSM_ERR_COMM, "%s: %s", #call, g_nccl.GetErrorString(_r));       \
-    } while (0)
-
 // Static sparse exchange: packed send buffer -> the ghost region of every peer (grouped send/recv).
 static int sparse_exchange(psm_handle* h, const float* sendbuf, const std::vector<long long>& sp, float* recvbuf,
                            const std::vector<long long>& rp, int width) {
@@ -772,7 +857,12 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
 
     PrepArgs pa{d_cells, h->n_cells, h->cfg.input_cols, mode, h->d_uv, h->d_pprev, h->d_uprev, h->d_sc};
     launch_prep(pa, s); ++nl;
-    if (multi) {
+    const bool p2p = multi && h->p2p;
+    const P2PArgs* d_p2p = p2p ? h->d_p2p : nullptr;
+    if (p2p) {
+        // exchange 1 over peer memory: maxima + ghost cells are pushed, the gather kernel waits on its mailbox
+        launch_p2p_push_cells(h->d_p2p, h->d_uv, h->d_cell_send_idx, h->cell_send_ptr[h->world], s); ++nl;
+    } else if (multi) {
         // exchange 1: max|U|^2, max|dU|^2 over all ranks (non-negative doubles order like their bit patterns)
         //             + the ghost cells other ranks' forward tables reference
         const long long nsend = h->cell_send_ptr[h->world];
@@ -786,7 +876,7 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     tick();   // prep
     float* grid0 = h->d_grid; float* grid1 = h->d_grid + h->grid_stride;
     GatherArgs ga{h->d_fv[0], h->d_fv[1], h->d_fv[2], h->d_fw[0], h->d_fw[1], h->d_fw[2], h->d_uv,
-                  grid0, grid1, h->G_pad / 4, sa};
+                  grid0, grid1, h->G_pad / 4, sa, d_p2p};
     if (h->fused_extract) {
         GatherExtractArgs ge{ga, h->d_rowcov, h->d_colcov, h->d_by0, h->d_bx0, h->d_xu, h->W / 4, h->plan.n_x + 1, S};
         launch_gather_extract(ge, s); ++nl;
@@ -864,10 +954,11 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         ++nl;
     }
     tick();   // pca_inverse
-    MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->C, S, h->W, multi ? h->d_means_loc : h->d_means,
+    MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->C, S, h->W, (multi && !p2p) ? h->d_means_loc : h->d_means,
                  h->d_rows, h->n_rows, h->d_row_start, h->d_row_sums};
     launch_means(ma, s, true); nl += 2;
-    if (multi)   // exchange 3: every rank contributes its own slots (zero elsewhere) -> identical means everywhere
+    if (p2p) { launch_p2p_push_means(h->d_p2p, h->d_tasks, h->n_tasks, h->world, h->d_means, s); ++nl; }   // exchange 3 over peer memory
+    else if (multi)   // exchange 3: every rank contributes its own slots (zero elsewhere) -> identical means everywhere
         NC(h, g_nccl.AllReduce(h->d_means_loc, h->d_means, (size_t)h->n_tasks_glob, ncclDouble, ncclSum, h->comm, s));
     tick();   // strip_means
     {
@@ -881,6 +972,7 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         oa.tasks = h->d_tasks; oa.n_fold_tasks = 0;    // a single CTA folding all tasks is slower than task_means_kernel (measured) oa.row_start = h->d_row_start; oa.row_sums = h->d_row_sums;
         oa.means_out = h->d_means;
         oa.host_skip = h->d_host_skip;
+        oa.p2p = d_p2p;
         launch_offsets(oa, s); ++nl;
     }
     tick();   // offsets
@@ -889,7 +981,9 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     launch_place(pl, s); ++nl;
     tick();   // place
     if (h->have_back && d_out) {
-        if (multi) {
+        if (p2p) {
+            launch_p2p_push_pix(h->d_p2p, h->d_field, h->d_pix_send_idx, h->F, h->field_stride, h->pix_send_ptr[h->world], s); ++nl;   // exchange 4 over peer memory
+        } else if (multi) {
             // exchange 4: the field pixels other ranks' grid->cell tables reference (rows next to a rank
             //             boundary, and pixel (0,0) for the raster quirk of PMP:481)
             const long long nsend = h->pix_send_ptr[h->world];
@@ -901,7 +995,7 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
             NC(h, g_nccl.GroupEnd());
         }
         BackArgs ba{h->d_bv[0], h->d_bv[1], h->d_bv[2], h->d_bw[0], h->d_bw[1], h->d_bw[2], h->d_field, h->n_cells,
-                    h->field_stride, h->d_pprev, d_out, h->F, h->cfg.additive, h->d_sc};
+                    h->field_stride, h->d_pprev, d_out, h->F, h->cfg.additive, h->d_sc, d_p2p};
         launch_back(ba, s); ++nl;
     }
     tick();   // back_gather
@@ -964,7 +1058,9 @@ static int submit_step(psm_handle* h, bool host, const double* in, double* out) 
 
 static int finish(psm_handle* h) {
     CU(h, cudaStreamSynchronize(h->stream));
-    return h->h_sc->skip ? PSM_SKIPPED : PSM_OK;
+    const int v = h->h_sc->skip;        // skip | comm_error << 8, written by offsets_kernel through mapped memory
+    if (v >> 8) PSM_FAIL(h, PSM_ERR_COMM, "a peer-memory exchange timed out (ranks out of step?)");
+    return (v & 1) ? PSM_SKIPPED : PSM_OK;
 }
 
 extern "C" int psm_predict(psm_handle* h, const double* cells, int64_t n_cells, double* p_out) {
@@ -1019,7 +1115,7 @@ extern "C" int psm_get_geometry(const psm_handle* h, psm_geometry* g) {
     const Plan& P = h->plan;
     g->grid_h = P.H; g->grid_w = P.W; g->shape = P.S; g->overlap = P.ov; g->n_x = P.n_x; g->n_y = P.n_y;
     g->p_i = P.p_i; g->p_j = P.p_j; g->n_blocks = P.B; g->n_fields = P.F; g->n_cells = h->n_cells;
-    g->n_tasks = (int32_t)P.tasks.size(); g->reserved = 0;
+    g->n_tasks = (int32_t)P.tasks.size(); g->peer_memory_exchange = h->p2p ? 1 : 0;
     g->row0 = h->row0; g->row1 = h->row1; g->ext_rows = h->ext_rows + h->local_ext; g->first_block = h->kb0; g->n_local_blocks = h->B;
     g->world = h->world; g->n_ghost_cells = h->n_ghost; g->n_ghost_pix = h->n_ghost_pix;
     return PSM_OK;

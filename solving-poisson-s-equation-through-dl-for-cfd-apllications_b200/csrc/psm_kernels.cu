@@ -29,6 +29,121 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Peer-memory exchange primitives (see psm_kernels.cuh).
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Thread 0 of the CTA waits until every peer in `mask` has raised flag[phase] to the current step, then the
+// CTA proceeds.  Bounded: after ~2 s the step is marked failed (PSM_ERR_COMM) instead of hanging the GPU.
+__device__ __forceinline__ void p2p_wait(const P2PArgs* P, int phase, unsigned int mask) {
+    if (threadIdx.x == 0) {
+        const unsigned int step = P->sc->step;
+        const PeerMail* mine = P->mail[P->rank];
+        const long long t0 = clock64();
+        for (int p = 0; p < P->world; ++p) {
+            if (!((mask >> p) & 1u) || p == P->rank) continue;
+            while ((int)(ld_acquire_sys(&mine->flag[phase][p]) - step) < 0) {
+                if (clock64() - t0 > 4000000000ll) { P->sc->comm_error = 1; break; }
+                __nanosleep(64);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// A push kernel runs on several CTAs; the LAST one to finish its stores (system-scope fence, then a
+// device-scope counter) raises the flags.  Returns true in thread 0..world-1 of that last CTA.
+__device__ __forceinline__ bool p2p_last_block(Scalars* sc, int phase) {
+    __shared__ bool s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&sc->push_done[phase], 1u);
+        s_last = (prev == gridDim.x - 1);
+        if (s_last) sc->push_done[phase] = 0u;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
+
+// Exchange 1 (after prep): my two running maxima to everyone, my cells that are ghost cells elsewhere.
+__global__ void __launch_bounds__(256) p2p_push_cells_kernel(const P2PArgs* pa, const float2* uv, const int32_t* send_idx) {
+    pdl_enter();
+    const P2PArgs& P = *pa;
+    const unsigned int step = P.sc->step + 1u;            // the last CTA publishes the increment
+    const long long nsend = P.cell_send_ptr[P.world];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nsend; e += (long long)gridDim.x * blockDim.x) {
+        int p = 0;
+        while (e >= P.cell_send_ptr[p + 1]) ++p;
+        P.uv_ghost[p][e - P.cell_send_ptr[p]] = uv[send_idx[e]];
+    }
+    if (!p2p_last_block(P.sc, 0)) return;
+    if (threadIdx.x == 0) P.sc->step = step;
+    if ((int)threadIdx.x < P.world) {
+        const int p = threadIdx.x;
+        PeerMail* m = P.mail[p];
+        m->maxima[P.rank][0] = P.sc->umax2_bits;
+        m->maxima[P.rank][1] = P.sc->dumax2_bits;
+        __threadfence_system();
+        st_release_sys(&m->flag[0][P.rank], step);
+    }
+}
+void launch_p2p_push_cells(const P2PArgs* d_pa, const float2* uv, const int32_t* send_idx, long long nsend, cudaStream_t s) {
+    long long want = (nsend + 255) / 256;
+    launch_k(p2p_push_cells_kernel, dim3((int)(want < 1 ? 1 : (want > 64 ? 64 : want))), dim3(256), 0, s, d_pa, uv, send_idx);
+}
+
+// Exchange 2 (after the strip means): my slots of the global mean array to everyone.
+__global__ void __launch_bounds__(256) p2p_push_means_kernel(const P2PArgs* pa, const DevTask* tasks, int n_tasks, const double* means) {
+    pdl_enter();
+    const P2PArgs& P = *pa;
+    const unsigned int step = P.sc->step;
+    const int total = n_tasks * P.world;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int p = e / n_tasks, i = e - p * n_tasks;
+        if (p == P.rank) continue;
+        const int slot = tasks[i].out;
+        P.means[p][slot] = means[slot];
+    }
+    if (!p2p_last_block(P.sc, 1)) return;
+    if ((int)threadIdx.x < P.world && (int)threadIdx.x != P.rank) st_release_sys(&P.mail[threadIdx.x]->flag[1][P.rank], step);
+}
+void launch_p2p_push_means(const P2PArgs* d_pa, const DevTask* tasks, int n_tasks, int world, const double* means, cudaStream_t s) {
+    long long want = ((long long)n_tasks * world + 255) / 256;
+    launch_k(p2p_push_means_kernel, dim3((int)(want < 1 ? 1 : (want > 32 ? 32 : want))), dim3(256), 0, s, d_pa, tasks, n_tasks, means);
+}
+
+// Exchange 3 (after the placement): my field pixels that other ranks' grid->cell tables reference.
+__global__ void __launch_bounds__(256) p2p_push_pix_kernel(const P2PArgs* pa, const float* field, const int32_t* send_idx, int F, long long my_stride) {
+    pdl_enter();
+    const P2PArgs& P = *pa;
+    const unsigned int step = P.sc->step;
+    const long long nsend = P.pix_send_ptr[P.world];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nsend * F; e += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(e / nsend);
+        const long long k = e - (long long)f * nsend;
+        int p = 0;
+        while (k >= P.pix_send_ptr[p + 1]) ++p;
+        P.field_ghost[p][(long long)f * P.field_stride[p] + (k - P.pix_send_ptr[p])] = field[(long long)f * my_stride + send_idx[k]];
+    }
+    if (!p2p_last_block(P.sc, 2)) return;
+    if ((int)threadIdx.x < P.world) {
+        const int p = threadIdx.x;
+        if (P.pix_send_ptr[p + 1] > P.pix_send_ptr[p]) st_release_sys(&P.mail[p]->flag[2][P.rank], step);
+    }
+}
+void launch_p2p_push_pix(const P2PArgs* d_pa, const float* field, const int32_t* send_idx, int F, long long my_stride, long long nsend, cudaStream_t s) {
+    long long want = (nsend * F + 255) / 256;
+    launch_k(p2p_push_pix_kernel, dim3((int)(want < 1 ? 1 : (want > 32 ? 32 : want))), dim3(256), 0, s, d_pa, field, send_idx, F, my_stride);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K0  prep: de-interleave the solver's double[n][ncol] rows, form the field to interpolate,
 //     running max of |U|^2 and |dU|^2.   PMP:267-273, SMC:386-405.
 //     The squares/sum are rounded separately (no FMA) so that U_max_norm is bit-identical to
@@ -97,10 +212,19 @@ __device__ __forceinline__ float2 ldg_f2(const float2* p) { return __ldg(p); }
 __global__ void __launch_bounds__(256) gather_kernel(GatherArgs a) {
     pdl_enter();
     Scalars* sc = a.sa.sc;
-    const double um = sqrt(__longlong_as_double((long long)sc->umax2_bits));
+    unsigned long long um2 = sc->umax2_bits, dm2 = sc->dumax2_bits;
+    if (a.p2p) {                                   // maxima over all ranks, pushed into my mailbox
+        p2p_wait(a.p2p, 0, 0xFFu);
+        const PeerMail* mine = a.p2p->mail[a.p2p->rank];
+        for (int p = 0; p < a.p2p->world; ++p) {
+            um2 = max(um2, *reinterpret_cast<const volatile unsigned long long*>(&mine->maxima[p][0]));
+            dm2 = max(dm2, *reinterpret_cast<const volatile unsigned long long*>(&mine->maxima[p][1]));
+        }
+    }
+    const double um = sqrt(__longlong_as_double((long long)um2));
     const float s0 = (float)(1.0 / (um * a.sa.max_abs_ux)), s1 = (float)(1.0 / (um * a.sa.max_abs_uy));
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const double dm = sqrt(__longlong_as_double((long long)sc->dumax2_bits));
+        const double dm = sqrt(__longlong_as_double((long long)dm2));
         sc->U_max_norm = um;
         sc->dU_max_norm = dm;
         sc->in_scale[0] = s0;
@@ -152,10 +276,19 @@ __global__ void __launch_bounds__(256) gather_extract_kernel(GatherExtractArgs e
     pdl_enter();
     const GatherArgs& a = e.g;
     Scalars* sc = a.sa.sc;
-    const double um = sqrt(__longlong_as_double((long long)sc->umax2_bits));
+    unsigned long long um2 = sc->umax2_bits, dm2 = sc->dumax2_bits;
+    if (a.p2p) {                                   // maxima over all ranks, pushed into my mailbox
+        p2p_wait(a.p2p, 0, 0xFFu);
+        const PeerMail* mine = a.p2p->mail[a.p2p->rank];
+        for (int p = 0; p < a.p2p->world; ++p) {
+            um2 = max(um2, *reinterpret_cast<const volatile unsigned long long*>(&mine->maxima[p][0]));
+            dm2 = max(dm2, *reinterpret_cast<const volatile unsigned long long*>(&mine->maxima[p][1]));
+        }
+    }
+    const double um = sqrt(__longlong_as_double((long long)um2));
     const float s0 = (float)(1.0 / (um * a.sa.max_abs_ux)), s1 = (float)(1.0 / (um * a.sa.max_abs_uy));
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const double dm = sqrt(__longlong_as_double((long long)sc->dumax2_bits));
+        const double dm = sqrt(__longlong_as_double((long long)dm2));
         sc->U_max_norm = um;
         sc->dU_max_norm = dm;
         sc->in_scale[0] = s0;
@@ -411,6 +544,7 @@ void launch_means(const MeansArgs& a, cudaStream_t s, bool fold_rows_here) {
 //      every rank evaluates this redundantly on the all-reduced means.
 __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
     pdl_enter();
+    if (a.p2p) p2p_wait(a.p2p, 1, 0xFFu);          // every rank's strip means have been pushed into a.means
     if (a.n_fold_tasks > 0) {      // fold the row partials of every task (one warp per task), FP64, fixed order
         const int lane = threadIdx.x & 31;
         for (int t = threadIdx.x >> 5; t < a.n_fold_tasks; t += blockDim.x >> 5) {
@@ -474,7 +608,7 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) a.coff[i] = (float)(a.offsets[i] + s_shift[i / a.B]);
     if (threadIdx.x == 0) {
         a.sc->umax2_bits = 0ull; a.sc->dumax2_bits = 0ull;      // re-arm the running maxima of prep
-        if (a.host_skip) { *reinterpret_cast<volatile int*>(a.host_skip) = a.sc->skip; __threadfence_system(); }
+        if (a.host_skip) { *reinterpret_cast<volatile int*>(a.host_skip) = a.sc->skip | (a.sc->comm_error << 8); __threadfence_system(); }
     }
 }
 void launch_offsets(const OffsetsArgs& a, cudaStream_t s) {
@@ -549,6 +683,7 @@ void launch_place(const PlaceArgs& a, cudaStream_t s) {
 //     (p = p_prev + delta_p) for the deltaU variant.
 __global__ void __launch_bounds__(256) back_kernel(BackArgs a) {
     pdl_enter();
+    if (a.p2p) p2p_wait(a.p2p, 2, a.p2p->pix_recv_mask);   // ghost pixels pushed by their owners
     const int skip = a.sc->skip;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
         const int i0 = __ldcs(a.v0 + i), i1 = __ldcs(a.v1 + i), i2 = __ldcs(a.v2 + i);

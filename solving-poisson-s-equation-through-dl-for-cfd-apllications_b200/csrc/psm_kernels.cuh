@@ -36,8 +36,35 @@ struct Scalars {
     float  out_scale;                // max_abs_p * U_max_norm^2 (SMC:551) or 1 (GRAD:537-538)
     int    skip;                     // 1: irrelevant time step (SMC:410-415) or no previous U yet
     int    have_prev;                // 5-column deltaU mode: U(t-1) is resident
-    int    pad;
+    unsigned int step;               // multi-GPU: id of the current step (flags of the peer-memory exchanges)
+    int    comm_error;               // multi-GPU: a peer flag did not arrive in time
+    unsigned int push_done[3];       // multi-GPU: CTAs of a push kernel that have finished their stores
 };
+
+// ---- multi-GPU exchanges over peer memory (NVLink P2P, cudaIpc-mapped buffers) ---------------------------
+// Every exchange of a step is a PUSH: the producing rank stores straight into the consumer's buffers
+// (ghost cells, strip-mean slots, ghost pixels, the two running maxima), fences at system scope and then
+// raises flag[phase][src] = step in the consumer's mailbox; the consuming kernel spins on its own mailbox
+// before touching the data.  No NCCL kernel sits on the step's critical path.
+constexpr int kMaxPeers = 8;
+struct PeerMail {
+    unsigned long long maxima[kMaxPeers][2];     // [src]: bit patterns of max|U|^2, max|dU|^2 of rank src
+    unsigned int flag[3][kMaxPeers];             // [phase][src]: step id the pushed data belongs to
+};
+struct P2PArgs {
+    int rank, world;
+    PeerMail* mail[kMaxPeers];                   // mail[p]: rank p's mailbox (own one included)
+    float2* uv_ghost[kMaxPeers];                 // where MY cells land in rank p's ghost-cell region
+    double* means[kMaxPeers];                    // rank p's strip-mean array (global slots)
+    float* field_ghost[kMaxPeers];               // where MY pixels land in rank p's ghost-pixel region (field 0)
+    long long field_stride[kMaxPeers];           // rank p's floats per field plane
+    long long cell_send_ptr[kMaxPeers + 1], pix_send_ptr[kMaxPeers + 1];
+    unsigned int pix_recv_mask;                  // peers this rank receives ghost pixels from
+    Scalars* sc;
+};
+void launch_p2p_push_cells(const P2PArgs* d_pa, const float2* uv, const int32_t* send_idx, long long nsend, cudaStream_t s);
+void launch_p2p_push_means(const P2PArgs* d_pa, const struct DevTask* tasks, int n_tasks, int world, const double* means, cudaStream_t s);
+void launch_p2p_push_pix(const P2PArgs* d_pa, const float* field, const int32_t* send_idx, int F, long long my_stride, long long nsend, cudaStream_t s);
 
 struct PrepArgs {
     const double* cells;  // [n][ncol]
@@ -67,6 +94,7 @@ struct GatherArgs {
     float* grid0; float* grid1;   // planes [H*W] (padded)
     long long n_pix4;             // number of 4-pixel groups
     ScalarArgs sa;                // thread 0 also publishes the step's scalars (U_max_norm, scales, skip rule)
+    const P2PArgs* p2p;           // multi-GPU over peer memory: wait for the pushed maxima + ghost cells first
 };
 void launch_gather(const GatherArgs& a, cudaStream_t s);
 
@@ -175,6 +203,7 @@ struct OffsetsArgs {
     const DevShiftTerm* terms; int term_start[3]; int shift_len[2];
     Scalars* sc;
     int* host_skip;                   // mapped pinned host word: the step's status without a copy node
+    const P2PArgs* p2p;               // multi-GPU over peer memory: wait for every rank's strip means first
     // single-GPU: the row partials are folded into means here (multi-GPU does it before the all-reduce)
     const DevTask* tasks; int n_fold_tasks; const int32_t* row_start; const double* row_sums; double* means_out;
 };
@@ -198,6 +227,7 @@ struct BackArgs {
     const double* p_prev; double* out;
     int n_fields; int additive;
     const Scalars* sc;
+    const P2PArgs* p2p;               // multi-GPU over peer memory: wait for the pushed ghost pixels first
 };
 void launch_back(const BackArgs& a, cudaStream_t s);
 

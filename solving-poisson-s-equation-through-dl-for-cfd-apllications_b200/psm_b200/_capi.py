@@ -56,7 +56,7 @@ class PsmGeometry(C.Structure):
     _fields_ = [('grid_h', C.c_int32), ('grid_w', C.c_int32), ('shape', C.c_int32), ('overlap', C.c_int32),
                 ('n_x', C.c_int32), ('n_y', C.c_int32), ('p_i', C.c_int32), ('p_j', C.c_int32),
                 ('n_blocks', C.c_int32), ('n_fields', C.c_int32), ('n_cells', C.c_int64),
-                ('n_tasks', C.c_int32), ('reserved', C.c_int32),
+                ('n_tasks', C.c_int32), ('peer_memory_exchange', C.c_int32),
                 ('row0', C.c_int32), ('row1', C.c_int32), ('ext_rows', C.c_int32), ('first_block', C.c_int32),
                 ('n_local_blocks', C.c_int32), ('world', C.c_int32),
                 ('n_ghost_cells', C.c_int64), ('n_ghost_pix', C.c_int64)]

@@ -37,7 +37,10 @@ def main():
     ap.add_argument('--variant', default='deltaU_to_deltaP')
     ap.add_argument('--near-wall', type=float, default=0.0)
     ap.add_argument('--halo', default='cells', choices=['cells', 'grid'])
+    ap.add_argument('--comm', default='p2p', choices=['p2p', 'nccl'])
     args = ap.parse_args()
+    if args.comm == 'nccl':
+        os.environ['PSM_COMM'] = 'nccl'
     rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', rank))
     dist.init_process_group('gloo')
@@ -61,7 +64,7 @@ def main():
     sm.comm_init(ids[0], rank, world)
     sm.init_shard(sh)
     out = None
-    for _ in range(5):                          # repeated steps: eager first, then the captured graph
+    for _ in range(8):                          # repeated steps: the captured graph is replayed, buffers are reused
         out, rc = sm.predict(cells[sh['owned_ids']])
     offsets = sm.stage('offsets')
     field = sm.stage('field')
@@ -105,6 +108,7 @@ def main():
             e_field = max(rel(fld[0], r['dp_dx']), rel(fld[1], r['dp_dy']))
         e_single = rel(full, single)
         e_sf = rel(fld, single_field)
+        assert geo['peer_memory_exchange'] == int(args.comm == 'p2p' and args.halo == 'cells'), geo
         print('mgpu %s world=%d: rel-L2 vs oracle cells %.2e field %.2e | vs single-GPU cells %.2e field %.2e | '
               'ghost cells/pix on rank0 %d/%d' % (variant, world, e_or, e_field, e_single, e_sf, geo['n_ghost_cells'], geo['n_ghost_pix']))
         ok = e_or < 1e-3 and e_field < 1e-3 and e_single < 1e-5 and e_sf < 1e-5

@@ -18,7 +18,8 @@ def _n_gpus():
         return 0
 
 
-@pytest.mark.parametrize("variant,extra", [('deltaU_to_deltaP', []), ('deltaU_to_deltaP', ['--near-wall', '0.05', '--halo', 'grid']),
+@pytest.mark.parametrize("variant,extra", [('deltaU_to_deltaP', []), ('deltaU_to_deltaP', ['--comm', 'nccl']),
+                                           ('deltaU_to_deltaP', ['--near-wall', '0.05', '--halo', 'grid']),
                                            ('U_to_gradP', []), ('U_to_gradP', ['--halo', 'grid'])])
 def test_two_rank_shards_match_oracle_and_single_gpu(variant, extra):
     if _n_gpus() < 2:
