@@ -35,6 +35,30 @@ from psm_b200 import synthetic as syn, tables as ptables    # noqa: E402
 HBM_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 
 
+# kernel measured by each HBM stage's CUDA events (key of profiles/traffic_*.json, written by profiles/summarize_full.py)
+STAGE_KERNEL = {'gather': 'gather_extract_kernel', 'back_gather': 'back_kernel', 'place': 'place_kernel',
+                'extract': 'extract_kernel', 'prep': 'prep_kernel<2, 5>'}
+
+
+def measured_traffic(workload, stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernel from the committed
+    `ncu --set full` capture of this workload (profiles/traffic_<workload>_*.json, newest round), else None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(REPO, 'profiles', 'traffic_%s_*.json' % workload)))
+    if not files:
+        return None, None
+    try:
+        d = json.load(open(files[-1]))
+        k = STAGE_KERNEL.get(stage)
+        if stage == 'prep' and k not in d:
+            k = next((x for x in d if x.startswith('prep_kernel')), k)
+        if stage == 'gather' and k not in d:
+            k = 'gather_kernel'
+        return (d[k]['dram_traffic_bytes'], os.path.basename(files[-1])) if k in d else (None, None)
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     try:
         with open(os.path.join(REPO, 'MEASURED_PEAKS.json')) as f:
@@ -91,15 +115,18 @@ def build_sharded_case(world, rank, variant, dist, mesh_kw=None, seed=0):
     return mesh, F, params, sh, time.time() - t0
 
 
-def stage_bytes(n_cells, G, B, C, pc_in, pc_p, ncol, S=128):
+def stage_bytes(n_cells, G, B, C, pc_in, pc_p, ncol, S=128, fused_extract=True):
     """Algorithmic bytes per step and stage (SURVEY.md section 8d / DESIGN.md): FP32 device storage,
-    f64 only at the ABI.  Overlap re-reads and L2-resident intermediates are NOT counted twice."""
+    f64 only at the ABI.  Overlap re-reads and L2-resident intermediates are NOT counted twice.
+    With the fused gather+extraction kernel (the default when W % 4 == 0) the block operand is written by the
+    gather itself: its bytes move from 'extract' to 'gather' and the grid is never re-read."""
     S2 = S * S
+    xu = 4 * B * 2 * S2
     return {
         # read rows, write float2 field + p_prev; 5-column mode also reads and rewrites the resident U(t-1)
         'prep': n_cells * (ncol * 8 + 8 + 8 + (32 if ncol == 5 else 0)),
-        'gather': G * (12 + 12 + 8) + 8 * n_cells,            # tables + 2 planes out + each cell value once
-        'extract': 8 * G + 4 * B * 2 * S2,                    # grid read once, operand written
+        'gather': G * (12 + 12 + 8) + 8 * n_cells + (xu if fused_extract else 0),   # tables + 2 planes out + each cell value once
+        'extract': 0 if fused_extract else 8 * G + xu,        # grid read once, operand written
         'pca_project': 4 * B * 2 * S2 + 4 * 2 * S2 * pc_in + 4 * B * pc_in,
         'mlp': 4 * (pc_in * 512 + 2 * 512 * 512 + 512 * pc_p) + 8 * B * pc_p,
         'pca_inverse': 4 * pc_p * S2 * C + 4 * B * S2 * C,
@@ -362,15 +389,18 @@ def main():
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        sb = stage_bytes(n, (geo['row1'] - geo['row0']) * geo['grid_w'], geo['n_local_blocks'], sm.n_fields, sm.pc_in, sm.pc_p, ncol)
+        fused = geo['grid_w'] % 4 == 0 and not os.environ.get('PSM_NO_FUSED_EXTRACT')
+        sb = stage_bytes(n, (geo['row1'] - geo['row0']) * geo['grid_w'], geo['n_local_blocks'], sm.n_fields, sm.pc_in, sm.pc_p, ncol,
+                         fused_extract=fused)
         stage_avg = dict(zip(psm_b200._capi.TIMING_NAMES, (stage_ms / args.steps).tolist()))
         stages = {k: {'ms': stage_avg[k], 'GBps': (sb[k] / (stage_avg[k] * 1e-3) / 1e9) if stage_avg.get(k, 0) > 0 else None}
                   for k in sb}
         hbm_stages = ['gather', 'back_gather', 'place', 'extract', 'prep']
         dom = max(hbm_stages, key=lambda k: stage_avg[k])
         ach = sb[dom] / (stage_avg[dom] * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(workload if world == 1 else 'n%d' % world, dom)
         roof = {'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peak_src,
+                'frac': ach / peaks['hbm_gbs'], 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': sb[dom]}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
