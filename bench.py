@@ -119,13 +119,14 @@ def stage_bytes(n_cells, G, B, C, pc_in, pc_p, ncol, S=128, fused_extract=True):
     """Algorithmic bytes per step and stage (SURVEY.md section 8d / DESIGN.md): FP32 device storage,
     f64 only at the ABI.  Overlap re-reads and L2-resident intermediates are NOT counted twice.
     With the fused gather+extraction kernel (the default when W % 4 == 0) the block operand is written by the
-    gather itself: its bytes move from 'extract' to 'gather' and the grid is never re-read."""
+    gather itself: its bytes move from 'extract' to 'gather'; the grid planes are neither written nor re-read."""
     S2 = S * S
     xu = 4 * B * 2 * S2
     return {
         # read rows, write float2 field + p_prev; 5-column mode also reads and rewrites the resident U(t-1)
         'prep': n_cells * (ncol * 8 + 8 + 8 + (32 if ncol == 5 else 0)),
-        'gather': G * (12 + 12 + 8) + 8 * n_cells + (xu if fused_extract else 0),   # tables + 2 planes out + each cell value once
+        # tables + each cell value once + (fused: the block operand | else: the two grid planes)
+        'gather': G * (12 + 12) + 8 * n_cells + (xu if fused_extract else 8 * G),
         'extract': 0 if fused_extract else 8 * G + xu,        # grid read once, operand written
         'pca_project': 4 * B * 2 * S2 + 4 * 2 * S2 * pc_in + 4 * B * pc_in,
         'mlp': 4 * (pc_in * 512 + 2 * 512 * 512 + 512 * pc_p) + 8 * B * pc_p,

@@ -291,6 +291,13 @@ int psm_plan_shift_lines(int32_t variant, int32_t grid_h, int32_t grid_w, int32_
 int psm_debug_gemm(int32_t device, int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
                    float* C, int32_t splits);
 
+/* Unit-test entry for the fused Dense-stack kernel (NNS:8-38): out[M][dims[n]] = Dense(linear)(relu(... relu(x W0 + b0) ...)),
+ * kernels[l] in the Keras layout [dims[l]][dims[l+1]].  mode = PSM_GEMM_TC_3XTF32 or PSM_GEMM_TC_TF32.
+ * clusters > 0 caps the number of 8-CTA clusters (to exercise the multi-tile-per-cluster loop). */
+int psm_debug_dense_stack(int32_t device, int32_t mode, int32_t M, int32_t n_layers, const int32_t* dims,
+                          const float* const* kernels, const float* const* biases, const float* x, float* out,
+                          int32_t clusters);
+
 int psm_api_version(void);
 
 #ifdef __cplusplus

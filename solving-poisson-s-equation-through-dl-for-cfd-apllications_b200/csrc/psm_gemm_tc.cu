@@ -458,6 +458,286 @@ int launch_dense_cluster(const TcGemm& t, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// The whole Dense stack in one launch (see psm_kernels.cuh).  192 threads: warp 0 = TMA producer, warp 1 = TMEM
+// allocator + MMA issuer, warps 2..5 = TMEM -> shared-memory parking; all six warps fold the cluster's partials.
+namespace {
+constexpr int S_BN = 64;
+constexpr int S_KS = 8;                                 // cluster size = K slices per output tile
+constexpr int S_STAGES = 3;
+constexpr int S_A_BYTES = BM * BK * 4, S_B_BYTES = S_BN * BK * 4;
+constexpr int S_STAGE = 2 * (S_A_BYTES + S_B_BYTES);    // A_hi | A_lo | B_hi | B_lo
+constexpr int S_PARK_LD = S_BN + 4;                     // floats per parked row: 16-byte aligned, conflict-free float4 rows
+constexpr int S_PARK = BM * S_PARK_LD * 4;
+constexpr int S_SMEM = S_STAGES * S_STAGE + 2 * S_PARK + 1024 + 256;
+
+__device__ __forceinline__ void st_dsmem_v4(uint32_t local_addr, uint32_t cta, float4 v) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+          "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+          "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1) dense_stack_kernel(const __grid_constant__ DenseStackArgs g) {
+    constexpr int BN = S_BN, KS = S_KS, STAGES = S_STAGES, A_BYTES = S_A_BYTES, B_BYTES = S_B_BYTES, STAGE = S_STAGE;
+    constexpr int ROWS = BM / KS;                                // rows of a tile folded by each CTA of the cluster
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t park0 = base + STAGES * STAGE;
+    const uint32_t bars = park0 + 2 * S_PARK;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = accum_bar + 8u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    pdl_launch_dependents();
+    int tr_n = 0;
+    auto stamp = [&]() {
+        if (g.trace && threadIdx.x == 64 && tr_n < 64) {
+            unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            g.trace[(size_t)blockIdx.x * 64 + tr_n++] = t;
+        }
+    };
+    stamp();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int z = blockIdx.x % KS;                               // rank in the cluster (cluster = 8 consecutive CTAs along x)
+    const int cl = blockIdx.x / KS, n_cl = gridDim.x / KS;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+    cluster_sync_all();          // every CTA of the cluster has started: its shared memory may be written remotely
+    if (warp == 0 && lane == 0) {
+        // the weights do not depend on the previous kernel: pull every tile this CTA will use into L2 while it drains
+        for (int l = 0; l < g.n_layers; ++l) {
+            const DenseLayerDesc& L = g.L[l];
+            const int kb_total = L.K / BK, kb_per = (kb_total + KS - 1) / KS;
+            const int kb0 = z * kb_per, nkb = max(min(kb_total - kb0, kb_per), 0);
+            const int n_tiles = L.N / BN;
+            for (int t = cl; t < n_tiles; t += n_cl)             // weight tiles repeat for every row tile
+                for (int it = 0; it < nkb; ++it) {
+                    tma_prefetch_l2_2d(reinterpret_cast<const CUtensorMap*>(g.maps + 4 * l + 2), (kb0 + it) * BK, t * BN);
+                    tma_prefetch_l2_2d(reinterpret_cast<const CUtensorMap*>(g.maps + 4 * l + 3), (kb0 + it) * BK, t * BN);
+                }
+        }
+    }
+    stamp();
+    pdl_wait();
+    stamp();
+
+    uint32_t it_pipe = 0;        // k-blocks this CTA has pushed through the pipeline (same count in producer and issuer)
+    uint32_t acc_phase = 0;      // completed accumulations of this CTA
+    uint32_t pb = 0;             // parking buffer of the current tile
+    const uint32_t idesc = make_idesc_tf32(BM, BN);
+
+    for (int l = 0; l < g.n_layers; ++l) {
+        const DenseLayerDesc& L = g.L[l];
+        const CUtensorMap* mA_hi = reinterpret_cast<const CUtensorMap*>(g.maps + 4 * l + 0);
+        const CUtensorMap* mA_lo = reinterpret_cast<const CUtensorMap*>(g.maps + 4 * l + 1);
+        const CUtensorMap* mB_hi = reinterpret_cast<const CUtensorMap*>(g.maps + 4 * l + 2);
+        const CUtensorMap* mB_lo = reinterpret_cast<const CUtensorMap*>(g.maps + 4 * l + 3);
+        const int kb_total = L.K / BK;
+        const int kb_per = (kb_total + KS - 1) / KS;
+        const int active = (kb_total + kb_per - 1) / kb_per;      // CTAs of the cluster that own >= 1 k-block
+        const int kb0 = z * kb_per;
+        const int nkb = max(min(kb_total - kb0, kb_per), 0);
+        const int n_tiles = L.N / BN;
+        const int tiles = (g.M / BM) * n_tiles;
+        for (int t = cl; t < tiles; t += n_cl) {
+            const int m0 = (t / n_tiles) * BM, n0 = (t % n_tiles) * BN;
+            if (warp == 0) {
+                if (lane == 0) {
+                    for (int it = 0; it < nkb; ++it) {
+                        const uint32_t i = it_pipe + it;
+                        const int s = i % STAGES;
+                        mbar_wait(empty_bar(s), ((i / STAGES) & 1) ^ 1);
+                        mbar_expect_tx(full_bar(s), 2 * (A_BYTES + B_BYTES));
+                        const uint32_t st = base + s * STAGE;
+                        const int kc = (kb0 + it) * BK;
+                        tma_load_2d(st, mA_hi, kc, m0, full_bar(s));
+                        tma_load_2d(st + A_BYTES, mA_lo, kc, m0, full_bar(s));
+                        tma_load_2d(st + 2 * A_BYTES, mB_hi, kc, n0, full_bar(s));
+                        tma_load_2d(st + 2 * A_BYTES + B_BYTES, mB_lo, kc, n0, full_bar(s));
+                    }
+                }
+                __syncwarp();
+            } else if (warp == 1) {
+                if (lane == 0) {
+                    for (int it = 0; it < nkb; ++it) {
+                        const uint32_t i = it_pipe + it;
+                        const int s = i % STAGES;
+                        mbar_wait(full_bar(s), (i / STAGES) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t st = base + s * STAGE;
+                        const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint32_t ko = k * UMMA_K * 4;
+                            umma_tf32(tmem_base, make_smem_desc(a_hi + ko), make_smem_desc(b_hi + ko), idesc, (it | k) != 0);
+                            if (g.three_pass) {
+                                umma_tf32(tmem_base, make_smem_desc(a_hi + ko), make_smem_desc(b_lo + ko), idesc, 1);
+                                umma_tf32(tmem_base, make_smem_desc(a_lo + ko), make_smem_desc(b_hi + ko), idesc, 1);
+                            }
+                        }
+                        umma_commit(empty_bar(s));
+                    }
+                    if (nkb > 0) umma_commit(accum_bar);
+                }
+                __syncwarp();
+            } else if (nkb > 0) {
+                mbar_wait(accum_bar, acc_phase & 1);
+                stamp();
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int q = warp & 3;
+                const int row = q * 32 + lane;
+                float v[64];
+                tmem_ld64(tmem_base + ((uint32_t)(q * 32) << 16), v);
+                stamp();
+                // push this row of the partial into the CTA that folds it: slot [z][row % 16] of CTA row / 16
+                const uint32_t dst = park0 + pb * S_PARK + (uint32_t)((z * ROWS + (row % ROWS)) * S_PARK_LD) * 4u;
+                const uint32_t owner = (uint32_t)(row / ROWS);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) st_dsmem_v4(dst + 16u * i, owner, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+            it_pipe += nkb;
+            if (nkb > 0) ++acc_phase;
+            stamp();
+            cluster_sync_all();                                  // every partial of this tile has landed in its folder's buffer
+            stamp();
+            {
+                // CTA z folds rows [z*16, z*16+16) x 64 columns from its OWN shared memory: slots 0..active-1, fixed order
+                const float* park = reinterpret_cast<const float*>(gen_base + (park0 + pb * S_PARK - base));
+                for (int e = threadIdx.x; e < ROWS * (BN / 4); e += kThreads) {
+                    const int rl = e / (BN / 4), c4 = e % (BN / 4);
+                    const int r = z * ROWS + rl;
+                    float4 acc = *reinterpret_cast<const float4*>(park + rl * S_PARK_LD + c4 * 4);
+                    for (int p = 1; p < active; ++p) {
+                        const float4 w = *reinterpret_cast<const float4*>(park + (p * ROWS + rl) * S_PARK_LD + c4 * 4);
+                        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+                    }
+                    const int n = n0 + c4 * 4;
+                    const size_t o = (size_t)(m0 + r) * L.N + n;
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(L.bias + n));
+                    float4 y;
+                    if (L.epi == EPI_BIAS_RELU) {
+                        y = make_float4(fmaxf(acc.x + b.x, 0.f), fmaxf(acc.y + b.y, 0.f), fmaxf(acc.z + b.z, 0.f), fmaxf(acc.w + b.w, 0.f));
+                    } else {
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(L.v1 + n));
+                        const float4 sh = __ldg(reinterpret_cast<const float4*>(L.v2 + n));
+                        y = make_float4((acc.x + b.x) * sc.x + sh.x, (acc.y + b.y) * sc.y + sh.y, (acc.z + b.z) * sc.z + sh.z,
+                                        (acc.w + b.w) * sc.w + sh.w);
+                    }
+                    if (L.out) *reinterpret_cast<float4*>(L.out + o) = y;
+                    if (L.out_hi) {
+                        float4 hi;
+                        hi.x = __uint_as_float(__float_as_uint(y.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(y.y) & 0xFFFFE000u);
+                        hi.z = __uint_as_float(__float_as_uint(y.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(y.w) & 0xFFFFE000u);
+                        *reinterpret_cast<float4*>(L.out_hi + o) = hi;
+                        *reinterpret_cast<float4*>(L.out_lo + o) = make_float4(y.x - hi.x, y.y - hi.y, y.z - hi.z, y.w - hi.w);
+                    }
+                }
+            }
+            stamp();
+            pb ^= 1;             // the other buffer is free: its readers passed the cluster barrier above
+        }
+        if (l + 1 < g.n_layers) {
+            // grid barrier: this layer's activations (generic-proxy stores) are read by the next layer's TMA loads
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const unsigned int target = (unsigned int)(l + 1) * gridDim.x;
+                __threadfence();
+                atomicAdd(g.barrier, 1u);
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(g.barrier) < target) {
+                    if (clock64() - t0 > 2000000000ll) { *g.error = 1; break; }
+                }
+                __threadfence();
+            }
+            __syncthreads();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            stamp();
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                          // nobody leaves while its shared memory is being read
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// Largest number of 8-CTA clusters of dense_stack_kernel the device holds at once (the kernel's grid barrier needs
+// every CTA resident).
+int dense_stack_prepare(int* max_clusters) {
+    if (cudaFuncSetAttribute(dense_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM) != cudaSuccess) return -1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(S_KS * 16); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = S_SMEM;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = S_KS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, dense_stack_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); return -1; }
+    *max_clusters = n;
+    return 0;
+}
+
+int launch_dense_stack(const DenseStackArgs& a, int clusters, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(S_KS * clusters, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = S_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = S_KS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, dense_stack_kernel, a) == cudaSuccess ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Host side: tensor maps (driver entry point fetched through the runtime: no link-time libcuda).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

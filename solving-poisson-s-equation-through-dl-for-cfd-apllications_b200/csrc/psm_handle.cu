@@ -23,6 +23,7 @@ namespace {
 thread_local std::string g_create_error;
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline bool env_on(const char* name) { const char* e = getenv(name); return e && e[0] && e[0] != '0'; }
 inline long long round_up_ll(long long v, long long m) { return (v + m - 1) / m * m; }
 }  // namespace
 
@@ -120,6 +121,7 @@ struct psm_handle {
     uint8_t* d_gmask = nullptr; uint16_t* d_owner = nullptr;
     int32_t *d_by0 = nullptr, *d_bx0 = nullptr;
     CoverEntry *d_rowcov = nullptr, *d_colcov = nullptr; bool fused_extract = false;   // gather writes the block operand itself
+    bool keep_grid = false;           // fused path: also store the grid planes every step (PSM_KEEP_GRID=1); else psm_get_stage rebuilds them
     DevTask* d_tasks = nullptr; DevRec* d_rec = nullptr; int n_tasks = 0 /* local */, rounds = 0;
     int2* d_rows = nullptr; int32_t* d_row_start = nullptr; double* d_row_sums = nullptr; int n_rows = 0;
     float* d_zc = nullptr;            // [B_pad][pc_in_pad]
@@ -135,6 +137,11 @@ struct psm_handle {
     TcGemm tc_proj{}, tc_inv{}; std::vector<TcGemm> tc_dense; std::vector<int> dense_splits; int tc_splits = 1;
     float* d_dpart = nullptr;       // split-K partials of the Dense layers   // tcgen05 path (gemm_mode 0/1)
     bool dense_cluster = true;      // Dense layers: cluster split-K with on-chip reduction (one launch per layer)
+    // whole Dense stack in one persistent launch (opt-in, PSM_DENSE_STACK=1: measured equal to the per-layer cluster
+    // kernels on the stage and slower for the step): weights and activations pre-split into tf32 hi / lo
+    bool dense_stack = false; int stack_clusters = 0;
+    std::vector<float*> d_Whi, d_Wlo; float* d_act_hi[2] = {nullptr, nullptr}; float* d_act_lo[2] = {nullptr, nullptr};
+    TensorMap128* d_stack_maps = nullptr; DenseStackArgs stack_args{};
     int launches = 0;
     cudaEvent_t ev[PSM_N_TIMINGS + 1] = {};
     bool ev_valid = false, ev_created = false;
@@ -318,6 +325,18 @@ extern "C" int psm_load_params(psm_handle* h, const psm_params* p) {
         TRY(upload(h, &db, b));
         h->d_W.push_back(dw);
         h->d_bias.push_back(db);
+        {   // 3xTF32 operands of the fused Dense stack: hi = the TF32 part, lo = the exact remainder
+            std::vector<float> whi(w.size()), wlo(w.size());
+            for (size_t i = 0; i < w.size(); ++i) {
+                uint32_t u; memcpy(&u, &w[i], 4); u &= 0xFFFFE000u;
+                memcpy(&whi[i], &u, 4); wlo[i] = w[i] - whi[i];
+            }
+            float *dh = nullptr, *dl = nullptr;
+            TRY(upload(h, &dh, whi));
+            TRY(upload(h, &dl, wlo));
+            h->d_Whi.push_back(dh);
+            h->d_Wlo.push_back(dl);
+        }
     }
     {   // de-standardisation (SMC:533 / 537)
         std::vector<float> s(h->pc_p_pad, 0.f), m(h->pc_p_pad, 0.f);
@@ -501,7 +520,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
         TRY(upload(h, &h->d_bx0, bx0));
         {   // which block rows / block columns cover a pixel row / a 4-pixel column group (fused gather + extraction)
             const int nrows_g = h->H + L.local_ext, nbr = L.blk_row1 - L.blk_row0;
-            bool ok = (W % 4 == 0) && L.ext_rows == 0 && !getenv("PSM_NO_FUSED_EXTRACT");
+            bool ok = (W % 4 == 0) && L.ext_rows == 0 && !env_on("PSM_NO_FUSED_EXTRACT");
             for (int j = 0; j < ncolb && ok; ++j) ok = (bx0[j] % 4 == 0);
             std::vector<CoverEntry> rcv(nrows_g), ccv(W / 4 + 1);
             for (int y = 0; y < nrows_g && ok; ++y) {
@@ -519,6 +538,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
                 ccv[xg] = ce;
             }
             h->fused_extract = ok;
+            h->keep_grid = env_on("PSM_KEEP_GRID");
             if (ok) { TRY(upload(h, &h->d_rowcov, rcv)); TRY(upload(h, &h->d_colcov, ccv)); }
         }
         // tasks: masked means first, then the shift-line sums; a task is evaluated by the rank holding `src`
@@ -656,7 +676,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
         // 64-column tiles x split-K partials (each CTA streams <= ~100 KB), folded by the reduce kernel.
         h->tc_dense.resize(h->n_dense);
         h->dense_splits.assign(h->n_dense, 1);
-        h->dense_cluster = !getenv("PSM_NO_DENSE_CLUSTER");
+        h->dense_cluster = !env_on("PSM_NO_DENSE_CLUSTER");
         if (h->dense_cluster && dense_cluster_prepare() != 0) PSM_FAIL(h, PSM_ERR_CUDA, "cannot opt in to the shared memory of the Dense cluster kernel");
         TRY(dalloc(h, &h->d_dpart, (size_t)8 * Bp * maxw));
         const float* in = h->d_xin;
@@ -686,6 +706,33 @@ static int init_local(psm_handle* h, LocalInit& L) {
         }
         TRY(mk(h->tc_inv, h->d_r, Bp, h->d_comp_out_t, S2 * h->C, h->pc_p_pad, h->d_blocks, S2 * h->C, 1, EPI_PCA_INV,
                h->d_pmean, nullptr, nullptr, 128));
+        // ---- the whole Dense stack as one persistent launch -------------------------------------------------
+        int max_cl = 0;
+        h->dense_stack = env_on("PSM_DENSE_STACK") && h->n_dense <= kMaxDense && dense_stack_prepare(&max_cl) == 0;
+        if (h->dense_stack) {
+            for (int i = 0; i < 2; ++i) { TRY(dalloc(h, &h->d_act_hi[i], (size_t)Bp * maxw)); TRY(dalloc(h, &h->d_act_lo[i], (size_t)Bp * maxw)); }
+            std::vector<TensorMap128> maps((size_t)4 * h->n_dense);
+            DenseStackArgs& sa = h->stack_args;
+            sa = DenseStackArgs{};
+            int max_tiles = 1;
+            for (int l = 0; l < h->n_dense; ++l) {
+                const bool last = (l == h->n_dense - 1);
+                const int K = h->dims_pad[l], N = h->dims_pad[l + 1];
+                if (make_kmajor_map(&maps[4 * l + 0], h->d_act_hi[l & 1], Bp, K, K, 128) != 0 ||
+                    make_kmajor_map(&maps[4 * l + 1], h->d_act_lo[l & 1], Bp, K, K, 128) != 0 ||
+                    make_kmajor_map(&maps[4 * l + 2], h->d_Whi[l], N, K, K, 64) != 0 ||
+                    make_kmajor_map(&maps[4 * l + 3], h->d_Wlo[l], N, K, K, 64) != 0)
+                    PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed (Dense stack)");
+                sa.L[l] = DenseLayerDesc{K, N, last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU, h->d_bias[l], h->d_out_s, h->d_out_m,
+                                         last ? h->d_r : nullptr, last ? nullptr : h->d_act_hi[(l + 1) & 1],
+                                         last ? nullptr : h->d_act_lo[(l + 1) & 1]};
+                max_tiles = std::max(max_tiles, (Bp / 128) * (N / 64));
+            }
+            TRY(upload(h, &h->d_stack_maps, maps));
+            sa.maps = h->d_stack_maps; sa.n_layers = h->n_dense; sa.M = Bp; sa.three_pass = three;
+            sa.barrier = &h->d_sc->dense_barrier; sa.error = &h->d_sc->comm_error;
+            h->stack_clusters = std::min(std::min(max_cl, 16), max_tiles);
+        }
     }
     if (L.world > 1) TRY(setup_p2p(h));
     if (h->cfg.enable_timings) TRY(psm_set_timings(h, 1));
@@ -855,6 +902,7 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     int nl = 0, te = 1;
     auto tick = [&]() { if (h->ev_valid) cudaEventRecord(h->ev[te], s); ++te; };
 
+    ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], deltas ? h->maxs[3] : 1.0, deltas ? 1 : 0, h->cfg.skip_threshold, mode, 0};
     PrepArgs pa{d_cells, h->n_cells, h->cfg.input_cols, mode, h->d_uv, h->d_pprev, h->d_uprev, h->d_sc};
     launch_prep(pa, s); ++nl;
     const bool p2p = multi && h->p2p;
@@ -872,13 +920,12 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         TRY(sparse_exchange(h, h->d_cell_send, h->cell_send_ptr, reinterpret_cast<float*>(h->d_uv + h->n_cells), h->cell_recv_ptr, 2));
         NC(h, g_nccl.GroupEnd());
     }
-    ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], deltas ? h->maxs[3] : 1.0, deltas ? 1 : 0, h->cfg.skip_threshold, mode};
     tick();   // prep
     float* grid0 = h->d_grid; float* grid1 = h->d_grid + h->grid_stride;
     GatherArgs ga{h->d_fv[0], h->d_fv[1], h->d_fv[2], h->d_fw[0], h->d_fw[1], h->d_fw[2], h->d_uv,
-                  grid0, grid1, h->G_pad / 4, sa, d_p2p};
+                  grid0, grid1, h->G_pad / 4, sa, 0, d_p2p};
     if (h->fused_extract) {
-        GatherExtractArgs ge{ga, h->d_rowcov, h->d_colcov, h->d_by0, h->d_bx0, h->d_xu, h->W / 4, h->plan.n_x + 1, S};
+        GatherExtractArgs ge{ga, h->d_rowcov, h->d_colcov, h->d_by0, h->d_bx0, h->d_xu, h->W / 4, h->plan.n_x + 1, S, h->keep_grid ? 1 : 0};
         launch_gather_extract(ge, s); ++nl;
     } else {
         launch_gather(ga, s); ++nl;
@@ -913,11 +960,15 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         }
         ++nl;
         ReduceArgs r{h->d_part, tc ? h->tc_splits : h->splits, Bp, h->pc_in_pad, h->d_zc, h->d_in_a, h->d_in_b, h->d_xin,
-                     RED_STANDARDISE, nullptr};
+                     RED_STANDARDISE, nullptr, nullptr, nullptr};
+        if (tc && h->dense_stack) { r.x_hi = h->d_act_hi[0]; r.x_lo = h->d_act_lo[0]; }
         launch_reduce_standardise(r, s); ++nl;
     }
     tick();   // pca_project
-    if (tc && h->dense_cluster) {
+    if (tc && h->dense_stack) {
+        if (launch_dense_stack(h->stack_args, h->stack_clusters, s) != 0) PSM_FAIL(h, PSM_ERR_CUDA, "Dense stack launch: %s", cudaGetErrorString(cudaGetLastError()));
+        ++nl;
+    } else if (tc && h->dense_cluster) {
         for (int l = 0; l < h->n_dense; ++l) {
             if (launch_dense_cluster(h->tc_dense[l], s) != 0) PSM_FAIL(h, PSM_ERR_CUDA, "Dense cluster launch: %s", cudaGetErrorString(cudaGetLastError()));
             ++nl;
@@ -1059,7 +1110,7 @@ static int submit_step(psm_handle* h, bool host, const double* in, double* out) 
 static int finish(psm_handle* h) {
     CU(h, cudaStreamSynchronize(h->stream));
     const int v = h->h_sc->skip;        // skip | comm_error << 8, written by offsets_kernel through mapped memory
-    if (v >> 8) PSM_FAIL(h, PSM_ERR_COMM, "a peer-memory exchange timed out (ranks out of step?)");
+    if (v >> 8) PSM_FAIL(h, PSM_ERR_COMM, "a device-side wait timed out (peer-memory exchange: ranks out of step? / Dense-stack grid barrier)");
     return (v & 1) ? PSM_SKIPPED : PSM_OK;
 }
 
@@ -1169,6 +1220,15 @@ extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_
         case PSM_STAGE_GRID: {
             const int64_t gl = (int64_t)(h->H + h->local_ext + h->ext_rows) * h->W;
             TRY(need(2 * gl * 4));
+            if (h->fused_extract && !h->keep_grid) {
+                // the fused gather writes only the block operand: rebuild the planes of the LAST step from the
+                // still-resident cell field and the scales that step published
+                ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], 1.0, 0, 0.0, 0, 1};
+                GatherArgs ga{h->d_fv[0], h->d_fv[1], h->d_fv[2], h->d_fw[0], h->d_fw[1], h->d_fw[2], h->d_uv,
+                              h->d_grid, h->d_grid + h->grid_stride, h->G_pad / 4, sa, 1, nullptr};
+                launch_gather(ga, h->stream);
+                CU(h, cudaStreamSynchronize(h->stream));
+            }
             CU(h, cudaMemcpy(out, h->d_grid, gl * 4, cudaMemcpyDeviceToHost));
             CU(h, cudaMemcpy((char*)out + gl * 4, h->d_grid + h->grid_stride, gl * 4, cudaMemcpyDeviceToHost));
             return PSM_OK;
@@ -1275,5 +1335,97 @@ extern "C" int psm_debug_gemm(int32_t device, int32_t mode, int32_t M, int32_t N
         if (rc == PSM_OK) cudaMemcpy(C, dC, nC * 4, cudaMemcpyDeviceToHost);
     }
     cudaFree(dA); cudaFree(dB); cudaFree(dC);
+    return rc;
+}
+
+// Unit-test entry of the fused Dense stack: out[M][dims[n]] = Dense(linear)(relu(...relu(x W0 + b0)...)), Keras layout
+// kernels[l][in][out].  M is padded to 128 and the widths to 128 internally, like the handle does.
+extern "C" int psm_debug_dense_stack(int32_t device, int32_t mode, int32_t M, int32_t n_layers, const int32_t* dims,
+                                     const float* const* kernels, const float* const* biases, const float* x, float* out,
+                                     int32_t clusters) {
+    if (!dims || !kernels || !biases || !x || !out || M < 1 || n_layers < 1 || n_layers > kMaxDense || mode < 0 || mode > 1) return PSM_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return PSM_ERR_CUDA;
+    int max_cl = 0;
+    if (tc_gemm_prepare() != 0 || dense_stack_prepare(&max_cl) != 0) return PSM_ERR_CUDA;
+    const int Mp = round_up(M, 128);
+    std::vector<int> dp(n_layers + 1);
+    int maxw = 0;
+    for (int i = 0; i <= n_layers; ++i) { if (dims[i] < 1) return PSM_ERR_INVALID; dp[i] = round_up(dims[i], 128); maxw = std::max(maxw, dp[i]); }
+    std::vector<void*> dev;
+    auto dmal = [&](size_t n) -> float* { void* q = nullptr; if (cudaMalloc(&q, n * 4) != cudaSuccess) return nullptr; cudaMemset(q, 0, n * 4); dev.push_back(q); return (float*)q; };
+    auto split = [](const std::vector<float>& v, std::vector<float>& hi, std::vector<float>& lo) {
+        hi.resize(v.size()); lo.resize(v.size());
+        for (size_t i = 0; i < v.size(); ++i) { uint32_t u; memcpy(&u, &v[i], 4); u &= 0xFFFFE000u; memcpy(&hi[i], &u, 4); lo[i] = v[i] - hi[i]; }
+    };
+    int rc = PSM_OK;
+    float* act_hi[2] = {dmal((size_t)Mp * maxw), dmal((size_t)Mp * maxw)};
+    float* act_lo[2] = {dmal((size_t)Mp * maxw), dmal((size_t)Mp * maxw)};
+    float* d_out = dmal((size_t)Mp * dp[n_layers]);
+    float* d_one = dmal(maxw); float* d_zero = dmal(maxw);
+    unsigned int* d_bar = (unsigned int*)dmal(2);
+    TensorMap128* d_maps = (TensorMap128*)dmal((size_t)4 * n_layers * sizeof(TensorMap128) / 4);
+    if (!act_hi[0] || !act_hi[1] || !act_lo[0] || !act_lo[1] || !d_out || !d_one || !d_zero || !d_bar || !d_maps) rc = PSM_ERR_CUDA;
+    DenseStackArgs sa{};
+    std::vector<TensorMap128> maps((size_t)4 * n_layers);
+    int max_tiles = 1;
+    if (rc == PSM_OK) {
+        std::vector<float> ones(maxw, 1.f), xp((size_t)Mp * dp[0], 0.f), hi, lo;
+        cudaMemcpy(d_one, ones.data(), maxw * 4, cudaMemcpyHostToDevice);
+        for (int m = 0; m < M; ++m) for (int k = 0; k < dims[0]; ++k) xp[(size_t)m * dp[0] + k] = x[(size_t)m * dims[0] + k];
+        split(xp, hi, lo);
+        cudaMemcpy(act_hi[0], hi.data(), hi.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(act_lo[0], lo.data(), lo.size() * 4, cudaMemcpyHostToDevice);
+        for (int l = 0; l < n_layers && rc == PSM_OK; ++l) {
+            const int K = dp[l], N = dp[l + 1];
+            std::vector<float> w((size_t)N * K, 0.f), b(N, 0.f);
+            for (int i = 0; i < dims[l]; ++i) for (int o = 0; o < dims[l + 1]; ++o) w[(size_t)o * K + i] = kernels[l][(size_t)i * dims[l + 1] + o];
+            for (int o = 0; o < dims[l + 1]; ++o) b[o] = biases[l][o];
+            split(w, hi, lo);
+            float* dh = dmal(w.size()); float* dl = dmal(w.size()); float* db = dmal(N);
+            if (!dh || !dl || !db) { rc = PSM_ERR_CUDA; break; }
+            cudaMemcpy(dh, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(dl, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(db, b.data(), N * 4, cudaMemcpyHostToDevice);
+            const bool last = (l == n_layers - 1);
+            if (make_kmajor_map(&maps[4 * l + 0], act_hi[l & 1], Mp, K, K, 128) != 0 || make_kmajor_map(&maps[4 * l + 1], act_lo[l & 1], Mp, K, K, 128) != 0 ||
+                make_kmajor_map(&maps[4 * l + 2], dh, N, K, K, 64) != 0 || make_kmajor_map(&maps[4 * l + 3], dl, N, K, K, 64) != 0) { rc = PSM_ERR_CUDA; break; }
+            sa.L[l] = DenseLayerDesc{K, N, last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU, db, d_one, d_zero, last ? d_out : nullptr,
+                                     last ? nullptr : act_hi[(l + 1) & 1], last ? nullptr : act_lo[(l + 1) & 1]};
+            max_tiles = std::max(max_tiles, (Mp / 128) * (N / 64));
+        }
+    }
+    if (rc == PSM_OK) {
+        cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(TensorMap128), cudaMemcpyHostToDevice);
+        sa.maps = d_maps; sa.n_layers = n_layers; sa.M = Mp; sa.three_pass = (mode == PSM_GEMM_TC_3XTF32) ? 1 : 0;
+        sa.barrier = d_bar; sa.error = (int*)(d_bar + 1);
+        int cl = std::min(std::min(max_cl, 16), max_tiles);
+        if (clusters > 0) cl = std::min(cl, clusters);
+        const bool trace = getenv("PSM_TRACE_DENSE") != nullptr;
+        if (trace) sa.trace = (unsigned long long*)dmal((size_t)cl * 8 * 64 * 2);
+        for (int rep = 0; rep < (trace ? 3 : 1) && rc == PSM_OK; ++rep) {
+            cudaMemset(d_bar, 0, 8);
+            if (launch_dense_stack(sa, cl, 0) != 0 || cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = PSM_ERR_CUDA;
+        }
+        if (trace && rc == PSM_OK) {
+            std::vector<unsigned long long> tr((size_t)cl * 8 * 64);
+            cudaMemcpy(tr.data(), sa.trace, tr.size() * 8, cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull;
+            for (int b = 0; b < cl * 8; ++b) if (tr[(size_t)b * 64] && tr[(size_t)b * 64] < t0) t0 = tr[(size_t)b * 64];
+            for (int b : {0, 1, 7, 8, cl * 8 - 1}) {
+                fprintf(stderr, "dense_stack trace CTA %3d (ns since first CTA start):", b);
+                for (int i = 0; i < 64 && tr[(size_t)b * 64 + i]; ++i) fprintf(stderr, " %llu", tr[(size_t)b * 64 + i] - t0);
+                fprintf(stderr, "\n");
+            }
+        }
+    }
+    if (rc == PSM_OK) {
+        unsigned int st[2];
+        cudaMemcpy(st, d_bar, 8, cudaMemcpyDeviceToHost);
+        if (st[1]) rc = PSM_ERR_COMM;
+        std::vector<float> o((size_t)Mp * dp[n_layers]);
+        cudaMemcpy(o.data(), d_out, o.size() * 4, cudaMemcpyDeviceToHost);
+        for (int m = 0; m < M; ++m) for (int k = 0; k < dims[n_layers]; ++k) out[(size_t)m * dims[n_layers] + k] = o[(size_t)m * dp[n_layers] + k];
+    }
+    for (void* q : dev) cudaFree(q);
     return rc;
 }

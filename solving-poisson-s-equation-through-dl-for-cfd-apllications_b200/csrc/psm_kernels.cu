@@ -148,6 +148,26 @@ void launch_p2p_push_pix(const P2PArgs* d_pa, const float* field, const int32_t*
 //     running max of |U|^2 and |dU|^2.   PMP:267-273, SMC:386-405.
 //     The squares/sum are rounded separately (no FMA) so that U_max_norm is bit-identical to
 //     np.max(np.sqrt(np.square(Ux) + np.square(Uy))).
+// U_max_norm, the input / output scales and the skip rule (SMC:404-419,551) from the two running maxima.
+__device__ __forceinline__ void publish_scalars(const ScalarArgs& sa, unsigned long long um2, unsigned long long dm2, float& s0, float& s1) {
+    Scalars* sc = sa.sc;
+    const double um = sqrt(__longlong_as_double((long long)um2));
+    const double dm = sqrt(__longlong_as_double((long long)dm2));
+    s0 = (float)(1.0 / (um * sa.max_abs_ux)); s1 = (float)(1.0 / (um * sa.max_abs_uy));
+    sc->U_max_norm = um;
+    sc->dU_max_norm = dm;
+    sc->in_scale[0] = s0;
+    sc->in_scale[1] = s1;
+    sc->out_scale = (float)(sa.dimensionalise ? sa.out_scale_base * um * um : sa.out_scale_base);
+    int skip = 0;
+    if (sa.mode != 0) {
+        if (sa.skip_threshold > 0.0 && (dm / um) < sa.skip_threshold) skip = 1;     // SMC:410-415
+        if (sa.mode == 2 && !sc->have_prev) skip = 1;                              // no U(t-1) yet
+    }
+    sc->skip = skip;
+    sc->have_prev = 1;
+}
+
 template <int MODE, int NCOL>
 __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
     pdl_enter();
@@ -209,9 +229,11 @@ __device__ __forceinline__ float2 ldg_f2(const float2* p) { return __ldg(p); }
 // The step's scalars come straight from the running maxima of prep (all-reduced over ranks in the multi-GPU
 // path): every thread derives the two input scales itself; thread 0 publishes U_max_norm, the output scale
 // and the skip rule (SMC:404-419,551) for the later kernels.  The maxima are re-armed by offsets_kernel.
-__global__ void __launch_bounds__(256) gather_kernel(GatherArgs a) {
-    pdl_enter();
+// Scalars of the step, derived by every thread from the running maxima of prep; thread 0 of CTA 0 publishes them.
+template <bool READY>
+__device__ __forceinline__ void step_scales(const GatherArgs& a, float& s0, float& s1) {
     Scalars* sc = a.sa.sc;
+    if (READY) { s0 = sc->in_scale[0]; s1 = sc->in_scale[1]; return; }
     unsigned long long um2 = sc->umax2_bits, dm2 = sc->dumax2_bits;
     if (a.p2p) {                                   // maxima over all ranks, pushed into my mailbox
         p2p_wait(a.p2p, 0, 0xFFu);
@@ -221,111 +243,88 @@ __global__ void __launch_bounds__(256) gather_kernel(GatherArgs a) {
             dm2 = max(dm2, *reinterpret_cast<const volatile unsigned long long*>(&mine->maxima[p][1]));
         }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) publish_scalars(a.sa, um2, dm2, s0, s1);
     const double um = sqrt(__longlong_as_double((long long)um2));
-    const float s0 = (float)(1.0 / (um * a.sa.max_abs_ux)), s1 = (float)(1.0 / (um * a.sa.max_abs_uy));
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const double dm = sqrt(__longlong_as_double((long long)dm2));
-        sc->U_max_norm = um;
-        sc->dU_max_norm = dm;
-        sc->in_scale[0] = s0;
-        sc->in_scale[1] = s1;
-        sc->out_scale = (float)(a.sa.dimensionalise ? a.sa.out_scale_base * um * um : a.sa.out_scale_base);
-        int skip = 0;
-        if (a.sa.mode != 0) {
-            if (a.sa.skip_threshold > 0.0 && (dm / um) < a.sa.skip_threshold) skip = 1;     // SMC:410-415
-            if (a.sa.mode == 2 && !sc->have_prev) skip = 1;                                // no U(t-1) yet
-        }
-        sc->skip = skip;
-        sc->have_prev = 1;
-    }
+    s0 = (float)(1.0 / (um * a.sa.max_abs_ux)); s1 = (float)(1.0 / (um * a.sa.max_abs_uy));
+}
+
+struct PixTables { int4 i0, i1, i2; float4 q0, q1, q2; };
+__device__ __forceinline__ PixTables load_tables(const GatherArgs& a, long long g) {
+    PixTables t;
+    t.i0 = __ldcs(reinterpret_cast<const int4*>(a.v0) + g);
+    t.i1 = __ldcs(reinterpret_cast<const int4*>(a.v1) + g);
+    t.i2 = __ldcs(reinterpret_cast<const int4*>(a.v2) + g);
+    t.q0 = __ldcs(reinterpret_cast<const float4*>(a.w0) + g);
+    t.q1 = __ldcs(reinterpret_cast<const float4*>(a.w1) + g);
+    t.q2 = __ldcs(reinterpret_cast<const float4*>(a.w2) + g);
+    return t;
+}
+// four pixels: weighted gather (UTL:88-89), scaling (SMC:441-442), NaN -> 0 (SMC:438)
+__device__ __forceinline__ void gather4(const float2* __restrict__ uv, const PixTables& t, float s0, float s1, float4& ox, float4& oy) {
+    const int4 i0 = t.i0, i1 = t.i1, i2 = t.i2; const float4 q0 = t.q0, q1 = t.q1, q2 = t.q2;
+    float2 a0 = ldg_f2(uv + i0.x), b0 = ldg_f2(uv + i1.x), c0 = ldg_f2(uv + i2.x);
+    float2 a1 = ldg_f2(uv + i0.y), b1 = ldg_f2(uv + i1.y), c1 = ldg_f2(uv + i2.y);
+    float2 a2 = ldg_f2(uv + i0.z), b2 = ldg_f2(uv + i1.z), c2 = ldg_f2(uv + i2.z);
+    float2 a3 = ldg_f2(uv + i0.w), b3 = ldg_f2(uv + i1.w), c3 = ldg_f2(uv + i2.w);
+    ox.x = (a0.x * q0.x + b0.x * q1.x + c0.x * q2.x) * s0;  oy.x = (a0.y * q0.x + b0.y * q1.x + c0.y * q2.x) * s1;
+    ox.y = (a1.x * q0.y + b1.x * q1.y + c1.x * q2.y) * s0;  oy.y = (a1.y * q0.y + b1.y * q1.y + c1.y * q2.y) * s1;
+    ox.z = (a2.x * q0.z + b2.x * q1.z + c2.x * q2.z) * s0;  oy.z = (a2.y * q0.z + b2.y * q1.z + c2.y * q2.z) * s1;
+    ox.w = (a3.x * q0.w + b3.x * q1.w + c3.x * q2.w) * s0;  oy.w = (a3.y * q0.w + b3.y * q1.w + c3.y * q2.w) * s1;
+    ox.x = (ox.x != ox.x) ? 0.f : ox.x; ox.y = (ox.y != ox.y) ? 0.f : ox.y;
+    ox.z = (ox.z != ox.z) ? 0.f : ox.z; ox.w = (ox.w != ox.w) ? 0.f : ox.w;
+    oy.x = (oy.x != oy.x) ? 0.f : oy.x; oy.y = (oy.y != oy.y) ? 0.f : oy.y;
+    oy.z = (oy.z != oy.z) ? 0.f : oy.z; oy.w = (oy.w != oy.w) ? 0.f : oy.w;
+}
+
+// The tables are static: every thread loads those of its first pixel group BEFORE waiting for the previous
+// kernel (programmatic dependent launch), so the first DRAM round trip overlaps the previous kernel's tail.
+template <bool READY>
+__global__ void __launch_bounds__(256) gather_kernel(GatherArgs a) {
+    pdl_launch_dependents();
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < a.n_pix4; g += stride) {
-        const int4 i0 = __ldcs(reinterpret_cast<const int4*>(a.v0) + g);
-        const int4 i1 = __ldcs(reinterpret_cast<const int4*>(a.v1) + g);
-        const int4 i2 = __ldcs(reinterpret_cast<const int4*>(a.v2) + g);
-        const float4 q0 = __ldcs(reinterpret_cast<const float4*>(a.w0) + g);
-        const float4 q1 = __ldcs(reinterpret_cast<const float4*>(a.w1) + g);
-        const float4 q2 = __ldcs(reinterpret_cast<const float4*>(a.w2) + g);
-        float2 a0 = ldg_f2(a.uv + i0.x), b0 = ldg_f2(a.uv + i1.x), c0 = ldg_f2(a.uv + i2.x);
-        float2 a1 = ldg_f2(a.uv + i0.y), b1 = ldg_f2(a.uv + i1.y), c1 = ldg_f2(a.uv + i2.y);
-        float2 a2 = ldg_f2(a.uv + i0.z), b2 = ldg_f2(a.uv + i1.z), c2 = ldg_f2(a.uv + i2.z);
-        float2 a3 = ldg_f2(a.uv + i0.w), b3 = ldg_f2(a.uv + i1.w), c3 = ldg_f2(a.uv + i2.w);
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    PixTables t{};
+    if (g < a.n_pix4) t = load_tables(a, g);
+    pdl_wait();
+    float s0, s1;
+    step_scales<READY>(a, s0, s1);
+    while (g < a.n_pix4) {
         float4 ox, oy;
-        ox.x = (a0.x * q0.x + b0.x * q1.x + c0.x * q2.x) * s0;  oy.x = (a0.y * q0.x + b0.y * q1.x + c0.y * q2.x) * s1;
-        ox.y = (a1.x * q0.y + b1.x * q1.y + c1.x * q2.y) * s0;  oy.y = (a1.y * q0.y + b1.y * q1.y + c1.y * q2.y) * s1;
-        ox.z = (a2.x * q0.z + b2.x * q1.z + c2.x * q2.z) * s0;  oy.z = (a2.y * q0.z + b2.y * q1.z + c2.y * q2.z) * s1;
-        ox.w = (a3.x * q0.w + b3.x * q1.w + c3.x * q2.w) * s0;  oy.w = (a3.y * q0.w + b3.y * q1.w + c3.y * q2.w) * s1;
-        // grid[np.isnan(grid)] = 0  (SMC:438)
-        ox.x = (ox.x != ox.x) ? 0.f : ox.x; ox.y = (ox.y != ox.y) ? 0.f : ox.y;
-        ox.z = (ox.z != ox.z) ? 0.f : ox.z; ox.w = (ox.w != ox.w) ? 0.f : ox.w;
-        oy.x = (oy.x != oy.x) ? 0.f : oy.x; oy.y = (oy.y != oy.y) ? 0.f : oy.y;
-        oy.z = (oy.z != oy.z) ? 0.f : oy.z; oy.w = (oy.w != oy.w) ? 0.f : oy.w;
+        gather4(a.uv, t, s0, s1, ox, oy);
         reinterpret_cast<float4*>(a.grid0)[g] = ox;
         reinterpret_cast<float4*>(a.grid1)[g] = oy;
+        g += stride;
+        if (g < a.n_pix4) t = load_tables(a, g);
     }
 }
 void launch_gather(const GatherArgs& a, cudaStream_t s) {
     long long want = (a.n_pix4 + 255) / 256;
     int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
-    launch_k(gather_kernel, dim3(blocks), dim3(256), 0, s, a);
+    if (a.scales_ready || a.sa.replay) launch_k(gather_kernel<true>, dim3(blocks), dim3(256), 0, s, a);
+    else launch_k(gather_kernel<false>, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // K1+K2 fused (see psm_kernels.cuh): identical arithmetic to gather_kernel, then one 128-bit store per
 // covering block and channel.
-__global__ void __launch_bounds__(256) gather_extract_kernel(GatherExtractArgs e) {
-    pdl_enter();
+template <bool READY>
+__global__ void __launch_bounds__(256, 4) gather_extract_kernel(GatherExtractArgs e) {
+    pdl_launch_dependents();
     const GatherArgs& a = e.g;
-    Scalars* sc = a.sa.sc;
-    unsigned long long um2 = sc->umax2_bits, dm2 = sc->dumax2_bits;
-    if (a.p2p) {                                   // maxima over all ranks, pushed into my mailbox
-        p2p_wait(a.p2p, 0, 0xFFu);
-        const PeerMail* mine = a.p2p->mail[a.p2p->rank];
-        for (int p = 0; p < a.p2p->world; ++p) {
-            um2 = max(um2, *reinterpret_cast<const volatile unsigned long long*>(&mine->maxima[p][0]));
-            dm2 = max(dm2, *reinterpret_cast<const volatile unsigned long long*>(&mine->maxima[p][1]));
-        }
-    }
-    const double um = sqrt(__longlong_as_double((long long)um2));
-    const float s0 = (float)(1.0 / (um * a.sa.max_abs_ux)), s1 = (float)(1.0 / (um * a.sa.max_abs_uy));
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const double dm = sqrt(__longlong_as_double((long long)dm2));
-        sc->U_max_norm = um;
-        sc->dU_max_norm = dm;
-        sc->in_scale[0] = s0;
-        sc->in_scale[1] = s1;
-        sc->out_scale = (float)(a.sa.dimensionalise ? a.sa.out_scale_base * um * um : a.sa.out_scale_base);
-        int skip = 0;
-        if (a.sa.mode != 0) {
-            if (a.sa.skip_threshold > 0.0 && (dm / um) < a.sa.skip_threshold) skip = 1;     // SMC:410-415
-            if (a.sa.mode == 2 && !sc->have_prev) skip = 1;                                // no U(t-1) yet
-        }
-        sc->skip = skip;
-        sc->have_prev = 1;
-    }
     const long long stride = (long long)gridDim.x * blockDim.x;
     const int S2 = e.S * e.S;
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < a.n_pix4; g += stride) {
-        const int4 i0 = __ldcs(reinterpret_cast<const int4*>(a.v0) + g);
-        const int4 i1 = __ldcs(reinterpret_cast<const int4*>(a.v1) + g);
-        const int4 i2 = __ldcs(reinterpret_cast<const int4*>(a.v2) + g);
-        const float4 q0 = __ldcs(reinterpret_cast<const float4*>(a.w0) + g);
-        const float4 q1 = __ldcs(reinterpret_cast<const float4*>(a.w1) + g);
-        const float4 q2 = __ldcs(reinterpret_cast<const float4*>(a.w2) + g);
-        float2 a0 = ldg_f2(a.uv + i0.x), b0 = ldg_f2(a.uv + i1.x), c0 = ldg_f2(a.uv + i2.x);
-        float2 a1 = ldg_f2(a.uv + i0.y), b1 = ldg_f2(a.uv + i1.y), c1 = ldg_f2(a.uv + i2.y);
-        float2 a2 = ldg_f2(a.uv + i0.z), b2 = ldg_f2(a.uv + i1.z), c2 = ldg_f2(a.uv + i2.z);
-        float2 a3 = ldg_f2(a.uv + i0.w), b3 = ldg_f2(a.uv + i1.w), c3 = ldg_f2(a.uv + i2.w);
+    long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    PixTables t{};
+    if (g < a.n_pix4) t = load_tables(a, g);
+    pdl_wait();
+    float s0, s1;
+    step_scales<READY>(a, s0, s1);
+    while (g < a.n_pix4) {
         float4 ox, oy;
-        ox.x = (a0.x * q0.x + b0.x * q1.x + c0.x * q2.x) * s0;  oy.x = (a0.y * q0.x + b0.y * q1.x + c0.y * q2.x) * s1;
-        ox.y = (a1.x * q0.y + b1.x * q1.y + c1.x * q2.y) * s0;  oy.y = (a1.y * q0.y + b1.y * q1.y + c1.y * q2.y) * s1;
-        ox.z = (a2.x * q0.z + b2.x * q1.z + c2.x * q2.z) * s0;  oy.z = (a2.y * q0.z + b2.y * q1.z + c2.y * q2.z) * s1;
-        ox.w = (a3.x * q0.w + b3.x * q1.w + c3.x * q2.w) * s0;  oy.w = (a3.y * q0.w + b3.y * q1.w + c3.y * q2.w) * s1;
-        ox.x = (ox.x != ox.x) ? 0.f : ox.x; ox.y = (ox.y != ox.y) ? 0.f : ox.y;
-        ox.z = (ox.z != ox.z) ? 0.f : ox.z; ox.w = (ox.w != ox.w) ? 0.f : ox.w;
-        oy.x = (oy.x != oy.x) ? 0.f : oy.x; oy.y = (oy.y != oy.y) ? 0.f : oy.y;
-        oy.z = (oy.z != oy.z) ? 0.f : oy.z; oy.w = (oy.w != oy.w) ? 0.f : oy.w;
-        reinterpret_cast<float4*>(a.grid0)[g] = ox;
-        reinterpret_cast<float4*>(a.grid1)[g] = oy;
+        gather4(a.uv, t, s0, s1, ox, oy);
+        if (e.store_grid) {
+            reinterpret_cast<float4*>(a.grid0)[g] = ox;
+            reinterpret_cast<float4*>(a.grid1)[g] = oy;
+        }
         const int y = (int)(g / e.W4), xg = (int)(g - (long long)y * e.W4);
         const CoverEntry rc = e.rowcov[y];
         const CoverEntry cc = e.colcov[xg];
@@ -340,12 +339,15 @@ __global__ void __launch_bounds__(256) gather_extract_kernel(GatherExtractArgs e
                 *reinterpret_cast<float4*>(dst + S2) = oy;
             }
         }
+        g += stride;
+        if (g < a.n_pix4) t = load_tables(a, g);
     }
 }
 void launch_gather_extract(const GatherExtractArgs& a, cudaStream_t s) {
     long long want = (a.g.n_pix4 + 255) / 256;
-    int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
-    launch_k(gather_extract_kernel, dim3(blocks), dim3(256), 0, s, a);
+    int blocks = (int)(want < (long long)kSMs * 4 ? (want > 0 ? want : 1) : kSMs * 4);     // one resident wave (4 CTAs / SM), grid-stride
+    if (a.g.scales_ready) launch_k(gather_extract_kernel<true>, dim3(blocks), dim3(256), 0, s, a);
+    else launch_k(gather_extract_kernel<false>, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -480,6 +482,10 @@ __global__ void __launch_bounds__(256) reduce_standardise_kernel(ReduceArgs a) {
         else if (a.kind == RED_BIAS_RELU) o = fmaxf(tot + a.bias[n], 0.f);
         else o = (tot + a.bias[n]) * a.a[n] + a.b[n];
         a.x[i] = o;
+        if (a.x_hi) {
+            const float hi = __uint_as_float(__float_as_uint(o) & 0xFFFFE000u);
+            a.x_hi[i] = hi; a.x_lo[i] = o - hi;
+        }
     }
 }
 void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {
@@ -495,21 +501,29 @@ void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {
 //      warp per task folds its rows -- rectangles range from 1 x 1 to 120 x 128 pixels, so the work
 //      is balanced per row, not per task.
 __global__ void __launch_bounds__(256) row_sums_kernel(MeansArgs a) {
-    pdl_enter();
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= a.n_rows) return;
-    const int2 ri = a.rows[r];                                   // (task, block-local y)
-    const DevTask t = a.tasks[ri.x];
+    const bool live = r < a.n_rows;
+    // the row list, the task and the flow mask are static: fetched before waiting for the predicted blocks
+    int2 ri = make_int2(0, 0);
+    DevTask t{};
+    bool m0 = false, m1 = false, m2 = false, m3 = false;
+    const int x = lane * 4;
+    if (live) {
+        ri = a.rows[r];                                          // (task, block-local y)
+        t = a.tasks[ri.x];
+        m0 = x + 0 >= t.x0 && x + 0 < t.x1; m1 = x + 1 >= t.x0 && x + 1 < t.x1;
+        m2 = x + 2 >= t.x0 && x + 2 < t.x1; m3 = x + 3 >= t.x0 && x + 3 < t.x1;
+        if (t.kind == 0) {
+            const uint8_t* msk = a.gmask + (long long)(t.my0 + ri.y) * a.W + t.mx0;
+            m0 = m0 && msk[x + 0]; m1 = m1 && msk[x + 1]; m2 = m2 && msk[x + 2]; m3 = m3 && msk[x + 3];
+        }
+    }
+    pdl_wait();
+    if (!live) return;
     const float* src = a.blocks + (((long long)t.src * a.C + t.ch) * a.S + ri.y) * a.S;
     const float4 v = reinterpret_cast<const float4*>(src)[lane];  // the whole 128-pixel block row
-    const int x = lane * 4;
-    bool m0 = x + 0 >= t.x0 && x + 0 < t.x1, m1 = x + 1 >= t.x0 && x + 1 < t.x1;
-    bool m2 = x + 2 >= t.x0 && x + 2 < t.x1, m3 = x + 3 >= t.x0 && x + 3 < t.x1;
-    if (t.kind == 0) {
-        const uint8_t* msk = a.gmask + (long long)(t.my0 + ri.y) * a.W + t.mx0;
-        m0 = m0 && msk[x + 0]; m1 = m1 && msk[x + 1]; m2 = m2 && msk[x + 2]; m3 = m3 && msk[x + 3];
-    }
     double sum = 0.0;
     if (m0) sum += (double)v.x;
     if (m1) sum += (double)v.y;
@@ -608,6 +622,7 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) a.coff[i] = (float)(a.offsets[i] + s_shift[i / a.B]);
     if (threadIdx.x == 0) {
         a.sc->umax2_bits = 0ull; a.sc->dumax2_bits = 0ull;      // re-arm the running maxima of prep
+        a.sc->dense_barrier = 0u;                               // ... and the grid barrier of the Dense stack
         if (a.host_skip) { *reinterpret_cast<volatile int*>(a.host_skip) = a.sc->skip | (a.sc->comm_error << 8); __threadfence_system(); }
     }
 }
@@ -682,12 +697,16 @@ void launch_place(const PlaceArgs& a, cudaStream_t s) {
 //     interpolate_fill, previous-pressure fallback for NaN / near-wall cells; SMC:644-645
 //     (p = p_prev + delta_p) for the deltaU variant.
 __global__ void __launch_bounds__(256) back_kernel(BackArgs a) {
-    pdl_enter();
+    pdl_launch_dependents();
+    // static tables of the first cell before the wait (see gather_kernel)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int i0 = 0, i1 = 0, i2 = 0; float q0 = 0.f, q1 = 0.f, q2 = 0.f;
+    if (i < a.n) { i0 = __ldcs(a.v0 + i); i1 = __ldcs(a.v1 + i); i2 = __ldcs(a.v2 + i); q0 = __ldcs(a.w0 + i); q1 = __ldcs(a.w1 + i); q2 = __ldcs(a.w2 + i); }
+    pdl_wait();
     if (a.p2p) p2p_wait(a.p2p, 2, a.p2p->pix_recv_mask);   // ghost pixels pushed by their owners
     const int skip = a.sc->skip;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
-        const int i0 = __ldcs(a.v0 + i), i1 = __ldcs(a.v1 + i), i2 = __ldcs(a.v2 + i);
-        const float q0 = __ldcs(a.w0 + i), q1 = __ldcs(a.w1 + i), q2 = __ldcs(a.w2 + i);
+    while (i < a.n) {
         if (a.n_fields == 1) {
             const double pp = a.p_prev[i];
             double out = pp;
@@ -705,6 +724,8 @@ __global__ void __launch_bounds__(256) back_kernel(BackArgs a) {
             }
             reinterpret_cast<double2*>(a.out)[i] = make_double2(o0, o1);
         }
+        i += stride;
+        if (i < a.n) { i0 = __ldcs(a.v0 + i); i1 = __ldcs(a.v1 + i); i2 = __ldcs(a.v2 + i); q0 = __ldcs(a.w0 + i); q1 = __ldcs(a.w1 + i); q2 = __ldcs(a.w2 + i); }
     }
 }
 void launch_back(const BackArgs& a, cudaStream_t s) {

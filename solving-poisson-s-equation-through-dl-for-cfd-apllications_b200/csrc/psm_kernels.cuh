@@ -39,6 +39,7 @@ struct Scalars {
     unsigned int step;               // multi-GPU: id of the current step (flags of the peer-memory exchanges)
     int    comm_error;               // multi-GPU: a peer flag did not arrive in time
     unsigned int push_done[3];       // multi-GPU: CTAs of a push kernel that have finished their stores
+    unsigned int dense_barrier;      // grid barrier of dense_stack_kernel (arrivals of the current step; re-armed by offsets_kernel)
 };
 
 // ---- multi-GPU exchanges over peer memory (NVLink P2P, cudaIpc-mapped buffers) ---------------------------
@@ -66,6 +67,15 @@ void launch_p2p_push_cells(const P2PArgs* d_pa, const float2* uv, const int32_t*
 void launch_p2p_push_means(const P2PArgs* d_pa, const struct DevTask* tasks, int n_tasks, int world, const double* means, cudaStream_t s);
 void launch_p2p_push_pix(const P2PArgs* d_pa, const float* field, const int32_t* send_idx, int F, long long my_stride, long long nsend, cudaStream_t s);
 
+struct ScalarArgs {
+    Scalars* sc;
+    double max_abs_ux, max_abs_uy, out_scale_base;  // out_scale = base * (dimensionalise ? U^2 : 1)
+    int dimensionalise;
+    double skip_threshold;
+    int mode;
+    int replay;           // 1: re-evaluate the gather of the LAST step from the scales it published (psm_get_stage)
+};
+
 struct PrepArgs {
     const double* cells;  // [n][ncol]
     long long n;
@@ -78,13 +88,6 @@ struct PrepArgs {
 };
 void launch_prep(const PrepArgs& a, cudaStream_t s);
 
-struct ScalarArgs {
-    Scalars* sc;
-    double max_abs_ux, max_abs_uy, out_scale_base;  // out_scale = base * (dimensionalise ? U^2 : 1)
-    int dimensionalise;
-    double skip_threshold;
-    int mode;
-};
 
 // K1: cell -> grid barycentric gather over the folded tables (SoA, padded to a multiple of 4).
 struct GatherArgs {
@@ -94,6 +97,7 @@ struct GatherArgs {
     float* grid0; float* grid1;   // planes [H*W] (padded)
     long long n_pix4;             // number of 4-pixel groups
     ScalarArgs sa;                // thread 0 also publishes the step's scalars (U_max_norm, scales, skip rule)
+    int scales_ready;             // 1: use the scales already published (replay of the last step, psm_get_stage)
     const P2PArgs* p2p;           // multi-GPU over peer memory: wait for the pushed maxima + ghost cells first
 };
 void launch_gather(const GatherArgs& a, cudaStream_t s);
@@ -108,6 +112,7 @@ struct GatherExtractArgs {
     const CoverEntry* colcov;     // [W/4]             idx = block position within its row
     const int32_t* by0; const int32_t* bx0;
     float* xu; int W4; int ncolb; int S;
+    int store_grid;               // 0: only the block operand is written (the grid planes are rebuilt on demand by psm_get_stage)
 };
 void launch_gather_extract(const GatherExtractArgs& a, cudaStream_t s);
 
@@ -156,6 +161,30 @@ void launch_tc_gemm(const TcGemm& t, cudaStream_t s);
 int dense_cluster_prepare();
 int launch_dense_cluster(const TcGemm& t, cudaStream_t s);
 
+// The whole Dense stack (NNS:8-38: Dense(relu) x (n-1) -> Dense(linear), de-standardisation SMC:533) in ONE launch
+// (psm_gemm_tc.cu).  Persistent clusters of 8 CTAs: a cluster evaluates one 128 x 64 output tile of the current
+// layer, its CTAs split K, park their partial accumulators in shared memory and fold them through distributed
+// shared memory (fixed order); bias / ReLU / affine fused; activations are written pre-split into hi = tf32(x) and
+// lo = x - hi so that the next layer's 3xTF32 passes read them straight through TMA (weights are split at load).
+// Layers are separated by a grid barrier (all CTAs are co-resident: grid <= what the device holds at once).
+constexpr int kMaxDense = 16;
+struct DenseLayerDesc {
+    int K, N, epi;                    // padded widths (multiples of 128); EPI_BIAS_RELU or EPI_BIAS_AFFINE
+    const float* bias; const float* v1; const float* v2;
+    float* out;                       // fp32 result [M][N] (may be NULL for hidden layers)
+    float* out_hi; float* out_lo;     // split result [M][N] read by the next layer (may be NULL after the last)
+};
+struct DenseStackArgs {
+    const TensorMap128* maps;         // DEVICE memory, [n_layers][4]: A_hi, A_lo (box 128 x 32), W_hi, W_lo (box 64 x 32)
+    int n_layers, M, three_pass;
+    unsigned int* barrier;            // zero before the launch
+    int* error;                       // set to 1 if the grid barrier timed out (never on a healthy device)
+    unsigned long long* trace;        // optional (debug): [CTA][64] globaltimer stamps
+    DenseLayerDesc L[kMaxDense];
+};
+int dense_stack_prepare(int* max_clusters);
+int launch_dense_stack(const DenseStackArgs& a, int clusters, cudaStream_t s);
+
 // Split-K reduction + per-block constant + standardisation (SMC:494,512).
 // Also the split-K epilogue of the Dense layers: relu(sum + bias[n]) or (sum + bias[n]) * s[n] + m[n].
 enum ReduceKind { RED_STANDARDISE = 0, RED_BIAS_RELU = 1, RED_BIAS_AFFINE = 2 };
@@ -166,6 +195,7 @@ struct ReduceArgs {
     float* x;
     int kind;
     const float* bias;    // RED_BIAS_*: [N]
+    float* x_hi; float* x_lo;   // optional: the result split into tf32(x) and x - tf32(x) (operand of dense_stack_kernel)
 };
 void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s);
 

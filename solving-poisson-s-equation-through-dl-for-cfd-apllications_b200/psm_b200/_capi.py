@@ -104,6 +104,8 @@ SYMBOLS = {
     'psm_set_timings': (C.c_int, [C.c_void_p, C.c_int32]),
     'psm_get_launch_count': (C.c_int, [C.c_void_p]),
     'psm_debug_gemm': (C.c_int, [C.c_int32] * 5 + [c_float_p, c_float_p, c_float_p, C.c_int32]),
+    'psm_debug_dense_stack': (C.c_int, [C.c_int32] * 4 + [c_int32_p, C.POINTER(c_float_p), C.POINTER(c_float_p), c_float_p, c_float_p,
+                                        C.c_int32]),
     'psm_plan_sizes': (C.c_int, [C.c_int32] * 5 + [c_uint8_p, c_int32_p, c_int32_p, c_int32_p]),
     'psm_plan_compile': (C.c_int, [C.c_int32] * 5 + [c_uint8_p] + [c_int32_p] * 5),
     'psm_plan_shift_lines': (C.c_int, [C.c_int32] * 5 + [c_uint8_p, c_int32_p, c_int32_p]),

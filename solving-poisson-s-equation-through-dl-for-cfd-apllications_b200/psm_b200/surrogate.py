@@ -59,6 +59,25 @@ def debug_gemm(A, B, mode=0, splits=1, device=0):
     return Cc
 
 
+def debug_dense_stack(x, kernels, biases, mode=0, clusters=0, device=0):
+    """The fused Dense-stack kernel on its own (tests): Keras-layout kernels [in][out], ReLU between layers,
+    linear last layer.  Returns float32 [M, out]."""
+    lib = capi.load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    ks = [np.ascontiguousarray(k, dtype=np.float32) for k in kernels]
+    bs = [np.ascontiguousarray(b, dtype=np.float32) for b in biases]
+    dims = np.array([x.shape[1]] + [k.shape[1] for k in ks], dtype=np.int32)
+    n = len(ks)
+    kp = (capi.c_float_p * n)(*[_ptr(k, C.c_float) for k in ks])
+    bp = (capi.c_float_p * n)(*[_ptr(b, C.c_float) for b in bs])
+    out = np.empty((x.shape[0], int(dims[-1])), dtype=np.float32)
+    rc = lib.psm_debug_dense_stack(device, mode, x.shape[0], n, _ptr(dims, C.c_int32), kp, bp, _ptr(x, C.c_float),
+                                   _ptr(out, C.c_float), clusters)
+    if rc < 0:
+        raise capi.PsmError(rc, 'psm_debug_dense_stack failed')
+    return out
+
+
 class PressureSurrogate:
     """One mesh, one GPU, one stream.  Mirrors the lifetime of the reference's module globals
     (PMP:103-118 params, PMP:193 tables) behind an explicit handle."""

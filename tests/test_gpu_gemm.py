@@ -45,3 +45,41 @@ def test_3xtf32_is_exact_on_tf32_representable_inputs():
     for mode in (_capi.GEMM_TC_TF32, _capi.GEMM_TC_3XTF32):
         C = psm_b200.debug_gemm(A, B, mode=mode)[0]
         np.testing.assert_array_equal(C.astype(np.float64), ref)
+
+
+STACKS = [  # M, dims, clusters cap
+    (121, [128, 512, 512, 512, 128], 0),     # MLP_small at configs[1] (UTL:437-439): one 128-row tile
+    (124, [45, 512, 512, 512, 48], 0),       # the shipped thesis model (PMP:121-134): widths padded to 128
+    (441, [128, 512, 512, 512, 128], 0),     # configs[4]: four row tiles, 32 output tiles per layer over 16 clusters
+    (300, [100, 256, 640, 70], 3),           # uneven widths, more tiles than clusters
+    (64, [128, 128], 0),                     # a single linear layer
+]
+
+
+@pytest.mark.parametrize("M,dims,clusters", STACKS)
+@pytest.mark.parametrize("mode", [_capi.GEMM_TC_3XTF32, _capi.GEMM_TC_TF32])
+def test_dense_stack_matches_numpy(mode, M, dims, clusters):
+    rng = np.random.default_rng(M + sum(dims))
+    x = rng.standard_normal((M, dims[0])).astype(np.float32)
+    ks = [(rng.standard_normal((dims[i], dims[i + 1])) / np.sqrt(dims[i])).astype(np.float32) for i in range(len(dims) - 1)]
+    bs = [(0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32) for i in range(len(dims) - 1)]
+    out = psm_b200.debug_dense_stack(x, ks, bs, mode=mode, clusters=clusters)
+    a = x.astype(np.float64)
+    for i, (k, b) in enumerate(zip(ks, bs)):
+        a = a @ k.astype(np.float64) + b.astype(np.float64)
+        if i < len(ks) - 1:
+            a = np.maximum(a, 0.0)
+    assert not np.isnan(out).any()
+    err = rel_l2(out.astype(np.float64), a)
+    assert err < (2e-5 if mode == _capi.GEMM_TC_3XTF32 else 5e-3), err
+
+
+def test_dense_stack_is_deterministic():
+    rng = np.random.default_rng(5)
+    dims = [128, 512, 512, 128]
+    x = rng.standard_normal((200, dims[0])).astype(np.float32)
+    ks = [(rng.standard_normal((dims[i], dims[i + 1])) / np.sqrt(dims[i])).astype(np.float32) for i in range(3)]
+    bs = [np.zeros(dims[i + 1], np.float32) for i in range(3)]
+    a = psm_b200.debug_dense_stack(x, ks, bs)
+    b = psm_b200.debug_dense_stack(x, ks, bs, clusters=2)
+    np.testing.assert_array_equal(a, b)
