@@ -425,7 +425,13 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             float o;
             if (g.epi == EPI_BIAS_RELU) o = fmaxf(acc + __ldg(g.v0 + n), 0.f);
             else o = (acc + __ldg(g.v0 + n)) * __ldg(g.v1 + n) + __ldg(g.v2 + n);
-            if (m < g.M) g.C[(size_t)m * g.ldc + n] = o;
+            if (m < g.M) {
+                g.C[(size_t)m * g.ldc + n] = o;
+                if (g.C_hi) {                                    // operand of the transposed PCA inverse, pre-split
+                    const float hi = __uint_as_float(__float_as_uint(o) & 0xFFFFE000u);
+                    g.C_hi[(size_t)m * g.ldc + n] = hi; g.C_lo[(size_t)m * g.ldc + n] = o - hi;
+                }
+            }
         }
     }
     cluster_sync_all();                                          // nobody leaves while its shared memory is being read
@@ -735,6 +741,188 @@ int launch_dense_stack(const DenseStackArgs& a, int clusters, cudaStream_t s) {
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     return cudaLaunchKernelEx(&cfg, dense_stack_kernel, a) == cudaSuccess ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PCA inverse (SMC:541,551), transposed:  blocks^T[pixel][block] = comp_out_t[pixel][K] * r[block][K]^T.
+// One CTA per 128 output pixels: its 128 x K slice of the output PCA matrix is read from HBM exactly once (the
+// A operand, split hi/lo on chip), the de-standardised coordinates of ALL blocks stream through as the B operand
+// (pre-split by the last Dense layer, L2-resident), and the accumulator -- TMEM lane = pixel, column = block -- is
+// written with fully coalesced rows: for a fixed block the 32 lanes of a warp store 32 consecutive pixels.
+// Four 128-column accumulators rotate in TMEM, so the epilogue of one block chunk overlaps the MMAs of the next.
+namespace {
+constexpr int I_KB = 4;                                  // k-blocks of the A slice held in shared memory (K <= 128)
+constexpr int I_NB = 128;                                // blocks per chunk = UMMA N
+constexpr int I_A_TILE = BM * BK * 4;                    // 16 KB
+constexpr int I_B_TILE = I_NB * BK * 4;                  // 16 KB
+constexpr int I_BSTAGES = 2;
+constexpr int I_SMEM = 2 * I_KB * I_A_TILE + I_BSTAGES * 2 * I_B_TILE + 1024 + 256;
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+pca_inverse_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                     const __grid_constant__ CUtensorMap tmBlo, InvTArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_hi = base, a_lo = base + I_KB * I_A_TILE, b_ring = base + 2 * I_KB * I_A_TILE;
+    const uint32_t bars = b_ring + I_BSTAGES * 2 * I_B_TILE;
+    const uint32_t a_full = bars, a_conv = bars + 8;
+    auto b_full = [&](int s) { return bars + 16u + 8u * s; };
+    auto b_empty = [&](int s) { return bars + 16u + 8u * (I_BSTAGES + s); };
+    auto acc_full = [&](int b) { return bars + 16u + 8u * (2 * I_BSTAGES + b); };
+    auto acc_empty = [&](int b) { return bars + 16u + 8u * (2 * I_BSTAGES + 4 + b); };
+    const uint32_t tmem_slot = bars + 16u + 8u * (2 * I_BSTAGES + 8);
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = blockIdx.x * BM;                               // first output pixel (row of comp_out_t) of this CTA
+    const int kb_n = g.K / BK;                                    // <= I_KB
+    const int n_chunks = g.Mb / I_NB;                             // block chunks (Mb = padded block count)
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1); mbar_init(a_conv, 128);
+        for (int s = 0; s < I_BSTAGES; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int b = 0; b < 4; ++b) { mbar_init(acc_full(b), 1); mbar_init(acc_empty(b), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // the PCA matrix is static: its slice is requested before waiting for the Dense stack
+            mbar_expect_tx(a_full, (uint32_t)(kb_n * I_A_TILE));
+            for (int kb = 0; kb < kb_n; ++kb) tma_load_2d(a_hi + kb * I_A_TILE, &tmA, kb * BK, p0, a_full);
+            pdl_wait();
+            uint32_t it = 0;
+            for (int c = 0; c < n_chunks; ++c)
+                for (int kb = 0; kb < kb_n; ++kb, ++it) {
+                    const int s = it % I_BSTAGES;
+                    mbar_wait(b_empty(s), ((it / I_BSTAGES) & 1) ^ 1);
+                    mbar_expect_tx(b_full(s), 2 * I_B_TILE);
+                    const uint32_t st = b_ring + s * 2 * I_B_TILE;
+                    tma_load_2d(st, &tmBhi, kb * BK, c * I_NB, b_full(s));
+                    tma_load_2d(st + I_B_TILE, &tmBlo, kb * BK, c * I_NB, b_full(s));
+                }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(BM, I_NB);
+            mbar_wait(a_conv, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            uint32_t it = 0;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int buf = c & 3;
+                mbar_wait(acc_empty(buf), ((c >> 2) & 1) ^ 1);   // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * I_NB);
+                for (int kb = 0; kb < kb_n; ++kb, ++it) {
+                    const int s = it % I_BSTAGES;
+                    mbar_wait(b_full(s), (it / I_BSTAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = b_ring + s * 2 * I_B_TILE;
+                    const uint32_t ah = a_hi + kb * I_A_TILE, al = a_lo + kb * I_A_TILE, bh = st, bl = st + I_B_TILE;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint32_t ko = k * UMMA_K * 4;
+                        umma_tf32(tacc, make_smem_desc(ah + ko), make_smem_desc(bh + ko), idesc, (kb | k) != 0);
+                        if (g.three_pass) {
+                            umma_tf32(tacc, make_smem_desc(ah + ko), make_smem_desc(bl + ko), idesc, 1);
+                            umma_tf32(tacc, make_smem_desc(al + ko), make_smem_desc(bh + ko), idesc, 1);
+                        }
+                    }
+                    umma_commit(b_empty(s));
+                }
+                umma_commit(acc_full(buf));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- converters: split the A slice once (hi in place, lo beside it) ----
+        const int t = threadIdx.x - 64;
+        mbar_wait(a_full, 0);
+        {
+            float4* hi4 = reinterpret_cast<float4*>(gen_base + (a_hi - base));
+            float4* lo4 = reinterpret_cast<float4*>(gen_base + (a_lo - base));
+            const int n4 = kb_n * I_A_TILE / 16;
+#pragma unroll 4
+            for (int i = t; i < n4; i += 128) {
+                const float4 v = hi4[i];
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                hi4[i] = h; lo4[i] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(a_conv);
+        }
+        // ---- epilogue: thread <-> pixel (TMEM lane); 32 blocks per tcgen05.ld; coalesced 128 B rows per block ----
+        pdl_wait();                                              // g.sc->out_scale belongs to this step
+        const int q = warp & 3;
+        const int P = p0 + q * 32 + lane;                        // planar pixel index (c*S*S + ly*S + lx)
+        const float pm = __ldg(g.pmean + P);
+        const float o_scale = g.sc->out_scale;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int buf = c & 3;
+            mbar_wait(acc_full(buf), (c >> 2) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int j0 = 0; j0 < I_NB; j0 += 32) {
+                const int b0 = c * I_NB + j0;
+                if (b0 >= g.B) break;                            // padding blocks are never stored
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * I_NB + j0), v);
+                float* dst = g.blocks + (size_t)b0 * g.block_stride + P;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (b0 + j < g.B) dst[(size_t)j * g.block_stride] = (v[j] + pm) * o_scale;
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(acc_empty(buf));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+int pca_inverse_t_prepare() {
+    return cudaFuncSetAttribute(pca_inverse_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I_SMEM) == cudaSuccess ? 0 : -1;
+}
+int pca_inverse_t_max_k() { return I_KB * BK; }
+
+void launch_pca_inverse_t(const InvT& t, cudaStream_t s) {
+    const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(&t.mapA);
+    const CUtensorMap& bh = *reinterpret_cast<const CUtensorMap*>(&t.mapBhi);
+    const CUtensorMap& bl = *reinterpret_cast<const CUtensorMap*>(&t.mapBlo);
+    launch_k(pca_inverse_t_kernel, dim3(t.args.n_pix / BM), dim3(kThreads), I_SMEM, s, a, bh, bl, t.args);
 }
 
 // ------------------------------------------------------------------------------------------------

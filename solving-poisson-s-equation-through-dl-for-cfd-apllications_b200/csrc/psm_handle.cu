@@ -119,11 +119,13 @@ struct psm_handle {
     int32_t *d_fv[3] = {nullptr, nullptr, nullptr}; float* d_fw[3] = {nullptr, nullptr, nullptr};
     int32_t *d_bv[3] = {nullptr, nullptr, nullptr}; float* d_bw[3] = {nullptr, nullptr, nullptr};
     uint8_t* d_gmask = nullptr; uint16_t* d_owner = nullptr;
+    // single GPU: the placement folded into the grid->cell gather (back table re-indexed into the predicted blocks)
+    bool fuse_place = false; bool field_stale = false; bool no_fused_offsets = false;
+    int32_t* d_bb[3] = {nullptr, nullptr, nullptr}; uint16_t* d_bo[3] = {nullptr, nullptr, nullptr};
     int32_t *d_by0 = nullptr, *d_bx0 = nullptr;
     CoverEntry *d_rowcov = nullptr, *d_colcov = nullptr; bool fused_extract = false;   // gather writes the block operand itself
     bool keep_grid = false;           // fused path: also store the grid planes every step (PSM_KEEP_GRID=1); else psm_get_stage rebuilds them
     DevTask* d_tasks = nullptr; DevRec* d_rec = nullptr; int n_tasks = 0 /* local */, rounds = 0;
-    int2* d_rows = nullptr; int32_t* d_row_start = nullptr; double* d_row_sums = nullptr; int n_rows = 0;
     float* d_zc = nullptr;            // [B_pad][pc_in_pad]
 
     // ---- per-step buffers ---------------------------------------------------------------------------
@@ -139,6 +141,7 @@ struct psm_handle {
     bool dense_cluster = true;      // Dense layers: cluster split-K with on-chip reduction (one launch per layer)
     // whole Dense stack in one persistent launch (opt-in, PSM_DENSE_STACK=1: measured equal to the per-layer cluster
     // kernels on the stage and slower for the step): weights and activations pre-split into tf32 hi / lo
+    bool inv_t = false; InvT tc_inv_t{}; float *d_r_hi = nullptr, *d_r_lo = nullptr;   // transposed PCA inverse (default)
     bool dense_stack = false; int stack_clusters = 0;
     std::vector<float*> d_Whi, d_Wlo; float* d_act_hi[2] = {nullptr, nullptr}; float* d_act_lo[2] = {nullptr, nullptr};
     TensorMap128* d_stack_maps = nullptr; DenseStackArgs stack_args{};
@@ -514,6 +517,23 @@ static int init_local(psm_handle* h, LocalInit& L) {
             ow[q] = (uint16_t)(o - kb0);
         }
         TRY(upload(h, &h->d_owner, ow));
+        h->fuse_place = (L.world == 1) && L.have_back && !env_on("PSM_NO_FUSED_PLACE");
+        h->no_fused_offsets = env_on("PSM_NO_FUSED_OFFSETS");
+        if (h->fuse_place) {
+            // pixel -> (last-writer block, offset inside the blocks array) is static: re-index the back table
+            for (int j = 0; j < 3; ++j) {
+                std::vector<int32_t> bb(N); std::vector<uint16_t> bo(N);
+                for (long long c = 0; c < N; ++c) {
+                    const long long q = L.bv[j][c];
+                    if (q < 0) { bb[c] = -1; bo[c] = 0; continue; }          // keep p_prev marker (vertex 0 only)
+                    const int o = ow[q];
+                    const int y = (int)(q / W), x = (int)(q - (long long)y * W);
+                    bb[c] = (int32_t)(((long long)o * h->C) * S2 + (long long)(y - (P.y0[kb0 + o] - L.row0)) * S + (x - P.x0[kb0 + o]));
+                    bo[c] = (uint16_t)o;
+                }
+                TRY(upload(h, &h->d_bb[j], bb)); TRY(upload(h, &h->d_bo[j], bo));
+            }
+        }
         std::vector<int32_t> by0(h->B_pad, 0), bx0(h->B_pad, 0);
         for (int k = 0; k < h->B; ++k) { by0[k] = P.y0[kb0 + k] - L.row0; bx0[k] = P.x0[kb0 + k]; }
         TRY(upload(h, &h->d_by0, by0));
@@ -567,17 +587,6 @@ static int init_local(psm_handle* h, LocalInit& L) {
         h->n_tasks = (int)tk.size();
         TRY(upload(h, &h->d_tasks, tk));
         TRY(upload(h, &h->d_terms, terms));
-        std::vector<int2> rows;
-        std::vector<int32_t> row_start(tk.size() + 1, 0);
-        for (size_t i = 0; i < tk.size(); ++i) {
-            row_start[i] = (int32_t)rows.size();
-            for (int y = tk[i].y0; y < tk[i].y1; ++y) rows.push_back(make_int2((int)i, y));
-        }
-        row_start[tk.size()] = (int32_t)rows.size();
-        h->n_rows = (int)rows.size();
-        TRY(upload(h, &h->d_rows, rows));
-        TRY(upload(h, &h->d_row_start, row_start));
-        TRY(dalloc(h, &h->d_row_sums, rows.size()));
         std::vector<DevRec> rc2(P.rec.size());
         for (size_t i = 0; i < rc2.size(); ++i) rc2[i] = DevRec{P.rec[i].ta, P.rec[i].tb, P.rec[i].parent, P.rec[i].is_nan};
         TRY(upload(h, &h->d_rec, rc2));
@@ -666,7 +675,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
                       int epi, const float* v0, const float* v1, const float* v2, int bn) -> int {
             if (make_kmajor_map(&g.mapA, A, a_rows, K, K, 128) != 0 || make_kmajor_map(&g.mapB, Bm, b_rows, K, K, bn) != 0)
                 PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-            g.args = TcGemmArgs{Cp, a_rows, b_rows, K, ldc, splits, epi, three, v0, v1, v2, h->d_sc};
+            g.args = TcGemmArgs{Cp, a_rows, b_rows, K, ldc, splits, epi, three, v0, v1, v2, h->d_sc, nullptr, nullptr};
             g.bn = bn;
             return 0;
         };
@@ -706,6 +715,21 @@ static int init_local(psm_handle* h, LocalInit& L) {
         }
         TRY(mk(h->tc_inv, h->d_r, Bp, h->d_comp_out_t, S2 * h->C, h->pc_p_pad, h->d_blocks, S2 * h->C, 1, EPI_PCA_INV,
                h->d_pmean, nullptr, nullptr, 128));
+        // ---- transposed PCA inverse: needs the last Dense layer to deliver r pre-split (cluster or stack kernel) ----
+        h->inv_t = !env_on("PSM_NO_INV_T") && h->dense_cluster && h->pc_p_pad <= pca_inverse_t_max_k() && (S2 * h->C) % 128 == 0 &&
+                   pca_inverse_t_prepare() == 0;
+        if (h->inv_t) {
+            TRY(dalloc(h, &h->d_r_hi, (size_t)Bp * h->pc_p_pad));
+            TRY(dalloc(h, &h->d_r_lo, (size_t)Bp * h->pc_p_pad));
+            h->tc_dense[h->n_dense - 1].args.C_hi = h->d_r_hi;
+            h->tc_dense[h->n_dense - 1].args.C_lo = h->d_r_lo;
+            InvT& it = h->tc_inv_t;
+            if (make_kmajor_map(&it.mapA, h->d_comp_out_t, S2 * h->C, h->pc_p_pad, h->pc_p_pad, 128) != 0 ||
+                make_kmajor_map(&it.mapBhi, h->d_r_hi, Bp, h->pc_p_pad, h->pc_p_pad, 128) != 0 ||
+                make_kmajor_map(&it.mapBlo, h->d_r_lo, Bp, h->pc_p_pad, h->pc_p_pad, 128) != 0)
+                PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed (PCA inverse)");
+            it.args = InvTArgs{h->d_blocks, (long long)S2 * h->C, h->B, Bp, h->pc_p_pad, S2 * h->C, three, h->d_pmean, h->d_sc};
+        }
         // ---- the whole Dense stack as one persistent launch -------------------------------------------------
         int max_cl = 0;
         h->dense_stack = env_on("PSM_DENSE_STACK") && h->n_dense <= kMaxDense && dense_stack_prepare(&max_cl) == 0;
@@ -724,8 +748,8 @@ static int init_local(psm_handle* h, LocalInit& L) {
                     make_kmajor_map(&maps[4 * l + 3], h->d_Wlo[l], N, K, K, 64) != 0)
                     PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed (Dense stack)");
                 sa.L[l] = DenseLayerDesc{K, N, last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU, h->d_bias[l], h->d_out_s, h->d_out_m,
-                                         last ? h->d_r : nullptr, last ? nullptr : h->d_act_hi[(l + 1) & 1],
-                                         last ? nullptr : h->d_act_lo[(l + 1) & 1]};
+                                         last ? h->d_r : nullptr, last ? h->d_r_hi : h->d_act_hi[(l + 1) & 1],
+                                         last ? h->d_r_lo : h->d_act_lo[(l + 1) & 1]};
                 max_tiles = std::max(max_tiles, (Bp / 128) * (N / 64));
             }
             TRY(upload(h, &h->d_stack_maps, maps));
@@ -1000,36 +1024,34 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
         GemmArgs g{};
         g.A = h->d_r; g.B = h->d_comp_out_t; g.C = h->d_blocks; g.M = Bp; g.N = S2 * h->C; g.K = h->pc_p_pad;
         g.lda = g.K; g.ldb = g.K; g.ldc = g.N; g.splits = 1; g.epi = EPI_PCA_INV; g.v0 = h->d_pmean; g.sc = h->d_sc;
-        if (tc) launch_tc_gemm(h->tc_inv, s);
+        if (tc && h->inv_t) launch_pca_inverse_t(h->tc_inv_t, s);
+        else if (tc) launch_tc_gemm(h->tc_inv, s);
         else launch_sgemm(g, s);
         ++nl;
     }
     tick();   // pca_inverse
-    MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->C, S, h->W, (multi && !p2p) ? h->d_means_loc : h->d_means,
-                 h->d_rows, h->n_rows, h->d_row_start, h->d_row_sums};
-    launch_means(ma, s, true); nl += 2;
+    OffsetsArgs oa{};
+    oa.rec = h->d_rec; oa.B = h->Bg; oa.F = h->F; oa.rounds = h->rounds; oa.ref_bc = h->cfg.ref_bc; oa.means = h->d_means;
+    oa.dbuf0 = h->d_dbuf[0]; oa.dbuf1 = h->d_dbuf[1]; oa.pbuf0 = h->d_pbuf[0]; oa.pbuf1 = h->d_pbuf[1];
+    oa.offsets = h->d_offsets; oa.coff = h->d_coff; oa.terms = h->d_terms;
+    for (int f = 0; f < 3; ++f) oa.term_start[f] = h->term_start[f];
+    for (int f = 0; f < 2; ++f) oa.shift_len[f] = h->plan.shift_len[f];
+    oa.sc = h->d_sc;
+    oa.host_skip = h->d_host_skip;
+    oa.p2p = d_p2p;
+    const bool fuse_offsets = !multi && h->n_tasks > 0 && h->Bg * h->F <= 1024 && !h->no_fused_offsets;
+    MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->C, S, h->W, (multi && !p2p) ? h->d_means_loc : h->d_means};
+    launch_means(ma, fuse_offsets ? &oa : nullptr, s); ++nl;
     if (p2p) { launch_p2p_push_means(h->d_p2p, h->d_tasks, h->n_tasks, h->world, h->d_means, s); ++nl; }   // exchange 3 over peer memory
     else if (multi)   // exchange 3: every rank contributes its own slots (zero elsewhere) -> identical means everywhere
         NC(h, g_nccl.AllReduce(h->d_means_loc, h->d_means, (size_t)h->n_tasks_glob, ncclDouble, ncclSum, h->comm, s));
     tick();   // strip_means
-    {
-        OffsetsArgs oa{};
-        oa.rec = h->d_rec; oa.B = h->Bg; oa.F = h->F; oa.rounds = h->rounds; oa.ref_bc = h->cfg.ref_bc; oa.means = h->d_means;
-        oa.dbuf0 = h->d_dbuf[0]; oa.dbuf1 = h->d_dbuf[1]; oa.pbuf0 = h->d_pbuf[0]; oa.pbuf1 = h->d_pbuf[1];
-        oa.offsets = h->d_offsets; oa.coff = h->d_coff; oa.terms = h->d_terms;
-        for (int f = 0; f < 3; ++f) oa.term_start[f] = h->term_start[f];
-        for (int f = 0; f < 2; ++f) oa.shift_len[f] = h->plan.shift_len[f];
-        oa.sc = h->d_sc;
-        oa.tasks = h->d_tasks; oa.n_fold_tasks = 0;    // a single CTA folding all tasks is slower than task_means_kernel (measured) oa.row_start = h->d_row_start; oa.row_sums = h->d_row_sums;
-        oa.means_out = h->d_means;
-        oa.host_skip = h->d_host_skip;
-        oa.p2p = d_p2p;
-        launch_offsets(oa, s); ++nl;
-    }
+    if (!fuse_offsets) { launch_offsets(oa, s); ++nl; }
     tick();   // offsets
     PlaceArgs pl{h->d_blocks, h->d_owner, h->d_by0, h->d_bx0, h->d_coff, h->d_field, h->Bg, h->kb0, h->C, h->F, S, h->H, h->W,
                  h->field_stride};
-    launch_place(pl, s); ++nl;
+    const bool fuse_place = h->fuse_place && d_out != nullptr;
+    if (!fuse_place) { launch_place(pl, s); ++nl; }
     tick();   // place
     if (h->have_back && d_out) {
         if (p2p) {
@@ -1046,7 +1068,11 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
             NC(h, g_nccl.GroupEnd());
         }
         BackArgs ba{h->d_bv[0], h->d_bv[1], h->d_bv[2], h->d_bw[0], h->d_bw[1], h->d_bw[2], h->d_field, h->n_cells,
-                    h->field_stride, h->d_pprev, d_out, h->F, h->cfg.additive, h->d_sc, d_p2p};
+                    h->field_stride, h->d_pprev, d_out, h->F, h->cfg.additive, h->d_sc, d_p2p, nullptr, nullptr, nullptr, nullptr, 0, 0};
+        if (fuse_place) {
+            ba.v0 = h->d_bb[0]; ba.v1 = h->d_bb[1]; ba.v2 = h->d_bb[2]; ba.o0 = h->d_bo[0]; ba.o1 = h->d_bo[1]; ba.o2 = h->d_bo[2];
+            ba.field = h->d_blocks; ba.plane = S2; ba.coff = h->d_coff; ba.n_blocks = h->Bg; ba.block_plane = S2;
+        }
         launch_back(ba, s); ++nl;
     }
     tick();   // back_gather
@@ -1071,6 +1097,7 @@ static int enqueue_step(psm_handle* h, bool host, const double* in, double* out)
 
 static int submit_step(psm_handle* h, bool host, const double* in, double* out) {
     h->last_host = host;
+    h->field_stale = h->fuse_place && (host || out != nullptr);    // the placement is folded into the grid->cell gather
     if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
     if (!h->use_graphs || h->ev_valid || h->eager_steps > 0) {   // per-stage events: eager launches (event nodes of a graph carry no usable timestamps)
         if (h->eager_steps > 0) --h->eager_steps;
@@ -1251,6 +1278,14 @@ extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_
             return PSM_OK;
         case PSM_STAGE_FIELD:
             TRY(need((int64_t)h->F * h->G * 4));
+            if (h->field_stale) {
+                // the step folded the placement into the grid->cell gather: materialise the field of the LAST step now
+                PlaceArgs pl{h->d_blocks, h->d_owner, h->d_by0, h->d_bx0, h->d_coff, h->d_field, h->Bg, h->kb0, h->C, h->F, h->S, h->H, h->W,
+                             h->field_stride};
+                launch_place(pl, h->stream);
+                CU(h, cudaStreamSynchronize(h->stream));
+                h->field_stale = false;
+            }
             CU(h, cudaMemcpy2D(out, (size_t)h->G * 4, h->d_field, (size_t)h->field_stride * 4, (size_t)h->G * 4, h->F, cudaMemcpyDeviceToHost));
             return PSM_OK;
         case PSM_STAGE_SCALARS: {
@@ -1326,7 +1361,7 @@ extern "C" int psm_debug_gemm(int32_t device, int32_t mode, int32_t M, int32_t N
             if (tc_gemm_prepare() != 0 || make_kmajor_map(&t.mapA, dA, M, K, K, 128) != 0 ||
                 make_kmajor_map(&t.mapB, dB, N, K, K, tc_gemm_bn(N)) != 0) rc = PSM_ERR_CUDA;
             else {
-                t.args = TcGemmArgs{dC, M, N, K, N, splits, EPI_PARTIAL, mode == PSM_GEMM_TC_3XTF32 ? 1 : 0, nullptr, nullptr, nullptr, nullptr};
+                t.args = TcGemmArgs{dC, M, N, K, N, splits, EPI_PARTIAL, mode == PSM_GEMM_TC_3XTF32 ? 1 : 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
                 t.bn = tc_gemm_bn(N);
                 launch_tc_gemm(t, 0);
             }

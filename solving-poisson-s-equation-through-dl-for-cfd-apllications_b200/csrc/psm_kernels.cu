@@ -500,54 +500,68 @@ void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {
 //      Two deterministic passes (no atomics): one warp per (task, row) writes a row partial, then one
 //      warp per task folds its rows -- rectangles range from 1 x 1 to 120 x 128 pixels, so the work
 //      is balanced per row, not per task.
-__global__ void __launch_bounds__(256) row_sums_kernel(MeansArgs a) {
+// One CTA per task: warp w takes rows y0+w, y0+w+8, ... of the rectangle (each lane 4 pixels of the 128-pixel block
+// row, FP64), then the 8 warp partials are folded in a fixed order -- deterministic, no atomics, one launch.
+// The task list and the flow mask are static: they are fetched before waiting for the predicted blocks.
+__device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
+
+__device__ void offsets_body(const OffsetsArgs& a);
+
+template <bool FUSE_OFFSETS>
+__global__ void __launch_bounds__(256) task_means_kernel(MeansArgs a, OffsetsArgs oa) {
     pdl_launch_dependents();
-    const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const bool live = r < a.n_rows;
-    // the row list, the task and the flow mask are static: fetched before waiting for the predicted blocks
-    int2 ri = make_int2(0, 0);
-    DevTask t{};
-    bool m0 = false, m1 = false, m2 = false, m3 = false;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const DevTask t = a.tasks[blockIdx.x];
     const int x = lane * 4;
-    if (live) {
-        ri = a.rows[r];                                          // (task, block-local y)
-        t = a.tasks[ri.x];
-        m0 = x + 0 >= t.x0 && x + 0 < t.x1; m1 = x + 1 >= t.x0 && x + 1 < t.x1;
-        m2 = x + 2 >= t.x0 && x + 2 < t.x1; m3 = x + 3 >= t.x0 && x + 3 < t.x1;
-        if (t.kind == 0) {
-            const uint8_t* msk = a.gmask + (long long)(t.my0 + ri.y) * a.W + t.mx0;
-            m0 = m0 && msk[x + 0]; m1 = m1 && msk[x + 1]; m2 = m2 && msk[x + 2]; m3 = m3 && msk[x + 3];
-        }
+    const bool c0 = x + 0 >= t.x0 && x + 0 < t.x1, c1 = x + 1 >= t.x0 && x + 1 < t.x1;
+    const bool c2 = x + 2 >= t.x0 && x + 2 < t.x1, c3 = x + 3 >= t.x0 && x + 3 < t.x1;
+    const uint8_t* msk = a.gmask + (long long)t.my0 * a.W + t.mx0 + x;
+    unsigned int mk = 0x01010101u;                               // mask bytes of this lane's 4 pixels in the first row
+    if (t.kind == 0 && t.y0 + w < t.y1) {
+        const uint8_t* m = msk + (long long)(t.y0 + w) * a.W;
+        mk = (unsigned)m[0] | ((unsigned)m[1] << 8) | ((unsigned)m[2] << 16) | ((unsigned)m[3] << 24);
     }
     pdl_wait();
-    if (!live) return;
-    const float* src = a.blocks + (((long long)t.src * a.C + t.ch) * a.S + ri.y) * a.S;
-    const float4 v = reinterpret_cast<const float4*>(src)[lane];  // the whole 128-pixel block row
+    const float* src = a.blocks + ((long long)t.src * a.C + t.ch) * a.S * a.S + x;
     double sum = 0.0;
-    if (m0) sum += (double)v.x;
-    if (m1) sum += (double)v.y;
-    if (m2) sum += (double)v.z;
-    if (m3) sum += (double)v.w;
+    for (int y = t.y0 + w; y < t.y1; y += 8) {
+        const float4 v = *reinterpret_cast<const float4*>(src + (long long)y * a.S);
+        if (c0 && (mk & 0x000000FFu)) sum += (double)v.x;
+        if (c1 && (mk & 0x0000FF00u)) sum += (double)v.y;
+        if (c2 && (mk & 0x00FF0000u)) sum += (double)v.z;
+        if (c3 && (mk & 0xFF000000u)) sum += (double)v.w;
+        if (t.kind == 0 && y + 8 < t.y1) {
+            const uint8_t* m = msk + (long long)(y + 8) * a.W;
+            mk = (unsigned)m[0] | ((unsigned)m[1] << 8) | ((unsigned)m[2] << 16) | ((unsigned)m[3] << 24);
+        }
+    }
     sum = warp_sum(sum);
-    if (lane == 0) a.row_sums[r] = sum;
+    __shared__ double part[8];
+    if (lane == 0) part[w] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = part[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) tot += part[k];
+        a.means[t.out] = t.kind ? tot : ((t.count > 0) ? tot / (double)t.count : CUDART_NAN);
+    }
+    if (FUSE_OFFSETS) {
+        // single GPU: the LAST CTA to publish its mean runs the offset recurrence (a few hundred scalars) right here
+        __shared__ bool s_last;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int prev = atomicAdd(&oa.sc->means_done, 1u);
+            s_last = (prev == gridDim.x - 1);
+            if (s_last) { oa.sc->means_done = 0u; __threadfence(); }
+        }
+        __syncthreads();
+        if (s_last) offsets_body(oa);
+    }
 }
-__global__ void __launch_bounds__(256) task_means_kernel(MeansArgs a) {
-    pdl_enter();
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= a.n_tasks) return;
-    const int r0 = a.row_start[t], r1 = a.row_start[t + 1];
-    double sum = 0.0;
-    for (int r = r0 + lane; r < r1; r += 32) sum += a.row_sums[r];
-    sum = warp_sum(sum);
-    const DevTask tk = a.tasks[t];
-    if (lane == 0) a.means[tk.out] = tk.kind ? sum : ((tk.count > 0) ? sum / (double)tk.count : CUDART_NAN);
-}
-void launch_means(const MeansArgs& a, cudaStream_t s, bool fold_rows_here) {
+void launch_means(const MeansArgs& a, const OffsetsArgs* fused, cudaStream_t s) {
     if (a.n_tasks <= 0) return;
-    launch_k(row_sums_kernel, dim3((a.n_rows + 7) / 8), dim3(256), 0, s, a);
-    if (fold_rows_here) launch_k(task_means_kernel, dim3((a.n_tasks + 7) / 8), dim3(256), 0, s, a);
+    if (fused) launch_k(task_means_kernel<true>, dim3(a.n_tasks), dim3(256), (size_t)fused->B * fused->F * 24, s, a, *fused);
+    else launch_k(task_means_kernel<false>, dim3(a.n_tasks), dim3(256), 0, s, a, OffsetsArgs{});
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -556,21 +570,7 @@ void launch_means(const MeansArgs& a, cudaStream_t s, bool fold_rows_here) {
 //      ceil(log2(depth)) rounds; then the global shift of SMC:350 / GRAD:358-361 from the per-run
 //      line sums.  Single CTA: the whole problem is a few thousand scalars.  In the multi-GPU path
 //      every rank evaluates this redundantly on the all-reduced means.
-__global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
-    pdl_enter();
-    if (a.p2p) p2p_wait(a.p2p, 1, 0xFFu);          // every rank's strip means have been pushed into a.means
-    if (a.n_fold_tasks > 0) {      // fold the row partials of every task (one warp per task), FP64, fixed order
-        const int lane = threadIdx.x & 31;
-        for (int t = threadIdx.x >> 5; t < a.n_fold_tasks; t += blockDim.x >> 5) {
-            const int r0 = a.row_start[t], r1 = a.row_start[t + 1];
-            double sum = 0.0;
-            for (int r = r0 + lane; r < r1; r += 32) sum += a.row_sums[r];
-            sum = warp_sum(sum);
-            const DevTask tk = a.tasks[t];
-            if (lane == 0) a.means_out[tk.out] = tk.kind ? sum : ((tk.count > 0) ? sum / (double)tk.count : CUDART_NAN);
-        }
-        __syncthreads();
-    }
+__device__ void offsets_body(const OffsetsArgs& a) {
     const int n = a.B * a.F;
     // pointer jumping in shared memory when the forest fits (n <= kOffsetsSmemMax), else in the global scratch
     extern __shared__ unsigned char off_smem[];
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const DevRec r = a.rec[i];
         const int f = i / a.B;
-        double d = a.means[r.ta] - (r.tb >= 0 ? a.means[r.tb] : a.ref_bc);
+        double d = ld_cg_f64(a.means + r.ta) - (r.tb >= 0 ? ld_cg_f64(a.means + r.tb) : a.ref_bc);
         d_cur[i] = d;
         p_cur[i] = (r.parent >= 0) ? f * a.B + r.parent : -1;
     }
@@ -600,14 +600,13 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
         int32_t* tp = p_cur; p_cur = p_nxt; p_nxt = tp;
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) a.offsets[i] = d_cur[i];
-    __syncthreads();
     __shared__ double red[32];
     __shared__ double s_shift[2];
     for (int f = 0; f < a.F; ++f) {
         double acc = 0.0;
         for (int i = a.term_start[f] + threadIdx.x; i < a.term_start[f + 1]; i += blockDim.x) {
             const DevShiftTerm t = a.terms[i];
-            acc += (double)t.coef * (a.means[t.task] - (double)t.n * a.offsets[f * a.B + t.block]);
+            acc += (double)t.coef * (ld_cg_f64(a.means + t.task) - (double)t.n * d_cur[f * a.B + t.block]);
         }
         acc = warp_sum(acc);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -619,12 +618,17 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
         }
         __syncthreads();
     }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) a.coff[i] = (float)(a.offsets[i] + s_shift[i / a.B]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a.coff[i] = (float)(d_cur[i] + s_shift[i / a.B]);
     if (threadIdx.x == 0) {
         a.sc->umax2_bits = 0ull; a.sc->dumax2_bits = 0ull;      // re-arm the running maxima of prep
         a.sc->dense_barrier = 0u;                               // ... and the grid barrier of the Dense stack
         if (a.host_skip) { *reinterpret_cast<volatile int*>(a.host_skip) = a.sc->skip | (a.sc->comm_error << 8); __threadfence_system(); }
     }
+}
+__global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
+    pdl_enter();
+    if (a.p2p) p2p_wait(a.p2p, 1, 0xFFu);          // every rank's strip means have been pushed into a.means
+    offsets_body(a);
 }
 void launch_offsets(const OffsetsArgs& a, cudaStream_t s) {
     const int n = a.B * a.F;
@@ -696,42 +700,60 @@ void launch_place(const PlaceArgs& a, cudaStream_t s) {
 // K8  grid -> cell gather.  PMP:481-496: result[indices] (folded into the vertex ids at init),
 //     interpolate_fill, previous-pressure fallback for NaN / near-wall cells; SMC:644-645
 //     (p = p_prev + delta_p) for the deltaU variant.
+template <bool FROM_BLOCKS>
 __global__ void __launch_bounds__(256) back_kernel(BackArgs a) {
     pdl_launch_dependents();
     // static tables of the first cell before the wait (see gather_kernel)
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     int i0 = 0, i1 = 0, i2 = 0; float q0 = 0.f, q1 = 0.f, q2 = 0.f;
-    if (i < a.n) { i0 = __ldcs(a.v0 + i); i1 = __ldcs(a.v1 + i); i2 = __ldcs(a.v2 + i); q0 = __ldcs(a.w0 + i); q1 = __ldcs(a.w1 + i); q2 = __ldcs(a.w2 + i); }
+    int b0 = 0, b1 = 0, b2 = 0;
+    auto load = [&]() {
+        i0 = __ldcs(a.v0 + i); i1 = __ldcs(a.v1 + i); i2 = __ldcs(a.v2 + i);
+        q0 = __ldcs(a.w0 + i); q1 = __ldcs(a.w1 + i); q2 = __ldcs(a.w2 + i);
+        if (FROM_BLOCKS) { b0 = __ldcs(a.o0 + i); b1 = __ldcs(a.o1 + i); b2 = __ldcs(a.o2 + i); }
+    };
+    if (i < a.n) load();
     pdl_wait();
     if (a.p2p) p2p_wait(a.p2p, 2, a.p2p->pix_recv_mask);   // ghost pixels pushed by their owners
     const int skip = a.sc->skip;
+    const float* __restrict__ src = a.field;               // the assembled field, or the predicted blocks
     while (i < a.n) {
         if (a.n_fields == 1) {
             const double pp = a.p_prev[i];
             double out = pp;
             if (i0 >= 0 && !skip) {
-                const float v = __ldg(a.field + i0) * q0 + __ldg(a.field + i1) * q1 + __ldg(a.field + i2) * q2;
+                float f0 = __ldg(src + i0), f1 = __ldg(src + i1), f2 = __ldg(src + i2);
+                if (FROM_BLOCKS) { f0 -= __ldg(a.coff + b0); f1 -= __ldg(a.coff + b1); f2 -= __ldg(a.coff + b2); }   // SMC:243,350
+                const float v = f0 * q0 + f1 * q1 + f2 * q2;
                 if (v == v) out = a.additive ? pp + (double)v : (double)v;
             }
             a.out[i] = out;
         } else {
             double o0 = CUDART_NAN, o1 = CUDART_NAN;
             if (i0 >= 0) {
-                const float* f1 = a.field + a.plane;
-                o0 = (double)(__ldg(a.field + i0) * q0 + __ldg(a.field + i1) * q1 + __ldg(a.field + i2) * q2);
-                o1 = (double)(__ldg(f1 + i0) * q0 + __ldg(f1 + i1) * q1 + __ldg(f1 + i2) * q2);
+                const float* s1 = src + a.plane;
+                float f0 = __ldg(src + i0), f1 = __ldg(src + i1), f2 = __ldg(src + i2);
+                float g0 = __ldg(s1 + i0), g1 = __ldg(s1 + i1), g2 = __ldg(s1 + i2);
+                if (FROM_BLOCKS) {
+                    const float* c1 = a.coff + a.n_blocks;
+                    f0 -= __ldg(a.coff + b0); f1 -= __ldg(a.coff + b1); f2 -= __ldg(a.coff + b2);
+                    g0 -= __ldg(c1 + b0); g1 -= __ldg(c1 + b1); g2 -= __ldg(c1 + b2);
+                }
+                o0 = (double)(f0 * q0 + f1 * q1 + f2 * q2);
+                o1 = (double)(g0 * q0 + g1 * q1 + g2 * q2);
             }
             reinterpret_cast<double2*>(a.out)[i] = make_double2(o0, o1);
         }
         i += stride;
-        if (i < a.n) { i0 = __ldcs(a.v0 + i); i1 = __ldcs(a.v1 + i); i2 = __ldcs(a.v2 + i); q0 = __ldcs(a.w0 + i); q1 = __ldcs(a.w1 + i); q2 = __ldcs(a.w2 + i); }
+        if (i < a.n) load();
     }
 }
 void launch_back(const BackArgs& a, cudaStream_t s) {
     long long want = (a.n + 255) / 256;
     int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
-    launch_k(back_kernel, dim3(blocks), dim3(256), 0, s, a);
+    if (a.o0) launch_k(back_kernel<true>, dim3(blocks), dim3(256), 0, s, a);
+    else launch_k(back_kernel<false>, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // Static sparse exchange (multi-GPU): contiguous send buffer from an index list.

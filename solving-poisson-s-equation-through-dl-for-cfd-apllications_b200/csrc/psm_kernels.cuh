@@ -39,6 +39,7 @@ struct Scalars {
     unsigned int step;               // multi-GPU: id of the current step (flags of the peer-memory exchanges)
     int    comm_error;               // multi-GPU: a peer flag did not arrive in time
     unsigned int push_done[3];       // multi-GPU: CTAs of a push kernel that have finished their stores
+    unsigned int means_done;         // CTAs of task_means_kernel that have published their mean (the last one runs the offsets)
     unsigned int dense_barrier;      // grid barrier of dense_stack_kernel (arrivals of the current step; re-armed by offsets_kernel)
 };
 
@@ -149,6 +150,7 @@ struct TcGemmArgs {
     int three_pass;       // 1: hi/lo split (3xTF32, FP32-class accuracy), 0: single-pass TF32
     const float* v0; const float* v1; const float* v2;
     const Scalars* sc;
+    float* C_hi; float* C_lo;  // dense_cluster_kernel: optional tf32 hi / lo split of the result (same layout as C)
 };
 struct TcGemm { TensorMap128 mapA, mapB; TcGemmArgs args; int bn; };   // bn: N tile (64 or 128) the B map was built for
 int make_kmajor_map(TensorMap128* out, const float* ptr, int rows, int cols, int ld, int box_rows);
@@ -160,6 +162,22 @@ void launch_tc_gemm(const TcGemm& t, cudaStream_t s);
 // (psm_gemm_tc.cu).  t.args.splits = cluster size along K (1, 2, 4 or 8); N % 64 == 0.
 int dense_cluster_prepare();
 int launch_dense_cluster(const TcGemm& t, cudaStream_t s);
+
+// PCA inverse, transposed (psm_gemm_tc.cu): one CTA per 128 output pixels, all blocks as the MMA N dimension.
+struct InvTArgs {
+    float* blocks;            // [B][C][S][S]: element (block b, planar pixel P) at b * block_stride + P
+    long long block_stride;   // C*S*S
+    int B, Mb;                // real / padded (multiple of 128) block count
+    int K;                    // padded pc_p (<= pca_inverse_t_max_k())
+    int n_pix;                // C*S*S (multiple of 128)
+    int three_pass;
+    const float* pmean;       // [n_pix] planar
+    const Scalars* sc;        // out_scale
+};
+struct InvT { TensorMap128 mapA, mapBhi, mapBlo; InvTArgs args; };
+int pca_inverse_t_prepare();
+int pca_inverse_t_max_k();
+void launch_pca_inverse_t(const InvT& t, cudaStream_t s);
 
 // The whole Dense stack (NNS:8-38: Dense(relu) x (n-1) -> Dense(linear), de-standardisation SMC:533) in ONE launch
 // (psm_gemm_tc.cu).  Persistent clusters of 8 CTAs: a cluster evaluates one 128 x 64 output tile of the current
@@ -215,11 +233,7 @@ struct MeansArgs {
     const uint8_t* gmask;             // GLOBAL [H][W]
     int C, S, W;
     double* means;                    // GLOBAL slots (this rank writes only its own)
-    const int2* rows; int n_rows;     // (local task, block-local y) of every rectangle row, grouped by task
-    const int32_t* row_start;         // [n_tasks + 1] first row of each task
-    double* row_sums;                 // [n_rows] scratch
 };
-void launch_means(const MeansArgs& a, cudaStream_t s, bool fold_rows_here);
 
 // K6b: offset recurrence (pointer jumping over the parent forest) + global shift from the line sums.
 struct DevRec { int32_t ta, tb, parent, is_nan; };
@@ -234,10 +248,10 @@ struct OffsetsArgs {
     Scalars* sc;
     int* host_skip;                   // mapped pinned host word: the step's status without a copy node
     const P2PArgs* p2p;               // multi-GPU over peer memory: wait for every rank's strip means first
-    // single-GPU: the row partials are folded into means here (multi-GPU does it before the all-reduce)
-    const DevTask* tasks; int n_fold_tasks; const int32_t* row_start; const double* row_sums; double* means_out;
 };
 void launch_offsets(const OffsetsArgs& a, cudaStream_t s);
+// `fused` != NULL (single GPU, B*F <= 1024): the last CTA of the means kernel also runs the offsets (no second launch)
+void launch_means(const MeansArgs& a, const OffsetsArgs* fused, cudaStream_t s);
 
 // K7: placement through the owner map.
 struct PlaceArgs {
@@ -258,6 +272,11 @@ struct BackArgs {
     int n_fields; int additive;
     const Scalars* sc;
     const P2PArgs* p2p;               // multi-GPU over peer memory: wait for the pushed ghost pixels first
+    // K7 folded into K8 (single GPU): v0..v2 index the predicted BLOCKS (pixel -> last-writer block and its local
+    // offset are static) and the block correction is subtracted on the fly -- the field is never materialised
+    const uint16_t* o0; const uint16_t* o1; const uint16_t* o2;   // owner block of each vertex pixel (NULL: gather from `field`)
+    const float* coff;                // [F][n_blocks]
+    int n_blocks; int block_plane;    // S*S: distance between the channels of one block
 };
 void launch_back(const BackArgs& a, cudaStream_t s);
 
