@@ -187,6 +187,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ===================== converters (3xTF32 split), then epilogue =====================
         const int t = threadIdx.x - 64;                        // 0..127
+        const bool keep_hi = g.three_pass != 2;                // 2: the tensor core truncates the raw FP32 tile to TF32 itself
         if (g.three_pass) {
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % STAGES;
@@ -207,13 +208,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int i = t; i < A_BYTES / 16; i += 128) {
                     float4 hi, lo;
                     split4(a_hi[i], hi, lo);
-                    a_hi[i] = hi; a_lo[i] = lo;
+                    if (keep_hi) a_hi[i] = hi;
+                    a_lo[i] = lo;
                 }
 #pragma unroll 4
                 for (int i = t; i < B_BYTES / 16; i += 128) {
                     float4 hi, lo;
                     split4(b_hi[i], hi, lo);
-                    b_hi[i] = hi; b_lo[i] = lo;
+                    if (keep_hi) b_hi[i] = hi;
+                    b_lo[i] = lo;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
                 mbar_arrive(conv_bar(s));
@@ -367,6 +370,7 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         __syncwarp();
     } else {
         const int t = threadIdx.x - 64;
+        const bool keep_hi = g.three_pass != 2;
         if (g.three_pass) {
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % STAGES;
@@ -384,9 +388,9 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
                 };
 #pragma unroll 4
-                for (int j = t; j < A_BYTES / 16; j += 128) { float4 hi, lo; split4(a_hi[j], hi, lo); a_hi[j] = hi; a_lo[j] = lo; }
+                for (int j = t; j < A_BYTES / 16; j += 128) { float4 hi, lo; split4(a_hi[j], hi, lo); if (keep_hi) a_hi[j] = hi; a_lo[j] = lo; }
 #pragma unroll 4
-                for (int j = t; j < B_BYTES / 16; j += 128) { float4 hi, lo; split4(b_hi[j], hi, lo); b_hi[j] = hi; b_lo[j] = lo; }
+                for (int j = t; j < B_BYTES / 16; j += 128) { float4 hi, lo; split4(b_hi[j], hi, lo); if (keep_hi) b_hi[j] = hi; b_lo[j] = lo; }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(conv_bar(s));
             }
@@ -863,6 +867,7 @@ pca_inverse_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
         // ---- converters: split the A slice once (hi in place, lo beside it) ----
         const int t = threadIdx.x - 64;
+        const bool keep_hi = g.three_pass != 2;
         mbar_wait(a_full, 0);
         {
             float4* hi4 = reinterpret_cast<float4*>(gen_base + (a_hi - base));
@@ -876,7 +881,8 @@ pca_inverse_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
                 h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
                 h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                hi4[i] = h; lo4[i] = l;
+                if (keep_hi) hi4[i] = h;
+                lo4[i] = l;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_arrive(a_conv);

@@ -670,7 +670,9 @@ static int init_local(psm_handle* h, LocalInit& L) {
     if (h->cfg.gemm_mode != PSM_GEMM_FP32_SIMT) {
         // TMA tensor maps + argument blocks of the tcgen05 GEMMs (all pointers are fixed for the handle's life)
         if (tc_gemm_prepare() != 0) PSM_FAIL(h, PSM_ERR_CUDA, "cannot opt in to %d B of shared memory for the tcgen05 GEMM", 197888);
-        const int three = (h->cfg.gemm_mode == PSM_GEMM_TC_3XTF32) ? 1 : 0;
+        // 3xTF32: 1 = converters store the masked hi tile, 2 = the raw FP32 tile is the hi operand (the tensor core drops
+        // the low 13 mantissa bits itself -- verified bit-exact by tests/test_gpu_gemm.py::test_tf32_operand_truncation)
+        const int three = (h->cfg.gemm_mode == PSM_GEMM_TC_3XTF32) ? (env_on("PSM_TF32_MASK_HI") ? 1 : 2) : 0;
         auto mk = [&](TcGemm& g, const float* A, int a_rows, const float* Bm, int b_rows, int K, float* Cp, int ldc, int splits,
                       int epi, const float* v0, const float* v1, const float* v2, int bn) -> int {
             if (make_kmajor_map(&g.mapA, A, a_rows, K, K, 128) != 0 || make_kmajor_map(&g.mapB, Bm, b_rows, K, K, bn) != 0)
@@ -1361,7 +1363,7 @@ extern "C" int psm_debug_gemm(int32_t device, int32_t mode, int32_t M, int32_t N
             if (tc_gemm_prepare() != 0 || make_kmajor_map(&t.mapA, dA, M, K, K, 128) != 0 ||
                 make_kmajor_map(&t.mapB, dB, N, K, K, tc_gemm_bn(N)) != 0) rc = PSM_ERR_CUDA;
             else {
-                t.args = TcGemmArgs{dC, M, N, K, N, splits, EPI_PARTIAL, mode == PSM_GEMM_TC_3XTF32 ? 1 : 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+                t.args = TcGemmArgs{dC, M, N, K, N, splits, EPI_PARTIAL, mode == PSM_GEMM_TC_3XTF32 ? (env_on("PSM_TF32_MASK_HI") ? 1 : 2) : 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
                 t.bn = tc_gemm_bn(N);
                 launch_tc_gemm(t, 0);
             }

@@ -500,50 +500,67 @@ void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {
 //      Two deterministic passes (no atomics): one warp per (task, row) writes a row partial, then one
 //      warp per task folds its rows -- rectangles range from 1 x 1 to 120 x 128 pixels, so the work
 //      is balanced per row, not per task.
-// One CTA per task: warp w takes rows y0+w, y0+w+8, ... of the rectangle (each lane 4 pixels of the 128-pixel block
-// row, FP64), then the 8 warp partials are folded in a fixed order -- deterministic, no atomics, one launch.
+// One CTA (8 warps) per task: warp w takes rows y0+w, y0+w+8, ... of the rectangle (each lane 4 pixels of the
+// 128-pixel block row, FP64), then the 8 warp partials are folded by a fixed butterfly -- deterministic, no
+// atomics, one launch.
 // The task list and the flow mask are static: they are fetched before waiting for the predicted blocks.
 __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
 
 __device__ void offsets_body(const OffsetsArgs& a);
 
 template <bool FUSE_OFFSETS>
-__global__ void __launch_bounds__(256) task_means_kernel(MeansArgs a, OffsetsArgs oa) {
+__global__ void __launch_bounds__(256, 3) task_means_kernel(MeansArgs a, OffsetsArgs oa) {
     pdl_launch_dependents();
+    constexpr int NW = 8, NR = 16;                               // warps per CTA; rectangles have up to 128 rows -> <= 16 rows per warp
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const DevTask t = a.tasks[blockIdx.x];
     const int x = lane * 4;
     const bool c0 = x + 0 >= t.x0 && x + 0 < t.x1, c1 = x + 1 >= t.x0 && x + 1 < t.x1;
     const bool c2 = x + 2 >= t.x0 && x + 2 < t.x1, c3 = x + 3 >= t.x0 && x + 3 < t.x1;
+    // bit 4k+j: pixel j of this lane's row k counts (inside the rectangle columns, and inside the flow mask for a
+    // masked mean) -- static, evaluated before the wait
+    const unsigned int cols = (c0 ? 1u : 0u) | (c1 ? 2u : 0u) | (c2 ? 4u : 0u) | (c3 ? 8u : 0u);
+    unsigned long long bits = 0ull;
     const uint8_t* msk = a.gmask + (long long)t.my0 * a.W + t.mx0 + x;
-    unsigned int mk = 0x01010101u;                               // mask bytes of this lane's 4 pixels in the first row
-    if (t.kind == 0 && t.y0 + w < t.y1) {
-        const uint8_t* m = msk + (long long)(t.y0 + w) * a.W;
-        mk = (unsigned)m[0] | ((unsigned)m[1] << 8) | ((unsigned)m[2] << 16) | ((unsigned)m[3] << 24);
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        const int y = t.y0 + w + k * NW;
+        if (y < t.y1) {
+            unsigned int mrow = 0xFu;
+            if (t.kind == 0) {
+                const uint8_t* m = msk + (long long)y * a.W;      // byte loads: W and the block origin need not be multiples of 4
+                mrow = (m[0] ? 1u : 0u) | (m[1] ? 2u : 0u) | (m[2] ? 4u : 0u) | (m[3] ? 8u : 0u);
+            }
+            bits |= (unsigned long long)(mrow & cols) << (4 * k);
+        }
     }
     pdl_wait();
     const float* src = a.blocks + ((long long)t.src * a.C + t.ch) * a.S * a.S + x;
     double sum = 0.0;
-    for (int y = t.y0 + w; y < t.y1; y += 8) {
-        const float4 v = *reinterpret_cast<const float4*>(src + (long long)y * a.S);
-        if (c0 && (mk & 0x000000FFu)) sum += (double)v.x;
-        if (c1 && (mk & 0x0000FF00u)) sum += (double)v.y;
-        if (c2 && (mk & 0x00FF0000u)) sum += (double)v.z;
-        if (c3 && (mk & 0xFF000000u)) sum += (double)v.w;
-        if (t.kind == 0 && y + 8 < t.y1) {
-            const uint8_t* m = msk + (long long)(y + 8) * a.W;
-            mk = (unsigned)m[0] | ((unsigned)m[1] << 8) | ((unsigned)m[2] << 16) | ((unsigned)m[3] << 24);
+    for (int k0 = 0; k0 < NR; k0 += 4) {                         // batches of 4 rows in flight; most rectangles need one batch
+        if (t.y0 + w + k0 * NW >= t.y1) break;
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int y = min(t.y0 + w + (k0 + k) * NW, t.y1 - 1);   // rows past the rectangle: re-read its last row, not counted
+            v[k] = __ldcg(reinterpret_cast<const float4*>(src + (long long)y * a.S));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned int b = (unsigned int)(bits >> (4 * (k0 + k)));
+            if (b & 1u) sum += (double)v[k].x;
+            if (b & 2u) sum += (double)v[k].y;
+            if (b & 4u) sum += (double)v[k].z;
+            if (b & 8u) sum += (double)v[k].w;
         }
     }
     sum = warp_sum(sum);
-    __shared__ double part[8];
+    __shared__ double part[NW];
     if (lane == 0) part[w] = sum;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double tot = part[0];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) tot += part[k];
-        a.means[t.out] = t.kind ? tot : ((t.count > 0) ? tot / (double)t.count : CUDART_NAN);
+    if (w == 0) {
+        const double tot = warp_sum(lane < NW ? part[lane] : 0.0);   // fixed butterfly: deterministic
+        if (lane == 0) a.means[t.out] = t.kind ? tot : ((t.count > 0) ? tot / (double)t.count : CUDART_NAN);
     }
     if (FUSE_OFFSETS) {
         // single GPU: the LAST CTA to publish its mean runs the offset recurrence (a few hundred scalars) right here

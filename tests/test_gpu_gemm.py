@@ -83,3 +83,17 @@ def test_dense_stack_is_deterministic():
     a = psm_b200.debug_dense_stack(x, ks, bs)
     b = psm_b200.debug_dense_stack(x, ks, bs, clusters=2)
     np.testing.assert_array_equal(a, b)
+
+
+def test_tf32_operand_truncation(monkeypatch):
+    """The 3xTF32 kernels feed the raw FP32 tile as the `hi` operand and rely on the tensor core dropping the low 13
+    mantissa bits (truncation).  If the hardware rounded instead, hi + lo != x: the result must be bit-identical to
+    the variant whose converters store the explicitly masked hi tile."""
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((128, 512)).astype(np.float32)
+    B = rng.standard_normal((128, 512)).astype(np.float32)
+    monkeypatch.delenv('PSM_TF32_MASK_HI', raising=False)
+    c_raw = psm_b200.debug_gemm(A, B, mode=_capi.GEMM_TC_3XTF32)[0]
+    monkeypatch.setenv('PSM_TF32_MASK_HI', '1')
+    c_mask = psm_b200.debug_gemm(A, B, mode=_capi.GEMM_TC_3XTF32)[0]
+    np.testing.assert_array_equal(c_raw, c_mask)
