@@ -370,9 +370,20 @@ def main():
         host_step()
     state['skipped'] = 0
     barrier()
-    e2e_s = sum(host_step() for _ in range(args.steps))
+    e2e_each = [host_step() for _ in range(args.steps)]
+    e2e_s = sum(e2e_each)
     assert state['skipped'] == 0, 'a timed step was short-cut by the skip rule'
     assert np.isfinite(h_out.numpy()).all()
+    barrier()
+    # where the end-to-end time goes (separate short pass with the per-stage events on: eager launches, not timed above)
+    sm.set_timings(True)
+    e2e_parts = np.zeros(3)
+    for _ in range(5):
+        host_step()
+        tm = sm.timings()
+        e2e_parts += np.array([tm['h2d'], sum(tm[k2] for k2 in psm_b200._capi.TIMING_NAMES[1:-1]), tm['d2h']])
+    e2e_parts /= 5
+    sm.set_timings(False)
     barrier()
     clocks = sampler.stop()
     if world > 1:
@@ -416,7 +427,9 @@ def main():
                 'scaling': scaling, 'vs_baseline': None, 'dtype': 'f32 (f64 at the ABI and in the offset chain)',
                 'data': 'synthetic', 'config': cfg, 'clocks': clocks,
                 'e2e': {'value': e2e, 'unit': 'cells/s', 'h2d_bytes_per_step': int(n * ncol * 8),
-                        'd2h_bytes_per_step': int(n * sm.n_fields * 8), 'ms_per_step': e2e_s / args.steps * 1e3},
+                        'd2h_bytes_per_step': int(n * sm.n_fields * 8), 'ms_per_step': e2e_s / args.steps * 1e3,
+                        'p50_ms': float(np.percentile(e2e_each, 50) * 1e3), 'p99_ms': float(np.percentile(e2e_each, 99) * 1e3),
+                        'device_events_ms': {'h2d': float(e2e_parts[0]), 'kernels': float(e2e_parts[1]), 'd2h': float(e2e_parts[2])}},
                 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': cpu, 'stages': stages,
                 'geometry': geo, 'init_tables_s': t_init, 'n_cells_total': n_total}
         print(json.dumps(line))

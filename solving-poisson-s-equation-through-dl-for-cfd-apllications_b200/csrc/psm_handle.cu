@@ -558,7 +558,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
                 ccv[xg] = ce;
             }
             h->fused_extract = ok;
-            h->keep_grid = env_on("PSM_KEEP_GRID");
+            h->keep_grid = env_on("PSM_KEEP_GRID") || L.send_rows > 0;     // grid-row halo: rank-1 reads this rank's first rows
             if (ok) { TRY(upload(h, &h->d_rowcov, rcv)); TRY(upload(h, &h->d_colcov, ccv)); }
         }
         // tasks: masked means first, then the shift-line sums; a task is evaluated by the rank holding `src`

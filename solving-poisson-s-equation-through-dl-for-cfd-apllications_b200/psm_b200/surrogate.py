@@ -59,6 +59,76 @@ def debug_gemm(A, B, mode=0, splits=1, device=0):
     return Cc
 
 
+def _marshal_params(p):
+    """dict -> (PsmParams, arrays that must stay alive while the struct is in use)."""
+    f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)     # noqa: E731
+    P = capi.PsmParams()
+    maxs = list(np.asarray(p['maxs'], dtype=np.float64)) + [1.0] * 5
+    P.maxs = (C.c_double * 5)(*maxs[:5])
+    cin, cout = f64(p['pca_in_components']), f64(p['pca_out_components'])
+    min_, mout = f64(p['pca_in_mean']), f64(p['pca_out_mean'])
+    P.pc_in, P.pc_p = cin.shape[0], cout.shape[0]
+    P.n_out_channels = int(p.get('n_out_channels', 1))
+    keep = [cin, cout, min_, mout]
+    P.pca_in_components, P.pca_in_mean = _ptr(cin, C.c_double), _ptr(min_, C.c_double)
+    P.pca_out_components, P.pca_out_mean = _ptr(cout, C.c_double), _ptr(mout, C.c_double)
+    if p.get('standardization', 'std') == 'std':
+        P.standardization = capi.PSM_STD
+        for name in ('mean_in', 'std_in', 'mean_out', 'std_out'):
+            a = f64(p[name])
+            keep.append(a)
+            setattr(P, name, _ptr(a, C.c_double))
+    else:
+        P.standardization = capi.PSM_MAX_ABS
+        P.max_abs_input_PCA = float(p['max_abs_input_PCA'])
+        P.max_abs_output_PCA = float(p['max_abs_output_PCA'])
+    ws = [np.ascontiguousarray(w, dtype=np.float32) for w in p['mlp_weights']]
+    bs = [np.ascontiguousarray(b, dtype=np.float32) for b in p['mlp_biases']]
+    dims = np.ascontiguousarray([ws[0].shape[0]] + [w.shape[1] for w in ws], dtype=np.int32)
+    P.n_dense = len(ws)
+    P.layer_dims = _ptr(dims, C.c_int32)
+    wp = (capi.c_float_p * len(ws))(*[_ptr(w, C.c_float) for w in ws])
+    bp = (capi.c_float_p * len(bs))(*[_ptr(b, C.c_float) for b in bs])
+    P.dense_kernels, P.dense_biases = wp, bp
+    keep += ws + bs + [dims, wp, bp]
+    return P, keep
+
+
+def _marshal_tables(t):
+    """dict from ``psm_b200.tables.build_tables`` -> (PsmTables, arrays to keep alive)."""
+    T = capi.PsmTables()
+    T.n_cells, T.grid_h, T.grid_w = int(t['n_cells']), int(t['H']), int(t['W'])
+    vert = np.ascontiguousarray(t['vert'], dtype=np.int32)
+    wts = np.ascontiguousarray(t['weights'], dtype=np.float64)
+    ind = np.ascontiguousarray(t['indices'], dtype=np.int64)
+    sdf = np.ascontiguousarray(t['sdfunct'], dtype=np.float64).reshape(T.grid_h, T.grid_w)
+    T.vert, T.weights = _ptr(vert, C.c_int32), _ptr(wts, C.c_double)
+    T.indices, T.sdfunct = _ptr(ind, C.c_int64), _ptr(sdf, C.c_double)
+    keep = [vert, wts, ind, sdf]
+    if t.get('vert_back') is not None:
+        vb = np.ascontiguousarray(t['vert_back'], dtype=np.int32)
+        wb = np.ascontiguousarray(t['weights_back'], dtype=np.float64)
+        T.vert_back, T.weights_back = _ptr(vb, C.c_int32), _ptr(wb, C.c_double)
+        keep += [vb, wb]
+    return T, keep
+
+
+def save_params(p, path, shape=128):
+    """Write the model artefacts to the flat binary container ``psm_load_params_file`` reads (host only, no GPU)."""
+    P, keep = _marshal_params(p)
+    rc = capi.load().psm_save_params(C.byref(P), int(shape), str(path).encode())
+    if rc < 0:
+        raise capi.PsmError(rc, 'psm_save_params failed for %s' % path)
+
+
+def save_tables(t, path):
+    """Write the once-per-mesh tables to the flat binary container ``psm_init_from_file`` reads (host only, no GPU)."""
+    T, keep = _marshal_tables(t)
+    rc = capi.load().psm_save_tables(C.byref(T), str(path).encode())
+    if rc < 0:
+        raise capi.PsmError(rc, 'psm_save_tables failed for %s' % path)
+
+
 def debug_dense_stack(x, kernels, biases, mode=0, clusters=0, device=0):
     """The fused Dense-stack kernel on its own (tests): Keras-layout kernels [in][out], ReLU between layers,
     linear last layer.  Returns float32 [M, out]."""
@@ -130,59 +200,33 @@ class PressureSurrogate:
     # ------------------------------------------------------------------ init
     def load_params(self, p):
         """``p``: dict as produced by ``psm_b200.synthetic.make_params`` / ``psm_b200.params.load_reference_dir``."""
-        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
-        P = capi.PsmParams()
-        maxs = list(np.asarray(p['maxs'], dtype=np.float64)) + [1.0] * 5
-        P.maxs = (C.c_double * 5)(*maxs[:5])
-        cin, cout = f64(p['pca_in_components']), f64(p['pca_out_components'])
-        min_, mout = f64(p['pca_in_mean']), f64(p['pca_out_mean'])
-        P.pc_in, P.pc_p = cin.shape[0], cout.shape[0]
-        P.n_out_channels = int(p.get('n_out_channels', 1))
-        keep = [cin, cout, min_, mout]
-        P.pca_in_components, P.pca_in_mean = _ptr(cin, C.c_double), _ptr(min_, C.c_double)
-        P.pca_out_components, P.pca_out_mean = _ptr(cout, C.c_double), _ptr(mout, C.c_double)
-        if p.get('standardization', 'std') == 'std':
-            P.standardization = capi.PSM_STD
-            for name in ('mean_in', 'std_in', 'mean_out', 'std_out'):
-                a = f64(p[name])
-                keep.append(a)
-                setattr(P, name, _ptr(a, C.c_double))
-        else:
-            P.standardization = capi.PSM_MAX_ABS
-            P.max_abs_input_PCA = float(p['max_abs_input_PCA'])
-            P.max_abs_output_PCA = float(p['max_abs_output_PCA'])
-        ws = [np.ascontiguousarray(w, dtype=np.float32) for w in p['mlp_weights']]
-        bs = [np.ascontiguousarray(b, dtype=np.float32) for b in p['mlp_biases']]
-        dims = np.ascontiguousarray([ws[0].shape[0]] + [w.shape[1] for w in ws], dtype=np.int32)
-        P.n_dense = len(ws)
-        P.layer_dims = _ptr(dims, C.c_int32)
-        wp = (capi.c_float_p * len(ws))(*[_ptr(w, C.c_float) for w in ws])
-        bp = (capi.c_float_p * len(bs))(*[_ptr(b, C.c_float) for b in bs])
-        P.dense_kernels, P.dense_biases = wp, bp
-        keep += ws + bs + [dims, wp, bp]
+        P, keep = _marshal_params(p)
         self._check(self.lib.psm_load_params(self._h, C.byref(P)))
         self.pc_in, self.pc_p = P.pc_in, P.pc_p
         return self
 
+    def load_params_file(self, path, pc=None):
+        """Artefacts from the flat file written by ``save_params`` (route B of INTEGRATION.md).  ``pc`` = (pc_in, pc_p)
+        if the caller wants them mirrored on the Python object (the library reads them from the file)."""
+        self._check(self.lib.psm_load_params_file(self._h, str(path).encode()))
+        if pc is not None:
+            self.pc_in, self.pc_p = pc
+        return self
+
     def init_tables(self, t):
         """``t``: dict from ``psm_b200.tables.build_tables`` (PMP:172-247 equivalent)."""
-        T = capi.PsmTables()
-        T.n_cells, T.grid_h, T.grid_w = int(t['n_cells']), int(t['H']), int(t['W'])
-        vert = np.ascontiguousarray(t['vert'], dtype=np.int32)
-        wts = np.ascontiguousarray(t['weights'], dtype=np.float64)
-        ind = np.ascontiguousarray(t['indices'], dtype=np.int64)
-        sdf = np.ascontiguousarray(t['sdfunct'], dtype=np.float64).reshape(T.grid_h, T.grid_w)
-        T.vert, T.weights = _ptr(vert, C.c_int32), _ptr(wts, C.c_double)
-        T.indices, T.sdfunct = _ptr(ind, C.c_int64), _ptr(sdf, C.c_double)
-        keep = [vert, wts, ind, sdf]
-        if t.get('vert_back') is not None:
-            vb = np.ascontiguousarray(t['vert_back'], dtype=np.int32)
-            wb = np.ascontiguousarray(t['weights_back'], dtype=np.float64)
-            T.vert_back, T.weights_back = _ptr(vb, C.c_int32), _ptr(wb, C.c_double)
-            keep += [vb, wb]
+        T, keep = _marshal_tables(t)
         self._check(self.lib.psm_init_with_tables(self._h, C.byref(T)))
-        self.n_cells, self.H, self.W = T.n_cells, T.grid_h, T.grid_w
+        return self._after_init()
+
+    def init_from_file(self, path):
+        """Tables from the flat file written by ``save_tables`` / ``python -m psm_b200.tables_file``."""
+        self._check(self.lib.psm_init_from_file(self._h, str(path).encode()))
+        return self._after_init()
+
+    def _after_init(self):
         g = self.geometry()
+        self.n_cells, self.H, self.W = g['n_cells'], g['grid_h'], g['grid_w']
         self.n_blocks = g['n_blocks']
         return self
 
