@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PSM_API_VERSION 2
+#define PSM_API_VERSION 3
 
 typedef struct psm_handle psm_handle;
 
@@ -67,6 +67,10 @@ typedef struct psm_config {
                                  p_prev (0.05 in PMP); <= 0 disables (PMS:430-432)               */
     int32_t enable_timings;   /* 1 -> record per-stage CUDA events (psm_get_timings)             */
     int32_t gemm_mode;        /* psm_gemm_mode_code; 0 (default) = tcgen05 3xTF32                */
+    double  filter_sigma;     /* > 0: Gaussian post-filter of the assembled field(s), the reference's
+                                 `apply_filter` (SMC:353-356, GRAD:366-367: scipy.ndimage.gaussian_filter,
+                                 sigma (10, 10), mode 'reflect', truncate 4); 0 = off (EP:105 default).
+                                 Single-GPU handles only.                                        */
 } psm_config;
 
 /* How the three dense contractions (PCA projection, Dense stack, PCA inverse) are evaluated.

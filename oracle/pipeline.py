@@ -13,6 +13,8 @@ import numpy as np
 
 from . import interp as _interp
 from . import domain as _domain
+import scipy.ndimage as _ndimage
+
 from . import assemble as _assemble
 
 
@@ -136,7 +138,7 @@ class DeltasOracle:
         return n_x, n_y, origins, indices_list
 
     # ------------------------------------------------------------------ step
-    def time_step(self, Ux, Uy, dUx, dUy, threshold=1e-4):
+    def time_step(self, Ux, Uy, dUx, dUy, threshold=1e-4, apply_filter=False):
         """SMC:382-575 (inference part).  Returns a dict of intermediates; ``None`` for an
         'irrelevant' time step (SMC:407-415)."""
         P = self.params
@@ -190,6 +192,8 @@ class DeltasOracle:
         field, offsets, shift = _assemble.assemble_deltas(
             blocks[..., 0], x_array, indices_list, n_x, n_y, shape, overlap, W, H,
             Ref_BC=0.0, return_offsets=True)                                      # SMC:570-575
+        if apply_filter:                                                          # SMC:353-356 (the same SciPy call)
+            field = _ndimage.gaussian_filter(field, sigma=(10, 10), order=0)
         return dict(U_max_norm=U_max_norm, grid=grid[0], x_array=x_array, z=input_transformed,
                     x_input=x_input, mlp_out=mlp_out, blocks=blocks, offsets=offsets, shift=shift,
                     field=field, n_x=n_x, n_y=n_y, origins=origins, indices_list=indices_list)
@@ -278,7 +282,7 @@ class GradPOracle:
                 indices_list.append([i, j])
         return n_x, n_y, origins, indices_list
 
-    def time_step(self, Ux, Uy):
+    def time_step(self, Ux, Uy, apply_filter=False):
         """GRAD:429-547 (inference part)."""
         P = self.params
         Ux = np.asarray(Ux, dtype=np.float64).reshape(-1, 1)
@@ -315,6 +319,8 @@ class GradPOracle:
             f, offs, sh = _assemble.assemble_gradp(name, blocks[..., ch], x_array, indices_list, n_x, n_y,
                                                    shape, avance, W, H, Ref_BC=0.0, return_offsets=True)
             out[name] = f[0, :, :, 0]
+            if apply_filter:                                                      # GRAD:366-367
+                out[name] = _ndimage.gaussian_filter(out[name], sigma=(10, 10), order=0)
             out[name + '_offsets'] = offs
             out[name + '_shift'] = sh
         out.update(U_max_norm=U_max_norm, grid=grid[0], x_array=x_array, z=input_transformed,

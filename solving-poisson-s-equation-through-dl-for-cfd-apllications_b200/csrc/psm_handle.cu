@@ -121,6 +121,7 @@ struct psm_handle {
     uint8_t* d_gmask = nullptr; uint16_t* d_owner = nullptr;
     // single GPU: the placement folded into the grid->cell gather (back table re-indexed into the predicted blocks)
     bool fuse_place = false; bool field_stale = false; bool no_fused_offsets = false;
+    int filter_radius = 0; float* d_gauss_w = nullptr; float* d_filter_tmp = nullptr;   // optional post-filter (SMC:353-356)
     int32_t* d_bb[3] = {nullptr, nullptr, nullptr}; uint16_t* d_bo[3] = {nullptr, nullptr, nullptr};
     int32_t *d_by0 = nullptr, *d_bx0 = nullptr;
     CoverEntry *d_rowcov = nullptr, *d_colcov = nullptr; bool fused_extract = false;   // gather writes the block operand itself
@@ -207,6 +208,7 @@ extern "C" int psm_create(psm_handle** out, const psm_config* cfg) {
     if (cfg->variant != PSM_DELTAU_TO_DELTAP && cfg->variant != PSM_U_TO_GRADP) { g_create_error = "unknown variant"; return PSM_ERR_INVALID; }
     if (cfg->shape != 128) { g_create_error = "only shape == 128 is supported"; return PSM_ERR_INVALID; }
     if (cfg->gemm_mode < 0 || cfg->gemm_mode > 2) { g_create_error = "unknown gemm_mode"; return PSM_ERR_INVALID; }
+    if (!(cfg->filter_sigma >= 0.0) || cfg->filter_sigma > 1000.0) { g_create_error = "filter_sigma must be in [0, 1000]"; return PSM_ERR_INVALID; }
     if (cfg->input_cols != 5 && !(cfg->input_cols == 7 && cfg->variant == PSM_DELTAU_TO_DELTAP)) {
         g_create_error = "input_cols must be 5, or 7 for deltaU_to_deltaP"; return PSM_ERR_INVALID;
     }
@@ -517,7 +519,21 @@ static int init_local(psm_handle* h, LocalInit& L) {
             ow[q] = (uint16_t)(o - kb0);
         }
         TRY(upload(h, &h->d_owner, ow));
-        h->fuse_place = (L.world == 1) && L.have_back && !env_on("PSM_NO_FUSED_PLACE");
+        if (h->cfg.filter_sigma > 0.0) {
+            // scipy.ndimage.gaussian_filter1d: radius = int(truncate * sigma + 0.5), truncate = 4; weights normalised in FP64
+            if (L.world > 1) PSM_FAIL(h, PSM_ERR_INVALID, "the Gaussian post-filter is not available on a sharded handle");
+            const double sd = h->cfg.filter_sigma;
+            const int lw = (int)(4.0 * sd + 0.5);
+            std::vector<double> wd(2 * lw + 1);
+            double sum = 0.0;
+            for (int i = -lw; i <= lw; ++i) { wd[i + lw] = std::exp(-0.5 / (sd * sd) * (double)i * (double)i); sum += wd[i + lw]; }
+            std::vector<float> wf(2 * lw + 1);
+            for (int i = 0; i <= 2 * lw; ++i) wf[i] = (float)(wd[i] / sum);
+            h->filter_radius = lw;
+            TRY(upload(h, &h->d_gauss_w, wf));
+            TRY(dalloc(h, &h->d_filter_tmp, (size_t)G));
+        }
+        h->fuse_place = (L.world == 1) && L.have_back && !env_on("PSM_NO_FUSED_PLACE") && h->filter_radius == 0;
         h->no_fused_offsets = env_on("PSM_NO_FUSED_OFFSETS");
         if (h->fuse_place) {
             // pixel -> (last-writer block, offset inside the blocks array) is static: re-index the back table
@@ -1054,6 +1070,13 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
                  h->field_stride};
     const bool fuse_place = h->fuse_place && d_out != nullptr;
     if (!fuse_place) { launch_place(pl, s); ++nl; }
+    if (h->filter_radius > 0)
+        for (int f = 0; f < h->F; ++f) {      // axis 0, then axis 1, like scipy.ndimage.gaussian_filter
+            float* fld = h->d_field + (size_t)f * h->field_stride;
+            launch_gauss(GaussArgs{fld, h->d_filter_tmp, h->H, h->W, h->d_gauss_w, h->filter_radius, 0}, s);
+            launch_gauss(GaussArgs{h->d_filter_tmp, fld, h->H, h->W, h->d_gauss_w, h->filter_radius, 1}, s);
+            nl += 2;
+        }
     tick();   // place
     if (h->have_back && d_out) {
         if (p2p) {

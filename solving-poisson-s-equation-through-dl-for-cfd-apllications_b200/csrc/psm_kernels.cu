@@ -714,6 +714,47 @@ void launch_place(const PlaceArgs& a, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Optional Gaussian post-filter, one separable pass.  SciPy's 'reflect' boundary (half-sample symmetric:
+// d c b a | a b c d | d c b a), periodic with period 2n for kernels longer than the axis.
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    const int p = 2 * n;
+    i %= p;
+    if (i < 0) i += p;
+    return i < n ? i : p - 1 - i;
+}
+__global__ void __launch_bounds__(256) gauss_kernel(GaussArgs a) {
+    pdl_enter();
+    extern __shared__ float gw[];
+    for (int i = threadIdx.x; i < 2 * a.radius + 1; i += blockDim.x) gw[i] = a.w[i];
+    __syncthreads();
+    const long long total = (long long)a.H * a.W;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        const int y = (int)(q / a.W), x = (int)(q - (long long)y * a.W);
+        float acc = 0.f;
+        if (a.axis == 0) {
+            const bool inside = y - a.radius >= 0 && y + a.radius < a.H;
+            for (int k = -a.radius; k <= a.radius; ++k) {
+                const int yy = inside ? y + k : reflect_index(y + k, a.H);
+                acc = fmaf(gw[k + a.radius], __ldg(a.in + (long long)yy * a.W + x), acc);
+            }
+        } else {
+            const float* row = a.in + (long long)y * a.W;
+            const bool inside = x - a.radius >= 0 && x + a.radius < a.W;
+            for (int k = -a.radius; k <= a.radius; ++k) {
+                const int xx = inside ? x + k : reflect_index(x + k, a.W);
+                acc = fmaf(gw[k + a.radius], __ldg(row + xx), acc);
+            }
+        }
+        a.out[q] = acc;
+    }
+}
+void launch_gauss(const GaussArgs& a, cudaStream_t s) {
+    long long want = ((long long)a.H * a.W + 255) / 256;
+    int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
+    launch_k(gauss_kernel, dim3(blocks), dim3(256), (size_t)(2 * a.radius + 1) * sizeof(float), s, a);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K8  grid -> cell gather.  PMP:481-496: result[indices] (folded into the vertex ids at init),
 //     interpolate_fill, previous-pressure fallback for NaN / near-wall cells; SMC:644-645
 //     (p = p_prev + delta_p) for the deltaU variant.

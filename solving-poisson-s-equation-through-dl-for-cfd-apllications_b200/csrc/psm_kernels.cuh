@@ -263,6 +263,15 @@ struct PlaceArgs {
 };
 void launch_place(const PlaceArgs& a, cudaStream_t s);
 
+// Optional post-filter (SMC:353-356 / GRAD:366-367): scipy.ndimage.gaussian_filter(field, sigma, mode='reflect'),
+// i.e. correlate1d along axis 0, then along axis 1, with the normalised kernel exp(-x^2 / 2 sigma^2), |x| <= radius.
+struct GaussArgs {
+    const float* in; float* out; int H, W;
+    const float* w;       // [2 * radius + 1] weights (computed in FP64 on the host like SciPy, rounded to FP32)
+    int radius; int axis; // 0: along y, 1: along x
+};
+void launch_gauss(const GaussArgs& a, cudaStream_t s);
+
 // K8: grid -> cell gather, fallbacks (PMP:481-496).
 struct BackArgs {
     const int32_t* v0; const int32_t* v1; const int32_t* v2;   // flat pixel ids, v0 < 0: keep p_prev

@@ -32,7 +32,7 @@ class PsmConfig(C.Structure):
     _fields_ = [('variant', C.c_int32), ('device', C.c_int32), ('delta', C.c_double), ('shape', C.c_int32),
                 ('overlap', C.c_int32), ('input_cols', C.c_int32), ('additive', C.c_int32),
                 ('ref_bc', C.c_double), ('skip_threshold', C.c_double), ('near_wall_sdf', C.c_double),
-                ('enable_timings', C.c_int32), ('gemm_mode', C.c_int32)]
+                ('enable_timings', C.c_int32), ('gemm_mode', C.c_int32), ('filter_sigma', C.c_double)]
 
 
 class PsmParams(C.Structure):

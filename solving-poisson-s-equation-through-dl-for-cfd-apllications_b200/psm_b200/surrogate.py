@@ -153,7 +153,7 @@ class PressureSurrogate:
     (PMP:103-118 params, PMP:193 tables) behind an explicit handle."""
 
     def __init__(self, variant='deltaU_to_deltaP', device=0, delta=5e-3, shape=128, overlap=None, input_cols=None,
-                 additive=True, ref_bc=0.0, skip_threshold=1e-4, near_wall_sdf=0.0, timings=False, gemm_mode=0):
+                 additive=True, ref_bc=0.0, skip_threshold=1e-4, near_wall_sdf=0.0, timings=False, gemm_mode=0, filter_sigma=0.0):
         if variant not in _VARIANT_CODE:
             raise ValueError('variant must be one of %s' % list(_VARIANT_CODE))
         self.lib = capi.load()
@@ -168,7 +168,7 @@ class PressureSurrogate:
         cfg = capi.PsmConfig(variant=_VARIANT_CODE[variant], device=device, delta=delta, shape=shape, overlap=overlap,
                              input_cols=input_cols, additive=int(additive), ref_bc=ref_bc,
                              skip_threshold=skip_threshold, near_wall_sdf=near_wall_sdf,
-                             enable_timings=int(timings), gemm_mode=int(gemm_mode))
+                             enable_timings=int(timings), gemm_mode=int(gemm_mode), filter_sigma=float(filter_sigma))
         self._h = C.c_void_p()
         rc = self.lib.psm_create(C.byref(self._h), C.byref(cfg))
         if rc < 0:

@@ -262,8 +262,11 @@ def golden_smc(name, mesh_kw, seed, pc_in=24, pc_p=20):
                 cap['blocks'] = np.array(array, copy=True)
                 cap['indices_list'] = np.array(indices_list)
                 cap['n_x'], cap['n_y'] = n_x, n_y
+                a2 = np.array(array, copy=True)          # the reference corrects `array` in place
                 cap['field'], _ = orig(array, indices_list, n_x, n_y, *rest)
                 cap['blocks_corrected'] = np.array(array, copy=True)
+                # same call with apply_filter=True (SMC:353-356: scipy.ndimage.gaussian_filter, sigma (10, 10))
+                cap['field_filtered'], _ = orig(a2, indices_list, n_x, n_y, True, *rest[1:])
                 raise _Captured()
 
             ev.assemble_prediction = wrapped
@@ -282,7 +285,8 @@ def golden_smc(name, mesh_kw, seed, pc_in=24, pc_p=20):
         sdfunct=ev.sdfunct[:, :, 0].astype(np.float32), sdfunct_nonzero_sha=np.array(sha(ev.sdfunct != 0)),
         x_array_sub=ev.x_array[:, ::8, ::8, :], blocks_sub=cap['blocks'][:, ::4, ::4],
         offsets=(cap['blocks'] - cap['blocks_corrected']).reshape(cap['blocks'].shape[0], -1)[:, 0],
-        indices_list=cap['indices_list'], n_x=cap['n_x'], n_y=cap['n_y'], field=cap['field'])
+        indices_list=cap['indices_list'], n_x=cap['n_x'], n_y=cap['n_y'], field=cap['field'],
+        field_filtered_sub=cap['field_filtered'][::2, ::2])
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
     print(name, 'grid', out['grid_shape'], 'blocks', cap['blocks'].shape, 'nan in field', int(np.isnan(cap['field']).sum()))
 

@@ -40,6 +40,10 @@ def test_deltas_oracle_matches_reference(name):
     np.testing.assert_allclose(r['offsets'], z['offsets'], rtol=0, atol=2e-6 * scale)
     assert np.array_equal(np.isnan(r['field']), np.isnan(z['field']))
     np.testing.assert_allclose(r['field'], z['field'], rtol=0, atol=4e-6 * scale)
+    # the optional Gaussian post-filter of the reference (apply_filter=True, SMC:353-356)
+    rf = o.time_step(F['Ux'], F['Uy'], F['dUx'], F['dUy'], apply_filter=True)
+    assert np.array_equal(np.isnan(rf['field'][::2, ::2]), np.isnan(z['field_filtered_sub']))
+    np.testing.assert_allclose(rf['field'][::2, ::2], z['field_filtered_sub'], rtol=0, atol=4e-6 * scale)
 
 
 def test_deltas_raster_loop_equals_vectorised():
