@@ -8,13 +8,13 @@ mkdir -p $OUT
 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_$TAG.log
 python bench.py > $OUT/bench_${TAG}_c2.json 2> $OUT/bench_${TAG}_c2.err; echo "bench c2 rc=$?"
 python bench.py --workload c5 --no-cpu-baseline > $OUT/bench_${TAG}_c5.json 2> $OUT/bench_${TAG}_c5.err; echo "bench c5 rc=$?"
-K='regex:^(prep|gather|extract|tc_gemm|dense_cluster|reduce_standardise|row_sums|task_means|offsets|place|back|p2p)'
+K='regex:^(void )?(psm::)?(prep|gather|extract|tc_gemm|dense_cluster|dense_stack|pca_inverse_t|reduce_standardise|task_means|offsets|place|back|gauss|p2p)'
 CMD="python bench.py --steps 4 --warmup 3 --no-cpu-baseline"
 $CMD > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
 $CMD > $OUT/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k "$K" -s 60 -c 20 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k "$K" -s 44 -c 11 -f -o $OUT/prof_$TAG $CMD > $OUT/ncu_full_$TAG.log 2>&1
 echo "full capture rc=$?"
 tail -3 $OUT/pytest_$TAG.log
 cat $OUT/bench_${TAG}_c2.json

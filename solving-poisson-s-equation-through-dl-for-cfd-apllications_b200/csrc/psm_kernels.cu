@@ -508,7 +508,9 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p);
 
 __device__ void offsets_body(const OffsetsArgs& a);
 
-template <bool FUSE_OFFSETS>
+// MODE 0: means only; 1: single GPU, the last CTA also runs the offsets; 2: multi-GPU over peer memory -- every CTA
+// pushes its mean into all peers' arrays, the last CTA raises the flags, waits for the peers' and runs the offsets.
+template <int MODE>
 __global__ void __launch_bounds__(256, 3) task_means_kernel(MeansArgs a, OffsetsArgs oa) {
     pdl_launch_dependents();
     constexpr int NW = 8, NR = 16;                               // warps per CTA; rectangles have up to 128 rows -> <= 16 rows per warp
@@ -560,11 +562,18 @@ __global__ void __launch_bounds__(256, 3) task_means_kernel(MeansArgs a, Offsets
     __syncthreads();
     if (w == 0) {
         const double tot = warp_sum(lane < NW ? part[lane] : 0.0);   // fixed butterfly: deterministic
-        if (lane == 0) a.means[t.out] = t.kind ? tot : ((t.count > 0) ? tot / (double)t.count : CUDART_NAN);
+        const double val = t.kind ? tot : ((t.count > 0) ? tot / (double)t.count : CUDART_NAN);
+        if (lane == 0) a.means[t.out] = val;
+        if (MODE == 2) {                                         // exchange 2: my slot of every peer's mean array (NVLink store)
+            const P2PArgs& P = *oa.p2p;
+            if (lane < P.world && lane != P.rank) P.means[lane][t.out] = val;
+            __threadfence_system();
+        }
     }
-    if (FUSE_OFFSETS) {
-        // single GPU: the LAST CTA to publish its mean runs the offset recurrence (a few hundred scalars) right here
+    if (MODE != 0) {
+        // the LAST CTA to publish its mean runs the offset recurrence (a few hundred scalars) right here
         __shared__ bool s_last;
+        __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
             const unsigned int prev = atomicAdd(&oa.sc->means_done, 1u);
@@ -572,13 +581,23 @@ __global__ void __launch_bounds__(256, 3) task_means_kernel(MeansArgs a, Offsets
             if (s_last) { oa.sc->means_done = 0u; __threadfence(); }
         }
         __syncthreads();
-        if (s_last) offsets_body(oa);
+        if (!s_last) return;
+        if (MODE == 2) {
+            const P2PArgs& P = *oa.p2p;
+            if ((int)threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
+                __threadfence_system();
+                st_release_sys(&P.mail[threadIdx.x]->flag[1][P.rank], P.sc->step);
+            }
+            p2p_wait(oa.p2p, 1, 0xFFu);                          // every rank's strip means have arrived
+        }
+        offsets_body(oa);
     }
 }
 void launch_means(const MeansArgs& a, const OffsetsArgs* fused, cudaStream_t s) {
     if (a.n_tasks <= 0) return;
-    if (fused) launch_k(task_means_kernel<true>, dim3(a.n_tasks), dim3(256), (size_t)fused->B * fused->F * 24, s, a, *fused);
-    else launch_k(task_means_kernel<false>, dim3(a.n_tasks), dim3(256), 0, s, a, OffsetsArgs{});
+    if (fused && fused->p2p) launch_k(task_means_kernel<2>, dim3(a.n_tasks), dim3(256), (size_t)fused->B * fused->F * 24, s, a, *fused);
+    else if (fused) launch_k(task_means_kernel<1>, dim3(a.n_tasks), dim3(256), (size_t)fused->B * fused->F * 24, s, a, *fused);
+    else launch_k(task_means_kernel<0>, dim3(a.n_tasks), dim3(256), 0, s, a, OffsetsArgs{});
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -639,7 +658,8 @@ __device__ void offsets_body(const OffsetsArgs& a) {
     if (threadIdx.x == 0) {
         a.sc->umax2_bits = 0ull; a.sc->dumax2_bits = 0ull;      // re-arm the running maxima of prep
         a.sc->dense_barrier = 0u;                               // ... and the grid barrier of the Dense stack
-        if (a.host_skip) { *reinterpret_cast<volatile int*>(a.host_skip) = a.sc->skip | (a.sc->comm_error << 8); __threadfence_system(); }
+        // status word in mapped host memory: visible to the host once the step's kernels have completed (stream sync)
+        if (a.host_skip) *reinterpret_cast<volatile int*>(a.host_skip) = a.sc->skip | (a.sc->comm_error << 8);
     }
 }
 __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
