@@ -36,8 +36,8 @@ HBM_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 
 
 # kernel measured by each HBM stage's CUDA events (key of profiles/traffic_*.json, written by profiles/summarize_full.py)
-STAGE_KERNEL = {'gather': 'gather_extract_kernel', 'back_gather': 'back_kernel', 'place': 'place_kernel',
-                'extract': 'extract_kernel', 'prep': 'prep_kernel<2, 5>'}
+STAGE_KERNEL = {'gather': ('gather_extract_kernel', 'gather_kernel'), 'back_gather': ('back_kernel',), 'place': ('place_kernel',),
+                'extract': ('extract_kernel',), 'prep': ('prep_kernel',)}
 
 
 def measured_traffic(workload, stage):
@@ -49,14 +49,13 @@ def measured_traffic(workload, stage):
         return None, None
     try:
         d = json.load(open(files[-1]))
-        k = STAGE_KERNEL.get(stage)
-        if stage == 'prep' and k not in d:
-            k = next((x for x in d if x.startswith('prep_kernel')), k)
-        if stage == 'gather' and k not in d:
-            k = 'gather_kernel'
-        return (d[k]['dram_traffic_bytes'], os.path.basename(files[-1])) if k in d else (None, None)
+        for base in STAGE_KERNEL.get(stage, ()):
+            for k in d:                                   # template instances are listed as name<args>
+                if k == base or k.startswith(base + '<'):
+                    return d[k]['dram_traffic_bytes'], os.path.basename(files[-1])
     except Exception:
-        return None, None
+        pass
+    return None, None
 
 
 def measured_peaks():

@@ -1057,8 +1057,7 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     oa.sc = h->d_sc;
     oa.host_skip = h->d_host_skip;
     oa.p2p = d_p2p;
-    // one GPU, or peer-memory exchange: the means kernel pushes its results itself and its last CTA runs the offsets
-    const bool fuse_offsets = (!multi || p2p) && h->n_tasks > 0 && h->Bg * h->F <= 1024 && !h->no_fused_offsets;
+    const bool fuse_offsets = !multi && h->n_tasks > 0 && h->Bg * h->F <= 1024 && !h->no_fused_offsets;
     MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->C, S, h->W, (multi && !p2p) ? h->d_means_loc : h->d_means};
     launch_means(ma, fuse_offsets ? &oa : nullptr, s); ++nl;
     if (p2p && !fuse_offsets) { launch_p2p_push_means(h->d_p2p, h->d_tasks, h->n_tasks, h->world, h->d_means, s); ++nl; }   // exchange 3 over peer memory

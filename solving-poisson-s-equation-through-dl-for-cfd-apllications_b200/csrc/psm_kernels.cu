@@ -508,8 +508,9 @@ __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p);
 
 __device__ void offsets_body(const OffsetsArgs& a);
 
-// MODE 0: means only; 1: single GPU, the last CTA also runs the offsets; 2: multi-GPU over peer memory -- every CTA
-// pushes its mean into all peers' arrays, the last CTA raises the flags, waits for the peers' and runs the offsets.
+// MODE 0: means only; 1: single GPU, the last CTA also runs the offsets.  (Pushing the means to the peers from here and
+// waiting for theirs in the last CTA was measured slower at 2 GPUs -- one system-scope fence per CTA -- than the separate
+// push kernel + offsets kernel, so the multi-GPU path keeps those.)
 template <int MODE>
 __global__ void __launch_bounds__(256, 3) task_means_kernel(MeansArgs a, OffsetsArgs oa) {
     pdl_launch_dependents();
@@ -564,11 +565,6 @@ __global__ void __launch_bounds__(256, 3) task_means_kernel(MeansArgs a, Offsets
         const double tot = warp_sum(lane < NW ? part[lane] : 0.0);   // fixed butterfly: deterministic
         const double val = t.kind ? tot : ((t.count > 0) ? tot / (double)t.count : CUDART_NAN);
         if (lane == 0) a.means[t.out] = val;
-        if (MODE == 2) {                                         // exchange 2: my slot of every peer's mean array (NVLink store)
-            const P2PArgs& P = *oa.p2p;
-            if (lane < P.world && lane != P.rank) P.means[lane][t.out] = val;
-            __threadfence_system();
-        }
     }
     if (MODE != 0) {
         // the LAST CTA to publish its mean runs the offset recurrence (a few hundred scalars) right here
@@ -582,21 +578,12 @@ __global__ void __launch_bounds__(256, 3) task_means_kernel(MeansArgs a, Offsets
         }
         __syncthreads();
         if (!s_last) return;
-        if (MODE == 2) {
-            const P2PArgs& P = *oa.p2p;
-            if ((int)threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
-                __threadfence_system();
-                st_release_sys(&P.mail[threadIdx.x]->flag[1][P.rank], P.sc->step);
-            }
-            p2p_wait(oa.p2p, 1, 0xFFu);                          // every rank's strip means have arrived
-        }
         offsets_body(oa);
     }
 }
 void launch_means(const MeansArgs& a, const OffsetsArgs* fused, cudaStream_t s) {
     if (a.n_tasks <= 0) return;
-    if (fused && fused->p2p) launch_k(task_means_kernel<2>, dim3(a.n_tasks), dim3(256), (size_t)fused->B * fused->F * 24, s, a, *fused);
-    else if (fused) launch_k(task_means_kernel<1>, dim3(a.n_tasks), dim3(256), (size_t)fused->B * fused->F * 24, s, a, *fused);
+    if (fused) launch_k(task_means_kernel<1>, dim3(a.n_tasks), dim3(256), (size_t)fused->B * fused->F * 24, s, a, *fused);
     else launch_k(task_means_kernel<0>, dim3(a.n_tasks), dim3(256), 0, s, a, OffsetsArgs{});
 }
 
