@@ -277,18 +277,38 @@ namespace {
 constexpr int D_BN = 64;
 constexpr int D_STAGES = 2;
 constexpr int D_A_BYTES = BM * BK * 4, D_B_BYTES = D_BN * BK * 4, D_STAGE = 2 * (D_A_BYTES + D_B_BYTES);
-constexpr int D_PARK = BM * (D_BN + 1) * 4;            // partial accumulator, row stride 65 floats (bank-conflict free)
+constexpr int D_PARK_LD = D_BN + 4;                    // floats per received row (16-byte aligned, conflict-free float4 rows)
+constexpr int D_PARK = BM * D_PARK_LD * 4;             // receive buffer: [KS slices][128 / KS rows][D_PARK_LD]
 constexpr int D_SMEM = D_STAGES * D_STAGE + D_PARK + 1024 + 256;
 
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float ld_dsmem(uint32_t local_addr, uint32_t cta) {
-    uint32_t remote; float v;
+__device__ __forceinline__ void st_dsmem_v4(uint32_t local_addr, uint32_t cta, float4 v) {
+    uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
-    return v;
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+          "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+          "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 }  // namespace
 
@@ -329,6 +349,7 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+    cluster_sync_all();                                          // every CTA of the cluster runs: its shared memory may be written remotely
     pdl_wait();                                                  // barriers + TMEM are set up while the previous kernel drains
 
     if (warp == 0) {
@@ -395,50 +416,62 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 mbar_arrive(conv_bar(s));
             }
         }
-        // park the partial accumulator: thread <-> row (TMEM lane), row stride 65 floats
+        // push the partial accumulator: thread <-> row (TMEM lane); row r goes to slot [z][r % rows_per] of CTA r / rows_per
         if (nkb > 0) {
             mbar_wait(accum_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        float* prow = reinterpret_cast<float*>(gen_base + (park - base)) + row * (BN + 1);
-        for (int c = 0; c < BN; c += 16) {
-            float v[16];
-            if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-            else {
+        float v[64];
+        if (nkb > 0) tmem_ld64(tmem_base + ((uint32_t)(q * 32) << 16), v);
+        else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) prow[c + i] = v[i];
+            for (int i = 0; i < 64; ++i) v[i] = 0.f;
         }
+        const int rows_per = BM / KS;
+        const uint32_t dst = park + (uint32_t)((blockIdx.z * rows_per + (row % rows_per)) * D_PARK_LD) * 4u;
+        const uint32_t owner = (uint32_t)(row / rows_per);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) st_dsmem_v4(dst + 16u * i, owner, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster_sync_all();                                          // all KS partials are parked
+    cluster_sync_all();                                          // all KS partials of my rows have landed in my buffer
     {
-        // CTA z folds rows [z*rows_per, ...) of the tile: 192 threads, one (row, column) per thread per pass
+        // CTA z folds rows [z*rows_per, ...) from its OWN shared memory (slices 0..KS-1 in a fixed order: deterministic),
+        // applies bias + ReLU (or bias + de-standardisation, SMC:533) and stores 256-byte row segments
         const int rows_per = BM / KS;
-        const int r_lo = blockIdx.z * rows_per;
-        for (int e = threadIdx.x; e < rows_per * BN; e += kThreads) {
-            const int r = r_lo + e / BN, c = e % BN;
-            const uint32_t addr = park + (uint32_t)(r * (BN + 1) + c) * 4u;
-            float acc = 0.f;
-            for (int z = 0; z < KS; ++z) acc += ld_dsmem(addr, (uint32_t)z);
-            const int n = n0 + c, m = m0 + r;
-            float o;
-            if (g.epi == EPI_BIAS_RELU) o = fmaxf(acc + __ldg(g.v0 + n), 0.f);
-            else o = (acc + __ldg(g.v0 + n)) * __ldg(g.v1 + n) + __ldg(g.v2 + n);
+        const float* buf = reinterpret_cast<const float*>(gen_base + (park - base));
+        for (int e = threadIdx.x; e < rows_per * (BN / 4); e += kThreads) {
+            const int rl = e / (BN / 4), c4 = e % (BN / 4);
+            float4 acc = *reinterpret_cast<const float4*>(buf + rl * D_PARK_LD + c4 * 4);
+            for (int p = 1; p < KS; ++p) {
+                const float4 w = *reinterpret_cast<const float4*>(buf + (p * rows_per + rl) * D_PARK_LD + c4 * 4);
+                acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+            }
+            const int n = n0 + c4 * 4, m = m0 + blockIdx.z * rows_per + rl;
+            const float4 b = __ldg(reinterpret_cast<const float4*>(g.v0 + n));
+            float4 o;
+            if (g.epi == EPI_BIAS_RELU) {
+                o = make_float4(fmaxf(acc.x + b.x, 0.f), fmaxf(acc.y + b.y, 0.f), fmaxf(acc.z + b.z, 0.f), fmaxf(acc.w + b.w, 0.f));
+            } else {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(g.v1 + n));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(g.v2 + n));
+                o = make_float4((acc.x + b.x) * sc.x + sh.x, (acc.y + b.y) * sc.y + sh.y, (acc.z + b.z) * sc.z + sh.z, (acc.w + b.w) * sc.w + sh.w);
+            }
             if (m < g.M) {
-                g.C[(size_t)m * g.ldc + n] = o;
+                const size_t off = (size_t)m * g.ldc + n;
+                *reinterpret_cast<float4*>(g.C + off) = o;
                 if (g.C_hi) {                                    // operand of the transposed PCA inverse, pre-split
-                    const float hi = __uint_as_float(__float_as_uint(o) & 0xFFFFE000u);
-                    g.C_hi[(size_t)m * g.ldc + n] = hi; g.C_lo[(size_t)m * g.ldc + n] = o - hi;
+                    float4 hi;
+                    hi.x = __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u);
+                    hi.z = __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u);
+                    *reinterpret_cast<float4*>(g.C_hi + off) = hi;
+                    *reinterpret_cast<float4*>(g.C_lo + off) = make_float4(o.x - hi.x, o.y - hi.y, o.z - hi.z, o.w - hi.w);
                 }
             }
         }
     }
-    cluster_sync_all();                                          // nobody leaves while its shared memory is being read
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
@@ -480,11 +513,6 @@ constexpr int S_PARK_LD = S_BN + 4;                     // floats per parked row
 constexpr int S_PARK = BM * S_PARK_LD * 4;
 constexpr int S_SMEM = S_STAGES * S_STAGE + 2 * S_PARK + 1024 + 256;
 
-__device__ __forceinline__ void st_dsmem_v4(uint32_t local_addr, uint32_t cta, float4 v) {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
@@ -492,26 +520,6 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
-    uint32_t r[64];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
-        "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
-          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
-          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
-          "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
-          "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 }  // namespace
 
