@@ -299,6 +299,10 @@ def main():
         sm.init_tables(tables)
         cells_np = syn.pack_cells(mesh, F, with_delta=(ncol == 7))
     geo = sm.geometry()
+    if world > 1:       # name the transport the handle actually selected
+        cfg['workload'] = cfg['workload'].replace('NCCL halo / ghost / strip-mean exchanges',
+                                                  'ghost-cell / strip-mean / ghost-pixel exchanges pushed over NVLink peer memory (cudaIpc)'
+                                                  if geo.get('peer_memory_exchange') else 'NCCL ghost-cell / strip-mean / ghost-pixel exchanges')
     # two alternating time levels, U and U + dU: with 5 columns the device forms dU = +-(dU) itself (never zero,
     # so the reference's skip rule SMC:410-415 never short-cuts a timed step); with 7 columns both carry dU
     cells_b = cells_np.copy()

@@ -141,4 +141,4 @@ def test_library_exports_every_declared_symbol():
     lib = _capi.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.psm_api_version() == 2
+    assert lib.psm_api_version() == 3
