@@ -5,6 +5,7 @@
 
 #include <math_constants.h>
 
+#include <cstdint>
 #include <cstdlib>
 
 namespace psm {
@@ -212,7 +213,126 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
     }
 }
 
+// Bulk-copy variant (default when the row buffer is 16-byte aligned): persistent CTAs stream 256-row tiles of the
+// solver's row-major buffer (and of the resident U(t-1)) into shared memory with cp.async.bulk + mbarrier, four tiles
+// in flight per CTA, so HBM sees long contiguous bursts instead of 8-byte column picks at a 40-byte stride; the
+// threads then pick their row's columns from shared memory.  Same arithmetic and rounding as prep_kernel.
+namespace {
+constexpr int kPrepRows = 256, kPrepStages = 4;
+__device__ __forceinline__ uint32_t prep_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void prep_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void prep_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+}  // namespace
+
+template <int MODE, int NCOL>
+__global__ void __launch_bounds__(kPrepRows) prep_bulk_kernel(PrepArgs a) {
+    pdl_enter();
+    constexpr int ROWS = kPrepRows, ST = kPrepStages;
+    constexpr uint32_t TILE = ROWS * NCOL * 8, UP = (MODE == 2) ? ROWS * 16 : 0;
+    extern __shared__ __align__(128) unsigned char prep_smem[];
+    double* tiles = reinterpret_cast<double*>(prep_smem);                        // [ST][ROWS*NCOL]
+    double2* ups = reinterpret_cast<double2*>(prep_smem + (size_t)ST * TILE);    // [ST][ROWS]
+    __shared__ unsigned long long bars[ST];
+    const long long n_tiles = a.n / ROWS;                                        // full tiles; the tail goes the plain way
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < ST; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(prep_smem_u32(&bars[s])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long t, int s) {
+        const uint32_t bar = prep_smem_u32(&bars[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TILE + UP) : "memory");
+        prep_bulk_load(prep_smem_u32(tiles + (size_t)s * ROWS * NCOL), a.cells + t * ROWS * NCOL, TILE, bar);
+        if (MODE == 2) prep_bulk_load(prep_smem_u32(ups + (size_t)s * ROWS), a.u_prev + t * ROWS * 2, UP, bar);
+    };
+    if (threadIdx.x == 0)
+        for (int k = 0; k < ST; ++k) {
+            const long long t = blockIdx.x + (long long)k * gridDim.x;
+            if (t < n_tiles) issue(t, k);
+        }
+    double m_u = 0.0, m_d = 0.0;
+    double* __restrict__ p_prev = a.p_prev;
+    float2* __restrict__ uv = a.uv;
+    double2* __restrict__ u_prev = reinterpret_cast<double2*>(a.u_prev);
+    auto row_work = [&](long long i, double ux, double uy, double pp, double gx, double gy, double2 prev) {
+        double fx, fy;
+        if (MODE == 0) { fx = ux; fy = uy; }
+        else if (MODE == 1) { fx = gx; fy = gy; }
+        else { fx = ux - prev.x; fy = uy - prev.y; u_prev[i] = make_double2(ux, uy); }
+        p_prev[i] = pp;
+        m_u = fmax(m_u, __dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)));
+        if (MODE != 0) m_d = fmax(m_d, __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)));
+        uv[i] = make_float2((float)fx, (float)fy);
+    };
+    int k = 0;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+        const int s = k % ST;
+        prep_mbar_wait(prep_smem_u32(&bars[s]), (k / ST) & 1);
+        const double* row = tiles + (size_t)s * ROWS * NCOL + threadIdx.x * NCOL;
+        const double ux = row[0], uy = row[1], pp = row[4];
+        const double gx = (MODE == 1) ? row[NCOL - 2] : 0.0, gy = (MODE == 1) ? row[NCOL - 1] : 0.0;
+        const double2 prev = (MODE == 2) ? ups[(size_t)s * ROWS + threadIdx.x] : make_double2(0.0, 0.0);
+        __syncthreads();                                         // every thread has its row: the stage can be refilled
+        if (threadIdx.x == 0) {
+            const long long tn = t + (long long)ST * gridDim.x;
+            if (tn < n_tiles) issue(tn, s);
+        }
+        row_work(t * ROWS + threadIdx.x, ux, uy, pp, gx, gy, prev);
+    }
+    // tail rows (fewer than one tile): plain loads, spread over the CTAs
+    for (long long i = n_tiles * ROWS + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        const double* row = a.cells + i * NCOL;
+        const double2 prev = (MODE == 2) ? u_prev[i] : make_double2(0.0, 0.0);
+        row_work(i, row[0], row[1], row[4], MODE == 1 ? row[NCOL - 2] : 0.0, MODE == 1 ? row[NCOL - 1] : 0.0, prev);
+    }
+    m_u = warp_max(m_u);
+    m_d = warp_max(m_d);
+    __shared__ double s_u[8], s_d[8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_u[w] = m_u; s_d[w] = m_d; }
+    __syncthreads();
+    if (w == 0) {
+        m_u = (l < 8) ? s_u[l] : 0.0;
+        m_d = (l < 8) ? s_d[l] : 0.0;
+        m_u = warp_max(m_u);
+        m_d = warp_max(m_d);
+        if (l == 0) {
+            atomicMax(&a.sc->umax2_bits, (unsigned long long)__double_as_longlong(m_u));
+            atomicMax(&a.sc->dumax2_bits, (unsigned long long)__double_as_longlong(m_d));
+        }
+    }
+}
+template <int MODE, int NCOL>
+static void launch_prep_bulk(const PrepArgs& a, cudaStream_t s) {
+    const size_t smem = (size_t)kPrepStages * (kPrepRows * NCOL * 8 + (MODE == 2 ? kPrepRows * 16 : 0));
+    static bool opted[64] = {};                                                    // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!opted[dev & 63]) { cudaFuncSetAttribute(prep_bulk_kernel<MODE, NCOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); opted[dev & 63] = true; }
+    const long long tiles = a.n / kPrepRows;
+    const int per_sm = (int)(200 * 1024 / (smem + 1024));                         // resident CTAs per SM by shared memory
+    long long blocks = (long long)kSMs * (per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm));
+    if (blocks > tiles) blocks = tiles > 0 ? tiles : 1;
+    launch_k(prep_bulk_kernel<MODE, NCOL>, dim3((int)blocks), dim3(kPrepRows), smem, s, a);
+}
+
 void launch_prep(const PrepArgs& a, cudaStream_t s) {
+    static const bool bulk_ok = [] { const char* v = getenv("PSM_NO_PREP_BULK"); return !(v && v[0] && v[0] != '0'); }();
+    if (bulk_ok && (reinterpret_cast<uintptr_t>(a.cells) & 15) == 0 && a.n >= kPrepRows) {
+        if (a.mode == 0) launch_prep_bulk<0, 5>(a, s);
+        else if (a.mode == 1) launch_prep_bulk<1, 7>(a, s);
+        else launch_prep_bulk<2, 5>(a, s);
+        return;
+    }
     long long want = (a.n + 255) / 256;
     int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
     if (a.mode == 0) launch_k(prep_kernel<0, 5>, dim3(blocks), dim3(256), 0, s, a);
