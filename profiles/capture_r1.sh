@@ -8,6 +8,7 @@ mkdir -p $OUT
 python -m pytest tests -m gpu -x -q > $OUT/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_$TAG.log
 python bench.py > $OUT/bench_${TAG}_c2.json 2> $OUT/bench_${TAG}_c2.err; echo "bench c2 rc=$?"
 python bench.py --workload c5 --no-cpu-baseline > $OUT/bench_${TAG}_c5.json 2> $OUT/bench_${TAG}_c5.err; echo "bench c5 rc=$?"
+python bench.py --variant U_to_gradP --no-cpu-baseline > $OUT/bench_${TAG}_c3.json 2> $OUT/bench_${TAG}_c3.err; echo "bench c3 rc=$?"
 K='regex:^(void )?(psm::)?(prep|gather|extract|tc_gemm|dense_cluster|dense_stack|pca_inverse_t|reduce_standardise|task_means|offsets|place|back|gauss|p2p)'
 CMD="python bench.py --steps 4 --warmup 3 --no-cpu-baseline"
 $CMD > $OUT/plain_$TAG.log 2>&1 &&
