@@ -207,3 +207,82 @@ def assemble_gradp(field, array, x_array, indices_list, n_x, n_y, shape, avance,
     if return_offsets:
         return result, offsets, shift
     return result
+
+
+def assemble_thesis(array, x_array, indices_list, n_x, n_y, shape, avance, shape_x, shape_y, return_offsets=False):
+    """PMP:372-473 (thesis solver module): blocks in extraction order -- right -> left, plus the extra left-most
+    column tagged ``-1`` -- each corrected by a scalar and written into the result (later blocks win), then the
+    global shift PMP:472.  ``array`` [B,S,S] is corrected on a copy.  Every quirk is kept: the right-strip
+    correction chain of row 0 (``BC_ant_0``), the ``-1`` column chained through ``BC_up_`` (whose middle-row
+    update is an UNMASKED mean, PMP:437), the ``BC_alter`` fallback when ``BC_ups`` is NaN."""
+    array = np.array(array, dtype=np.float64, copy=True)
+    result = np.empty(shape=(shape_y, shape_x))
+    BC_up = 0
+    BC_alter = 0
+    BC_ups = np.zeros(n_x + 1)
+    offsets = np.zeros(array.shape[0])
+    p_j = (shape_x - shape) - n_x * shape + n_x * avance
+    p = shape_y - (shape * (n_y + 1) - n_y * avance)
+    for i in range(array.shape[0]):
+        idx = list(indices_list[i])
+        flow_bool = x_array[i, :, :, 2]
+        res = array[i]
+        if idx[0] == 0:
+            if idx[1] == n_x:
+                BC_coor = _mmean(res[:, (shape - avance):shape], flow_bool[:, (shape - avance):shape]) - BC_up
+                res -= BC_coor
+                BC_ups[idx[1]] = _mmean(res[(shape - avance):shape, (shape - avance):shape],
+                                        flow_bool[(shape - avance):shape, (shape - avance):shape])
+            elif idx[1] == -1:
+                BC_coor = _mmean(res[:, p_j:p_j + avance], flow_bool[:, p_j:p_j + avance]) - BC_ant_0
+                res -= BC_coor
+                BC_up_ = _mmean(res[(shape - avance):shape, p_j:p_j + avance], flow_bool[(shape - avance):shape, p_j:p_j + avance])
+            else:
+                BC_coor = _mmean(res[:, (shape - avance):shape], flow_bool[:, (shape - avance):shape]) - BC_ant_0
+                res -= BC_coor
+                BC_ups[idx[1]] = _mmean(res[(shape - avance):shape, :], flow_bool[(shape - avance):shape, :])
+            BC_ant_0 = _mmean(res[:, 0:avance], flow_bool[:, 0:avance])
+        elif idx[0] == n_y + 1:
+            if idx[1] == -1:
+                BC_coor = _mmean(res[shape - p - avance:shape - p, p_j:p_j + avance],
+                                 flow_bool[shape - p - avance:shape - p, p_j:p_j + avance]) - BC_up_
+                res -= BC_coor
+            else:
+                if np.isnan(BC_ups[idx[1]]):
+                    BC_coor = _mmean(res[:, shape - avance:shape], flow_bool[:, shape - avance:shape]) - BC_alter
+                else:
+                    BC_coor = _mmean(res[shape - p - avance:shape - p, :], flow_bool[shape - p - avance:shape - p, :]) - BC_ups[idx[1]]
+                res -= BC_coor
+        else:
+            if idx[1] == -1:
+                BC_coor = _mmean(res[0:avance, p_j:p_j + avance], flow_bool[0:avance, p_j:p_j + avance]) - BC_up_
+                res -= BC_coor
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore", category=RuntimeWarning)
+                    BC_up_ = np.mean(res[(shape - avance):shape, p_j:p_j + avance])          # PMP:437 -- no mask
+            else:
+                if np.isnan(BC_ups[idx[1]]):
+                    BC_coor = _mmean(res[:, shape - avance:shape], flow_bool[:, shape - avance:shape]) - BC_alter
+                else:
+                    BC_coor = _mmean(res[0:avance, :], flow_bool[0:avance, :]) - BC_ups[idx[1]]
+                res -= BC_coor
+                BC_ups[idx[1]] = _mmean(res[(shape - avance):shape, :], flow_bool[(shape - avance):shape, :])
+        offsets[i] = BC_coor
+        BC_alter = _mmean(res[:, 0:avance], flow_bool[:, 0:avance])                       # PMP:449
+        st = shape - avance
+        if idx == [n_y + 1, -1]:
+            wdt = shape_x - (n_x + 1) * st - avance
+            result[(shape_y - st):shape_y, 0:wdt] = res[avance:shape, 0:wdt]
+        elif idx[1] == -1:
+            result[idx[0] * st:idx[0] * st + shape, 0:shape] = res
+        elif idx[0] == n_y + 1:
+            j = n_x - idx[1]
+            result[(shape_y - st):shape_y, shape_x - shape - j * st:shape_x - j * st] = res[avance:shape, :]
+        else:
+            j = n_x - idx[1]
+            result[idx[0] * st:idx[0] * st + shape, shape_x - shape - j * st:shape_x - j * st] = res
+    shift = np.mean(3 * result[:, -1] - result[:, -2]) / 3                             # PMP:472
+    result -= shift
+    if return_offsets:
+        return result, offsets, shift
+    return result

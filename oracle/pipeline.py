@@ -333,3 +333,94 @@ class GradPOracle:
         variant has no previous-gradient fallback)."""
         unif = field[tuple(self.indices.T)]
         return _interp.interpolate_fill(unif, self.vert_back, self.weights_back)
+
+
+class ThesisOracle:
+    """Thesis solver module (PMP: ``init_func`` PMP:172-247, ``py_func`` PMP:249-517): U -> p on blocks cut with
+    ``avance = int(0.1 * 128) = 12`` shared columns, extra left-most block column, scalar max-abs PCA scaling,
+    distance channel fed unscaled (PMP:292), forward interpolation WITHOUT the NaN fill (PMP:64-65,280-281)."""
+
+    def __init__(self, params, delta=5e-3, shape=128):
+        self.params = params
+        self.delta = delta
+        self.shape = shape
+        self.avance = int(0.1 * shape)                                            # PMP:304
+
+    def init_func(self, cell_xy, top, obst, ux_probe, tables=None):
+        cell_xy = np.asarray(cell_xy, dtype=np.float64)
+        x_min = round(np.min(cell_xy[:, 0]), 2)                                   # PMP:197-201
+        x_max = round(np.max(cell_xy[:, 0]), 2)
+        y_min = round(np.min(cell_xy[:, 1]), 2)
+        y_max = round(np.max(cell_xy[:, 1]), 2)
+        X0, Y0 = _interp.create_uniform_grid(x_min, x_max, y_min, y_max, self.delta)
+        self.X0, self.Y0 = X0, Y0
+        xy0 = np.concatenate((np.expand_dims(X0, axis=1), np.expand_dims(Y0, axis=1)), axis=-1)
+        if tables is None:
+            self.vert, self.weights = _interp.interp_weights(cell_xy, xy0, idw_fallback=False)      # PMP:210
+            self.vert_back, self.weights_back = _interp.interp_weights(xy0, cell_xy, idw_fallback=False)   # PMP:211
+        else:
+            self.vert, self.weights, self.vert_back, self.weights_back = tables
+        domain_bool, sdf, _ = _domain.domain_dist(xy0, np.asarray(top), np.asarray(obst), 'pmp')    # PMP:214
+        self.grid_shape_y = int(round((y_max - y_min) / self.delta))
+        self.grid_shape_x = int(round((x_max - x_min) / self.delta))
+        ux_interp = _interp.interpolate_fill(np.asarray(ux_probe, dtype=np.float64), self.vert, self.weights)   # PMP:230-231
+        # PMP:225 allocates `indices` with np.empty; the raster leaves invalid points untouched -- zero in practice
+        self.indices, self.sdfunct = _domain.index_raster(X0, Y0, self.delta, self.grid_shape_y, self.grid_shape_x,
+                                                          domain_bool, ux_interp, sdf)
+        return 0
+
+    def block_plan(self):
+        """PMP:303-332: right -> left, and after the last regular block of every row the block at x = 0 tagged -1."""
+        H, W, shape, avance = self.grid_shape_y, self.grid_shape_x, self.shape, self.avance
+        n_x = int((W - shape) / (shape - avance))
+        n_y = int((H - shape) / (shape - avance))
+        origins, indices_list = [], []
+        for i in range(n_y + 2):
+            for j in range(n_x + 1):
+                x_0 = (W - shape) - j * shape + j * avance
+                y_0 = (H - shape) if i == n_y + 1 else i * shape - i * avance
+                origins.append((y_0, x_0))
+                indices_list.append([i, n_x - j])
+                if j == n_x:
+                    origins.append((y_0, 0))
+                    indices_list.append([i, -1])
+        return n_x, n_y, origins, indices_list
+
+    def py_func(self, Ux, Uy, p_prev, near_wall_sdf=0.05):
+        """PMP:249-517 on one rank.  Returns a dict with the cell pressures ``p`` and intermediates."""
+        P = self.params
+        Ux = np.asarray(Ux, dtype=np.float64).reshape(-1, 1)
+        Uy = np.asarray(Uy, dtype=np.float64).reshape(-1, 1)
+        p_prev = np.asarray(p_prev, dtype=np.float64)
+        U_max_norm = np.max(np.sqrt(np.square(Ux) + np.square(Uy)))              # PMP:270
+        Ux_interp = _interp.interpolate(Ux / U_max_norm, self.vert, self.weights)     # PMP:280-281 (no NaN fill)
+        Uy_interp = _interp.interpolate(Uy / U_max_norm, self.vert, self.weights)
+        H, W = self.grid_shape_y, self.grid_shape_x
+        grid = np.zeros(shape=(1, H, W, 3))
+        grid[0, :, :, 0:1][tuple(self.indices.T)] = Ux_interp.reshape(-1, 1) / P.maxs[0]      # PMP:290-292
+        grid[0, :, :, 1:2][tuple(self.indices.T)] = Uy_interp.reshape(-1, 1) / P.maxs[1]
+        grid[0, :, :, 2:3] = self.sdfunct                                         # unscaled
+        grid[np.isnan(grid)] = 0
+        shape, avance = self.shape, self.avance
+        n_x, n_y, origins, indices_list = self.block_plan()
+        x_array = np.concatenate([grid[0:1, y0:y0 + shape, x0:x0 + shape, 0:3] for (y0, x0) in origins])
+        N = x_array.shape[0]
+        input_flat = x_array.reshape((N, -1))
+        input_transformed = pca_transform(input_flat, P.pca_in_components, P.pca_in_mean)     # PMP:349
+        x_input = input_transformed / P.max_abs_input_PCA                         # PMP:351
+        res_concat = mlp_forward(x_input, P.mlp_weights, P.mlp_biases)            # PMP:360
+        mlp_out = res_concat.copy()
+        res_flat_inv = np.dot(res_concat * P.max_abs_output_PCA, P.pca_out_components) + P.pca_out_mean   # PMP:365
+        blocks = res_flat_inv.reshape((N, shape, shape, 1))
+        field, offsets, shift = _assemble.assemble_thesis(blocks[..., 0], x_array, indices_list, n_x, n_y, shape, avance,
+                                                          W, H, return_offsets=True)
+        p_adim_unif = field[tuple(self.indices.T)]                                # PMP:481
+        p_interp = _interp.interpolate_fill(p_adim_unif, self.vert_back, self.weights_back)   # PMP:485
+        p = p_interp * P.maxs[3] * pow(U_max_norm, 2.0)                           # PMP:490
+        if near_wall_sdf is not None:
+            sdf_mesh = _interp.interpolate_fill(self.sdfunct[:, :, 0], self.vert_back, self.weights_back)   # PMP:492
+            p[sdf_mesh < near_wall_sdf] = p_prev[sdf_mesh < near_wall_sdf]
+        p[np.isnan(p_interp)] = p_prev[np.isnan(p_interp)]                        # PMP:496
+        return dict(p=p, U_max_norm=U_max_norm, grid=grid[0], x_array=x_array, x_input=x_input, mlp_out=mlp_out,
+                    blocks=blocks, field=field, offsets=offsets, shift=shift, n_x=n_x, n_y=n_y, origins=origins,
+                    indices_list=indices_list)

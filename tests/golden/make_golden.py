@@ -374,23 +374,62 @@ def golden_pmp_init(name, mesh_kw, seed):
     print(name, 'grid', out['grid_shape'])
 
 
+def golden_pmp_step(name, mesh_kw, seed, pc_in=24, pc_p=20):
+    """Run the reference solver-side module end to end: ``init_func`` then ``py_func`` (PMP:249-517) -- the call the
+    PISO loop makes (FOAM/PythonComm.H:24-27).  PC_input is cut at 0.995 and PC_p at 0.95 (PMP:112-113)."""
+    mesh = syn.make_mesh(seed=seed, **mesh_kw)
+    F = syn.make_fields(mesh, seed=seed)
+    P = syn.make_params(seed=seed, pc_in=pc_in, pc_p=pc_p, standardization='max_abs')
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        write_param_files(tmp, P, extra=8, var=0.95, model_name='weights.h5')
+        rng = np.random.default_rng(99)
+        comp, mean = P['pca_in_components'], P['pca_in_mean']
+        more = (rng.standard_normal((8, comp.shape[1])) / np.sqrt(comp.shape[1])).astype(comp.dtype)
+        with open(os.path.join(tmp, 'ipca_input_more.pkl'), 'wb') as f:
+            pickle.dump(make_pca(np.concatenate([comp, more]), mean, evr_for(pc_in + 8, pc_in, 0.995)), f)
+        os.chdir(tmp)
+        try:
+            sys.path.insert(0, os.path.join(REF, 'Thesis_Work/Chapter5/parallelized/test_case'))
+            sys.modules.pop('python_module', None)             # the module reads its artefacts at import time
+            import python_module as PMP
+            assert (PMP.PC_input, PMP.PC_p) == (pc_in, pc_p), (PMP.PC_input, PMP.PC_p)
+            PMP.memory = lambda: ''
+            arr = syn.pack_cells(mesh, F, with_delta=False)
+            PMP.init_func(arr, mesh['top'], mesh['obst'], 0)
+            p = np.array(PMP.py_func(arr, 0), dtype=np.float64)
+        finally:
+            os.chdir(cwd)
+    out = dict(mesh_kw=np.array(repr(mesh_kw)), seed=seed, pc_in=pc_in, pc_p=pc_p,
+               grid_shape=np.array([PMP.grid_shape_y, PMP.grid_shape_x]), p=p,
+               indices_sha=np.array(sha(PMP.indices.astype(np.int64))))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, 'grid', out['grid_shape'], 'cells', p.shape, 'kept p_prev at', int((p == arr[:, 4]).sum()), 'cells')
+
+
 GOLDEN_CASES = {
     # name: (kind, mesh kwargs, seed)
     'smc_small': ('smc', dict(H=240, W=330, nx=130, ny=90, R=0.1), 11),
     'smc_bigobst': ('smc', dict(H=240, W=330, nx=130, ny=90, R=0.35, center=(0.3575, -0.0375)), 12),      # empty strips -> NaN chains
     'grad_small': ('grad', dict(H=240, W=340, nx=130, ny=90, R=0.1), 13),
     'pmp_init_small': ('pmp_init', dict(H=240, W=340, nx=130, ny=90, R=0.1), 14),
+    'pmp_step_small': ('pmp_step', dict(H=260, W=380, nx=150, ny=100, R=0.1), 15),
 }
 
 
 def main():
+    only = set(sys.argv[1:])                                   # optional: names of the cases to (re)generate
     install_stand_ins()
     sys.path.insert(0, os.path.join(REF, 'Improved_SM/deltaU_to_deltaP/source'))
     for name, (kind, mesh_kw, seed) in GOLDEN_CASES.items():
+        if only and name not in only:
+            continue
         if kind == 'smc':
             golden_smc(name, mesh_kw, seed)
         elif kind == 'grad':
             golden_grad(name, mesh_kw, seed)
+        elif kind == 'pmp_step':
+            golden_pmp_step(name, mesh_kw, seed)
         else:
             golden_pmp_init(name, mesh_kw, seed)
 

@@ -110,3 +110,23 @@ def test_pmp_init_tables_match_reference():
     ind, sdfunct = odomain.index_raster(X0, Y0, 5e-3, H, W, dom, probe, sdf)
     assert sha(ind.astype(np.int64)) == str(z['indices_sha'])
     np.testing.assert_allclose(sdfunct[:, :, 0], z['sdfunct'], rtol=1e-6, atol=1e-7)
+
+
+def test_thesis_oracle_matches_reference_py_func():
+    """ThesisOracle (PMP init_func + py_func restated) against the pressures the reference module itself returned."""
+    from oracle.pipeline import ThesisOracle
+    z, mesh_kw, seed = load_golden("pmp_step_small")
+    mesh = syn.make_mesh(seed=seed, **mesh_kw)
+    F = syn.make_fields(mesh, seed=seed)
+    P = oracle_params(syn.make_params(seed=seed, pc_in=int(z['pc_in']), pc_p=int(z['pc_p']), standardization='max_abs'))
+    o = ThesisOracle(P)
+    o.init_func(mesh['cells'], mesh['top'], mesh['obst'], F['Ux'])
+    assert [o.grid_shape_y, o.grid_shape_x] == list(z['grid_shape'])
+    assert sha(o.indices.astype(np.int64)) == str(z['indices_sha'])
+    r = o.py_func(F['Ux'], F['Uy'], F['p_prev'])
+    assert len(r['origins']) == (r['n_y'] + 2) * (r['n_x'] + 2)                  # the extra -1 column
+    kept_ref = z['p'] == F['p_prev']
+    kept = r['p'] == F['p_prev']
+    assert np.array_equal(kept, kept_ref)
+    scale = np.abs(z['p'] - F['p_prev']).max()
+    np.testing.assert_allclose(r['p'], z['p'], rtol=0, atol=5e-6 * scale)
