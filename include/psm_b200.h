@@ -179,7 +179,8 @@ enum psm_stage_code {
     PSM_STAGE_OFFSETS = 4,    /* double [F][B]     per-block corrections BC_coor (SMC:243)       */
     PSM_STAGE_FIELD = 5,      /* float [F][H][W]   assembled field(s) (SMC:350)                  */
     PSM_STAGE_SCALARS = 6,    /* double [4]        U_max_norm, dU_max_norm, shift[0], shift[1]   */
-    PSM_STAGE_MEANS = 7       /* double [n_tasks]  masked strip means                            */
+    PSM_STAGE_MEANS = 7,      /* double [n_tasks]  masked strip means                            */
+    PSM_STAGE_XU = 8          /* float [B][2][S][S] extracted blocks, channels 0,1 (SMC:464-492), planar */
 };
 
 /* ---- lifetime -------------------------------------------------------------------------- */

@@ -1321,6 +1321,10 @@ extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_
             o[0] = sc.U_max_norm; o[1] = sc.dU_max_norm; o[2] = sc.shift[0]; o[3] = sc.shift[1];
             return PSM_OK;
         }
+        case PSM_STAGE_XU:
+            TRY(need((int64_t)h->B * 2 * S2 * 4));
+            CU(h, cudaMemcpy(out, h->d_xu, (size_t)h->B * 2 * S2 * 4, cudaMemcpyDeviceToHost));
+            return PSM_OK;
         case PSM_STAGE_MEANS:
             TRY(need((int64_t)h->plan.tasks.size() * 8));
             CU(h, cudaMemcpy(out, h->d_means, h->plan.tasks.size() * 8, cudaMemcpyDeviceToHost));

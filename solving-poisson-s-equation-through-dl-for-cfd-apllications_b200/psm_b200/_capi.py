@@ -15,7 +15,7 @@ PSM_DELTAU_TO_DELTAP, PSM_U_TO_GRADP = 0, 1
 PSM_STD, PSM_MAX_ABS = 0, 1
 GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_FP32_SIMT = 0, 1, 2
 (STAGE_GRID, STAGE_XINPUT, STAGE_MLPOUT, STAGE_BLOCKS, STAGE_OFFSETS, STAGE_FIELD, STAGE_SCALARS,
- STAGE_MEANS) = range(8)
+ STAGE_MEANS, STAGE_XU) = range(9)
 UNIQUE_ID_BYTES = 128
 N_TIMINGS = 12
 TIMING_NAMES = ('h2d', 'prep', 'gather', 'extract', 'pca_project', 'mlp', 'pca_inverse', 'strip_means',

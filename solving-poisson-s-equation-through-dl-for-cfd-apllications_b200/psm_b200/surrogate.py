@@ -344,6 +344,7 @@ class PressureSurrogate:
             'field': (capi.STAGE_FIELD, (F, self.H, self.W), np.float32),
             'scalars': (capi.STAGE_SCALARS, (4,), np.float64),
             'means': (capi.STAGE_MEANS, (g['n_tasks'],), np.float64),
+            'xu': (capi.STAGE_XU, (B, 2, S, S), np.float32),
         }[name]
         out = np.empty(spec[1], dtype=spec[2])
         self._check(self.lib.psm_get_stage(self._h, spec[0], out.ctypes.data, out.nbytes))
