@@ -40,7 +40,11 @@ enum psm_status_code {
 
 enum psm_variant_code {
     PSM_DELTAU_TO_DELTAP = 0, /* SMC: right->left plan, 1 output channel, p = p_prev + delta_p   */
-    PSM_U_TO_GRADP = 1        /* GRAD: left->right plan, 2 output channels {dp/dx, dp/dy}        */
+    PSM_U_TO_GRADP = 1,       /* GRAD: left->right plan, 2 output channels {dp/dx, dp/dy}        */
+    PSM_THESIS_U_TO_P = 2     /* PMP (the solver module the reference ships, python_module.py): U -> p, shared columns
+                                 `avance` = 12 (psm_config.overlap), extra left-most block column, scalar max-abs PCA scaling,
+                                 distance channel unscaled (PMP:292), forward interpolation without the NaN fill (PMP:64-65),
+                                 p_out = p (not p_prev + dp).  Single-GPU handles only.             */
 };
 
 enum psm_standardization_code {

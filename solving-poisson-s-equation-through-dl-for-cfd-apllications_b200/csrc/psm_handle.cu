@@ -205,7 +205,7 @@ extern "C" const char* psm_last_error(const psm_handle* h) { return h ? h->err.c
 extern "C" int psm_create(psm_handle** out, const psm_config* cfg) {
     if (!out || !cfg) { g_create_error = "psm_create: NULL argument"; return PSM_ERR_INVALID; }
     *out = nullptr;
-    if (cfg->variant != PSM_DELTAU_TO_DELTAP && cfg->variant != PSM_U_TO_GRADP) { g_create_error = "unknown variant"; return PSM_ERR_INVALID; }
+    if (cfg->variant != PSM_DELTAU_TO_DELTAP && cfg->variant != PSM_U_TO_GRADP && cfg->variant != PSM_THESIS_U_TO_P) { g_create_error = "unknown variant"; return PSM_ERR_INVALID; }
     if (cfg->shape != 128) { g_create_error = "only shape == 128 is supported"; return PSM_ERR_INVALID; }
     if (cfg->gemm_mode < 0 || cfg->gemm_mode > 2) { g_create_error = "unknown gemm_mode"; return PSM_ERR_INVALID; }
     if (!(cfg->filter_sigma >= 0.0) || cfg->filter_sigma > 1000.0) { g_create_error = "filter_sigma must be in [0, 1000]"; return PSM_ERR_INVALID; }
@@ -483,7 +483,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
     int rc = compile_plan(h->cfg.variant, L.H, W, S, h->cfg.overlap, L.mask_global, h->plan);
     if (rc) PSM_FAIL(h, rc, "%s", h->plan.error.c_str());
     const Plan& P = h->plan;
-    const int ncolb = P.n_x + 1;
+    const int ncolb = P.ncolb;
     if (L.blk_row1 < 0) L.blk_row1 = P.n_y + 2;
     if (L.blk_row0 < 0 || L.blk_row1 > P.n_y + 2 || L.blk_row0 >= L.blk_row1) PSM_FAIL(h, PSM_ERR_INVALID, "bad block-row range [%d,%d)", L.blk_row0, L.blk_row1);
     h->Bg = P.B; h->kb0 = L.blk_row0 * ncolb; h->B = (L.blk_row1 - L.blk_row0) * ncolb;
@@ -586,7 +586,8 @@ static int init_local(psm_handle* h, LocalInit& L) {
         for (int i = 0; i < n_means; ++i) {
             const Task& s = P.tasks[i];
             if (s.src < kb0 || s.src >= kb1) continue;
-            tk.push_back(DevTask{s.src - kb0, 0, s.ch, s.y0, s.y1, s.x0, s.x1, s.count, P.y0[s.msk], P.x0[s.msk], i, 0});
+            if (s.msk >= 0) tk.push_back(DevTask{s.src - kb0, 0, s.ch, s.y0, s.y1, s.x0, s.x1, s.count, P.y0[s.msk], P.x0[s.msk], i, 0});
+            else tk.push_back(DevTask{s.src - kb0, 2, s.ch, s.y0, s.y1, s.x0, s.x1, s.count, 0, 0, i, 0});      // plain mean (PMP:437)
         }
         std::vector<DevShiftTerm> terms;
         int slot = n_means;
@@ -667,7 +668,8 @@ static int init_local(psm_handle* h, LocalInit& L) {
     {
         const size_t nl = (size_t)Hl * W;
         std::vector<float> sdfn(nl, 0.f);
-        for (size_t q = 0; q < nl; ++q) sdfn[q] = (float)(L.sdf_rows[q] / h->maxs[2]);
+        const double dist_scale = (h->cfg.variant == PSM_THESIS_U_TO_P) ? 1.0 : h->maxs[2];     // PMP:292 feeds the distance unscaled
+        for (size_t q = 0; q < nl; ++q) sdfn[q] = (float)(L.sdf_rows[q] / dist_scale);
         float* d_sdfn = nullptr; float* d_sdfb = nullptr;
         CU(h, cudaMalloc(&d_sdfn, nl * sizeof(float)));
         CU(h, cudaMalloc(&d_sdfb, (size_t)Bp * S2 * sizeof(float)));
@@ -817,7 +819,9 @@ extern "C" int psm_init_with_tables(psm_handle* h, const psm_tables* t) {
             const long long m = src[q];
             if (m < 0) continue;
             const double* wm = t->weights + 3 * m;
-            const bool neg = (wm[0] < 0) || (wm[1] < 0) || (wm[2] < 0);          // -> NaN (UTL:89) -> 0 (SMC:438)
+            // negative weight -> NaN (interpolate_fill, UTL:89) -> 0 (SMC:438); the thesis module interpolates without
+            // the fill (PMP:64-65,280-281): outside points keep their extrapolated value
+            const bool neg = h->cfg.variant != PSM_THESIS_U_TO_P && ((wm[0] < 0) || (wm[1] < 0) || (wm[2] < 0));
             for (int j = 0; j < 3; ++j) {
                 const int32_t vi = t->vert[3 * m + j];
                 if (vi < 0 || vi >= N) PSM_FAIL(h, PSM_ERR_INVALID, "vert out of range at %lld", m);
@@ -862,6 +866,7 @@ extern "C" int psm_init_sharded(psm_handle* h, const psm_shard* s) {
         PSM_FAIL(h, PSM_ERR_INVALID, "bad shard");
     if (s->world > 1 && (!s->cell_send_ptr || !s->cell_recv_ptr || !s->pix_send_ptr || !s->pix_recv_ptr)) PSM_FAIL(h, PSM_ERR_INVALID, "missing exchange lists");
     if ((s->rank == s->world - 1 && s->ext_rows) || (s->rank == 0 && s->send_rows)) PSM_FAIL(h, PSM_ERR_INVALID, "halo rows at the ends of the rank chain");
+    if (h->cfg.variant == PSM_THESIS_U_TO_P) PSM_FAIL(h, PSM_ERR_INVALID, "the thesis variant is not available on a sharded handle");
     CU(h, cudaSetDevice(h->cfg.device));
     LocalInit L;
     L.rank = s->rank; L.world = s->world; L.H = s->grid_h; L.W = s->grid_w; L.row0 = s->row0; L.row1 = s->row1;
@@ -944,7 +949,8 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     int nl = 0, te = 1;
     auto tick = [&]() { if (h->ev_valid) cudaEventRecord(h->ev[te], s); ++te; };
 
-    ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], deltas ? h->maxs[3] : 1.0, deltas ? 1 : 0, h->cfg.skip_threshold, mode, 0};
+    const bool dim = h->cfg.variant != PSM_U_TO_GRADP;        // blocks re-dimensionalised by max_abs_p * U^2 (SMC:551, PMP:490); GRAD: none
+    ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], dim ? h->maxs[3] : 1.0, dim ? 1 : 0, h->cfg.skip_threshold, mode, 0};
     PrepArgs pa{d_cells, h->n_cells, h->cfg.input_cols, mode, h->d_uv, h->d_pprev, h->d_uprev, h->d_sc};
     launch_prep(pa, s); ++nl;
     const bool p2p = multi && h->p2p;
@@ -967,7 +973,7 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     GatherArgs ga{h->d_fv[0], h->d_fv[1], h->d_fv[2], h->d_fw[0], h->d_fw[1], h->d_fw[2], h->d_uv,
                   grid0, grid1, h->G_pad / 4, sa, 0, d_p2p};
     if (h->fused_extract) {
-        GatherExtractArgs ge{ga, h->d_rowcov, h->d_colcov, h->d_by0, h->d_bx0, h->d_xu, h->W / 4, h->plan.n_x + 1, S, h->keep_grid ? 1 : 0};
+        GatherExtractArgs ge{ga, h->d_rowcov, h->d_colcov, h->d_by0, h->d_bx0, h->d_xu, h->W / 4, h->plan.ncolb, S, h->keep_grid ? 1 : 0};
         launch_gather_extract(ge, s); ++nl;
     } else {
         launch_gather(ga, s); ++nl;

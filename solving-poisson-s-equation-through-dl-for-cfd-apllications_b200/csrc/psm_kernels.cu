@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(256, 3) task_means_kernel(MeansArgs a, Offsets
     __syncthreads();
     if (w == 0) {
         const double tot = warp_sum(lane < NW ? part[lane] : 0.0);   // fixed butterfly: deterministic
-        const double val = t.kind ? tot : ((t.count > 0) ? tot / (double)t.count : CUDART_NAN);
+        const double val = (t.kind == 1) ? tot : ((t.count > 0) ? tot / (double)t.count : CUDART_NAN);   // 1: line sum; 0 / 2: masked / plain mean
         if (lane == 0) a.means[t.out] = val;
     }
     if (MODE != 0) {

@@ -220,7 +220,7 @@ void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s);
 // K6a: masked rectangle means (and the plain line sums of the global shift) of the predicted blocks.
 struct DevTask {
     int32_t src;                      // LOCAL block the values come from
-    int32_t kind;                     // 0: masked mean, 1: plain sum (shift-line run)
+    int32_t kind;                     // 0: masked mean, 1: plain sum (shift-line run), 2: plain mean (no mask, PMP:437)
     int32_t ch, y0, y1, x0, x1;       // channel, block-local rectangle
     int32_t count;                    // mask pixels in the rectangle (0 -> NaN mean)
     int32_t my0, mx0;                 // GLOBAL grid origin of the block whose flow mask applies

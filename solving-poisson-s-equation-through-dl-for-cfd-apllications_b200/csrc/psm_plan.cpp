@@ -1,6 +1,7 @@
 // Plan compiler: see psm_plan.h.  Reference semantics followed:
 //   deltaU_to_deltaP : SMC:461-479 (plan), SMC:203-348 (corrections + placement), SMC:350 (shift)
 //   U_to_gradP       : GRAD:479-500 (plan), GRAD:269-356, GRAD:358-361
+//   thesis U -> p    : PMP:303-332 (plan with the extra -1 column), PMP:372-467 (corrections + placement), PMP:472
 #include "psm_plan.h"
 
 #include <cmath>
@@ -37,7 +38,7 @@ struct Builder {
         auto key = std::make_tuple(src, msk, ch, y0, y1, x0, x1);
         auto it = dedupe.find(key);
         if (it != dedupe.end()) return it->second;
-        Task t{src, msk, ch, y0, y1, x0, x1, count(msk, y0, y1, x0, x1)};
+        Task t{src, msk, ch, y0, y1, x0, x1, msk >= 0 ? count(msk, y0, y1, x0, x1) : (y1 - y0) * (x1 - x0)};
         P.tasks.push_back(t);
         int id = (int)P.tasks.size() - 1;
         dedupe.emplace(key, id);
@@ -55,15 +56,136 @@ struct Ups {
 
 }  // namespace
 
+// Runs of the two shift lines through the owner map (shared by all variants).
+static void build_shift_lines(Plan& P) {
+    const int H = P.H, W = P.W;
+    for (int f = 0; f < P.F; ++f) {
+        const int axis = P.shift_axis[f];
+        const int len = axis == 0 ? H : W;
+        P.shift_len[f] = len;
+        for (int s2 = 0; s2 < 2; ++s2) {
+            const int line = s2 == 0 ? P.shift_a[f] : P.shift_b[f];
+            const int coef = s2 == 0 ? 3 : -1;
+            int i = 0;
+            while (i < len) {
+                const int o = P.owner[axis == 0 ? (size_t)i * W + line : (size_t)line * W + i];
+                int e = i + 1;
+                while (e < len && P.owner[axis == 0 ? (size_t)e * W + line : (size_t)line * W + e] == o) ++e;
+                LineTask t{};
+                t.src = o; t.ch = f; t.coef = coef; t.n = e - i;
+                if (axis == 0) { t.y0 = i - P.y0[o]; t.y1 = e - P.y0[o]; t.x0 = line - P.x0[o]; t.x1 = t.x0 + 1; }
+                else           { t.x0 = i - P.x0[o]; t.x1 = e - P.x0[o]; t.y0 = line - P.y0[o]; t.y1 = t.y0 + 1; }
+                P.lines[f].push_back(t);
+                i = e;
+            }
+        }
+    }
+}
+
+// Thesis solver module (PMP:303-332, 372-472): stride S - avance, blocks right -> left and, after the last regular
+// block of every row, the block at x = 0 tagged -1; its own correction chain (see oracle/assemble.py:assemble_thesis).
+static int compile_thesis_plan(int H, int W, int S, int av, const uint8_t* mask, Plan& P) {
+    const int st = P.stride;
+    P.C = P.F = 1;
+    P.n_x = (W - S) / st;                                      // PMP:306  int()
+    P.n_y = (H - S) / st;                                      // PMP:307
+    const int n_x = P.n_x, n_y = P.n_y;
+    P.p_i = H - (st * n_y + S);                                // `p`, PMP:407
+    P.p_j = (W - S) - n_x * st;                                // PMP:391
+    const int p = P.p_i, p_j = P.p_j;
+    if (S - p - av < 0) { P.error = "thesis plan: bottom strip outside the block"; return PSM_ERR_GEOMETRY; }
+    P.ncolb = n_x + 2;
+    P.B = (n_y + 2) * P.ncolb;
+    if (P.B >= 65535) { P.error = "too many blocks for the 16-bit owner map"; return PSM_ERR_GEOMETRY; }
+    const int B = P.B;
+    for (int i = 0; i < n_y + 2; ++i) {
+        const int y_0 = (i == n_y + 1) ? H - S : i * st;
+        for (int j = 0; j <= n_x; ++j) {
+            P.idx_i.push_back(i); P.idx_j.push_back(n_x - j); P.y0.push_back(y_0); P.x0.push_back((W - S) - j * st);
+        }
+        P.idx_i.push_back(i); P.idx_j.push_back(-1); P.y0.push_back(y_0); P.x0.push_back(0);       // PMP:323-329
+    }
+    // placement (PMP:453-467)
+    P.py0.assign(B, 0); P.py1.assign(B, S); P.px0.assign(B, 0); P.px1.assign(B, S);
+    for (int k = 0; k < B; ++k) {
+        if (P.idx_i[k] == n_y + 1) {
+            P.py0[k] = av;                                                         // res[avance:shape]
+            if (P.idx_j[k] == -1) P.px1[k] = W - (n_x + 1) * st - av;              // PMP:454
+        }
+    }
+    P.owner.assign((size_t)H * W, -1);
+    for (int k = 0; k < B; ++k)
+        for (int ly = P.py0[k]; ly < P.py1[k]; ++ly) {
+            int32_t* row = &P.owner[(size_t)(P.y0[k] + ly) * W + P.x0[k]];
+            for (int lx = P.px0[k]; lx < P.px1[k]; ++lx) row[lx] = k;
+        }
+    for (size_t q = 0; q < P.owner.size(); ++q)
+        if (P.owner[q] < 0) { P.error = "placement does not cover the grid"; return PSM_ERR_GEOMETRY; }
+
+    Builder bld(P, mask);
+    P.rec.assign((size_t)B, Rec{-1, -1, -1, 0});
+    std::vector<int> depth((size_t)B, 0);
+    Rec* rec = P.rec.data();
+    auto set = [&](int k, int ta, int tb, int parent) {
+        Rec r{ta, tb, parent, 0};
+        r.is_nan = bld.tnan(ta) || (tb >= 0 && (bld.tnan(tb) || rec[parent].is_nan));
+        rec[k] = r;
+        depth[k] = (parent >= 0) ? depth[parent] + 1 : 0;
+        if (depth[k] > P.max_depth) P.max_depth = depth[k];
+    };
+    Ups ups(n_x + 1);
+    int up_task = -1, up_block = -1; bool up_nan = false;      // BC_up_ : the chain of the -1 column
+    auto set_ups = [&](int k, int j, int y0, int y1, int x0, int x1) {
+        ups.task[j] = bld.task(k, k, 0, y0, y1, x0, x1); ups.block[j] = k;
+        ups.nan[j] = bld.tnan(ups.task[j]) || rec[k].is_nan;
+    };
+    auto left_of_prev = [&](int k) { return bld.task(k - 1, k - 1, 0, 0, S, 0, av); };   // BC_ant_0 / BC_alter: previous block's own left strip
+    for (int k = 0; k < B; ++k) {
+        const int ii = P.idx_i[k], jj = P.idx_j[k];
+        if (ii == 0) {
+            if (jj == n_x) {                                                       // PMP:387-391
+                set(k, bld.task(k, k, 0, 0, S, S - av, S), -1, -1);                // - BC_up (= 0)
+                set_ups(k, jj, S - av, S, S - av, S);
+            } else if (jj == -1) {                                                 // PMP:394-398
+                set(k, bld.task(k, k, 0, 0, S, p_j, p_j + av), left_of_prev(k), k - 1);
+                up_task = bld.task(k, k, 0, S - av, S, p_j, p_j + av); up_block = k;
+                up_nan = bld.tnan(up_task) || rec[k].is_nan;
+            } else {                                                               // PMP:399-402
+                set(k, bld.task(k, k, 0, 0, S, S - av, S), left_of_prev(k), k - 1);
+                set_ups(k, jj, S - av, S, 0, S);
+            }
+        } else if (ii == n_y + 1) {
+            if (jj == -1) set(k, bld.task(k, k, 0, S - p - av, S - p, p_j, p_j + av), up_task, up_block);   // PMP:408-410
+            else if (ups.nan[jj]) set(k, bld.task(k, k, 0, 0, S, S - av, S), left_of_prev(k), k - 1);      // PMP:415-416
+            else set(k, bld.task(k, k, 0, S - p - av, S - p, 0, S), ups.task[jj], ups.block[jj]);          // PMP:418
+        } else {
+            if (jj == -1) {                                                        // PMP:432-437
+                set(k, bld.task(k, k, 0, 0, av, p_j, p_j + av), up_task, up_block);
+                up_task = bld.task(k, -1, 0, S - av, S, p_j, p_j + av); up_block = k;   // np.mean WITHOUT the mask
+                up_nan = rec[k].is_nan;
+            } else {
+                if (ups.nan[jj]) set(k, bld.task(k, k, 0, 0, S, S - av, S), left_of_prev(k), k - 1);       // PMP:441-442
+                else set(k, bld.task(k, k, 0, 0, av, 0, S), ups.task[jj], ups.block[jj]);                  // PMP:444
+                set_ups(k, jj, S - av, S, 0, S);                                                          // PMP:446
+            }
+        }
+    }
+    (void)up_nan;
+    P.shift_axis[0] = 0; P.shift_a[0] = W - 1; P.shift_b[0] = W - 2;              // PMP:472
+    build_shift_lines(P);
+    return 0;
+}
+
 int compile_plan(int variant, int H, int W, int S, int ov, const uint8_t* mask, Plan& P) {
     P = Plan();
     P.variant = variant; P.H = H; P.W = W; P.S = S; P.ov = ov; P.stride = S - ov;
-    if (variant != PSM_DELTAU_TO_DELTAP && variant != PSM_U_TO_GRADP) { P.error = "unknown variant"; return PSM_ERR_INVALID; }
+    if (variant != PSM_DELTAU_TO_DELTAP && variant != PSM_U_TO_GRADP && variant != PSM_THESIS_U_TO_P) { P.error = "unknown variant"; return PSM_ERR_INVALID; }
     if (S != 128) { P.error = "only shape == 128 is supported (the reference hard-codes 128**2 at SMC:307)"; return PSM_ERR_INVALID; }
     if (ov <= 0 || ov >= S) { P.error = "overlap must be in (0, shape)"; return PSM_ERR_INVALID; }
     if (H < S || W <= S) { P.error = "grid smaller than one block"; return PSM_ERR_GEOMETRY; }
     if (!mask) { P.error = "mask is NULL"; return PSM_ERR_INVALID; }
     const int st = P.stride;
+    if (variant == PSM_THESIS_U_TO_P) return compile_thesis_plan(H, W, S, ov, mask, P);
     const bool grad = (variant == PSM_U_TO_GRADP);
     P.C = P.F = grad ? 2 : 1;
     P.n_x = (int)std::ceil((double)(W - S) / (double)st);      // SMC:461 / GRAD:479
@@ -78,6 +200,7 @@ int compile_plan(int variant, int H, int W, int S, int ov, const uint8_t* mask, 
     }
     if (n_x < 1) { P.error = "n_x == 0: the reference reads an unbound block (SMC:239)"; return PSM_ERR_GEOMETRY; }
     P.B = (n_y + 2) * (n_x + 1);
+    P.ncolb = n_x + 1;
     if (P.B >= 65535) { P.error = "too many blocks for the 16-bit owner map"; return PSM_ERR_GEOMETRY; }
     const int B = P.B;
 
@@ -195,27 +318,7 @@ int compile_plan(int variant, int H, int W, int S, int ov, const uint8_t* mask, 
     }
     // result -= mean(3*line_a - line_b)/3 through the owner map, as per-block runs: the placed value is
     // raw - c[owner], so every run contributes coef * (sum(raw) - n * c[owner]).
-    for (int f = 0; f < P.F; ++f) {
-        const int axis = P.shift_axis[f];
-        const int len = axis == 0 ? H : W;
-        P.shift_len[f] = len;
-        for (int s2 = 0; s2 < 2; ++s2) {
-            const int line = s2 == 0 ? P.shift_a[f] : P.shift_b[f];
-            const int coef = s2 == 0 ? 3 : -1;
-            int i = 0;
-            while (i < len) {
-                const int o = P.owner[axis == 0 ? (size_t)i * W + line : (size_t)line * W + i];
-                int e = i + 1;
-                while (e < len && P.owner[axis == 0 ? (size_t)e * W + line : (size_t)line * W + e] == o) ++e;
-                LineTask t{};
-                t.src = o; t.ch = f; t.coef = coef; t.n = e - i;
-                if (axis == 0) { t.y0 = i - P.y0[o]; t.y1 = e - P.y0[o]; t.x0 = line - P.x0[o]; t.x1 = t.x0 + 1; }
-                else           { t.x0 = i - P.x0[o]; t.x1 = e - P.x0[o]; t.y0 = line - P.y0[o]; t.y1 = t.y0 + 1; }
-                P.lines[f].push_back(t);
-                i = e;
-            }
-        }
-    }
+    build_shift_lines(P);
     return 0;
 }
 

@@ -18,7 +18,7 @@
 namespace psm {
 
 struct Task {
-    int32_t src, msk, ch;        // values from block `src`, channel `ch`; mask of block `msk`
+    int32_t src, msk, ch;        // values from block `src`, channel `ch`; mask of block `msk` (-1: no mask, plain mean)
     int32_t y0, y1, x0, x1;      // block-local rectangle [y0,y1) x [x0,x1)
     int32_t count;               // mask pixels in the rectangle (0 -> mean is NaN)
 };
@@ -39,6 +39,7 @@ struct Rec {
 struct Plan {
     int variant = 0, H = 0, W = 0, S = 0, ov = 0, stride = 0;
     int n_x = 0, n_y = 0, p_i = 0, p_j = 0, B = 0, F = 0, C = 0;
+    int ncolb = 0;                                   // blocks per block row (n_x + 1; n_x + 2 for the thesis plan)
     std::vector<int32_t> y0, x0, idx_i, idx_j;       // [B]
     std::vector<int32_t> py0, py1, px0, px1;         // [B] placement rectangle, block-local
     std::vector<int32_t> owner;                      // [H*W] last writer, -1 if none

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'libpsm_b200.so')
 
 PSM_OK, PSM_SKIPPED = 0, 1
 PSM_ERR_INVALID, PSM_ERR_CUDA, PSM_ERR_GEOMETRY, PSM_ERR_STATE, PSM_ERR_COMM = -1, -2, -3, -4, -5
-PSM_DELTAU_TO_DELTAP, PSM_U_TO_GRADP = 0, 1
+PSM_DELTAU_TO_DELTAP, PSM_U_TO_GRADP, PSM_THESIS_U_TO_P = 0, 1, 2
 PSM_STD, PSM_MAX_ABS = 0, 1
 GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_FP32_SIMT = 0, 1, 2
 (STAGE_GRID, STAGE_XINPUT, STAGE_MLPOUT, STAGE_BLOCKS, STAGE_OFFSETS, STAGE_FIELD, STAGE_SCALARS,

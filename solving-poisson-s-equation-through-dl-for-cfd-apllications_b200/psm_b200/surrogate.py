@@ -11,7 +11,8 @@ import numpy as np
 from . import _capi as capi
 from . import tables as _tables
 
-_VARIANT_CODE = {'deltaU_to_deltaP': capi.PSM_DELTAU_TO_DELTAP, 'U_to_gradP': capi.PSM_U_TO_GRADP}
+_VARIANT_CODE = {'deltaU_to_deltaP': capi.PSM_DELTAU_TO_DELTAP, 'U_to_gradP': capi.PSM_U_TO_GRADP,
+                 'thesis': capi.PSM_THESIS_U_TO_P}     # 'thesis': the solver module the reference ships (PMP), U -> p
 
 
 def _ptr(a, ctype):
@@ -158,8 +159,10 @@ class PressureSurrogate:
             raise ValueError('variant must be one of %s' % list(_VARIANT_CODE))
         self.lib = capi.load()
         self.variant = variant
-        if overlap is None:
-            overlap = 32 if variant == 'deltaU_to_deltaP' else 96       # EP:90 overlap_ratio 0.25 ; GRAD:708 avance
+        if overlap is None:       # EP:90 overlap_ratio 0.25 ; GRAD:708 avance ; PMP:304 avance = int(0.1 * 128)
+            overlap = {'deltaU_to_deltaP': 32, 'U_to_gradP': 96, 'thesis': 12}[variant]
+        if variant == 'thesis':
+            additive = False                                             # py_func returns p itself (PMP:490)
         if input_cols is None:
             input_cols = 7 if variant == 'deltaU_to_deltaP' else 5
         self.input_cols = input_cols

@@ -7,7 +7,8 @@ one call into the CUDA library (``psm_predict``) instead of NumPy/TensorFlow on 
 
 Artefacts are looked up like the reference does, in the current directory, but from ONE file:
 ``psm_params.npz`` (written by ``psm_b200.params.save_npz``), or set ``PSM_PARAMS`` to its path.
-Environment: ``PSM_VARIANT`` (deltaU_to_deltaP | U_to_gradP), ``PSM_DEVICE`` (CUDA ordinal),
+Environment: ``PSM_VARIANT`` (deltaU_to_deltaP | U_to_gradP | thesis = the arithmetic of the reference's own
+module: U -> p, avance 12, near-wall fallback 0.05), ``PSM_DEVICE`` (CUDA ordinal),
 ``PSM_INPUT_COLS`` (5 | 7).
 
 Differences from the reference module, all on the boundary rather than in the arithmetic:
@@ -31,7 +32,7 @@ def _surrogate():
         variant = os.environ.get('PSM_VARIANT', 'deltaU_to_deltaP')
         cols = int(os.environ.get('PSM_INPUT_COLS', '5'))
         sm = PressureSurrogate(variant=variant, device=int(os.environ.get('PSM_DEVICE', '0')), input_cols=cols,
-                               near_wall_sdf=float(os.environ.get('PSM_NEAR_WALL_SDF', '0')))
+                               near_wall_sdf=float(os.environ.get('PSM_NEAR_WALL_SDF', '0.05' if variant == 'thesis' else '0')))   # PMP:492-494
         sm.load_params(_params.load_npz(os.environ.get('PSM_PARAMS', 'psm_params.npz')))
         _state['sm'] = sm
     return _state['sm']

@@ -7,11 +7,15 @@ import pytest
 import psm_b200
 from psm_b200 import _capi
 from oracle import assemble as oasm
-from oracle.pipeline import DeltasOracle, GradPOracle
+from oracle.pipeline import DeltasOracle, GradPOracle, ThesisOracle
 
 
 def oracle_plan(variant, H, W, ov):
-    o = (DeltasOracle(None, overlap=ov) if variant == 'deltaU_to_deltaP' else GradPOracle(None, avance=ov))
+    if variant == 'thesis':
+        o = ThesisOracle(None)
+        assert o.avance == ov
+    else:
+        o = (DeltasOracle(None, overlap=ov) if variant == 'deltaU_to_deltaP' else GradPOracle(None, avance=ov))
     o.grid_shape_y, o.grid_shape_x = H, W
     return o.block_plan()
 
@@ -27,7 +31,10 @@ def eval_plan(plan, blocks, mask, ref_bc=0.0):
     org = plan['origins']
     means = np.zeros(len(plan['tasks']))
     for t, (src, msk, ch, y0, y1, x0, x1, cnt) in enumerate(plan['tasks']):
-        m = mask[org[msk, 0] + y0:org[msk, 0] + y1, org[msk, 1] + x0:org[msk, 1] + x1] != 0
+        if msk >= 0:
+            m = mask[org[msk, 0] + y0:org[msk, 0] + y1, org[msk, 1] + x0:org[msk, 1] + x1] != 0
+        else:                                                   # plain mean, no mask (PMP:437)
+            m = np.ones((y1 - y0, x1 - x0), bool)
         assert m.sum() == cnt
         with warnings.catch_warnings():
             warnings.simplefilter("ignore", category=RuntimeWarning)
@@ -85,6 +92,12 @@ CASES = [
     ('U_to_gradP', 96, 240, 340, None),
     ('U_to_gradP', 96, 240, 340, (120, 102, 20)),
     ('U_to_gradP', 96, 300, 421, (140, 200, 75)),
+    ('thesis', 12, 260, 380, None),
+    ('thesis', 12, 260, 380, (130, 120, 25)),
+    ('thesis', 12, 400, 500, (200, 150, 90)),              # empty strips -> NaN BC_ups -> BC_alter branch
+    ('thesis', 12, 130, 250, None),                         # n_y == 0: first and last row only
+    ('thesis', 12, 500, 700, (250, 520, 60)),
+    ('thesis', 12, 360, 128 + 116 * 2, None),               # p_j == 0: the -1 column's last-row write is empty
 ]
 
 
@@ -103,7 +116,11 @@ def test_closed_form_recurrence_equals_sequential_assembly(variant, ov, H, W, di
         x_array[k, :, :, 2] = mask[y0:y0 + 128, x0:x0 + 128] * 0.37
     c, fields = eval_plan(plan, blocks, mask)
     for f in range(F):
-        if variant == 'deltaU_to_deltaP':
+        if variant == 'thesis':
+            ref, offs, shift = oasm.assemble_thesis(blocks[:, 0], x_array, il, n_x, n_y, 128, ov, W, H, return_offsets=True)
+            mine = fields[0]
+            sh = np.mean(3 * mine[:, -1] - mine[:, -2]) / 3
+        elif variant == 'deltaU_to_deltaP':
             ref, offs, shift = oasm.assemble_deltas(blocks[:, 0], x_array, il, n_x, n_y, 128, ov, W, H, return_offsets=True)
             mine = fields[0]
             sh = np.mean(3 * mine[:, -1] - mine[:, -2]) / 3
@@ -125,7 +142,7 @@ def test_closed_form_recurrence_equals_sequential_assembly(variant, ov, H, W, di
             assert (y1 - y0) * (x1 - x0) == n
             acc += coef * (blocks[blk, f, y0:y1, x0:x1].sum() - n * c[f][blk])
             npx += n
-        L = H if (variant == 'deltaU_to_deltaP' or f == 0) else W
+        L = H if (variant != 'U_to_gradP' or f == 0) else W
         assert npx == 2 * L
         np.testing.assert_allclose(acc / L / 3, sh, rtol=0, atol=1e-11, equal_nan=True)
 
@@ -142,3 +159,13 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.psm_api_version() == 3
+
+
+@pytest.mark.parametrize("H,W", [(260, 380), (130, 250), (397, 998), (1000, 1000), (360, 360)])
+def test_thesis_block_plan_bit_exact(H, W):
+    """PMP:303-332: right -> left plus the extra -1 block per row, B = (n_y + 2)(n_x + 2)."""
+    plan = psm_b200.compile_plan('thesis', H, W, np.ones((H, W), np.uint8), overlap=12)
+    n_x, n_y, origins, il = oracle_plan('thesis', H, W, 12)
+    assert plan['n_blocks'] == (n_y + 2) * (n_x + 2) == len(origins)
+    np.testing.assert_array_equal(plan['origins'], np.array(origins, dtype=np.int32))
+    np.testing.assert_array_equal(plan['indices_list'], np.array(il, dtype=np.int32))
