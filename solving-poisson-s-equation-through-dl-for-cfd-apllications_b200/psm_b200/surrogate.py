@@ -166,7 +166,7 @@ class PressureSurrogate:
         if input_cols is None:
             input_cols = 7 if variant == 'deltaU_to_deltaP' else 5
         self.input_cols = input_cols
-        self.n_fields = 1 if variant == 'deltaU_to_deltaP' else 2
+        self.n_fields = 2 if variant == 'U_to_gradP' else 1
         self.delta = delta
         cfg = capi.PsmConfig(variant=_VARIANT_CODE[variant], device=device, delta=delta, shape=shape, overlap=overlap,
                              input_cols=input_cols, additive=int(additive), ref_bc=ref_bc,

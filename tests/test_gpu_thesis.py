@@ -1,0 +1,84 @@
+"""Thesis variant on the GPU: the arithmetic of the solver module the reference ships (python_module.py init_func +
+py_func, PMP:172-517) -- against the pressures that module itself returned (tests/golden/pmp_step_small.npz) and
+against the oracle's intermediates."""
+import numpy as np
+import pytest
+
+import psm_b200
+from psm_b200 import synthetic as syn, tables as ptables
+from oracle.pipeline import ThesisOracle
+from helpers import oracle_params, load_golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def case():
+    z, mesh_kw, seed = load_golden('pmp_step_small')
+    mesh = syn.make_mesh(seed=seed, **mesh_kw)
+    F = syn.make_fields(mesh, seed=seed)
+    params = syn.make_params(seed=seed, pc_in=int(z['pc_in']), pc_p=int(z['pc_p']), standardization='max_abs')
+    t = ptables.build_tables(mesh['cells'], mesh['top'], mesh['obst'], F['Ux'], variant='thesis')
+    o = ThesisOracle(oracle_params(params))
+    o.init_func(mesh['cells'], mesh['top'], mesh['obst'], F['Ux'])
+    sm = psm_b200.PressureSurrogate('thesis', near_wall_sdf=0.05)
+    sm.load_params(params)
+    sm.init_tables(t)
+    yield z, mesh, F, params, t, o, sm
+    sm.close()
+
+
+def test_thesis_tables_and_plan(case):
+    z, mesh, F, params, t, o, sm = case
+    np.testing.assert_array_equal(t['vert'], o.vert)
+    np.testing.assert_array_equal(t['weights'], o.weights)
+    np.testing.assert_array_equal(t['vert_back'], o.vert_back)
+    np.testing.assert_array_equal(t['indices'], o.indices)
+    assert np.array_equal(t['sdfunct'] != 0, o.sdfunct[:, :, 0] != 0)
+    origins, il = sm.plan()
+    n_x, n_y, o_orig, o_il = o.block_plan()
+    np.testing.assert_array_equal(origins, np.array(o_orig, np.int32))
+    np.testing.assert_array_equal(il, np.array(o_il, np.int32))
+    g = sm.geometry()
+    assert g['n_blocks'] == (n_y + 2) * (n_x + 2) and g['overlap'] == 12
+
+
+def test_thesis_step_matches_reference_module(case):
+    z, mesh, F, params, t, o, sm = case
+    cells = syn.pack_cells(mesh, F, with_delta=False)
+    p, rc = sm.predict(cells)
+    assert rc == 0
+    r = o.py_func(F['Ux'], F['Uy'], F['p_prev'])
+    scale = params['maxs'][3] * r['U_max_norm'] ** 2
+    assert rel_l2(sm.stage('x_input'), r['x_input']) < 1e-4
+    assert rel_l2(sm.stage('mlp_out'), r['mlp_out'] * params['max_abs_output_PCA']) < 1e-4
+    assert rel_l2(sm.stage('blocks')[:, 0], r['blocks'][..., 0] * scale) < 1e-4
+    np.testing.assert_allclose(sm.stage('offsets')[0], r['offsets'] * scale, rtol=0, atol=1e-4 * np.abs(r['offsets'] * scale).max())
+    assert rel_l2(sm.stage('field')[0], r['field'] * scale) < 1e-3
+    # the pressures the reference module itself returned
+    kept_ref = z['p'] == F['p_prev']
+    assert np.array_equal(p == F['p_prev'], kept_ref)                     # near-wall / NaN fallback to p_prev, PMP:492-496
+    assert rel_l2(p[~kept_ref], z['p'][~kept_ref]) < 1e-3
+    assert rel_l2(p, r['p']) < 1e-3
+    # second step on the same input: bit-identical
+    p2, _ = sm.predict(cells)
+    np.testing.assert_array_equal(p, p2)
+
+
+def test_thesis_module_surface(case, monkeypatch):
+    """python_module.init_func / py_func with PSM_VARIANT=thesis: the reference's names and argument order."""
+    z, mesh, F, params, t, o, sm = case
+    import importlib
+    import python_module as pm
+    importlib.reload(pm)
+    one = psm_b200.PressureSurrogate('thesis', near_wall_sdf=0.05)
+    one.load_params(params)
+    pm.set_surrogate(one)
+    try:
+        cells = syn.pack_cells(mesh, F, with_delta=False)
+        assert pm.init_func(cells, mesh['top'], mesh['obst'], 0) == 0
+        p = pm.py_func(cells, 0)
+        ref, _ = sm.predict(cells)
+        np.testing.assert_array_equal(p, ref)
+    finally:
+        one.close()
