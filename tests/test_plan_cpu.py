@@ -169,3 +169,65 @@ def test_thesis_block_plan_bit_exact(H, W):
     assert plan['n_blocks'] == (n_y + 2) * (n_x + 2) == len(origins)
     np.testing.assert_array_equal(plan['origins'], np.array(origins, dtype=np.int32))
     np.testing.assert_array_equal(plan['indices_list'], np.array(il, dtype=np.int32))
+
+
+def _random_mask(rng, H, W):
+    """Union of a few random discs / bars removed from the flow domain (some large enough to empty whole strips)."""
+    mask = np.ones((H, W), np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for _ in range(int(rng.integers(0, 4))):
+        cy, cx, r = rng.integers(0, H), rng.integers(0, W), rng.integers(5, max(6, min(H, W) // 3))
+        mask[((yy - cy) ** 2 + (xx - cx) ** 2) <= r * r] = 0
+    if rng.random() < 0.3:                                   # a bar: empties full-width / full-height strips
+        if rng.random() < 0.5:
+            y = int(rng.integers(0, H - 40)); mask[y:y + int(rng.integers(10, 40)), :] = 0
+        else:
+            x = int(rng.integers(0, W - 40)); mask[:, x:x + int(rng.integers(10, 40))] = 0
+    return mask
+
+
+@pytest.mark.parametrize("variant,ov", [('deltaU_to_deltaP', 32), ('U_to_gradP', 96), ('thesis', 12)])
+def test_random_geometries_against_the_literal_loops(variant, ov):
+    """Seeded sweep over grid sizes and obstacle masks: offsets, NaN pattern, assembled field and shift of the compiled
+    plan equal the reference loop restated in oracle/assemble.py -- including masks that empty strips (NaN branches)."""
+    rng = np.random.default_rng({'deltaU_to_deltaP': 101, 'U_to_gradP': 202, 'thesis': 303}[variant])
+    st = 128 - ov
+    done = 0
+    while done < 12:
+        H, W = int(rng.integers(130, 520)), int(rng.integers(260, 640))
+        if variant != 'thesis' and (H - 128) % st == 0:
+            continue
+        mask = _random_mask(rng, H, W)
+        try:
+            plan = psm_b200.compile_plan(variant, H, W, mask, overlap=ov)
+        except _capi.PsmError as e:                          # geometries the reference itself rejects (asserts, unbound names)
+            assert e.code == _capi.PSM_ERR_GEOMETRY
+            continue
+        B, F = plan['n_blocks'], plan['n_fields']
+        blocks = rng.standard_normal((B, F, 128, 128))
+        n_x, n_y, origins, il = oracle_plan(variant, H, W, ov)
+        x_array = np.zeros((B, 128, 128, 3))
+        for k, (y0, x0) in enumerate(origins):
+            x_array[k, :, :, 2] = mask[y0:y0 + 128, x0:x0 + 128] * 0.5
+        c, fields = eval_plan(plan, blocks, mask)
+        for f in range(F):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore", category=RuntimeWarning)
+                if variant == 'thesis':
+                    ref, offs, _ = oasm.assemble_thesis(blocks[:, 0], x_array, il, n_x, n_y, 128, ov, W, H, return_offsets=True)
+                elif variant == 'deltaU_to_deltaP':
+                    ref, offs, _ = oasm.assemble_deltas(blocks[:, 0], x_array, il, n_x, n_y, 128, ov, W, H, return_offsets=True)
+                else:
+                    ref, offs, _ = oasm.assemble_gradp(('dp_dx', 'dp_dy')[f], blocks[:, f], x_array, il, n_x, n_y, 128, ov, W, H,
+                                                       return_offsets=True)
+                    ref = ref[0, :, :, 0]
+                mine = fields[f]
+                if variant == 'U_to_gradP':
+                    sh = (np.mean(3 * mine[:, 0] - mine[:, 1]) / 3) if f == 0 else (np.mean(3 * mine[1, :] - mine[2, :]) / 3)
+                else:
+                    sh = np.mean(3 * mine[:, -1] - mine[:, -2]) / 3
+            assert np.array_equal(np.isnan(offs), np.isnan(c[f])), (H, W)
+            np.testing.assert_allclose(c[f], offs, rtol=0, atol=1e-11, equal_nan=True)
+            assert np.array_equal(np.isnan(ref), np.isnan(mine - sh)), (H, W)
+            np.testing.assert_allclose(mine - sh, ref, rtol=0, atol=1e-10, equal_nan=True)
+        done += 1
