@@ -46,6 +46,16 @@ def compile_plan(variant, H, W, mask, shape=128, overlap=32):
     return dict(origins=origins, indices_list=il, owner=owner, rec=rec, tasks=tasks, lines=lines, n_blocks=B, n_fields=F)
 
 
+def register_host_buffer(a):
+    """Page-lock a NumPy buffer that lives for the whole run (FOAM/PythonComm_init.H:53 allocates the solver's rows once),
+    so that psm_predict copies it at full PCIe speed and the step stays one CUDA graph.  Returns True on success."""
+    return capi.load().psm_register_host_buffer(C.c_void_p(a.ctypes.data), a.nbytes) == 0
+
+
+def unregister_host_buffer(a):
+    return capi.load().psm_unregister_host_buffer(C.c_void_p(a.ctypes.data)) == 0
+
+
 def debug_gemm(A, B, mode=0, splits=1, device=0):
     """C[splits, M, N] = A[M, K] @ B[N, K].T on the GPU with one of the library's GEMM kernels (tests)."""
     lib = capi.load()

@@ -23,8 +23,9 @@ import numpy as np
 
 from psm_b200 import PressureSurrogate, tables as _tables
 from psm_b200 import params as _params
+from psm_b200 import register_host_buffer, unregister_host_buffer
 
-_state = {'sm': None}
+_state = {'sm': None, 'in_key': None, 'in_pinned': None, 'out': None}
 
 
 def _surrogate():
@@ -56,7 +57,29 @@ def init_func(array, top_boundary, obst_boundary, placeholder=None):
 
 
 def py_func(array_in, placeholder=None):
-    """PMP:249-517.  Returns p [nCells] float64 (deltaU_to_deltaP: p_prev + delta_p) or
-    grad p [nCells, 2] (U_to_gradP)."""
-    out, _ = _surrogate().predict(array_in)
+    """PMP:249-517.  Returns p [nCells] float64 (deltaU_to_deltaP: p_prev + delta_p; thesis: p) or
+    grad p [nCells, 2] (U_to_gradP).
+
+    The solver wraps ONE C buffer that lives for the whole run (FOAM/PythonComm_init.H:53, PythonComm.H:17): when the
+    same address comes in a second time it is page-locked in place (no extra copy), and the result is written into one
+    persistent page-locked array -- so every step after the second is a single replayed CUDA graph at PCIe speed.  The
+    returned array is reused by the next call (the solver copies it out immediately, PythonComm.H:31-35)."""
+    sm = _surrogate()
+    a = np.ascontiguousarray(array_in, dtype=np.float64)
+    if a is array_in or (isinstance(array_in, np.ndarray) and np.shares_memory(a, array_in)):
+        key = (a.ctypes.data, a.nbytes)
+        if key == _state['in_key'] and _state['in_pinned'] != key:
+            if _state['in_pinned'] is not None:
+                unregister_host_buffer(_state['in_pinned_arr'])
+            if register_host_buffer(a):
+                _state['in_pinned'], _state['in_pinned_arr'] = key, a
+        _state['in_key'] = key
+    n = a.shape[0]
+    shape = (n,) if sm.n_fields == 1 else (n, 2)
+    if _state['out'] is None or _state['out'].shape != shape:
+        if _state['out'] is not None:
+            unregister_host_buffer(_state['out'])
+        _state['out'] = np.empty(shape, dtype=np.float64)
+        register_host_buffer(_state['out'])
+    out, _ = sm.predict(a, out=_state['out'])
     return out
