@@ -231,7 +231,7 @@ def _free_port():
 
 
 @pytest.mark.parametrize("variant,world,halo", [('deltaU_to_deltaP', 2, 'cells'), ('U_to_gradP', 2, 'cells'),
-                                                ('deltaU_to_deltaP', 3, 'grid')])
+                                                ('deltaU_to_deltaP', 3, 'grid'), ('deltaU_to_deltaP', 4, 'cells')])
 def test_sharded_step_over_gloo_equals_unsharded_oracle(variant, world, halo):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
