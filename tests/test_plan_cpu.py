@@ -231,3 +231,31 @@ def test_random_geometries_against_the_literal_loops(variant, ov):
             assert np.array_equal(np.isnan(ref), np.isnan(mine - sh)), (H, W)
             np.testing.assert_allclose(mine - sh, ref, rtol=0, atol=1e-10, equal_nan=True)
         done += 1
+
+
+@pytest.mark.parametrize("variant,ov,H,W", [('deltaU_to_deltaP', 32, 300, 420), ('U_to_gradP', 96, 240, 340), ('thesis', 12, 260, 380)])
+def test_per_block_constants_are_removed_by_the_offset_chain(variant, ov, H, W):
+    """Known-answer test: blocks that are pure per-block constants re-assemble to ONE constant field -- every strip
+    mean then equals the block's constant, so the chain cancels them exactly, in the literal loop and in the compiled
+    plan alike.  (For a non-constant truth the reference is only approximate: e.g. SMC:292 compares a 32-row strip with
+    the mean of a (128 - p_i)-row strip; equality of plan and loop on such fields is covered above.)"""
+    rng = np.random.default_rng(7)
+    mask = disc_mask(H, W, H // 2, W // 3, 18)
+    plan = psm_b200.compile_plan(variant, H, W, mask, overlap=ov)
+    B, F = plan['n_blocks'], plan['n_fields']
+    n_x, n_y, origins, il = oracle_plan(variant, H, W, ov)
+    blocks = np.zeros((B, F, 128, 128))
+    x_array = np.zeros((B, 128, 128, 3))
+    for k, (y0, x0) in enumerate(origins):
+        x_array[k, :, :, 2] = mask[y0:y0 + 128, x0:x0 + 128] * 0.5
+        blocks[k] += rng.standard_normal((F, 1, 1))
+    c, fields = eval_plan(plan, blocks, mask)
+    for f in range(F):
+        if variant == 'thesis':
+            ref = oasm.assemble_thesis(blocks[:, 0], x_array, il, n_x, n_y, 128, ov, W, H)
+        elif variant == 'deltaU_to_deltaP':
+            ref = oasm.assemble_deltas(blocks[:, 0], x_array, il, n_x, n_y, 128, ov, W, H)
+        else:
+            ref = oasm.assemble_gradp(('dp_dx', 'dp_dy')[f], blocks[:, f], x_array, il, n_x, n_y, 128, ov, W, H)[0, :, :, 0]
+        assert np.ptp(ref) < 1e-12 and np.ptp(fields[f]) < 1e-12
+        assert abs(ref.mean()) < 1e-12                         # ... and the global shift pins that constant to zero
