@@ -629,7 +629,7 @@ void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s) {
 // The task list and the flow mask are static: they are fetched before waiting for the predicted blocks.
 __device__ __forceinline__ double ld_cg_f64(const double* p) { return __ldcg(p); }
 
-__device__ void offsets_body(const OffsetsArgs& a);
+__device__ void offsets_body(const OffsetsArgs& a, const DevRec* rec, const DevShiftTerm* terms, unsigned char* scratch);
 
 // MODE 0: means only; 1: single GPU, the last CTA also runs the offsets.  (Pushing the means to the peers from here and
 // waiting for theirs in the last CTA was measured slower at 2 GPUs -- one system-scope fence per CTA -- than the separate
@@ -659,6 +659,17 @@ __global__ void __launch_bounds__(256, 3) task_means_kernel(MeansArgs a, Offsets
             }
             bits |= (unsigned long long)(mrow & cols) << (4 * k);
         }
+    }
+    // fused offsets: the static recurrence records and shift terms go to shared memory NOW (before the wait), so the
+    // serial tail of the last CTA does not start with two dependent round trips to L2 / HBM
+    extern __shared__ __align__(16) unsigned char mk_smem[];
+    DevRec* s_rec = nullptr; DevShiftTerm* s_terms = nullptr;
+    if (MODE != 0) {
+        const int n = oa.B * oa.F, nt = oa.term_start[oa.F];
+        s_rec = reinterpret_cast<DevRec*>(mk_smem + (((size_t)n * 24 + 15) & ~(size_t)15));
+        s_terms = reinterpret_cast<DevShiftTerm*>(s_rec + n);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_rec[i] = oa.rec[i];
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) s_terms[i] = oa.terms[i];
     }
     pdl_wait();
     const float* src = a.blocks + ((long long)t.src * a.C + t.ch) * a.S * a.S + x;
@@ -701,12 +712,16 @@ __global__ void __launch_bounds__(256, 3) task_means_kernel(MeansArgs a, Offsets
         }
         __syncthreads();
         if (!s_last) return;
-        offsets_body(oa);
+        offsets_body(oa, s_rec, s_terms, mk_smem);
     }
 }
 void launch_means(const MeansArgs& a, const OffsetsArgs* fused, cudaStream_t s) {
     if (a.n_tasks <= 0) return;
-    if (fused) launch_k(task_means_kernel<1>, dim3(a.n_tasks), dim3(256), (size_t)fused->B * fused->F * 24, s, a, *fused);
+    if (fused) {
+        const size_t n = (size_t)fused->B * fused->F;
+        const size_t smem = ((n * 24 + 15) & ~(size_t)15) + n * sizeof(DevRec) + (size_t)fused->term_start[fused->F] * sizeof(DevShiftTerm);
+        launch_k(task_means_kernel<1>, dim3(a.n_tasks), dim3(256), smem, s, a, *fused);
+    }
     else launch_k(task_means_kernel<0>, dim3(a.n_tasks), dim3(256), 0, s, a, OffsetsArgs{});
 }
 
@@ -716,17 +731,16 @@ void launch_means(const MeansArgs& a, const OffsetsArgs* fused, cudaStream_t s) 
 //      ceil(log2(depth)) rounds; then the global shift of SMC:350 / GRAD:358-361 from the per-run
 //      line sums.  Single CTA: the whole problem is a few thousand scalars.  In the multi-GPU path
 //      every rank evaluates this redundantly on the all-reduced means.
-__device__ void offsets_body(const OffsetsArgs& a) {
+__device__ void offsets_body(const OffsetsArgs& a, const DevRec* rec, const DevShiftTerm* terms, unsigned char* off_smem) {
     const int n = a.B * a.F;
     // pointer jumping in shared memory when the forest fits (n <= kOffsetsSmemMax), else in the global scratch
-    extern __shared__ unsigned char off_smem[];
     const bool in_smem = n <= kOffsetsSmemMax;
     double* d_cur = in_smem ? reinterpret_cast<double*>(off_smem) : a.dbuf0;
     double* d_nxt = in_smem ? d_cur + n : a.dbuf1;
     int32_t* p_cur = in_smem ? reinterpret_cast<int32_t*>(d_nxt + n) : a.pbuf0;
     int32_t* p_nxt = in_smem ? p_cur + n : a.pbuf1;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const DevRec r = a.rec[i];
+        const DevRec r = rec[i];
         const int f = i / a.B;
         double d = ld_cg_f64(a.means + r.ta) - (r.tb >= 0 ? ld_cg_f64(a.means + r.tb) : a.ref_bc);
         d_cur[i] = d;
@@ -751,7 +765,7 @@ __device__ void offsets_body(const OffsetsArgs& a) {
     for (int f = 0; f < a.F; ++f) {
         double acc = 0.0;
         for (int i = a.term_start[f] + threadIdx.x; i < a.term_start[f + 1]; i += blockDim.x) {
-            const DevShiftTerm t = a.terms[i];
+            const DevShiftTerm t = terms[i];
             acc += (double)t.coef * (ld_cg_f64(a.means + t.task) - (double)t.n * d_cur[f * a.B + t.block]);
         }
         acc = warp_sum(acc);
@@ -775,7 +789,8 @@ __device__ void offsets_body(const OffsetsArgs& a) {
 __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
     pdl_enter();
     if (a.p2p) p2p_wait(a.p2p, 1, 0xFFu);          // every rank's strip means have been pushed into a.means
-    offsets_body(a);
+    extern __shared__ unsigned char off_smem[];
+    offsets_body(a, a.rec, a.terms, off_smem);
 }
 void launch_offsets(const OffsetsArgs& a, cudaStream_t s) {
     const int n = a.B * a.F;
