@@ -32,12 +32,22 @@ def select_num_pc(explained_variance_ratio, var, max_num_PC):
     return a if 1 < a <= max_num_PC else max_num_PC
 
 
+def select_num_pc_thesis(explained_variance_ratio, var):
+    """PMP:112-113: ``int(argmax(cumsum > var))`` -- no lower bound, no cap (0.95 for p, 0.995 for the input)."""
+    return int(np.argmax(np.asarray(explained_variance_ratio).cumsum() > var))
+
+
 def from_reference_objects(maxs, pca_in, pca_p, dense_kernels, dense_biases, var_in=0.95, var_p=0.95,
-                           max_num_PC=128, scaler=None, maxs_PCA=None, n_out_channels=1):
+                           max_num_PC=128, scaler=None, maxs_PCA=None, n_out_channels=1, thesis=False):
     """Assemble the dict from the reference's own artefact objects (unpickled PCA objects with
-    ``components_``/``mean_``/``explained_variance_ratio_``, Keras weight lists)."""
-    pc_in = select_num_pc(pca_in.explained_variance_ratio_, var_in, max_num_PC)
-    pc_p = select_num_pc(pca_p.explained_variance_ratio_, var_p, max_num_PC)
+    ``components_``/``mean_``/``explained_variance_ratio_``, Keras weight lists).  ``thesis=True`` applies the
+    component cuts of the solver module (PMP:112-113: 0.995 for the input, 0.95 for p, uncapped) instead of SMC:86-87."""
+    if thesis:
+        pc_in = select_num_pc_thesis(pca_in.explained_variance_ratio_, 0.995)
+        pc_p = select_num_pc_thesis(pca_p.explained_variance_ratio_, 0.95)
+    else:
+        pc_in = select_num_pc(pca_in.explained_variance_ratio_, var_in, max_num_PC)
+        pc_p = select_num_pc(pca_p.explained_variance_ratio_, var_p, max_num_PC)
     p = dict(maxs=np.asarray(maxs, dtype=np.float64), n_out_channels=n_out_channels,
              pca_in_components=np.asarray(pca_in.components_)[:pc_in], pca_in_mean=np.asarray(pca_in.mean_),
              pca_out_components=np.asarray(pca_p.components_)[:pc_p], pca_out_mean=np.asarray(pca_p.mean_),
