@@ -367,6 +367,7 @@ class ThesisOracle:
         # PMP:225 allocates `indices` with np.empty; the raster leaves invalid points untouched -- zero in practice
         self.indices, self.sdfunct = _domain.index_raster(X0, Y0, self.delta, self.grid_shape_y, self.grid_shape_x,
                                                           domain_bool, ux_interp, sdf)
+        self.valid_rows = np.asarray(domain_bool, dtype=bool) & ~np.isnan(ux_interp)      # rows PMP:233-243 writes
         return 0
 
     def block_plan(self):

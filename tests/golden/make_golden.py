@@ -346,6 +346,32 @@ def golden_grad(name, mesh_kw, seed, pc_in=24, pc_p=20):
     print(name, 'grid', out['grid_shape'], 'blocks', b0.shape, 'nan', int(np.isnan(r0).sum()), int(np.isnan(r1).sum()))
 
 
+
+class sentinel_empty:
+    """PMP:225 allocates ``indices`` with ``np.empty`` and its raster loop (PMP:233-243) writes only the valid rows, so the
+    other rows are uninitialised memory.  While ``init_func`` runs, ``np.empty`` is wrapped to pre-fill integer-free float
+    buffers with a sentinel: the rows the loop writes can then be told apart and ONLY those are hashed."""
+    VALUE = -7.0
+
+    def __enter__(self):
+        self._orig = np.empty
+
+        def filled(shape, *a, **k):
+            out = self._orig(shape, *a, **k)
+            if out.dtype.kind == 'f':
+                out.fill(self.VALUE)
+            return out
+        np.empty = filled
+        return self
+
+    def __exit__(self, *exc):
+        np.empty = self._orig
+
+
+def written_rows(indices):
+    return ~np.all(indices == sentinel_empty.VALUE, axis=1)
+
+
 def golden_pmp_init(name, mesh_kw, seed):
     """Run the reference solver-side ``init_func`` (PMP:172-247): both table directions,
     ``domain_dist`` ([::10] sub-sampling, 2-decimal bbox) and the raster loop."""
@@ -360,16 +386,19 @@ def golden_pmp_init(name, mesh_kw, seed):
             sys.path.insert(0, os.path.join(REF, 'Thesis_Work/Chapter5/parallelized/test_case'))
             import python_module as PMP
             arr = syn.pack_cells(mesh, F, with_delta=False)
-            PMP.init_func(arr, mesh['top'], mesh['obst'], 0)
+            with sentinel_empty():
+                PMP.init_func(arr, mesh['top'], mesh['obst'], 0)
         finally:
             os.chdir(cwd)
+    wr = written_rows(PMP.indices)
     out = dict(
         mesh_kw=np.array(repr(mesh_kw)), seed=seed,
         grid_shape=np.array([PMP.grid_shape_y, PMP.grid_shape_x]),
         vert_fwd_sha=np.array(sha(PMP.vert_OFtoNP.astype(np.int32))), weights_fwd_sub=PMP.weights_OFtoNP[::17],
         vert_back_sha=np.array(sha(PMP.vert_NPtoOF.astype(np.int32))), vert_back_sub=PMP.vert_NPtoOF[::5].astype(np.int32),
         weights_back_sub=PMP.weights_NPtoOF[::5],
-        indices_sha=np.array(sha(PMP.indices.astype(np.int64))), sdfunct=PMP.sdfunct[:, :, 0].astype(np.float32))
+        written_sha=np.array(sha(wr.astype(np.uint8))), indices_sha=np.array(sha(PMP.indices[wr].astype(np.int64))),
+        sdfunct=PMP.sdfunct[:, :, 0].astype(np.float32))
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
     print(name, 'grid', out['grid_shape'])
 
@@ -396,13 +425,16 @@ def golden_pmp_step(name, mesh_kw, seed, pc_in=24, pc_p=20):
             assert (PMP.PC_input, PMP.PC_p) == (pc_in, pc_p), (PMP.PC_input, PMP.PC_p)
             PMP.memory = lambda: ''
             arr = syn.pack_cells(mesh, F, with_delta=False)
-            PMP.init_func(arr, mesh['top'], mesh['obst'], 0)
+            with sentinel_empty():
+                PMP.init_func(arr, mesh['top'], mesh['obst'], 0)
+            wr = written_rows(PMP.indices)
+            PMP.indices[~wr] = 0           # what uninitialised memory holds 'in practice' (SURVEY.md 9.3): py_func reads these rows
             p = np.array(PMP.py_func(arr, 0), dtype=np.float64)
         finally:
             os.chdir(cwd)
     out = dict(mesh_kw=np.array(repr(mesh_kw)), seed=seed, pc_in=pc_in, pc_p=pc_p,
                grid_shape=np.array([PMP.grid_shape_y, PMP.grid_shape_x]), p=p,
-               indices_sha=np.array(sha(PMP.indices.astype(np.int64))))
+               written_sha=np.array(sha(wr.astype(np.uint8))), indices_sha=np.array(sha(PMP.indices[wr].astype(np.int64))))
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
     print(name, 'grid', out['grid_shape'], 'cells', p.shape, 'kept p_prev at', int((p == arr[:, 4]).sum()), 'cells')
 
