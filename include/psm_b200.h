@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PSM_API_VERSION 3
+#define PSM_API_VERSION 4
 
 typedef struct psm_handle psm_handle;
 
@@ -49,7 +49,9 @@ enum psm_variant_code {
 
 enum psm_standardization_code {
     PSM_STD = 0,              /* (z - mean_in) / std_in ; r * std_out + mean_out   SMC:505-512,532-533 */
-    PSM_MAX_ABS = 1           /* z / max_abs_input_PCA ; r * max_abs_output_PCA    SMC:521-523, GRAD:525,531 */
+    PSM_MAX_ABS = 1,          /* z / max_abs_input_PCA ; r * max_abs_output_PCA    SMC:521-523, GRAD:525,531 */
+    PSM_MIN_MAX = 2           /* (z - min_in) / (max_in - min_in) ; r * (max_out - min_out) + min_out   SMC:513-520,535-536.
+                                 min_* travel in the mean_* slots of psm_params, max_* in the std_* slots                 */
 };
 
 /* Constants the reference hard-codes or takes from argparse (EP:89-98; PMP:195,303-304). */
@@ -98,8 +100,8 @@ typedef struct psm_params {
     const double* pca_in_mean;         /* [S*S*3]                                               */
     const double* pca_out_components;  /* [pc_p][S*S*n_out_channels]                            */
     const double* pca_out_mean;        /* [S*S*n_out_channels]                                  */
-    const double* mean_in;  const double* std_in;    /* [pc_in]  (PSM_STD)                      */
-    const double* mean_out; const double* std_out;   /* [pc_p]   (PSM_STD)                      */
+    const double* mean_in;  const double* std_in;    /* [pc_in]  PSM_STD: mean, std;  PSM_MIN_MAX: min, max  */
+    const double* mean_out; const double* std_out;   /* [pc_p]   PSM_STD: mean, std;  PSM_MIN_MAX: min, max  */
     double  max_abs_input_PCA;    /* PSM_MAX_ABS                                                */
     double  max_abs_output_PCA;
     int32_t n_dense;              /* Dense layers incl. the linear output layer (4 for MLP_small, UTL:437-439) */
@@ -234,6 +236,22 @@ int psm_predict(psm_handle* h, const double* cells, int64_t n_cells, double* p_o
  * the handle's stream unless `sync` is non-zero.  The status of an asynchronous call is
  * reported by the next synchronous call or psm_synchronize. */
 int psm_predict_device(psm_handle* h, const double* d_cells, int64_t n_cells, double* d_p_out, int32_t sync);
+
+/* The same step on the solver's NATIVE field storage -- no row packing (the forAll fill loop of FOAM/PythonComm.H:2-9 and its
+ * double[nCells][5] buffer, FOAM/PythonComm_init.H:53, disappear; Cx, Cy are static and were consumed by init):
+ *   U   : host double[n_cells][u_stride], u_stride = 3 for OpenFOAM's `vector` (U.primitiveField().cdata()) or 2; only
+ *         components 0 and 1 are read.
+ *   dU  : deltaU_to_deltaP only, same layout, or NULL: the handle keeps U(t-1) resident and forms dU on the device (first
+ *         call returns PSM_SKIPPED), exactly as with 5-column rows.
+ *   p   : host double[n_cells] previous pressure (p.primitiveField().cdata()), or NULL: the output is then the raw prediction
+ *         (delta_p; 0 where the reference keeps p_prev, PMP:492-496) and the solver adds it to its own field (SMC:644-645).
+ *   out : host double[n_cells] (deltaU_to_deltaP / thesis) or double[n_cells][2] (U_to_gradP).
+ * 24 B (U) + 8 B (p) per cell go up instead of 40; the copy of p overlaps the kernels (only the last one reads it). */
+int psm_predict_fields(psm_handle* h, const double* U, int32_t u_stride, const double* dU, const double* p, int64_t n_cells,
+                       double* out);
+/* Device-pointer form of psm_predict_fields (p is read in place, nothing is copied); asynchronous unless `sync`. */
+int psm_predict_fields_device(psm_handle* h, const double* d_U, int32_t u_stride, const double* d_dU, const double* d_p,
+                              int64_t n_cells, double* d_out, int32_t sync);
 
 int psm_synchronize(psm_handle* h);
 

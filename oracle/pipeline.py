@@ -26,7 +26,7 @@ class SurrogateParams:
     def __init__(self, maxs, pca_in_components, pca_in_mean, pca_out_components, pca_out_mean,
                  mlp_weights, mlp_biases, standardization='std', mean_in=None, std_in=None,
                  mean_out=None, std_out=None, max_abs_input_PCA=None, max_abs_output_PCA=None,
-                 n_out_channels=1):
+                 n_out_channels=1, min_in=None, max_in=None, min_out=None, max_out=None):
         self.maxs = np.asarray(maxs, dtype=np.float64)
         self.pca_in_components = np.asarray(pca_in_components)       # [pc_in, S*S*3]
         self.pca_in_mean = np.asarray(pca_in_mean)                   # [S*S*3]
@@ -39,6 +39,7 @@ class SurrogateParams:
         self.mean_out, self.std_out = mean_out, std_out
         self.max_abs_input_PCA = max_abs_input_PCA
         self.max_abs_output_PCA = max_abs_output_PCA
+        self.min_in, self.max_in, self.min_out, self.max_out = min_in, max_in, min_out, max_out     # 'min_max', SMC:513-520
         self.n_out_channels = n_out_channels
 
     @property
@@ -176,6 +177,8 @@ class DeltasOracle:
 
         if P.standardization == 'std':                                            # SMC:505-523
             x_input = (input_transformed - P.mean_in) / P.std_in
+        elif P.standardization == 'min_max':
+            x_input = (input_transformed - P.min_in) / (P.max_in - P.min_in)
         elif P.standardization == 'max_abs':
             x_input = input_transformed / P.max_abs_input_PCA
         else:
@@ -184,6 +187,8 @@ class DeltasOracle:
         mlp_out = res_concat.copy()
         if P.standardization == 'std':                                            # SMC:532-537
             res_concat = (res_concat * P.std_out) + P.mean_out
+        elif P.standardization == 'min_max':
+            res_concat = res_concat * (P.max_out - P.min_out) + P.min_out
         else:
             res_concat = res_concat * P.max_abs_output_PCA
         res_flat_inv = np.dot(res_concat, P.pca_out_components) + P.pca_out_mean  # SMC:541

@@ -145,6 +145,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+    // The B operand of every caller is STATIC (PCA matrix / Dense kernel): the producer requests the B tiles of the first
+    // ring pass before waiting for the previous kernel, so their HBM / L2 latency overlaps its tail.
+    const int n_pre = g.b_static ? min(nkb, STAGES) : 0;
+    if (threadIdx.x == 0) {
+        for (int it = 0; it < n_pre; ++it) {
+            mbar_expect_tx(full_bar(it), A_BYTES + B_BYTES);
+            tma_load_2d(base + it * STAGE + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(it));
+        }
+    }
     pdl_wait();                                                  // barriers + TMEM are set up while the previous kernel drains
 
     if (warp == 0) {
@@ -153,11 +162,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
                 const uint32_t st = base + s * STAGE;
+                if (it >= n_pre) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
+                    tma_load_2d(st + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(s));
+                }
                 tma_load_2d(st, &tmA, (kb0 + it) * BK, m0, full_bar(s));
-                tma_load_2d(st + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(s));
             }
         }
     } else if (warp == 1) {
@@ -350,6 +361,14 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
     cluster_sync_all();                                          // every CTA of the cluster runs: its shared memory may be written remotely
+    // the Dense kernels are static: their tiles of the first ring pass are requested before waiting for the previous layer
+    const int n_pre = g.b_static ? min(nkb, STAGES) : 0;
+    if (threadIdx.x == 0) {
+        for (int it = 0; it < n_pre; ++it) {
+            mbar_expect_tx(full_bar(it), A_BYTES + B_BYTES);
+            tma_load_2d(base + it * STAGE + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(it));
+        }
+    }
     pdl_wait();                                                  // barriers + TMEM are set up while the previous kernel drains
 
     if (warp == 0) {
@@ -357,11 +376,13 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
                 const uint32_t st = base + s * STAGE;
+                if (it >= n_pre) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
+                    tma_load_2d(st + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(s));
+                }
                 tma_load_2d(st, &tmA, (kb0 + it) * BK, m0, full_bar(s));
-                tma_load_2d(st + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(s));
             }
         }
         __syncwarp();
@@ -896,8 +917,24 @@ pca_inverse_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_arrive(a_conv);
         }
         // ---- epilogue: thread <-> pixel (TMEM lane); 32 blocks per tcgen05.ld; coalesced 128 B rows per block ----
-        pdl_wait();                                              // g.sc->out_scale belongs to this step
         const int q = warp & 3;
+        // strip sums (StripRows): this CTA's static entry list, 32 entries per batch (lane i holds entry e_base + i); the
+        // first batch is fetched before the wait
+        const StripRows& sr = g.strips;
+        const bool strips = sr.row_ptr != nullptr;
+        int e = 0, e_end = 0, e_base = 0;
+        int my_src = 0x7fffffff, my_slot = 0; uint32_t my_w = 0u;
+        auto load_batch = [&](int base) {
+            const int idx = base + lane;
+            my_src = 0x7fffffff;
+            if (idx < e_end) { my_src = __ldg(sr.src + idx); my_slot = __ldg(sr.slot + idx); my_w = __ldg(sr.w + (size_t)q * sr.n_ent + idx); }
+        };
+        if (strips) {
+            e = __ldg(sr.row_ptr + blockIdx.x); e_end = __ldg(sr.row_ptr + blockIdx.x + 1);
+            e_base = e;
+            load_batch(e_base);
+        }
+        pdl_wait();                                              // g.sc->out_scale belongs to this step
         const int P = p0 + q * 32 + lane;                        // planar pixel index (c*S*S + ly*S + lx)
         const float pm = __ldg(g.pmean + P);
         const float o_scale = g.sc->out_scale;
@@ -912,8 +949,29 @@ pca_inverse_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * I_NB + j0), v);
                 float* dst = g.blocks + (size_t)b0 * g.block_stride + P;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (b0 + j < g.B) dst[(size_t)j * g.block_stride] = (v[j] + pm) * o_scale;
+                for (int j = 0; j < 32; ++j) {
+                    if (b0 + j < g.B) {
+                        const float o = (v[j] + pm) * o_scale;
+                        dst[(size_t)j * g.block_stride] = o;
+                        if (strips) {
+                            // every entry of this pixel row whose source is block b0 + j (warp-uniform control flow)
+                            while (e < e_end) {
+                                const int k = e - e_base;
+                                if (__shfl_sync(0xffffffffu, my_src, k) != b0 + j) break;
+                                const uint32_t wq = __shfl_sync(0xffffffffu, my_w, k);
+                                if (wq) {
+                                    float val = ((wq >> lane) & 1u) ? o : 0.f;
+#pragma unroll
+                                    for (int sh = 16; sh > 0; sh >>= 1) val += __shfl_xor_sync(0xffffffffu, val, sh);
+                                    const int sl = __shfl_sync(0xffffffffu, my_slot, k);
+                                    if (lane == 0) sr.rowpart[(size_t)sl * 4 + q] = val;
+                                }
+                                ++e;
+                                if (e - e_base == 32) { e_base = e; load_batch(e_base); }
+                            }
+                        }
+                    }
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(acc_empty(buf));

@@ -14,6 +14,8 @@
 #include "../../include/psm_b200.h"
 #include "psm_kernels.cuh"
 #include "psm_plan.h"
+#include "psm_internal.h"
+#include <cstdarg>
 
 using namespace psm;
 
@@ -25,6 +27,7 @@ thread_local std::string g_create_error;
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 inline bool env_on(const char* name) { const char* e = getenv(name); return e && e[0] && e[0] != '0'; }
 inline long long round_up_ll(long long v, long long m) { return (v + m - 1) / m * m; }
+inline long long Bp2_guard(int B) { return (B + 127) / 128 * 128; }
 }  // namespace
 
 // NCCL is bound at run time (dlopen) so that single-GPU callers need no NCCL at all and a process that
@@ -127,6 +130,9 @@ struct psm_handle {
     CoverEntry *d_rowcov = nullptr, *d_colcov = nullptr; bool fused_extract = false;   // gather writes the block operand itself
     bool keep_grid = false;           // fused path: also store the grid planes every step (PSM_KEEP_GRID=1); else psm_get_stage rebuilds them
     DevTask* d_tasks = nullptr; DevRec* d_rec = nullptr; int n_tasks = 0 /* local */, rounds = 0;
+    // strip sums out of the PCA-inverse epilogue (StripRows): static per-row entry lists + the row-partial table
+    int32_t *d_sr_rowptr = nullptr, *d_sr_src = nullptr, *d_sr_slot = nullptr; uint32_t* d_sr_w = nullptr; int sr_n_ent = 0;
+    float* d_rowpart = nullptr; bool strip_fuse = false;
     float* d_zc = nullptr;            // [B_pad][pc_in_pad]
 
     // ---- per-step buffers ---------------------------------------------------------------------------
@@ -152,11 +158,23 @@ struct psm_handle {
     bool last_host = false;
     // whole-step CUDA graphs, keyed by the caller's buffers (the solver passes the same ones every step,
     // FOAM/PythonComm_init.H:53)
-    struct StepGraph { const void* in = nullptr; void* out = nullptr; bool host = false, timed = false; cudaGraphExec_t exec = nullptr; unsigned long long used = 0; };
+    struct StepGraph { const void *in = nullptr, *in2 = nullptr, *in3 = nullptr; void* out = nullptr; int stride = 0; cudaGraphExec_t exec = nullptr; unsigned long long used = 0; };
     StepGraph graphs[4];             // small LRU: a solver alternates between at most a few buffer pairs
     unsigned long long graph_clock = 0;
     bool use_graphs = true;
     int eager_steps = 0;
+    // host entry points: a second stream copies the caller's p array while the kernels already run (only the last kernel reads it)
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_u = nullptr, ev_p = nullptr;
+    bool pprev_zero = false;          // d_pprev currently holds zeros (psm_predict_fields without p)
+    size_t cells_capacity = 0;        // doubles in d_cells
+};
+
+// What the first kernel of a step reads (device pointers): the solver's packed rows, or its native field arrays.
+struct StepInput {
+    const double* rows = nullptr;                                   // double[n][input_cols]
+    const double* U = nullptr; const double* dU = nullptr; int u_stride = 0;   // double[n][u_stride] (psm_predict_fields*)
+    const double* p_dev = nullptr;                                  // fields: previous pressure read in place (NULL: h->d_pprev)
+    bool wait_p = false;                                            // host fields path: the p copy runs on copy_stream
 };
 
 #define PSM_FAIL(h, code, ...)                                    \
@@ -198,6 +216,19 @@ static int upload(psm_handle* h, T** p, const std::vector<T>& v) {
     } while (0)
 
 
+namespace psm {
+int handle_shape(const psm_handle* h) { return h ? h->S : 0; }
+int handle_fail(psm_handle* h, int code, const char* fmt, ...) {
+    char b[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(b, sizeof b, fmt, ap);
+    va_end(ap);
+    if (h) h->err = b; else g_create_error = b;
+    return code;
+}
+}  // namespace psm
+
 extern "C" int psm_api_version(void) { return PSM_API_VERSION; }
 
 extern "C" const char* psm_last_error(const psm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -234,6 +265,10 @@ extern "C" int psm_create(psm_handle** out, const psm_config* cfg) {
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e); delete h; return PSM_ERR_CUDA;
     }
+    if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_u, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_p, cudaEventDisableTiming) != cudaSuccess) {
+        g_create_error = "cannot create the copy stream / events"; cudaStreamDestroy(h->stream); delete h; return PSM_ERR_CUDA;
+    }
     if (cudaHostAlloc((void**)&h->h_sc, sizeof(Scalars), cudaHostAllocMapped) != cudaSuccess) { g_create_error = "cudaMallocHost failed"; cudaStreamDestroy(h->stream); delete h; return PSM_ERR_CUDA; }
     memset(h->h_sc, 0, sizeof(Scalars));
     {
@@ -249,6 +284,9 @@ extern "C" int psm_destroy(psm_handle* h) {
     if (!h) return PSM_OK;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_u) cudaEventDestroy(h->ev_u);
+    if (h->ev_p) cudaEventDestroy(h->ev_p);
     for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -273,7 +311,8 @@ extern "C" int psm_load_params(psm_handle* h, const psm_params* p) {
     if (!p->pca_in_components || !p->pca_in_mean || !p->pca_out_components || !p->pca_out_mean || !p->layer_dims ||
         !p->dense_kernels || !p->dense_biases) PSM_FAIL(h, PSM_ERR_INVALID, "NULL parameter array");
     if (p->layer_dims[0] != p->pc_in || p->layer_dims[p->n_dense] != p->pc_p) PSM_FAIL(h, PSM_ERR_INVALID, "layer_dims must start at pc_in and end at pc_p");
-    if (p->standardization == PSM_STD && (!p->mean_in || !p->std_in || !p->mean_out || !p->std_out)) PSM_FAIL(h, PSM_ERR_INVALID, "PSM_STD needs mean/std arrays");
+    if (p->standardization != PSM_STD && p->standardization != PSM_MAX_ABS && p->standardization != PSM_MIN_MAX) PSM_FAIL(h, PSM_ERR_INVALID, "unknown standardization code %d", p->standardization);
+    if (p->standardization != PSM_MAX_ABS && (!p->mean_in || !p->std_in || !p->mean_out || !p->std_out)) PSM_FAIL(h, PSM_ERR_INVALID, "PSM_STD / PSM_MIN_MAX need the four per-component arrays");
     h->C = C; h->F = C; h->pc_in = p->pc_in; h->pc_p = p->pc_p; h->n_dense = p->n_dense; h->standardization = p->standardization;
     memcpy(h->maxs, p->maxs, sizeof h->maxs);
     // widths are padded to 128: the fused Dense kernel gives each of the 8 CTAs of a cluster N/8 (>= 16) columns
@@ -310,6 +349,7 @@ extern "C" int psm_load_params(psm_handle* h, const psm_params* p) {
         for (int n = 0; n < p->pc_in; ++n) {
             double a, m;
             if (p->standardization == PSM_STD) { a = 1.0 / p->std_in[n]; m = p->mean_in[n]; }      // SMC:512
+            else if (p->standardization == PSM_MIN_MAX) { a = 1.0 / (p->std_in[n] - p->mean_in[n]); m = p->mean_in[n]; }   // SMC:520 (min in mean_in, max in std_in)
             else { a = 1.0 / p->max_abs_input_PCA; m = 0.0; }                                      // SMC:523
             h->in_a[n] = (float)a;
             h->in_b[n] = (float)(-(mconst[n] + m) * a);
@@ -347,6 +387,7 @@ extern "C" int psm_load_params(psm_handle* h, const psm_params* p) {
         std::vector<float> s(h->pc_p_pad, 0.f), m(h->pc_p_pad, 0.f);
         for (int n = 0; n < p->pc_p; ++n) {
             if (p->standardization == PSM_STD) { s[n] = (float)p->std_out[n]; m[n] = (float)p->mean_out[n]; }
+            else if (p->standardization == PSM_MIN_MAX) { s[n] = (float)(p->std_out[n] - p->mean_out[n]); m[n] = (float)p->mean_out[n]; }   // SMC:536
             else { s[n] = (float)p->max_abs_output_PCA; m[n] = 0.f; }
         }
         TRY(upload(h, &h->d_out_s, s));
@@ -556,21 +597,21 @@ static int init_local(psm_handle* h, LocalInit& L) {
         TRY(upload(h, &h->d_bx0, bx0));
         {   // which block rows / block columns cover a pixel row / a 4-pixel column group (fused gather + extraction)
             const int nrows_g = h->H + L.local_ext, nbr = L.blk_row1 - L.blk_row0;
-            bool ok = (W % 4 == 0) && L.ext_rows == 0 && !env_on("PSM_NO_FUSED_EXTRACT");
+            bool ok = (W % 4 == 0) && L.ext_rows == 0 && !env_on("PSM_NO_FUSED_EXTRACT") && (long long)Bp2_guard(h->B) * 2 * S2 < (1ll << 31);
             for (int j = 0; j < ncolb && ok; ++j) ok = (bx0[j] % 4 == 0);
             std::vector<CoverEntry> rcv(nrows_g), ccv(W / 4 + 1);
             for (int y = 0; y < nrows_g && ok; ++y) {
                 CoverEntry ce{}; 
                 for (int r = 0; r < nbr; ++r) {
                     const int y0 = by0[r * ncolb];
-                    if (y >= y0 && y < y0 + S) { if (ce.n >= 7) { ok = false; break; } ce.idx[ce.n++] = (int16_t)r; }
+                    if (y >= y0 && y < y0 + S) { if (ce.n >= 7) { ok = false; break; } ce.off[ce.n++] = (int32_t)((long long)r * ncolb * 2 * S2 + (long long)(y - y0) * S); }
                 }
                 rcv[y] = ce;
             }
             for (int xg = 0; xg < W / 4 && ok; ++xg) {
                 CoverEntry ce{};
                 for (int j = 0; j < ncolb; ++j)
-                    if (xg * 4 >= bx0[j] && xg * 4 < bx0[j] + S) { if (ce.n >= 7) { ok = false; break; } ce.idx[ce.n++] = (int16_t)j; }
+                    if (xg * 4 >= bx0[j] && xg * 4 < bx0[j] + S) { if (ce.n >= 7) { ok = false; break; } ce.off[ce.n++] = (int32_t)((long long)j * 2 * S2 + (xg * 4 - bx0[j])); }
                 ccv[xg] = ce;
             }
             h->fused_extract = ok;
@@ -602,6 +643,38 @@ static int init_local(psm_handle* h, LocalInit& L) {
             h->term_start[f + 1] = (int)terms.size();
         }
         h->n_tasks = (int)tk.size();
+        {   // row partials of every task: slot = part_base + (row - y0); one entry per (task, block row it covers), grouped by the
+            // CTA of pca_inverse_t_kernel that holds that pixel row (r = channel * S + local row), sorted by source block
+            int n_slots = 0;
+            for (DevTask& t : tk) { t.part_base = n_slots; n_slots += t.y1 - t.y0; }
+            struct Ent { int32_t src, slot; uint32_t w[4]; };
+            std::vector<std::vector<Ent>> rows((size_t)h->C * S);
+            for (const DevTask& t : tk)
+                for (int ly = t.y0; ly < t.y1; ++ly) {
+                    Ent e{t.src, t.part_base + (ly - t.y0), {0u, 0u, 0u, 0u}};
+                    const uint8_t* mrow = (t.kind == 0) ? L.mask_global + (size_t)(t.my0 + ly) * W + t.mx0 : nullptr;
+                    for (int lx = t.x0; lx < t.x1; ++lx)
+                        if (!mrow || mrow[lx]) e.w[lx >> 5] |= 1u << (lx & 31);
+                    rows[(size_t)t.ch * S + ly].push_back(e);
+                }
+            std::vector<int32_t> rp((size_t)h->C * S + 1, 0), es, el;
+            size_t n_ent = 0;
+            for (auto& r : rows) n_ent += r.size();
+            std::vector<uint32_t> ew(4 * (n_ent ? n_ent : 1), 0u);
+            es.reserve(n_ent); el.reserve(n_ent);
+            for (size_t r = 0; r < rows.size(); ++r) {
+                std::stable_sort(rows[r].begin(), rows[r].end(), [](const Ent& a, const Ent& b) { return a.src < b.src; });
+                for (const Ent& e : rows[r]) {
+                    for (int q = 0; q < 4; ++q) ew[(size_t)q * n_ent + es.size()] = e.w[q];
+                    es.push_back(e.src); el.push_back(e.slot);
+                }
+                rp[r + 1] = (int32_t)es.size();
+            }
+            h->sr_n_ent = (int)n_ent;
+            if (es.empty()) { es.push_back(0); el.push_back(0); }
+            TRY(upload(h, &h->d_sr_rowptr, rp)); TRY(upload(h, &h->d_sr_src, es)); TRY(upload(h, &h->d_sr_slot, el)); TRY(upload(h, &h->d_sr_w, ew));
+            TRY(dalloc(h, &h->d_rowpart, (size_t)(n_slots ? n_slots : 1) * 4));
+        }
         TRY(upload(h, &h->d_tasks, tk));
         TRY(upload(h, &h->d_terms, terms));
         std::vector<DevRec> rc2(P.rec.size());
@@ -627,10 +700,11 @@ static int init_local(psm_handle* h, LocalInit& L) {
     const int Bp = h->B_pad;
     int maxw = 0;
     for (int d : h->dims_pad) maxw = d > maxw ? d : maxw;
-    TRY(dalloc(h, &h->d_cells, (size_t)N * ncol));
+    h->cells_capacity = (size_t)N * (ncol > 6 ? ncol : 6);          // rows, or U + dU as double[n][3] each (psm_predict_fields)
+    TRY(dalloc(h, &h->d_cells, h->cells_capacity));
     TRY(dalloc(h, &h->d_out, (size_t)N * h->F));
     TRY(dalloc(h, &h->d_pprev, (size_t)N));
-    if (h->cfg.variant == PSM_DELTAU_TO_DELTAP && ncol == 5) TRY(dalloc(h, &h->d_uprev, (size_t)N * 2));
+    if (h->cfg.variant == PSM_DELTAU_TO_DELTAP) TRY(dalloc(h, &h->d_uprev, (size_t)N * 2));     // resident U(t-1): 5-column rows, fields without dU
     TRY(dalloc(h, &h->d_uv, (size_t)Nall));
     TRY(dalloc(h, &h->d_grid, (size_t)h->grid_stride * 2));
     TRY(dalloc(h, &h->d_xu, (size_t)Bp * 2 * S2));
@@ -695,7 +769,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
                       int epi, const float* v0, const float* v1, const float* v2, int bn) -> int {
             if (make_kmajor_map(&g.mapA, A, a_rows, K, K, 128) != 0 || make_kmajor_map(&g.mapB, Bm, b_rows, K, K, bn) != 0)
                 PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-            g.args = TcGemmArgs{Cp, a_rows, b_rows, K, ldc, splits, epi, three, v0, v1, v2, h->d_sc, nullptr, nullptr};
+            g.args = TcGemmArgs{Cp, a_rows, b_rows, K, ldc, splits, epi, three, v0, v1, v2, h->d_sc, nullptr, nullptr, env_on("PSM_NO_PREFETCH") ? 0 : 1};
             g.bn = bn;
             return 0;
         };
@@ -748,7 +822,11 @@ static int init_local(psm_handle* h, LocalInit& L) {
                 make_kmajor_map(&it.mapBhi, h->d_r_hi, Bp, h->pc_p_pad, h->pc_p_pad, 128) != 0 ||
                 make_kmajor_map(&it.mapBlo, h->d_r_lo, Bp, h->pc_p_pad, h->pc_p_pad, 128) != 0)
                 PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed (PCA inverse)");
-            it.args = InvTArgs{h->d_blocks, (long long)S2 * h->C, h->B, Bp, h->pc_p_pad, S2 * h->C, three, h->d_pmean, h->d_sc};
+            it.args = InvTArgs{h->d_blocks, (long long)S2 * h->C, h->B, Bp, h->pc_p_pad, S2 * h->C, three, h->d_pmean, h->d_sc, StripRows{}};
+            // the masked strip sums come out of this kernel's epilogue (the blocks are not read again): needs the CTA <-> pixel-row
+            // match S == 128
+            h->strip_fuse = !env_on("PSM_NO_STRIP_FUSE") && S == 128 && h->n_tasks > 0;
+            if (h->strip_fuse) it.args.strips = StripRows{h->d_sr_rowptr, h->d_sr_src, h->d_sr_slot, h->d_sr_w, h->sr_n_ent, h->d_rowpart};
         }
         // ---- the whole Dense stack as one persistent launch -------------------------------------------------
         int max_cl = 0;
@@ -940,19 +1018,26 @@ static int sparse_exchange(psm_handle* h, const float* sendbuf, const std::vecto
     return PSM_OK;
 }
 
-static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
+static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
     cudaStream_t s = h->stream;
     const int S = h->S, S2 = S * S, Bp = h->B_pad;
     const bool deltas = h->cfg.variant == PSM_DELTAU_TO_DELTAP;
     const bool multi = h->world > 1;
-    const int mode = !deltas ? 0 : (h->cfg.input_cols == 7 ? 1 : 2);
+    const bool fields = in.U != nullptr;
+    const int mode = !deltas ? 0 : (fields ? (in.dU ? 1 : 2) : (h->cfg.input_cols == 7 ? 1 : 2));
     int nl = 0, te = 1;
     auto tick = [&]() { if (h->ev_valid) cudaEventRecord(h->ev[te], s); ++te; };
 
     const bool dim = h->cfg.variant != PSM_U_TO_GRADP;        // blocks re-dimensionalised by max_abs_p * U^2 (SMC:551, PMP:490); GRAD: none
     ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], dim ? h->maxs[3] : 1.0, dim ? 1 : 0, h->cfg.skip_threshold, mode, 0};
-    PrepArgs pa{d_cells, h->n_cells, h->cfg.input_cols, mode, h->d_uv, h->d_pprev, h->d_uprev, h->d_sc};
-    launch_prep(pa, s); ++nl;
+    if (fields) {
+        PrepFieldsArgs pf{in.U, in.dU, in.u_stride, h->n_cells, mode, h->d_uv, h->d_uprev, h->d_sc};
+        launch_prep_fields(pf, s); ++nl;
+    } else {
+        PrepArgs pa{in.rows, h->n_cells, h->cfg.input_cols, mode, h->d_uv, h->d_pprev, h->d_uprev, h->d_sc};
+        launch_prep(pa, s); ++nl;
+        h->pprev_zero = false;
+    }
     const bool p2p = multi && h->p2p;
     const P2PArgs* d_p2p = p2p ? h->d_p2p : nullptr;
     if (p2p) {
@@ -973,7 +1058,7 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     GatherArgs ga{h->d_fv[0], h->d_fv[1], h->d_fv[2], h->d_fw[0], h->d_fw[1], h->d_fw[2], h->d_uv,
                   grid0, grid1, h->G_pad / 4, sa, 0, d_p2p};
     if (h->fused_extract) {
-        GatherExtractArgs ge{ga, h->d_rowcov, h->d_colcov, h->d_by0, h->d_bx0, h->d_xu, h->W / 4, h->plan.ncolb, S, h->keep_grid ? 1 : 0};
+        GatherExtractArgs ge{ga, h->d_rowcov, h->d_colcov, h->d_xu, h->W / 4, S, h->keep_grid ? 1 : 0};
         launch_gather_extract(ge, s); ++nl;
     } else {
         launch_gather(ga, s); ++nl;
@@ -1065,7 +1150,9 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     oa.p2p = d_p2p;
     const bool fuse_offsets = !multi && h->n_tasks > 0 && h->Bg * h->F <= 1024 && !h->no_fused_offsets;
     MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->C, S, h->W, (multi && !p2p) ? h->d_means_loc : h->d_means};
-    launch_means(ma, fuse_offsets ? &oa : nullptr, s); ++nl;
+    if (tc && h->inv_t && h->strip_fuse) launch_fold(ma, h->d_rowpart, fuse_offsets ? &oa : nullptr, s);     // row partials left by the PCA-inverse epilogue
+    else launch_means(ma, fuse_offsets ? &oa : nullptr, s);
+    ++nl;
     if (p2p && !fuse_offsets) { launch_p2p_push_means(h->d_p2p, h->d_tasks, h->n_tasks, h->world, h->d_means, s); ++nl; }   // exchange 3 over peer memory
     else if (multi)   // exchange 3: every rank contributes its own slots (zero elsewhere) -> identical means everywhere
         NC(h, g_nccl.AllReduce(h->d_means_loc, h->d_means, (size_t)h->n_tasks_glob, ncclDouble, ncclSum, h->comm, s));
@@ -1098,8 +1185,9 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
                                     h->pix_recv_ptr, 1));
             NC(h, g_nccl.GroupEnd());
         }
+        if (in.wait_p) CU(h, cudaStreamWaitEvent(s, h->ev_p, 0));          // the caller's p array has landed in d_pprev
         BackArgs ba{h->d_bv[0], h->d_bv[1], h->d_bv[2], h->d_bw[0], h->d_bw[1], h->d_bw[2], h->d_field, h->n_cells,
-                    h->field_stride, h->d_pprev, d_out, h->F, h->cfg.additive, h->d_sc, d_p2p, nullptr, nullptr, nullptr, nullptr, 0, 0};
+                    h->field_stride, (fields && in.p_dev) ? in.p_dev : h->d_pprev, d_out, h->F, h->cfg.additive, h->d_sc, d_p2p, nullptr, nullptr, nullptr, nullptr, 0, 0};
         if (fuse_place) {
             ba.v0 = h->d_bb[0]; ba.v1 = h->d_bb[1]; ba.v2 = h->d_bb[2]; ba.o0 = h->d_bo[0]; ba.o1 = h->d_bo[1]; ba.o2 = h->d_bo[2];
             ba.field = h->d_blocks; ba.plane = S2; ba.coff = h->d_coff; ba.n_blocks = h->Bg; ba.block_plane = S2;
@@ -1113,50 +1201,39 @@ static int run_step(psm_handle* h, const double* d_cells, double* d_out) {
     return PSM_OK;
 }
 
-// Enqueue one step (optionally with the host copies around it) -- eagerly, or as a captured graph.
-static int enqueue_step(psm_handle* h, bool host, const double* in, double* out) {
-    if (host) {
-        CU(h, cudaMemcpyAsync(h->d_cells, in, (size_t)h->n_cells * h->cfg.input_cols * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        if (h->ev_valid) cudaEventRecord(h->ev[11], h->stream);
-        TRY(run_step(h, h->d_cells, h->d_out));
-        CU(h, cudaMemcpyAsync(out, h->d_out, (size_t)h->n_cells * h->F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    } else {
-        TRY(run_step(h, in, out));
-    }
-    return PSM_OK;     // the step's status word reaches the host through mapped memory (offsets_kernel)
-}
-
-static int submit_step(psm_handle* h, bool host, const double* in, double* out) {
-    h->last_host = host;
-    h->field_stale = h->fuse_place && (host || out != nullptr);    // the placement is folded into the grid->cell gather
+// Device entry points: one step as a captured CUDA graph, keyed by the caller's device buffers (a solver passes the same
+// ones every step); per-stage events, PSM_NO_GRAPHS=1 and the first multi-GPU steps launch eagerly.
+static int submit_device(psm_handle* h, const StepInput& in, double* out) {
+    h->last_host = false;
+    h->field_stale = h->fuse_place && out != nullptr;    // the placement is folded into the grid->cell gather
     if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
     if (!h->use_graphs || h->ev_valid || h->eager_steps > 0) {   // per-stage events: eager launches (event nodes of a graph carry no usable timestamps)
         if (h->eager_steps > 0) --h->eager_steps;
-        TRY(enqueue_step(h, host, in, out));
+        TRY(run_step(h, in, out));
     } else {
+        const void* k1 = in.U ? (const void*)in.U : (const void*)in.rows;
         psm_handle::StepGraph* g = nullptr;
         for (auto& c : h->graphs)
-            if (c.exec && c.in == in && c.out == out && c.host == host && c.timed == h->ev_valid) g = &c;
+            if (c.exec && c.in == k1 && c.in2 == in.dU && c.in3 == in.p_dev && c.out == out && c.stride == in.u_stride) g = &c;
         if (!g) {
             g = &h->graphs[0];
             for (auto& c : h->graphs) if (!c.exec) { g = &c; break; } else if (c.used < g->used) g = &c;
             if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; }
             cudaGraph_t graph = nullptr;
             CU(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            int rc = enqueue_step(h, host, in, out);
+            int rc = run_step(h, in, out);
             cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
             if (rc == PSM_OK && e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, graph, 0);
             if (graph) cudaGraphDestroy(graph);
             if (rc != PSM_OK || e != cudaSuccess) {
-                // e.g. a pageable host buffer that cannot be captured: same kernels, launched one by one
                 g->exec = nullptr;
                 cudaGetLastError();
                 h->use_graphs = false;
-                TRY(enqueue_step(h, host, in, out));
+                TRY(run_step(h, in, out));
                 if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
                 return PSM_OK;
             }
-            g->in = in; g->out = out; g->host = host; g->timed = h->ev_valid;
+            g->in = k1; g->in2 = in.dU; g->in3 = in.p_dev; g->out = out; g->stride = in.u_stride;
         }
         g->used = ++h->graph_clock;
         CU(h, cudaGraphLaunch(g->exec, h->stream));
@@ -1172,6 +1249,9 @@ static int finish(psm_handle* h) {
     return (v & 1) ? PSM_SKIPPED : PSM_OK;
 }
 
+// Host entry points launch EAGERLY: the CPU enqueues the eleven kernels while the DMA engine is still copying the inputs
+// (hundreds of microseconds), so nothing is gained by a graph -- and nothing depends on the caller re-using its buffers
+// (a Python caller may hand in a fresh temporary every step).
 extern "C" int psm_predict(psm_handle* h, const double* cells, int64_t n_cells, double* p_out) {
     if (!h) return PSM_ERR_INVALID;
     if (!h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "psm_predict before psm_init_with_tables");
@@ -1179,8 +1259,77 @@ extern "C" int psm_predict(psm_handle* h, const double* cells, int64_t n_cells, 
     if (n_cells != h->n_cells) PSM_FAIL(h, PSM_ERR_INVALID, "n_cells %lld does not match the initialised mesh (%lld)", (long long)n_cells, h->n_cells);
     if (!h->have_back) PSM_FAIL(h, PSM_ERR_STATE, "no grid->cell tables were given: use psm_predict_device(..., NULL, ...) + psm_get_stage(FIELD)");
     CU(h, cudaSetDevice(h->cfg.device));
-    TRY(submit_step(h, true, cells, p_out));
+    h->last_host = true;
+    h->field_stale = h->fuse_place;
+    if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
+    CU(h, cudaMemcpyAsync(h->d_cells, cells, (size_t)h->n_cells * h->cfg.input_cols * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->ev_valid) cudaEventRecord(h->ev[11], h->stream);
+    StepInput in; in.rows = h->d_cells;
+    if (h->eager_steps > 0) --h->eager_steps;
+    TRY(run_step(h, in, h->d_out));
+    CU(h, cudaMemcpyAsync(p_out, h->d_out, (size_t)h->n_cells * h->F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
     return finish(h);
+}
+
+static int check_fields(psm_handle* h, const void* U, int32_t u_stride, const void* dU, int64_t n_cells, const char* who) {
+    if (!h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "%s before init", who);
+    if (!U) PSM_FAIL(h, PSM_ERR_INVALID, "%s: NULL U", who);
+    if (u_stride != 2 && u_stride != 3) PSM_FAIL(h, PSM_ERR_INVALID, "%s: u_stride must be 3 (OpenFOAM vector) or 2", who);
+    if (n_cells != h->n_cells) PSM_FAIL(h, PSM_ERR_INVALID, "n_cells %lld does not match the initialised mesh (%lld)", (long long)n_cells, h->n_cells);
+    if (dU && h->cfg.variant != PSM_DELTAU_TO_DELTAP) PSM_FAIL(h, PSM_ERR_INVALID, "%s: dU is only meaningful for deltaU_to_deltaP", who);
+    return PSM_OK;
+}
+
+extern "C" int psm_predict_fields(psm_handle* h, const double* U, int32_t u_stride, const double* dU, const double* p, int64_t n_cells,
+                                  double* out) {
+    if (!h) return PSM_ERR_INVALID;
+    TRY(check_fields(h, U, u_stride, dU, n_cells, "psm_predict_fields"));
+    if (!out) PSM_FAIL(h, PSM_ERR_INVALID, "NULL output buffer");
+    if (!h->have_back) PSM_FAIL(h, PSM_ERR_STATE, "no grid->cell tables were given");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const size_t nu = (size_t)h->n_cells * u_stride;
+    h->last_host = true;
+    h->field_stale = h->fuse_place;
+    if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
+    CU(h, cudaMemcpyAsync(h->d_cells, U, nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (dU) CU(h, cudaMemcpyAsync(h->d_cells + nu, dU, nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->ev_valid) cudaEventRecord(h->ev[11], h->stream);
+    StepInput in; in.U = h->d_cells; in.dU = dU ? h->d_cells + nu : nullptr; in.u_stride = u_stride;
+    if (p) {
+        // p is read by the LAST kernel only: its copy starts when U has landed (so the two do not share the link) and runs on
+        // the copy stream while the kernels execute
+        CU(h, cudaEventRecord(h->ev_u, h->stream));
+        CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_u, 0));
+        CU(h, cudaMemcpyAsync(h->d_pprev, p, (size_t)h->n_cells * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+        CU(h, cudaEventRecord(h->ev_p, h->copy_stream));
+        in.wait_p = true;
+        h->pprev_zero = false;
+    } else if (!h->pprev_zero) {
+        CU(h, cudaMemsetAsync(h->d_pprev, 0, (size_t)h->n_cells * sizeof(double), h->stream));
+        h->pprev_zero = true;
+    }
+    if (h->eager_steps > 0) --h->eager_steps;
+    TRY(run_step(h, in, h->d_out));
+    CU(h, cudaMemcpyAsync(out, h->d_out, (size_t)h->n_cells * h->F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
+    return finish(h);
+}
+
+extern "C" int psm_predict_fields_device(psm_handle* h, const double* d_U, int32_t u_stride, const double* d_dU, const double* d_p,
+                                         int64_t n_cells, double* d_out, int32_t sync) {
+    if (!h) return PSM_ERR_INVALID;
+    TRY(check_fields(h, d_U, u_stride, d_dU, n_cells, "psm_predict_fields_device"));
+    if (d_out && !h->have_back) PSM_FAIL(h, PSM_ERR_STATE, "no grid->cell tables were given");
+    CU(h, cudaSetDevice(h->cfg.device));
+    StepInput in; in.U = d_U; in.dU = d_dU; in.u_stride = u_stride; in.p_dev = d_p;
+    if (!d_p && !h->pprev_zero) {
+        CU(h, cudaMemsetAsync(h->d_pprev, 0, (size_t)h->n_cells * sizeof(double), h->stream));
+        h->pprev_zero = true;
+    }
+    TRY(submit_device(h, in, d_out));
+    if (sync) return finish(h);
+    return PSM_OK;
 }
 
 extern "C" int psm_predict_device(psm_handle* h, const double* d_cells, int64_t n_cells, double* d_p_out, int32_t sync) {
@@ -1190,7 +1339,9 @@ extern "C" int psm_predict_device(psm_handle* h, const double* d_cells, int64_t 
     if (n_cells != h->n_cells) PSM_FAIL(h, PSM_ERR_INVALID, "n_cells does not match the initialised mesh");
     if (d_p_out && !h->have_back) PSM_FAIL(h, PSM_ERR_STATE, "no grid->cell tables were given");
     CU(h, cudaSetDevice(h->cfg.device));
-    TRY(submit_step(h, false, d_cells, d_p_out));
+    StepInput in; in.rows = d_cells;
+    h->pprev_zero = false;                  // prep writes column 4 into d_pprev (also on every replay of the captured step)
+    TRY(submit_device(h, in, d_p_out));
     if (sync) return finish(h);
     return PSM_OK;
 }
@@ -1396,7 +1547,7 @@ extern "C" int psm_debug_gemm(int32_t device, int32_t mode, int32_t M, int32_t N
             if (tc_gemm_prepare() != 0 || make_kmajor_map(&t.mapA, dA, M, K, K, 128) != 0 ||
                 make_kmajor_map(&t.mapB, dB, N, K, K, tc_gemm_bn(N)) != 0) rc = PSM_ERR_CUDA;
             else {
-                t.args = TcGemmArgs{dC, M, N, K, N, splits, EPI_PARTIAL, mode == PSM_GEMM_TC_3XTF32 ? (env_on("PSM_TF32_MASK_HI") ? 1 : 2) : 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+                t.args = TcGemmArgs{dC, M, N, K, N, splits, EPI_PARTIAL, mode == PSM_GEMM_TC_3XTF32 ? (env_on("PSM_TF32_MASK_HI") ? 1 : 2) : 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1};
                 t.bn = tc_gemm_bn(N);
                 launch_tc_gemm(t, 0);
             }

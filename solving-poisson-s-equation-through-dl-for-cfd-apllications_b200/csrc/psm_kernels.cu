@@ -327,9 +327,11 @@ static void launch_prep_bulk(const PrepArgs& a, cudaStream_t s) {
 }
 
 void launch_prep(const PrepArgs& a, cudaStream_t s) {
-    // opt-in (PSM_PREP_BULK=1): 10 % faster at 4 M cells, but repeated steps on the same input were NOT bit-identical with
-    // it (profiles/determinism_probe.py: a few cells per step pick up a stale row) -- off until that is understood
-    static const bool bulk_ok = [] { const char* v = getenv("PSM_PREP_BULK"); return v && v[0] && v[0] != '0'; }();
+    // Default: the bulk-copy kernel (contiguous cp.async.bulk bursts instead of 8-byte column picks at a 40-byte stride; 6.6 TB/s
+    // at 4 M cells).  Its round-1 race -- a stage refilled through the async proxy while generic reads of it were still in
+    // flight -- is closed by the fence.proxy.async before the CTA barrier (tests/test_gpu_fullsize.py replays steps bit for
+    // bit).  PSM_PREP_BULK=0 selects the plain kernel.
+    static const bool bulk_ok = [] { const char* v = getenv("PSM_PREP_BULK"); return !(v && v[0] == '0'); }();
     if (bulk_ok && (reinterpret_cast<uintptr_t>(a.cells) & 15) == 0 && a.n >= kPrepRows) {
         if (a.mode == 0) launch_prep_bulk<0, 5>(a, s);
         else if (a.mode == 1) launch_prep_bulk<1, 7>(a, s);
@@ -341,6 +343,56 @@ void launch_prep(const PrepArgs& a, cudaStream_t s) {
     if (a.mode == 0) launch_k(prep_kernel<0, 5>, dim3(blocks), dim3(256), 0, s, a);
     else if (a.mode == 1) launch_k(prep_kernel<1, 7>, dim3(blocks), dim3(256), 0, s, a);
     else launch_k(prep_kernel<2, 5>, dim3(blocks), dim3(256), 0, s, a);
+}
+
+// K0 on the solver's own field arrays (see psm_kernels.cuh).  Same arithmetic and rounding as prep_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(256) prep_fields_kernel(PrepFieldsArgs a) {
+    pdl_enter();
+    const double* __restrict__ U = a.U;
+    const double* __restrict__ dU = a.dU;
+    float2* __restrict__ uv = a.uv;
+    double2* __restrict__ u_prev = reinterpret_cast<double2*>(a.u_prev);
+    const int st = a.stride;
+    double m_u = 0.0, m_d = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
+        const double ux = __ldcs(U + i * st), uy = __ldcs(U + i * st + 1);
+        double fx, fy;
+        if (MODE == 0) { fx = ux; fy = uy; }
+        else if (MODE == 1) { fx = __ldcs(dU + i * st); fy = __ldcs(dU + i * st + 1); }
+        else {
+            const double2 prev = u_prev[i];
+            fx = ux - prev.x; fy = uy - prev.y;
+            u_prev[i] = make_double2(ux, uy);
+        }
+        m_u = fmax(m_u, __dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)));
+        if (MODE != 0) m_d = fmax(m_d, __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)));
+        uv[i] = make_float2((float)fx, (float)fy);
+    }
+    m_u = warp_max(m_u);
+    m_d = warp_max(m_d);
+    __shared__ double s_u[8], s_d[8];
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_u[w] = m_u; s_d[w] = m_d; }
+    __syncthreads();
+    if (w == 0) {
+        m_u = (l < 8) ? s_u[l] : 0.0;
+        m_d = (l < 8) ? s_d[l] : 0.0;
+        m_u = warp_max(m_u);
+        m_d = warp_max(m_d);
+        if (l == 0) {
+            atomicMax(&a.sc->umax2_bits, (unsigned long long)__double_as_longlong(m_u));
+            atomicMax(&a.sc->dumax2_bits, (unsigned long long)__double_as_longlong(m_d));
+        }
+    }
+}
+void launch_prep_fields(const PrepFieldsArgs& a, cudaStream_t s) {
+    long long want = (a.n + 255) / 256;
+    int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
+    if (a.mode == 0) launch_k(prep_fields_kernel<0>, dim3(blocks), dim3(256), 0, s, a);
+    else if (a.mode == 1) launch_k(prep_fields_kernel<1>, dim3(blocks), dim3(256), 0, s, a);
+    else launch_k(prep_fields_kernel<2>, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -428,49 +480,89 @@ void launch_gather(const GatherArgs& a, cudaStream_t s) {
 }
 
 // K1+K2 fused (see psm_kernels.cuh): identical arithmetic to gather_kernel, then one 128-bit store per
-// covering block and channel.
-template <bool READY>
-__global__ void __launch_bounds__(256, 4) gather_extract_kernel(GatherExtractArgs e) {
+// covering block and channel.  U pixel groups per thread are in flight at once: all their (static) table loads are issued
+// before the programmatic-dependent-launch wait, so a thread pays the HBM latency of the table stream once per U groups;
+// the store addresses come from two small static offset tables (no block-origin lookups, no local memory).
+__device__ __forceinline__ void store_cover(float* __restrict__ xu, const CoverEntry* __restrict__ rowcov, const CoverEntry* __restrict__ colcov,
+                                            unsigned int g, unsigned int W4, int S2, const float4& ox, const float4& oy) {
+    const unsigned int y = g / W4, xg = g - y * W4;
+    const int4* rp = reinterpret_cast<const int4*>(rowcov + y);
+    const int4* cp = reinterpret_cast<const int4*>(colcov + xg);
+    const int4 r0 = __ldg(rp), c0 = __ldg(cp);
+    const int rn = r0.x, cn = c0.x;
+    int4 r1 = make_int4(0, 0, 0, 0), c1 = make_int4(0, 0, 0, 0);
+    if (rn > 3) r1 = __ldg(rp + 1);
+    if (cn > 3) c1 = __ldg(cp + 1);
+    // rolled loops with register selects: no local-memory arrays, few live registers
+    auto pick = [](const int4& lo, const int4& hi, int k) {
+        int v = lo.y;
+        v = (k == 1) ? lo.z : v; v = (k == 2) ? lo.w : v; v = (k == 3) ? hi.x : v;
+        v = (k == 4) ? hi.y : v; v = (k == 5) ? hi.z : v; v = (k == 6) ? hi.w : v;
+        return v;
+    };
+    for (int r = 0; r < rn; ++r) {
+        float* row = xu + pick(r0, r1, r);
+        for (int c = 0; c < cn; ++c) {
+            float* dst = row + pick(c0, c1, c);
+            *reinterpret_cast<float4*>(dst) = ox;
+            *reinterpret_cast<float4*>(dst + S2) = oy;
+        }
+    }
+}
+
+template <bool READY, int U>
+__global__ void __launch_bounds__(256, U == 1 ? 4 : 3) gather_extract_kernel(GatherExtractArgs e) {
     pdl_launch_dependents();
     const GatherArgs& a = e.g;
-    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long T = (long long)gridDim.x * blockDim.x;
     const int S2 = e.S * e.S;
     long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    PixTables t{};
-    if (g < a.n_pix4) t = load_tables(a, g);
+    PixTables t[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (g + u * T < a.n_pix4) t[u] = load_tables(a, g + u * T);
     pdl_wait();
     float s0, s1;
     step_scales<READY>(a, s0, s1);
     while (g < a.n_pix4) {
-        float4 ox, oy;
-        gather4(a.uv, t, s0, s1, ox, oy);
-        if (e.store_grid) {
-            reinterpret_cast<float4*>(a.grid0)[g] = ox;
-            reinterpret_cast<float4*>(a.grid1)[g] = oy;
-        }
-        const int y = (int)(g / e.W4), xg = (int)(g - (long long)y * e.W4);
-        const CoverEntry rc = e.rowcov[y];
-        const CoverEntry cc = e.colcov[xg];
-        const int x = xg << 2;
-        for (int r = 0; r < rc.n; ++r) {
-            const int b_row = rc.idx[r] * e.ncolb;
-            const int ly = y - e.by0[b_row];
-            for (int c = 0; c < cc.n; ++c) {
-                const int b = b_row + cc.idx[c];
-                float* dst = e.xu + ((long long)b * 2) * S2 + ly * e.S + (x - e.bx0[b]);
-                *reinterpret_cast<float4*>(dst) = ox;
-                *reinterpret_cast<float4*>(dst + S2) = oy;
+        float4 ox[U], oy[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (g + u * T < a.n_pix4) gather4(a.uv, t[u], s0, s1, ox[u], oy[u]);
+        const long long gn = g + (long long)U * T;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (gn + u * T < a.n_pix4) t[u] = load_tables(a, gn + u * T);            // next pass: tables in flight during the stores
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long gu = g + u * T;
+            if (gu < a.n_pix4) {
+                if (e.store_grid) {
+                    reinterpret_cast<float4*>(a.grid0)[gu] = ox[u];
+                    reinterpret_cast<float4*>(a.grid1)[gu] = oy[u];
+                }
+                store_cover(e.xu, e.rowcov, e.colcov, (unsigned int)gu, (unsigned int)e.W4, S2, ox[u], oy[u]);
             }
         }
-        g += stride;
-        if (g < a.n_pix4) t = load_tables(a, g);
+        g = gn;
     }
 }
 void launch_gather_extract(const GatherExtractArgs& a, cudaStream_t s) {
+    // two groups in flight per thread (3 CTAs / SM); a mesh too small to give every thread of one resident wave a group keeps U = 1
+    static const int force_u = [] { const char* v = getenv("PSM_GATHER_U"); return v ? atoi(v) : 0; }();
+    const long long wave2 = (long long)kSMs * 3 * 256, wave1 = (long long)kSMs * 4 * 256;
+    const int U = force_u ? force_u : (a.g.n_pix4 > wave1 ? 2 : 1);
     long long want = (a.g.n_pix4 + 255) / 256;
-    int blocks = (int)(want < (long long)kSMs * 4 ? (want > 0 ? want : 1) : kSMs * 4);     // one resident wave (4 CTAs / SM), grid-stride
-    if (a.g.scales_ready) launch_k(gather_extract_kernel<true>, dim3(blocks), dim3(256), 0, s, a);
-    else launch_k(gather_extract_kernel<false>, dim3(blocks), dim3(256), 0, s, a);
+    if (U == 2) {
+        want = (a.g.n_pix4 + 511) / 512;
+        int blocks = (int)(want < wave2 / 256 ? (want > 0 ? want : 1) : wave2 / 256);
+        if (a.g.scales_ready) launch_k(gather_extract_kernel<true, 2>, dim3(blocks), dim3(256), 0, s, a);
+        else launch_k(gather_extract_kernel<false, 2>, dim3(blocks), dim3(256), 0, s, a);
+        return;
+    }
+    int blocks = (int)(want < wave1 / 256 ? (want > 0 ? want : 1) : wave1 / 256);     // one resident wave (4 CTAs / SM), grid-stride
+    if (a.g.scales_ready) launch_k(gather_extract_kernel<true, 1>, dim3(blocks), dim3(256), 0, s, a);
+    else launch_k(gather_extract_kernel<false, 1>, dim3(blocks), dim3(256), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -725,6 +817,60 @@ void launch_means(const MeansArgs& a, const OffsetsArgs* fused, cudaStream_t s) 
     else launch_k(task_means_kernel<0>, dim3(a.n_tasks), dim3(256), 0, s, a, OffsetsArgs{});
 }
 
+// K6a'  the masked means from the row partials of the PCA-inverse epilogue (StripRows in psm_kernels.cuh): one warp per
+//       task sums its 4 * rows FP32 partials in FP64 -- lane-strided, then a fixed butterfly: deterministic -- so the 8 MB of
+//       predicted blocks are not read a second time.  Same MODE switch as task_means_kernel.
+template <int MODE>
+__global__ void __launch_bounds__(256) task_fold_kernel(MeansArgs a, const float* __restrict__ rowpart, OffsetsArgs oa) {
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ti = blockIdx.x * 8 + w;
+    DevTask t{};
+    if (ti < a.n_tasks) t = a.tasks[ti];
+    extern __shared__ __align__(16) unsigned char mk_smem[];
+    DevRec* s_rec = nullptr; DevShiftTerm* s_terms = nullptr;
+    if (MODE != 0) {
+        const int n = oa.B * oa.F, nt = oa.term_start[oa.F];
+        s_rec = reinterpret_cast<DevRec*>(mk_smem + (((size_t)n * 24 + 15) & ~(size_t)15));
+        s_terms = reinterpret_cast<DevShiftTerm*>(s_rec + n);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_rec[i] = oa.rec[i];
+        for (int i = threadIdx.x; i < nt; i += blockDim.x) s_terms[i] = oa.terms[i];
+    }
+    pdl_wait();
+    if (ti < a.n_tasks) {
+        const float* p = rowpart + (long long)t.part_base * 4;
+        const int n = 4 * (t.y1 - t.y0);
+        double acc = 0.0;
+        for (int i = lane; i < n; i += 32) acc += (double)__ldcg(p + i);
+        acc = warp_sum(acc);
+        const double val = (t.kind == 1) ? acc : ((t.count > 0) ? acc / (double)t.count : CUDART_NAN);
+        if (lane == 0) a.means[t.out] = val;
+    }
+    if (MODE != 0) {
+        __shared__ bool s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int prev = atomicAdd(&oa.sc->means_done, 1u);
+            s_last = (prev == gridDim.x - 1);
+            if (s_last) { oa.sc->means_done = 0u; __threadfence(); }
+        }
+        __syncthreads();
+        if (!s_last) return;
+        offsets_body(oa, s_rec, s_terms, mk_smem);
+    }
+}
+void launch_fold(const MeansArgs& a, const float* rowpart, const OffsetsArgs* fused, cudaStream_t s) {
+    if (a.n_tasks <= 0) return;
+    const int blocks = (a.n_tasks + 7) / 8;
+    if (fused) {
+        const size_t n = (size_t)fused->B * fused->F;
+        const size_t smem = ((n * 24 + 15) & ~(size_t)15) + n * sizeof(DevRec) + (size_t)fused->term_start[fused->F] * sizeof(DevShiftTerm);
+        launch_k(task_fold_kernel<1>, dim3(blocks), dim3(256), smem, s, a, rowpart, *fused);
+    }
+    else launch_k(task_fold_kernel<0>, dim3(blocks), dim3(256), 0, s, a, rowpart, OffsetsArgs{});
+}
+
 // ------------------------------------------------------------------------------------------------
 // K6b  offsets.  c_k = m[a] - (m[b] - c[parent])  is a sum along the parent chain of
 //      d_k = m[a] - m[b] (roots: m[a] - Ref_BC), evaluated by pointer jumping in
@@ -952,7 +1098,108 @@ __global__ void __launch_bounds__(256) back_kernel(BackArgs a) {
         if (i < a.n) load();
     }
 }
+// Four consecutive cells per thread: nine 64/128-bit streaming table loads (issued before the wait) instead of thirty-six
+// scalar ones, two 128-bit p_prev loads, two 128-bit stores.  Per-cell arithmetic identical to back_kernel (bit-identical
+// results); the last n % 4 cells go through the scalar expressions in CTA 0.
+template <bool FROM_BLOCKS>
+__device__ __forceinline__ double back_one(const BackArgs& a, const float* __restrict__ src, int i0, int i1, int i2, float q0, float q1, float q2,
+                                           int b0, int b1, int b2, double pp, int skip) {
+    double out = pp;
+    if (i0 >= 0 && !skip) {
+        float f0 = __ldg(src + i0), f1 = __ldg(src + i1), f2 = __ldg(src + i2);
+        if (FROM_BLOCKS) { f0 -= __ldg(a.coff + b0); f1 -= __ldg(a.coff + b1); f2 -= __ldg(a.coff + b2); }   // SMC:243,350
+        const float v = f0 * q0 + f1 * q1 + f2 * q2;
+        if (v == v) out = a.additive ? pp + (double)v : (double)v;
+    }
+    return out;
+}
+template <bool FROM_BLOCKS>
+__device__ __forceinline__ double2 back_two(const BackArgs& a, const float* __restrict__ src, int i0, int i1, int i2, float q0, float q1, float q2,
+                                            int b0, int b1, int b2) {
+    double o0 = CUDART_NAN, o1 = CUDART_NAN;
+    if (i0 >= 0) {
+        const float* s1 = src + a.plane;
+        float f0 = __ldg(src + i0), f1 = __ldg(src + i1), f2 = __ldg(src + i2);
+        float g0 = __ldg(s1 + i0), g1 = __ldg(s1 + i1), g2 = __ldg(s1 + i2);
+        if (FROM_BLOCKS) {
+            const float* c1 = a.coff + a.n_blocks;
+            f0 -= __ldg(a.coff + b0); f1 -= __ldg(a.coff + b1); f2 -= __ldg(a.coff + b2);
+            g0 -= __ldg(c1 + b0); g1 -= __ldg(c1 + b1); g2 -= __ldg(c1 + b2);
+        }
+        o0 = (double)(f0 * q0 + f1 * q1 + f2 * q2);
+        o1 = (double)(g0 * q0 + g1 * q1 + g2 * q2);
+    }
+    return make_double2(o0, o1);
+}
+
+template <bool FROM_BLOCKS>
+__global__ void __launch_bounds__(256) back4_kernel(BackArgs a) {
+    pdl_launch_dependents();
+    const long long n4 = a.n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int4 v0 = make_int4(0, 0, 0, 0), v1 = v0, v2 = v0;
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0, w2 = w0;
+    uint2 o0 = make_uint2(0u, 0u), o1 = o0, o2 = o0;
+    auto load = [&]() {
+        v0 = __ldcs(reinterpret_cast<const int4*>(a.v0) + i); v1 = __ldcs(reinterpret_cast<const int4*>(a.v1) + i);
+        v2 = __ldcs(reinterpret_cast<const int4*>(a.v2) + i);
+        w0 = __ldcs(reinterpret_cast<const float4*>(a.w0) + i); w1 = __ldcs(reinterpret_cast<const float4*>(a.w1) + i);
+        w2 = __ldcs(reinterpret_cast<const float4*>(a.w2) + i);
+        if (FROM_BLOCKS) {
+            o0 = __ldcs(reinterpret_cast<const uint2*>(a.o0) + i); o1 = __ldcs(reinterpret_cast<const uint2*>(a.o1) + i);
+            o2 = __ldcs(reinterpret_cast<const uint2*>(a.o2) + i);
+        }
+    };
+    if (i < n4) load();
+    pdl_wait();
+    if (a.p2p) p2p_wait(a.p2p, 2, a.p2p->pix_recv_mask);   // ghost pixels pushed by their owners
+    const int skip = a.sc->skip;
+    const float* __restrict__ src = a.field;               // the assembled field, or the predicted blocks
+    while (i < n4) {
+        const int bA[4] = {(int)(o0.x & 0xFFFFu), (int)(o0.x >> 16), (int)(o0.y & 0xFFFFu), (int)(o0.y >> 16)};
+        const int bB[4] = {(int)(o1.x & 0xFFFFu), (int)(o1.x >> 16), (int)(o1.y & 0xFFFFu), (int)(o1.y >> 16)};
+        const int bC[4] = {(int)(o2.x & 0xFFFFu), (int)(o2.x >> 16), (int)(o2.y & 0xFFFFu), (int)(o2.y >> 16)};
+        const int iA[4] = {v0.x, v0.y, v0.z, v0.w}, iB[4] = {v1.x, v1.y, v1.z, v1.w}, iC[4] = {v2.x, v2.y, v2.z, v2.w};
+        const float qA[4] = {w0.x, w0.y, w0.z, w0.w}, qB[4] = {w1.x, w1.y, w1.z, w1.w}, qC[4] = {w2.x, w2.y, w2.z, w2.w};
+        if (a.n_fields == 1) {
+            const double2 pa = __ldcs(reinterpret_cast<const double2*>(a.p_prev) + 2 * i);
+            const double2 pb = __ldcs(reinterpret_cast<const double2*>(a.p_prev) + 2 * i + 1);
+            const double pp[4] = {pa.x, pa.y, pb.x, pb.y};
+            double r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[k] = back_one<FROM_BLOCKS>(a, src, iA[k], iB[k], iC[k], qA[k], qB[k], qC[k], bA[k], bB[k], bC[k], pp[k], skip);
+            __stcs(reinterpret_cast<double2*>(a.out) + 2 * i, make_double2(r[0], r[1]));
+            __stcs(reinterpret_cast<double2*>(a.out) + 2 * i + 1, make_double2(r[2], r[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                __stcs(reinterpret_cast<double2*>(a.out) + 4 * i + k, back_two<FROM_BLOCKS>(a, src, iA[k], iB[k], iC[k], qA[k], qB[k], qC[k], bA[k], bB[k], bC[k]));
+        }
+        i += stride;
+        if (i < n4) load();
+    }
+    if (blockIdx.x == 0 && (long long)threadIdx.x < (a.n & 3)) {     // the last n % 4 cells
+        const long long c = (n4 << 2) + threadIdx.x;
+        const int i0 = a.v0[c], i1 = a.v1[c], i2 = a.v2[c];
+        const float q0 = a.w0[c], q1 = a.w1[c], q2 = a.w2[c];
+        int b0 = 0, b1 = 0, b2 = 0;
+        if (FROM_BLOCKS) { b0 = a.o0[c]; b1 = a.o1[c]; b2 = a.o2[c]; }
+        if (a.n_fields == 1) a.out[c] = back_one<FROM_BLOCKS>(a, src, i0, i1, i2, q0, q1, q2, b0, b1, b2, a.p_prev[c], skip);
+        else reinterpret_cast<double2*>(a.out)[c] = back_two<FROM_BLOCKS>(a, src, i0, i1, i2, q0, q1, q2, b0, b1, b2);
+    }
+}
+
 void launch_back(const BackArgs& a, cudaStream_t s) {
+    static const bool scalar = [] { const char* v = getenv("PSM_BACK_SCALAR"); return v && v[0] == '1'; }();
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a.out) | reinterpret_cast<uintptr_t>(a.p_prev)) & 15) == 0;
+    if (!scalar && aligned && a.n >= 4) {
+        long long want = ((a.n >> 2) + 255) / 256;
+        int blocks = (int)(want < (long long)kSMs * 6 ? (want > 0 ? want : 1) : kSMs * 6);
+        if (a.o0) launch_k(back4_kernel<true>, dim3(blocks), dim3(256), 0, s, a);
+        else launch_k(back4_kernel<false>, dim3(blocks), dim3(256), 0, s, a);
+        return;
+    }
     long long want = (a.n + 255) / 256;
     int blocks = (int)(want < (long long)kSMs * 8 ? (want > 0 ? want : 1) : kSMs * 8);
     if (a.o0) launch_k(back_kernel<true>, dim3(blocks), dim3(256), 0, s, a);

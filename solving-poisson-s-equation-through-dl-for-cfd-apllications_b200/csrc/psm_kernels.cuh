@@ -89,6 +89,17 @@ struct PrepArgs {
 };
 void launch_prep(const PrepArgs& a, cudaStream_t s);
 
+// K0 for the solver's NATIVE field storage (psm_predict_fields): U as double[n][u_stride] (OpenFOAM `vector`: stride 3; only
+// components 0, 1 are read), optional dU in the same layout.  p_prev is not touched here: the caller's p array is copied
+// straight into the handle's p_prev buffer (concurrently with the kernels -- only the last kernel of the step reads it).
+struct PrepFieldsArgs {
+    const double* U; const double* dU;   // [n][stride]; dU may be NULL (mode 0 / 2)
+    int stride; long long n;
+    int mode;             // 0: field = U; 1: field = dU; 2: field = U - U_prev (resident)
+    float2* uv; double* u_prev; Scalars* sc;
+};
+void launch_prep_fields(const PrepFieldsArgs& a, cudaStream_t s);
+
 
 // K1: cell -> grid barycentric gather over the folded tables (SoA, padded to a multiple of 4).
 struct GatherArgs {
@@ -105,14 +116,16 @@ void launch_gather(const GatherArgs& a, cudaStream_t s);
 
 // K1+K2 fused: the gathered 4-pixel group goes straight into every overlapping block's operand row
 // (SMC:464-492), so the grid is never re-read.  Needs W % 4 == 0 and block columns on multiples of 4.
-// rowcov[y] / colcov[x/4]: {count, up to 7 covering block rows / block columns}.
-struct CoverEntry { int16_t n; int16_t idx[7]; };
+// rowcov[y] / colcov[x/4]: {count, up to 7 operand offsets}: a pixel group (y, xg) lands at
+// xu + rowcov[y].off[r] + colcov[xg].off[c] for every covering block row r and block column c, where
+// rowcov off = (first block of the row * 2 * S * S + local row * S) and colcov off = (position in the row * 2 * S * S + local x)
+// -- both static, so the store addresses need no block-origin lookups.
+struct CoverEntry { int32_t n; int32_t off[7]; };
 struct GatherExtractArgs {
     GatherArgs g;
-    const CoverEntry* rowcov;     // [rows gathered]   idx = local block row
-    const CoverEntry* colcov;     // [W/4]             idx = block position within its row
-    const int32_t* by0; const int32_t* bx0;
-    float* xu; int W4; int ncolb; int S;
+    const CoverEntry* rowcov;     // [rows gathered]
+    const CoverEntry* colcov;     // [W/4]
+    float* xu; int W4; int S;
     int store_grid;               // 0: only the block operand is written (the grid planes are rebuilt on demand by psm_get_stage)
 };
 void launch_gather_extract(const GatherExtractArgs& a, cudaStream_t s);
@@ -151,6 +164,8 @@ struct TcGemmArgs {
     const float* v0; const float* v1; const float* v2;
     const Scalars* sc;
     float* C_hi; float* C_lo;  // dense_cluster_kernel: optional tf32 hi / lo split of the result (same layout as C)
+    int b_static;              // 1: the B operand does not depend on earlier kernels of the step (weights): its first tiles are
+                               //    requested BEFORE the programmatic-dependent-launch wait
 };
 struct TcGemm { TensorMap128 mapA, mapB; TcGemmArgs args; int bn; };   // bn: N tile (64 or 128) the B map was built for
 int make_kmajor_map(TensorMap128* out, const float* ptr, int rows, int cols, int ld, int box_rows);
@@ -164,6 +179,18 @@ int dense_cluster_prepare();
 int launch_dense_cluster(const TcGemm& t, cudaStream_t s);
 
 // PCA inverse, transposed (psm_gemm_tc.cu): one CTA per 128 output pixels, all blocks as the MMA N dimension.
+// Masked strip sums out of the PCA-inverse epilogue: every CTA of pca_inverse_t_kernel holds one pixel row
+// (channel c, local row ly) of ALL predicted blocks in registers, so the row partial of every masked mean / line sum that
+// covers that row (SMC:233-316, GRAD:300-340, SMC:350) is one warp reduction away -- the blocks are not re-read.
+// Entries are static (built once per mesh), grouped by CTA row and sorted by source block.
+struct StripRows {
+    const int32_t* row_ptr;   // [C*S + 1] entries of pixel row r = c*S + ly; NULL: disabled
+    const int32_t* src;       // [n_ent] local source block (ascending within a row)
+    const int32_t* slot;      // [n_ent] row-partial slot
+    const uint32_t* w;        // [4][n_ent] lane masks per warp quarter: bit l of w[q] <=> pixel lx = 32 q + l counts
+    int n_ent;
+    float* rowpart;           // [n_slots][4] FP32 partial sums per (task, row, warp quarter); slots never counted stay 0
+};
 struct InvTArgs {
     float* blocks;            // [B][C][S][S]: element (block b, planar pixel P) at b * block_stride + P
     long long block_stride;   // C*S*S
@@ -173,6 +200,7 @@ struct InvTArgs {
     int three_pass;
     const float* pmean;       // [n_pix] planar
     const Scalars* sc;        // out_scale
+    StripRows strips;
 };
 struct InvT { TensorMap128 mapA, mapBhi, mapBlo; InvTArgs args; };
 int pca_inverse_t_prepare();
@@ -225,7 +253,7 @@ struct DevTask {
     int32_t count;                    // mask pixels in the rectangle (0 -> NaN mean)
     int32_t my0, mx0;                 // GLOBAL grid origin of the block whose flow mask applies
     int32_t out;                      // slot in the GLOBAL means array
-    int32_t pad;
+    int32_t part_base;                // first row-partial slot of this task (rows y0..y1-1 follow), see StripRows
 };
 struct MeansArgs {
     const DevTask* tasks; int n_tasks;        // tasks evaluated by this rank
@@ -252,6 +280,8 @@ struct OffsetsArgs {
 void launch_offsets(const OffsetsArgs& a, cudaStream_t s);
 // `fused` != NULL (single GPU, B*F <= 1024): the last CTA of the means kernel also runs the offsets (no second launch)
 void launch_means(const MeansArgs& a, const OffsetsArgs* fused, cudaStream_t s);
+// K6a': the same means from the row partials the PCA-inverse epilogue left (StripRows): one warp per task, FP64, fixed order
+void launch_fold(const MeansArgs& a, const float* rowpart, const OffsetsArgs* fused, cudaStream_t s);
 
 // K7: placement through the owner map.
 struct PlaceArgs {

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libpsm_b200.so')
 PSM_OK, PSM_SKIPPED = 0, 1
 PSM_ERR_INVALID, PSM_ERR_CUDA, PSM_ERR_GEOMETRY, PSM_ERR_STATE, PSM_ERR_COMM = -1, -2, -3, -4, -5
 PSM_DELTAU_TO_DELTAP, PSM_U_TO_GRADP, PSM_THESIS_U_TO_P = 0, 1, 2
-PSM_STD, PSM_MAX_ABS = 0, 1
+PSM_STD, PSM_MAX_ABS, PSM_MIN_MAX = 0, 1, 2
 GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_FP32_SIMT = 0, 1, 2
 (STAGE_GRID, STAGE_XINPUT, STAGE_MLPOUT, STAGE_BLOCKS, STAGE_OFFSETS, STAGE_FIELD, STAGE_SCALARS,
  STAGE_MEANS, STAGE_XU) = range(9)
@@ -90,6 +90,8 @@ SYMBOLS = {
     'psm_destroy': (C.c_int, [C.c_void_p]),
     'psm_predict': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'psm_predict_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    'psm_predict_fields': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    'psm_predict_fields_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
     'psm_synchronize': (C.c_int, [C.c_void_p]),
     'psm_get_stream': (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     'psm_register_host_buffer': (C.c_int, [C.c_void_p, C.c_int64]),

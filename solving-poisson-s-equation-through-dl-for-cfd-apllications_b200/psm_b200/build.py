@@ -3,6 +3,7 @@
 The built library lives next to this file (git-ignored, but it travels with the tree to the
 GPU box).  nvcc cross-compiles without a GPU.
 """
+import hashlib
 import os
 import subprocess
 import sys
@@ -11,17 +12,29 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), 'csrc')
 OUT = os.path.join(HERE, 'libpsm_b200.so')
 SOURCES = ['psm_plan.cpp', 'psm_files.cpp', 'psm_kernels.cu', 'psm_gemm_tc.cu', 'psm_handle.cu']
-HEADERS = ['psm_plan.h', 'psm_kernels.cuh', os.path.join('..', '..', 'include', 'psm_b200.h')]
+HEADERS = ['psm_plan.h', 'psm_kernels.cuh', 'psm_internal.h', os.path.join('..', '..', 'include', 'psm_b200.h')]
+STAMP = OUT + '.srchash'
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-std=c++17', '-lineinfo',
          '-Xcompiler', '-fPIC,-Wall,-Wno-unused-function', '-shared']
 
 
+def source_hash():
+    """SHA-256 over the compiler flags and the bytes of every source and header: a library that travelled with the tree is
+    reused only if it was built from exactly these bytes (file times say nothing after a copy)."""
+    h = hashlib.sha256(' '.join(FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        h.update(f.encode())
+        with open(os.path.join(CSRC, f), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def up_to_date():
-    if not os.path.exists(OUT):
+    if not (os.path.exists(OUT) and os.path.exists(STAMP)):
         return False
-    t = os.path.getmtime(OUT)
-    return all(os.path.getmtime(os.path.join(CSRC, f)) <= t for f in SOURCES + HEADERS)
+    with open(STAMP) as fh:
+        return fh.read().strip() == source_hash()
 
 
 def build(force=False, verbose=False):
@@ -34,6 +47,8 @@ def build(force=False, verbose=False):
         raise RuntimeError('nvcc failed building libpsm_b200.so')
     if verbose:
         sys.stderr.write(r.stderr)
+    with open(STAMP, 'w') as fh:
+        fh.write(source_hash() + '\n')
     return OUT
 
 

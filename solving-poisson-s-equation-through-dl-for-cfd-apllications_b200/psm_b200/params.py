@@ -53,7 +53,10 @@ def from_reference_objects(maxs, pca_in, pca_p, dense_kernels, dense_biases, var
              pca_out_components=np.asarray(pca_p.components_)[:pc_p], pca_out_mean=np.asarray(pca_p.mean_),
              mlp_weights=[np.asarray(w, dtype=np.float32) for w in dense_kernels],
              mlp_biases=[np.asarray(b, dtype=np.float32) for b in dense_biases])
-    if scaler is not None:
+    if scaler is not None and 'min_in' in scaler:       # min_max_values.npz (SMC:513-520)
+        p.update(standardization='min_max', min_in=scaler['min_in'], max_in=scaler['max_in'],
+                 min_out=scaler['min_out'], max_out=scaler['max_out'])
+    elif scaler is not None:
         p.update(standardization='std', mean_in=scaler['mean_in'], std_in=scaler['std_in'],
                  mean_out=scaler['mean_out'], std_out=scaler['std_out'])
     else:

@@ -83,16 +83,25 @@ def _marshal_params(p):
     keep = [cin, cout, min_, mout]
     P.pca_in_components, P.pca_in_mean = _ptr(cin, C.c_double), _ptr(min_, C.c_double)
     P.pca_out_components, P.pca_out_mean = _ptr(cout, C.c_double), _ptr(mout, C.c_double)
-    if p.get('standardization', 'std') == 'std':
+    method = p.get('standardization', 'std')
+    if method == 'std':                                  # SMC:505-512 (mean_std.npz)
         P.standardization = capi.PSM_STD
         for name in ('mean_in', 'std_in', 'mean_out', 'std_out'):
             a = f64(p[name])
             keep.append(a)
             setattr(P, name, _ptr(a, C.c_double))
-    else:
+    elif method == 'min_max':                            # SMC:513-520 (min_max_values.npz): min_* in the mean_* slots, max_* in the std_* slots
+        P.standardization = capi.PSM_MIN_MAX
+        for name, key in (('mean_in', 'min_in'), ('std_in', 'max_in'), ('mean_out', 'min_out'), ('std_out', 'max_out')):
+            a = f64(p[key])
+            keep.append(a)
+            setattr(P, name, _ptr(a, C.c_double))
+    elif method == 'max_abs':                            # SMC:521-523
         P.standardization = capi.PSM_MAX_ABS
         P.max_abs_input_PCA = float(p['max_abs_input_PCA'])
         P.max_abs_output_PCA = float(p['max_abs_output_PCA'])
+    else:
+        raise ValueError("standardization must be 'std', 'min_max' or 'max_abs' (SMC:505-525), got %r" % (method,))
     ws = [np.ascontiguousarray(w, dtype=np.float32) for w in p['mlp_weights']]
     bs = [np.ascontiguousarray(b, dtype=np.float32) for b in p['mlp_biases']]
     dims = np.ascontiguousarray([ws[0].shape[0]] + [w.shape[1] for w in ws], dtype=np.int32)
@@ -308,6 +317,34 @@ class PressureSurrogate:
             out = np.empty(n if self.n_fields == 1 else (n, 2), dtype=np.float64)
         rc = self._check(self.lib.psm_predict(self._h, cells.ctypes.data, n, out.ctypes.data))
         return out, rc
+
+    def predict_fields(self, U, p=None, dU=None, out=None):
+        """The step on the solver's native field arrays (``psm_predict_fields``): ``U`` host double[n, 3] (OpenFOAM ``vector``)
+        or [n, 2]; ``p`` host double[n] or None (then the raw prediction comes back); ``dU`` like ``U`` or None (resident
+        U(t-1)).  Returns (out, status)."""
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        if U.ndim != 2 or U.shape[1] not in (2, 3):
+            raise ValueError('U must be [n, 3] or [n, 2]')
+        n = U.shape[0]
+        if dU is not None:
+            dU = np.ascontiguousarray(dU, dtype=np.float64)
+            if dU.shape != U.shape:
+                raise ValueError('dU must have the shape of U')
+        if p is not None:
+            p = np.ascontiguousarray(p, dtype=np.float64)
+            if p.shape != (n,):
+                raise ValueError('p must be [n]')
+        if out is None:
+            out = np.empty(n if self.n_fields == 1 else (n, 2), dtype=np.float64)
+        rc = self._check(self.lib.psm_predict_fields(self._h, U.ctypes.data, U.shape[1], dU.ctypes.data if dU is not None else None,
+                                                     p.ctypes.data if p is not None else None, n, out.ctypes.data))
+        return out, rc
+
+    def predict_fields_device(self, d_U_ptr, u_stride, n_cells, d_out_ptr, d_p_ptr=0, d_dU_ptr=0, sync=True):
+        """Device-pointer form of ``predict_fields`` (ints from e.g. ``torch.Tensor.data_ptr()``; 0 = NULL)."""
+        vp = lambda x: C.c_void_p(x) if x else None      # noqa: E731
+        return self._check(self.lib.psm_predict_fields_device(self._h, vp(d_U_ptr), int(u_stride), vp(d_dU_ptr), vp(d_p_ptr),
+                                                              n_cells, vp(d_out_ptr), int(sync)))
 
     def predict_device(self, d_cells_ptr, n_cells, d_out_ptr, sync=True):
         """Device-pointer entry (ints from e.g. ``torch.Tensor.data_ptr()``); ``d_out_ptr`` may be 0."""

@@ -106,6 +106,11 @@ def make_params(seed=0, shape=128, n_out_channels=1, pc_in=128, pc_p=128, hidden
         p['std_in'] = rng.uniform(0.5, 1.5, size=pc_in)
         p['mean_out'] = 0.1 * rng.standard_normal(pc_p)
         p['std_out'] = rng.uniform(0.5, 1.5, size=pc_p)
+    elif standardization == 'min_max':                    # SMC:513-520 (min_max_values.npz)
+        p['min_in'] = -1.0 + 0.1 * rng.standard_normal(pc_in)
+        p['max_in'] = 1.0 + 0.1 * rng.standard_normal(pc_in)
+        p['min_out'] = -1.5 + 0.1 * rng.standard_normal(pc_p)
+        p['max_out'] = 1.5 + 0.1 * rng.standard_normal(pc_p)
     else:
         p['max_abs_input_PCA'] = 1.7
         p['max_abs_output_PCA'] = 2.3

@@ -54,3 +54,36 @@ def test_plain_c_driver(case):
     assert 'status 0' in r.stdout, r.stdout
     out = np.fromfile(d / 'p_out.bin', dtype=np.float64)
     np.testing.assert_array_equal(out, ref)
+
+
+def test_corrupt_or_foreign_files_are_rejected_with_a_message(case, tmp_path):
+    """A file for another block edge, a truncated payload or a header with absurd sizes must come back as PSM_ERR_INVALID with
+    psm_last_error set -- never an out-of-bounds read or an exception across the C boundary."""
+    d, cells, ref = case
+    good = (d / 'params.bin').read_bytes()
+
+    def load(blob, name):
+        path = tmp_path / name
+        path.write_bytes(blob)
+        with psm_b200.PressureSurrogate('deltaU_to_deltaP') as sm:
+            with pytest.raises(psm_b200.PsmError) as e:
+                sm.load_params_file(path)
+        assert e.value.code == -1 and len(str(e.value)) > 30, str(e.value)
+        return str(e.value)
+
+    hdr = np.frombuffer(good[8:32], dtype=np.int32).copy()
+    other = hdr.copy(); other[0] = 64                                # written for shape 64: the handle uses 128
+    assert 'shape' in load(good[:8] + other.tobytes() + good[32:], 'shape64.bin')
+    huge = hdr.copy(); huge[2] = 2 ** 30                             # pc_in that would drive a 10^14-byte allocation
+    assert 'pc_in' in load(good[:8] + huge.tobytes() + good[32:], 'huge.bin')
+    assert 'payload' in load(good[:-100], 'truncated.bin')
+    assert 'PSMPRM01' in load(b'NOTAFILE' + good[8:], 'magic.bin')
+    tgood = (d / 'tables.bin').read_bytes()
+    for blob, word in ((tgood[:-8], 'payload'), (tgood[:8] + np.int64(-5).tobytes() + tgood[16:], 'range')):
+        path = tmp_path / 't.bin'
+        path.write_bytes(blob)
+        with psm_b200.PressureSurrogate('deltaU_to_deltaP') as sm:
+            sm.load_params_file(d / 'params.bin')
+            with pytest.raises(psm_b200.PsmError) as e:
+                sm.init_from_file(path)
+        assert word in str(e.value), str(e.value)

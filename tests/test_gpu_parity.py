@@ -333,3 +333,76 @@ def test_gaussian_post_filter(variant):
             assert rel_l2(field[0], r['dp_dx']) < 1e-3 and rel_l2(field[1], r['dp_dy']) < 1e-3
     finally:
         c.sm.close()
+
+
+def test_min_max_standardisation_matches_oracle():
+    """SMC:513-520,535-536: the third standardisation method, (z - min) / (max - min) in, r * (max - min) + min out."""
+    mesh = syn.make_mesh(seed=8, **syn.CONFIGS['tiny'])
+    F = syn.make_fields(mesh, seed=8)
+    params = syn.make_params(seed=8, pc_in=40, pc_p=24, standardization='min_max')
+    t = ptables.build_tables(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'])
+    o = DeltasOracle(oracle_params(params))
+    o.compute_only_once(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'],
+                        tables=(t['vert'], t['weights'], t['vert_back'], t['weights_back']))
+    r = o.time_step(F['Ux'], F['Uy'], F['dUx'], F['dUy'])
+    with psm_b200.PressureSurrogate('deltaU_to_deltaP') as sm:
+        sm.load_params(params)
+        sm.init_tables(t)
+        out, rc = sm.predict(syn.pack_cells(mesh, F))
+        assert rc == 0
+        assert rel_l2(sm.stage('x_input'), r['x_input']) < 1e-4
+        assert rel_l2(sm.stage('field')[0], r['field']) < 1e-3
+    with pytest.raises(ValueError):
+        psm_b200.surrogate._marshal_params(dict(params, standardization='robust'))
+
+
+def test_native_field_entry_matches_the_row_entry(deltas_case):
+    """psm_predict_fields (the solver's own U / p arrays, no row packing) against psm_predict on the packed rows:
+    same kernels after the first one, so bit-identical; p = NULL returns the raw prediction; the resident-U(t-1) form
+    reproduces the 5-column behaviour (first call PSM_SKIPPED)."""
+    import torch
+    c = deltas_case
+    F, n = c.F, c.mesh['cells'].shape[0]
+    ref, rc = c.sm.predict(c.cells)
+    assert rc == 0
+    for stride in (3, 2):
+        U = np.zeros((n, stride)); U[:, 0], U[:, 1] = F['Ux'], F['Uy']
+        dU = np.zeros((n, stride)); dU[:, 0], dU[:, 1] = F['dUx'], F['dUy']
+        out, rc = c.sm.predict_fields(U, p=F['p_prev'], dU=dU)
+        assert rc == 0
+        np.testing.assert_array_equal(out, ref)
+        raw, rc = c.sm.predict_fields(U, p=None, dU=dU)
+        assert rc == 0
+        kept = ref == F['p_prev']
+        assert np.all(raw[kept] == 0.0)                                       # cells that keep p_prev: delta_p = 0
+        np.testing.assert_allclose(F['p_prev'] + raw, ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+    # a fresh buffer every call (what a Python caller does): nothing is keyed by the caller's pointers
+    for _ in range(3):
+        out, _ = c.sm.predict_fields(U.copy(), p=F['p_prev'].copy(), dU=dU.copy())
+        np.testing.assert_array_equal(out, ref)
+    # device-pointer form: p read in place
+    dUt, ddU, dp = torch.from_numpy(U).cuda(), torch.from_numpy(dU).cuda(), torch.from_numpy(F['p_prev']).cuda()
+    dout = torch.empty(n, dtype=torch.float64, device='cuda')
+    torch.cuda.synchronize()
+    for _ in range(3):                                                        # captured once, then replayed
+        assert c.sm.predict_fields_device(dUt.data_ptr(), 2, n, dout.data_ptr(), d_p_ptr=dp.data_ptr(), d_dU_ptr=ddU.data_ptr()) == 0
+        np.testing.assert_array_equal(dout.cpu().numpy(), ref)
+    # resident U(t-1): first call has nothing to difference against
+    with psm_b200.PressureSurrogate('deltaU_to_deltaP', input_cols=5) as sm5:
+        sm5.load_params(c.params)
+        sm5.init_tables(c.tables)
+        U3 = np.zeros((n, 3)); U3[:, 0], U3[:, 1] = F['Ux'] - F['dUx'], F['Uy'] - F['dUy']
+        out0, rc0 = sm5.predict_fields(U3, p=F['p_prev'])
+        assert rc0 == psm_b200.PSM_SKIPPED
+        np.testing.assert_array_equal(out0, F['p_prev'])
+        U3[:, 0], U3[:, 1] = F['Ux'], F['Uy']
+        out1, rc1 = sm5.predict_fields(U3, p=F['p_prev'])
+        assert rc1 == 0
+        rows5 = syn.pack_cells(c.mesh, F, with_delta=False)
+    with psm_b200.PressureSurrogate('deltaU_to_deltaP', input_cols=5) as sm5b:
+        sm5b.load_params(c.params)
+        sm5b.init_tables(c.tables)
+        prev = rows5.copy(); prev[:, 0] -= F['dUx']; prev[:, 1] -= F['dUy']
+        sm5b.predict(prev)
+        out_rows, _ = sm5b.predict(rows5)
+    np.testing.assert_array_equal(out1, out_rows)
