@@ -181,7 +181,10 @@ def partition(tables, cells_xy, world, variant='deltaU_to_deltaP', shape=128, ov
 # facts are global: the last invalid pixel (the (0,0) raster quirk, SMC:161,432) and who needs which
 # ghost cell; the caller moves the phase summaries between ranks (torch.distributed / MPI).
 def band_phase1(cells_xy, top, obst, probe_values, rank, world, variant='deltaU_to_deltaP', delta=5e-3, shape=128,
-                overlap=None, near_wall_sdf=0.0, margin_px=12, halo='cells'):
+                overlap=None, near_wall_sdf=0.0, margin_px=12, halo='cells', keep_raw=False):
+    """``keep_raw``: also keep this rank's rows of the UNFOLDED cells -> grid table (global cell ids, float64 weights) as
+    ``L['raw_vert']`` / ``L['raw_weights']`` -- concatenated over the ranks they are the global table of UTL:38-44 (bench.py
+    builds a single-GPU handle and the oracle from them to check the sharded run)."""
     from . import tables as T
     assert halo in ('cells', 'grid')
     if overlap is None:
@@ -230,6 +233,9 @@ def band_phase1(cells_xy, top, obst, probe_values, rank, world, variant='deltaU_
              local_ext_rows=lext, send_rows=0 if (rank == 0 or halo == 'cells') else overlap, ta=ta, tb=tb, owned=owned, cell_rank=cell_rank, fv=fv, fw=fw,
              sdfunct=np.ascontiguousarray(sdfunct[r0 - ta:r1 + ext - ta]), ok_rows=ok2, near_wall_sdf=near_wall_sdf,
              bbox=(x_min, x_max, y_min, y_max), delta=delta)
+    if keep_raw:
+        L['raw_vert'] = np.ascontiguousarray(gv[o0:o1].astype(np.int32))
+        L['raw_weights'] = np.ascontiguousarray(w[o0:o1])
     # grid -> cell table of the owned cells in closed form (tables.regular_grid_back_tables), hop and keep mask
     bvert, bw = T.regular_grid_back_tables(cells_xy[owned], Xr, Yc, W)
     brow = bvert // W
