@@ -158,6 +158,9 @@ typedef struct psm_shard {
     const int64_t* cell_recv_ptr;                                 /* ghost slots, grouped by owner    */
     const int64_t* pix_send_ptr;  const int32_t* pix_send_idx;    /* own pixel ids each peer needs    */
     const int64_t* pix_recv_ptr;                                  /* ghost pixel slots, by owner      */
+    const int64_t* ghost_pix;          /* [n_ghost_pix] GLOBAL pixel id (row * W + col) of every ghost pixel slot, or NULL.
+                                          With it (and the peer-memory transport) the grid->cell gather reads the owners' predicted
+                                          BLOCKS directly -- ghost pixels are pushed from the blocks, no field is assembled      */
 } psm_shard;
 
 /* Static geometry report (filled by psm_get_geometry). */
@@ -281,6 +284,17 @@ int psm_get_forward_table(const psm_handle* h, int32_t* vert, float* weights);
 
 /* Copy one device-resident intermediate of the LAST step to the host; n_bytes must match. */
 int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_bytes);
+
+/* U_to_gradP only (single-GPU handle): the pressure field recovered from the two assembled gradient fields of the LAST step, the way
+ * the reference's evaluation does it -- Evaluation.integrate_field on four quadrants around the obstacle (GRAD:371-416) and the
+ * stitch of timeStep (GRAD:585-628), quirks included (see oracle/integrate.py).  p_field: host double[H][W]. */
+typedef struct psm_integrate_geometry {
+    double min_x, max_x, min_y, max_y;    /* bounding box of the `top` boundary points (GRAD:205; xl, yl of GRAD:585-586)    */
+    double x0_min;                        /* X0.min(): x of the first grid column (GRAD:591)                                 */
+    int32_t center_row;                   /* the reference hard-codes 200 (GRAD:592); must cross the obstacle                 */
+    int32_t reserved;
+} psm_integrate_geometry;
+int psm_integrate_gradp(psm_handle* h, const psm_integrate_geometry* g, double* p_field);
 
 /* Per-stage milliseconds of the last step (enable_timings=1).  Order: h2d, prep, gather,
  * extract, pca_project, mlp, pca_inverse, strip_means, offsets, place, back_gather, d2h.

@@ -124,7 +124,12 @@ struct psm_handle {
     uint8_t* d_gmask = nullptr; uint16_t* d_owner = nullptr;
     // single GPU: the placement folded into the grid->cell gather (back table re-indexed into the predicted blocks)
     bool fuse_place = false; bool field_stale = false; bool no_fused_offsets = false;
+    // multi-GPU fused flow: ghost pixels pushed from the owners' blocks into the region behind d_blocks
+    bool mgpu_fused = false; long long ghost_base = 0; int32_t* d_pix_send_blk = nullptr;
     int filter_radius = 0; float* d_gauss_w = nullptr; float* d_filter_tmp = nullptr;   // optional post-filter (SMC:353-356)
+    std::vector<uint8_t> host_mask;   // [Hglob][W] flow mask (sdfunct != 0), host copy
+    bool plan_mask_at(int y, int x) const { return host_mask[(size_t)y * W + x] != 0; }
+    std::vector<uint8_t> sdf_int;     // U_to_gradP, single GPU: int(sdfunct) per pixel, the index array of GRAD:392 (psm_integrate_gradp)
     int32_t* d_bb[3] = {nullptr, nullptr, nullptr}; uint16_t* d_bo[3] = {nullptr, nullptr, nullptr};
     int32_t *d_by0 = nullptr, *d_bx0 = nullptr;
     CoverEntry *d_rowcov = nullptr, *d_colcov = nullptr; bool fused_extract = false;   // gather writes the block operand itself
@@ -424,6 +429,7 @@ struct LocalInit {
     std::vector<int32_t> bv[3]; std::vector<float> bw[3];      // [n_owned]
     std::vector<long long> cell_send_ptr, cell_recv_ptr, pix_send_ptr, pix_recv_ptr;
     std::vector<int32_t> cell_send_idx, pix_send_idx;
+    std::vector<long long> ghost_pix;          // global pixel id per ghost slot (empty: unknown -> legacy multi-GPU flow)
 };
 }  // namespace
 
@@ -431,8 +437,9 @@ struct LocalInit {
 // to the NCCL exchange when any rank cannot map a peer, when PSM_COMM=nccl, or in the grid-row halo mode.
 static int setup_p2p(psm_handle* h) {
     struct PeerInfo {
-        cudaIpcMemHandle_t uv, field, means, mail;
-        long long n_owned, G, field_stride;
+        cudaIpcMemHandle_t uv, field, means, mail, blocks;
+        long long n_owned, G, field_stride, ghost_base;
+        int fused;
         long long cell_recv_ptr[kMaxPeers + 1], pix_recv_ptr[kMaxPeers + 1];
         int ok;
     };
@@ -444,11 +451,14 @@ static int setup_p2p(psm_handle* h) {
     mine.ok = want;
     if (want) {
         if (cudaIpcGetMemHandle(&mine.uv, h->d_uv) != cudaSuccess || cudaIpcGetMemHandle(&mine.field, h->d_field) != cudaSuccess ||
-            cudaIpcGetMemHandle(&mine.means, h->d_means) != cudaSuccess || cudaIpcGetMemHandle(&mine.mail, h->d_mail) != cudaSuccess) {
+            cudaIpcGetMemHandle(&mine.means, h->d_means) != cudaSuccess || cudaIpcGetMemHandle(&mine.mail, h->d_mail) != cudaSuccess ||
+            cudaIpcGetMemHandle(&mine.blocks, h->d_blocks) != cudaSuccess) {
             mine.ok = 0; cudaGetLastError();
         }
     }
-    mine.n_owned = h->n_cells; mine.G = h->G; mine.field_stride = h->field_stride;
+    mine.n_owned = h->n_cells; mine.G = h->G; mine.field_stride = h->field_stride; mine.ghost_base = h->ghost_base;
+    // the fused flow needs the from-blocks back table, the strip sums out of the PCA-inverse epilogue and offsets that fit one CTA
+    mine.fused = (h->fuse_place && h->strip_fuse && h->inv_t && h->have_back && (long long)h->Bg * h->F <= 4096 && !h->no_fused_offsets) ? 1 : 0;
     for (int p = 0; p <= Wd && p <= kMaxPeers; ++p) { mine.cell_recv_ptr[p] = h->cell_recv_ptr[p]; mine.pix_recv_ptr[p] = h->pix_recv_ptr[p]; }
     // all-gather the descriptors (bytes) through NCCL
     PeerInfo* d_all = nullptr;
@@ -464,14 +474,15 @@ static int setup_p2p(psm_handle* h) {
     pa.rank = me; pa.world = Wd; pa.sc = h->d_sc;
     if (ok) {
         for (int p = 0; p < Wd && ok; ++p) {
-            void *uv = h->d_uv, *field = h->d_field, *means = h->d_means, *mail = h->d_mail;
+            void *uv = h->d_uv, *field = h->d_field, *means = h->d_means, *mail = h->d_mail, *blocks = h->d_blocks;
             if (p != me) {
                 auto open = [&](void** out, cudaIpcMemHandle_t hd) {
                     if (cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
                     h->ipc_opened.push_back(*out);
                     return true;
                 };
-                ok = open(&uv, all[p].uv) && open(&field, all[p].field) && open(&means, all[p].means) && open(&mail, all[p].mail);
+                ok = open(&uv, all[p].uv) && open(&field, all[p].field) && open(&means, all[p].means) && open(&mail, all[p].mail) &&
+                     open(&blocks, all[p].blocks);
                 if (!ok) break;
             }
             pa.mail[p] = static_cast<PeerMail*>(mail);
@@ -479,8 +490,12 @@ static int setup_p2p(psm_handle* h) {
             pa.uv_ghost[p] = static_cast<float2*>(uv) + all[p].n_owned + all[p].cell_recv_ptr[me];
             pa.field_ghost[p] = static_cast<float*>(field) + all[p].G + all[p].pix_recv_ptr[me];
             pa.field_stride[p] = all[p].field_stride;
+            pa.blk_ghost[p] = static_cast<float*>(blocks) + all[p].ghost_base;
+            pa.pix_slot0[p] = all[p].pix_recv_ptr[me];
         }
     }
+    bool fused = true;
+    for (int p = 0; p < Wd; ++p) fused = fused && all[p].fused;
     // every rank must take the same path: agree through one more tiny all-gather
     int* d_flag = nullptr;
     CU(h, cudaMalloc(&d_flag, sizeof(int) * Wd));
@@ -493,6 +508,8 @@ static int setup_p2p(psm_handle* h) {
     cudaFree(d_all); cudaFree(d_flag);
     for (int p = 0; p < Wd; ++p) ok = ok && flags[p];
     h->p2p = ok;
+    h->mgpu_fused = ok && fused;
+    if (!h->mgpu_fused && h->fuse_place) h->fuse_place = false;      // legacy flow: the assembled field + ghost pixels of the field
     if (!ok) return PSM_OK;                       // NCCL exchange
     for (int p = 0; p <= Wd; ++p) { pa.cell_send_ptr[p] = h->cell_send_ptr[p]; pa.pix_send_ptr[p] = h->pix_send_ptr[p]; }
     for (int p = Wd + 1; p <= kMaxPeers; ++p) { pa.cell_send_ptr[p] = pa.cell_send_ptr[Wd]; pa.pix_send_ptr[p] = pa.pix_send_ptr[Wd]; }
@@ -553,6 +570,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
     {
         std::vector<uint8_t> mask(L.mask_global, L.mask_global + (size_t)L.H * W);
         TRY(upload(h, &h->d_gmask, mask));
+        h->host_mask = mask;
         std::vector<uint16_t> ow(G);
         for (long long q = 0; q < G; ++q) {
             const int o = P.owner[(size_t)L.row0 * W + q];
@@ -574,21 +592,45 @@ static int init_local(psm_handle* h, LocalInit& L) {
             TRY(upload(h, &h->d_gauss_w, wf));
             TRY(dalloc(h, &h->d_filter_tmp, (size_t)G));
         }
-        h->fuse_place = (L.world == 1) && L.have_back && !env_on("PSM_NO_FUSED_PLACE") && h->filter_radius == 0;
+        // single GPU, or a shard that knows the global pixel of every ghost slot (fused multi-GPU flow)
+        const bool ghosts_known = L.n_ghost_pix == 0 || (long long)L.ghost_pix.size() == L.n_ghost_pix;
+        h->fuse_place = (L.world == 1 || (ghosts_known && L.ext_rows == 0 && L.send_rows == 0 && !env_on("PSM_MGPU_LEGACY"))) && L.have_back &&
+                        !env_on("PSM_NO_FUSED_PLACE") && h->filter_radius == 0 && P.B < 65536;
         h->no_fused_offsets = env_on("PSM_NO_FUSED_OFFSETS");
+        h->ghost_base = (long long)h->B_pad * h->C * S2;
         if (h->fuse_place) {
-            // pixel -> (last-writer block, offset inside the blocks array) is static: re-index the back table
+            // pixel -> (last-writer block, offset inside the blocks array) is static: re-index the back table.  Ghost pixels live
+            // behind the local blocks as [chunk][C][S*S]; the owner id is GLOBAL (it indexes the global offset array).
+            for (long long q : L.ghost_pix) if (q < 0 || q >= (long long)L.H * W) PSM_FAIL(h, PSM_ERR_INVALID, "ghost_pix out of range");
             for (int j = 0; j < 3; ++j) {
                 std::vector<int32_t> bb(N); std::vector<uint16_t> bo(N);
                 for (long long c = 0; c < N; ++c) {
                     const long long q = L.bv[j][c];
                     if (q < 0) { bb[c] = -1; bo[c] = 0; continue; }          // keep p_prev marker (vertex 0 only)
+                    if (q >= G) {                                            // ghost pixel: pushed by its owner
+                        const long long sl = q - G;
+                        bb[c] = (int32_t)(h->ghost_base + ((sl / S2) * h->C) * S2 + sl % S2);
+                        bo[c] = (uint16_t)P.owner[(size_t)L.ghost_pix[sl]];
+                        continue;
+                    }
                     const int o = ow[q];
                     const int y = (int)(q / W), x = (int)(q - (long long)y * W);
                     bb[c] = (int32_t)(((long long)o * h->C) * S2 + (long long)(y - (P.y0[kb0 + o] - L.row0)) * S + (x - P.x0[kb0 + o]));
-                    bo[c] = (uint16_t)o;
+                    bo[c] = (uint16_t)(kb0 + o);
                 }
                 TRY(upload(h, &h->d_bb[j], bb)); TRY(upload(h, &h->d_bo[j], bo));
+            }
+            if (L.world > 1) {      // where MY pixels that are ghost pixels elsewhere sit in my blocks (channel 0)
+                std::vector<int32_t> sb(L.pix_send_idx.size());
+                for (size_t e = 0; e < sb.size(); ++e) {
+                    const long long q = L.pix_send_idx[e];
+                    if (q < 0 || q >= G) PSM_FAIL(h, PSM_ERR_INVALID, "pix_send_idx out of range");
+                    const int o = ow[q];
+                    const int y = (int)(q / W), x = (int)(q - (long long)y * W);
+                    sb[e] = (int32_t)(((long long)o * h->C) * S2 + (long long)(y - (P.y0[kb0 + o] - L.row0)) * S + (x - P.x0[kb0 + o]));
+                }
+                if (sb.empty()) sb.push_back(0);
+                TRY(upload(h, &h->d_pix_send_blk, sb));
             }
         }
         std::vector<int32_t> by0(h->B_pad, 0), bx0(h->B_pad, 0);
@@ -728,7 +770,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
     TRY(dalloc(h, &h->d_act[0], (size_t)Bp * maxw));
     TRY(dalloc(h, &h->d_act[1], (size_t)Bp * maxw));
     TRY(dalloc(h, &h->d_r, (size_t)Bp * h->pc_p_pad));
-    TRY(dalloc(h, &h->d_blocks, (size_t)Bp * h->C * S2));
+    TRY(dalloc(h, &h->d_blocks, (size_t)Bp * h->C * S2 + (size_t)((L.n_ghost_pix + S2 - 1) / S2) * h->C * S2));   // + ghost pixels [chunk][C][S*S]
     TRY(dalloc(h, &h->d_means, (size_t)h->n_tasks_glob));
     for (int i = 0; i < 2; ++i) { TRY(dalloc(h, &h->d_dbuf[i], (size_t)h->F * h->Bg)); TRY(dalloc(h, &h->d_pbuf[i], (size_t)h->F * h->Bg)); }
     TRY(dalloc(h, &h->d_offsets, (size_t)h->F * h->Bg));
@@ -737,6 +779,10 @@ static int init_local(psm_handle* h, LocalInit& L) {
     TRY(dalloc(h, &h->d_sc, 1));
     TRY(dalloc(h, &h->d_zc, (size_t)Bp * h->pc_in_pad));
 
+    if (h->cfg.variant == PSM_U_TO_GRADP && L.world == 1) {
+        h->sdf_int.resize((size_t)L.H * W);
+        for (size_t q = 0; q < h->sdf_int.size(); ++q) { const double v = L.sdf_rows[q]; h->sdf_int[q] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : (int)v)); }
+    }
     // ---- static distance-channel contribution per block: zc[b][n] = sum_p sdf_n[b,p] * comp[n][p*3+2] ----
     // (grid[...,2] = sdfunct / max_abs_dist, SMC:434,443 -- constant for the mesh)
     {
@@ -973,6 +1019,7 @@ extern "C" int psm_init_sharded(psm_handle* h, const psm_shard* s) {
         if (L.pix_send_ptr[Wd] > 0 && !s->pix_send_idx) PSM_FAIL(h, PSM_ERR_INVALID, "pix_send_idx is NULL");
         L.cell_send_idx.assign(s->cell_send_idx, s->cell_send_idx + L.cell_send_ptr[Wd]);
         L.pix_send_idx.assign(s->pix_send_idx, s->pix_send_idx + L.pix_send_ptr[Wd]);
+        if (s->ghost_pix && s->n_ghost_pix > 0) L.ghost_pix.assign(s->ghost_pix, s->ghost_pix + s->n_ghost_pix);
     }
     return init_local(h, L);
 }
@@ -1030,17 +1077,23 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
 
     const bool dim = h->cfg.variant != PSM_U_TO_GRADP;        // blocks re-dimensionalised by max_abs_p * U^2 (SMC:551, PMP:490); GRAD: none
     ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], dim ? h->maxs[3] : 1.0, dim ? 1 : 0, h->cfg.skip_threshold, mode, 0};
+    const bool p2p = multi && h->p2p;
+    const P2PArgs* d_p2p = p2p ? h->d_p2p : nullptr;
+    // fused multi-GPU flow: the exchanges ride in the tails of prep and of the fold kernel (no push launches, no assembled field)
+    const bool mfused = p2p && h->mgpu_fused && d_out != nullptr;
+    P2PFused fx{};
+    if (mfused) fx = P2PFused{h->d_p2p, h->d_cell_send_idx, h->d_blocks, h->d_pix_send_blk, h->C, S2, h->pix_send_ptr[h->world]};
     if (fields) {
-        PrepFieldsArgs pf{in.U, in.dU, in.u_stride, h->n_cells, mode, h->d_uv, h->d_uprev, h->d_sc};
+        PrepFieldsArgs pf{in.U, in.dU, in.u_stride, h->n_cells, mode, h->d_uv, h->d_uprev, h->d_sc, fx};
         launch_prep_fields(pf, s); ++nl;
     } else {
-        PrepArgs pa{in.rows, h->n_cells, h->cfg.input_cols, mode, h->d_uv, h->d_pprev, h->d_uprev, h->d_sc};
+        PrepArgs pa{in.rows, h->n_cells, h->cfg.input_cols, mode, h->d_uv, h->d_pprev, h->d_uprev, h->d_sc, fx};
         launch_prep(pa, s); ++nl;
         h->pprev_zero = false;
     }
-    const bool p2p = multi && h->p2p;
-    const P2PArgs* d_p2p = p2p ? h->d_p2p : nullptr;
-    if (p2p) {
+    if (mfused) {
+        // exchange 1 happened in the tail of prep
+    } else if (p2p) {
         // exchange 1 over peer memory: maxima + ghost cells are pushed, the gather kernel waits on its mailbox
         launch_p2p_push_cells(h->d_p2p, h->d_uv, h->d_cell_send_idx, h->cell_send_ptr[h->world], s); ++nl;
     } else if (multi) {
@@ -1148,12 +1201,16 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
     oa.sc = h->d_sc;
     oa.host_skip = h->d_host_skip;
     oa.p2p = d_p2p;
-    const bool fuse_offsets = !multi && h->n_tasks > 0 && h->Bg * h->F <= 1024 && !h->no_fused_offsets;
+    const bool use_fold = tc && h->inv_t && h->strip_fuse;      // row partials left by the PCA-inverse epilogue
+    const bool fuse_offsets = (!multi || mfused) && h->n_tasks > 0 && h->Bg * h->F <= (use_fold ? 4096 : 1024) && !h->no_fused_offsets;
     MeansArgs ma{h->d_tasks, h->n_tasks, h->d_blocks, h->d_gmask, h->C, S, h->W, (multi && !p2p) ? h->d_means_loc : h->d_means};
-    if (tc && h->inv_t && h->strip_fuse) launch_fold(ma, h->d_rowpart, fuse_offsets ? &oa : nullptr, s);     // row partials left by the PCA-inverse epilogue
+    if (mfused && !(use_fold && fuse_offsets)) PSM_FAIL(h, PSM_ERR_STATE, "fused multi-GPU flow without the fold kernel");
+    if (use_fold) launch_fold(ma, h->d_rowpart, fuse_offsets ? &oa : nullptr, fx, s);
     else launch_means(ma, fuse_offsets ? &oa : nullptr, s);
     ++nl;
-    if (p2p && !fuse_offsets) { launch_p2p_push_means(h->d_p2p, h->d_tasks, h->n_tasks, h->world, h->d_means, s); ++nl; }   // exchange 3 over peer memory
+    if (mfused) {
+        // exchange 2 (strip means) and 3 (ghost pixels, straight from the blocks) happened inside the fold kernel
+    } else if (p2p && !fuse_offsets) { launch_p2p_push_means(h->d_p2p, h->d_tasks, h->n_tasks, h->world, h->d_means, s); ++nl; }   // exchange 3 over peer memory
     else if (multi)   // exchange 3: every rank contributes its own slots (zero elsewhere) -> identical means everywhere
         NC(h, g_nccl.AllReduce(h->d_means_loc, h->d_means, (size_t)h->n_tasks_glob, ncclDouble, ncclSum, h->comm, s));
     tick();   // strip_means
@@ -1161,7 +1218,7 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
     tick();   // offsets
     PlaceArgs pl{h->d_blocks, h->d_owner, h->d_by0, h->d_bx0, h->d_coff, h->d_field, h->Bg, h->kb0, h->C, h->F, S, h->H, h->W,
                  h->field_stride};
-    const bool fuse_place = h->fuse_place && d_out != nullptr;
+    const bool fuse_place = h->fuse_place && d_out != nullptr && (!multi || mfused);
     if (!fuse_place) { launch_place(pl, s); ++nl; }
     if (h->filter_radius > 0)
         for (int f = 0; f < h->F; ++f) {      // axis 0, then axis 1, like scipy.ndimage.gaussian_filter
@@ -1172,7 +1229,9 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
         }
     tick();   // place
     if (h->have_back && d_out) {
-        if (p2p) {
+        if (mfused) {
+            // ghost pixels already sit behind the local blocks (pushed by their owners from the fold kernel)
+        } else if (p2p) {
             launch_p2p_push_pix(h->d_p2p, h->d_field, h->d_pix_send_idx, h->F, h->field_stride, h->pix_send_ptr[h->world], s); ++nl;   // exchange 4 over peer memory
         } else if (multi) {
             // exchange 4: the field pixels other ranks' grid->cell tables reference (rows next to a rank
@@ -1489,6 +1548,74 @@ extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_
         default:
             PSM_FAIL(h, PSM_ERR_INVALID, "unknown stage %d", stage);
     }
+}
+
+// U_to_gradP: the pressure field recovered from the assembled gradient fields of the LAST step (GRAD:371-416, 585-628).
+extern "C" int psm_integrate_gradp(psm_handle* h, const psm_integrate_geometry* g, double* p_field) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "not initialised");
+    if (!g || !p_field) PSM_FAIL(h, PSM_ERR_INVALID, "psm_integrate_gradp: NULL argument");
+    if (h->cfg.variant != PSM_U_TO_GRADP || h->world != 1) PSM_FAIL(h, PSM_ERR_STATE, "psm_integrate_gradp needs a single-GPU U_to_gradP handle");
+    const int H = h->Hglob, W = h->W, cy = g->center_row;
+    if (cy < 1 || cy >= H) PSM_FAIL(h, PSM_ERR_GEOMETRY, "center_row %d is outside the %d grid rows (the reference hard-codes 200, GRAD:592)", cy, H);
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    // centre column: middle of the zero run (obstacle) of the distance field in the centre row, GRAD:591
+    const double sx = (g->max_x - g->min_x) / (double)(W - 1);
+    double lo = 0.0, hi = 0.0; bool any = false;
+    for (int x = 0; x < W; ++x)
+        if (!h->plan_mask_at(cy, x)) { const double xv = (x == W - 1) ? g->max_x : g->min_x + sx * x; if (!any) { lo = hi = xv; any = true; } else { if (xv < lo) lo = xv; if (xv > hi) hi = xv; } }
+    if (!any) PSM_FAIL(h, PSM_ERR_GEOMETRY, "row %d of the distance field has no zero (the obstacle must cross the centre row, GRAD:591)", cy);
+    const int cx = (int)(((hi + lo) / 2 - g->x0_min) / h->cfg.delta);
+    if (cx < 1 || cx >= W) PSM_FAIL(h, PSM_ERR_GEOMETRY, "centre column %d outside the grid", cx);
+    // the static fix-up list of every block-local row (GRAD:389-395 with nn = int(sdfunct[i_local, :]))
+    const int nloc = cy > H - cy ? cy : H - cy;
+    const int wmin = cx < W - cx + 1 ? cx : W - cx + 1;
+    std::vector<IntegrateFix> fix(nloc);
+    for (int i = 0; i < nloc; ++i) {
+        IntegrateFix f{};
+        const uint8_t* nn = h->sdf_int.data() + (size_t)i * W;
+        int last[256]; for (int v = 0; v < 256; ++v) last[v] = -1;
+        for (int k = 0; k < W; ++k) last[nn[k]] = k;
+        for (int v = 0; v < 256; ++v) {
+            if (last[v] < 0) continue;
+            if (v >= wmin) PSM_FAIL(h, PSM_ERR_GEOMETRY, "distance %d m indexes past a quadrant of width %d (the reference raises IndexError, GRAD:393)", v, wmin);
+            if (f.n >= 4) PSM_FAIL(h, PSM_ERR_GEOMETRY, "more than 4 distinct integer distances in one grid row");
+            f.pos[f.n] = v; f.prev[f.n] = last[v] > 0 ? nn[last[v] - 1] : -1; ++f.n;
+        }
+        fix[i] = f;
+    }
+    if (h->field_stale) {
+        PlaceArgs pl{h->d_blocks, h->d_owner, h->d_by0, h->d_bx0, h->d_coff, h->d_field, h->Bg, h->kb0, h->C, h->F, h->S, h->H, h->W, h->field_stride};
+        launch_place(pl, h->stream);
+        h->field_stale = false;
+    }
+    IntegrateFix* d_fix = nullptr; double *d_sdpx = nullptr, *d_anchor = nullptr, *d_corr = nullptr, *d_out = nullptr; int* d_status = nullptr;
+    const size_t G = (size_t)H * W;
+    int rc = PSM_OK;
+    if (cudaMalloc(&d_fix, fix.size() * sizeof(IntegrateFix)) != cudaSuccess || cudaMalloc(&d_sdpx, 2 * G * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&d_anchor, 4 * (size_t)H * sizeof(double)) != cudaSuccess || cudaMalloc(&d_corr, 2 * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&d_out, G * sizeof(double)) != cudaSuccess || cudaMalloc(&d_status, sizeof(int)) != cudaSuccess) rc = PSM_ERR_CUDA;
+    int status = 0;
+    if (rc == PSM_OK) {
+        cudaMemcpyAsync(d_fix, fix.data(), fix.size() * sizeof(IntegrateFix), cudaMemcpyHostToDevice, h->stream);
+        cudaMemsetAsync(d_status, 0, sizeof(int), h->stream);
+        cudaMemsetAsync(d_anchor, 0, 4 * (size_t)H * sizeof(double), h->stream);
+        // np.diff(np.linspace(a, b, n))[0] = (1 * step + a) - a, rounding included
+        const double sy = (g->max_y - g->min_y) / (double)(H - 1);
+        volatile double x1 = 1.0 * sx + g->min_x, y1 = 1.0 * sy + g->min_y;
+        const double dx = x1 - g->min_x, dy = y1 - g->min_y;
+        IntegrateArgs ia{h->d_field, h->d_field + h->field_stride, h->d_gmask, d_fix, H, W, cx, cy, dx, dy,
+                         d_sdpx, d_anchor, d_corr, d_status, d_out};
+        launch_integrate(ia, h->stream);
+        cudaMemcpyAsync(p_field, d_out, G * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = PSM_ERR_CUDA;
+    }
+    cudaFree(d_fix); cudaFree(d_sdpx); cudaFree(d_anchor); cudaFree(d_corr); cudaFree(d_out); cudaFree(d_status);
+    if (rc != PSM_OK) PSM_FAIL(h, rc, "psm_integrate_gradp: CUDA failure");
+    if (status) PSM_FAIL(h, PSM_ERR_GEOMETRY, "the two stitch columns have different numbers of flow pixels (numpy raises at GRAD:606)");
+    return PSM_OK;
 }
 
 extern "C" int psm_get_timings(psm_handle* h, float* ms, int32_t n) {

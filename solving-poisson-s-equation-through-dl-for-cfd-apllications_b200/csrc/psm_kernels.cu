@@ -169,6 +169,43 @@ __device__ __forceinline__ void publish_scalars(const ScalarArgs& sa, unsigned l
     sc->have_prev = 1;
 }
 
+
+// Multi-GPU fused flow: the LAST CTA of a prep kernel to finish pushes this rank's two running maxima and the cells that are
+// ghost cells elsewhere straight into the peers' buffers, fences at system scope and raises the phase-0 flags -- no separate
+// push launch.  Every CTA pays one device-scope fence + one atomic.
+__device__ __forceinline__ void prep_p2p_tail(const P2PFused& fx, const float2* uv, Scalars* sc) {
+    if (!fx.p2p) return;
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int prev = atomicAdd(&sc->push_done[0], 1u);
+        s_last = (prev == gridDim.x - 1);
+        if (s_last) { sc->push_done[0] = 0u; __threadfence(); }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    const P2PArgs& P = *fx.p2p;
+    const unsigned int step = P.sc->step + 1u;
+    const long long nsend = P.cell_send_ptr[P.world];
+    for (long long e = threadIdx.x; e < nsend; e += blockDim.x) {
+        int p = 0;
+        while (e >= P.cell_send_ptr[p + 1]) ++p;
+        P.uv_ghost[p][e - P.cell_send_ptr[p]] = __ldcg(uv + fx.cell_send_idx[e]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) P.sc->step = step;
+    if ((int)threadIdx.x < P.world) {
+        const int p = threadIdx.x;
+        PeerMail* m = P.mail[p];
+        m->maxima[P.rank][0] = *reinterpret_cast<volatile unsigned long long*>(&sc->umax2_bits);
+        m->maxima[P.rank][1] = *reinterpret_cast<volatile unsigned long long*>(&sc->dumax2_bits);
+        __threadfence_system();
+        st_release_sys(&m->flag[0][P.rank], step);
+    }
+}
+
 template <int MODE, int NCOL>
 __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
     pdl_enter();
@@ -211,6 +248,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
             atomicMax(&a.sc->dumax2_bits, (unsigned long long)__double_as_longlong(m_d));
         }
     }
+    prep_p2p_tail(a.fx, a.uv, a.sc);
 }
 
 // Bulk-copy variant (opt-in, see launch_prep): persistent CTAs stream 256-row tiles of the
@@ -311,6 +349,7 @@ __global__ void __launch_bounds__(kPrepRows) prep_bulk_kernel(PrepArgs a) {
             atomicMax(&a.sc->dumax2_bits, (unsigned long long)__double_as_longlong(m_d));
         }
     }
+    prep_p2p_tail(a.fx, a.uv, a.sc);
 }
 template <int MODE, int NCOL>
 static void launch_prep_bulk(const PrepArgs& a, cudaStream_t s) {
@@ -386,6 +425,7 @@ __global__ void __launch_bounds__(256) prep_fields_kernel(PrepFieldsArgs a) {
             atomicMax(&a.sc->dumax2_bits, (unsigned long long)__double_as_longlong(m_d));
         }
     }
+    prep_p2p_tail(a.fx, a.uv, a.sc);
 }
 void launch_prep_fields(const PrepFieldsArgs& a, cudaStream_t s) {
     long long want = (a.n + 255) / 256;
@@ -821,12 +861,13 @@ void launch_means(const MeansArgs& a, const OffsetsArgs* fused, cudaStream_t s) 
 //       task sums its 4 * rows FP32 partials in FP64 -- lane-strided, then a fixed butterfly: deterministic -- so the 8 MB of
 //       predicted blocks are not read a second time.  Same MODE switch as task_means_kernel.
 template <int MODE>
-__global__ void __launch_bounds__(256) task_fold_kernel(MeansArgs a, const float* __restrict__ rowpart, OffsetsArgs oa) {
+__global__ void __launch_bounds__(256) task_fold_kernel(MeansArgs a, const float* __restrict__ rowpart, OffsetsArgs oa, P2PFused fx, int n_task_ctas) {
     pdl_launch_dependents();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool push_cta = (MODE == 2) && (int)blockIdx.x >= n_task_ctas;          // MODE 2: CTAs behind the task CTAs push ghost pixels
     const int ti = blockIdx.x * 8 + w;
     DevTask t{};
-    if (ti < a.n_tasks) t = a.tasks[ti];
+    if (!push_cta && ti < a.n_tasks) t = a.tasks[ti];
     extern __shared__ __align__(16) unsigned char mk_smem[];
     DevRec* s_rec = nullptr; DevShiftTerm* s_terms = nullptr;
     if (MODE != 0) {
@@ -837,7 +878,21 @@ __global__ void __launch_bounds__(256) task_fold_kernel(MeansArgs a, const float
         for (int i = threadIdx.x; i < nt; i += blockDim.x) s_terms[i] = oa.terms[i];
     }
     pdl_wait();
-    if (ti < a.n_tasks) {
+    if (push_cta) {
+        // my predicted pixels that other ranks' grid->cell tables reference: straight from the blocks into their ghost regions
+        const P2PArgs& P = *fx.p2p;
+        const long long total = fx.n_pix_send * fx.C;
+        const long long stride = (long long)(gridDim.x - n_task_ctas) * blockDim.x;
+        for (long long e = (long long)(blockIdx.x - n_task_ctas) * blockDim.x + threadIdx.x; e < total; e += stride) {
+            const int f = (int)(e / fx.n_pix_send);
+            const long long k = e - (long long)f * fx.n_pix_send;
+            int p = 0;
+            while (k >= P.pix_send_ptr[p + 1]) ++p;
+            const long long slot = P.pix_slot0[p] + (k - P.pix_send_ptr[p]);
+            P.blk_ghost[p][((slot / fx.S2) * fx.C + f) * fx.S2 + slot % fx.S2] = __ldcg(fx.blocks + fx.pix_send_blk[k] + (long long)f * fx.S2);
+        }
+        __threadfence_system();
+    } else if (ti < a.n_tasks) {
         const float* p = rowpart + (long long)t.part_base * 4;
         const int n = 4 * (t.y1 - t.y0);
         double acc = 0.0;
@@ -857,18 +912,53 @@ __global__ void __launch_bounds__(256) task_fold_kernel(MeansArgs a, const float
         }
         __syncthreads();
         if (!s_last) return;
+        if (MODE == 2) {
+            // exchange of the strip means, in this CTA: my slots to every peer, flags for the means (phase 1) and for the ghost
+            // pixels the other CTAs pushed (phase 2; their system-scope fences precede the counter), then wait for the peers
+            const P2PArgs& P = *fx.p2p;
+            const unsigned int step = P.sc->step;
+            const int total = a.n_tasks * P.world;
+            for (int e = threadIdx.x; e < total; e += blockDim.x) {
+                const int p = e / a.n_tasks, i = e - p * a.n_tasks;
+                if (p == P.rank) continue;
+                const int slot = a.tasks[i].out;
+                P.means[p][slot] = ld_cg_f64(a.means + slot);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if ((int)threadIdx.x < P.world && (int)threadIdx.x != P.rank) {
+                const int p = threadIdx.x;
+                st_release_sys(&P.mail[p]->flag[1][P.rank], step);
+                if (P.pix_send_ptr[p + 1] > P.pix_send_ptr[p]) st_release_sys(&P.mail[p]->flag[2][P.rank], step);
+            }
+            p2p_wait(fx.p2p, 1, 0xFFu);
+        }
         offsets_body(oa, s_rec, s_terms, mk_smem);
     }
 }
-void launch_fold(const MeansArgs& a, const float* rowpart, const OffsetsArgs* fused, cudaStream_t s) {
+void launch_fold(const MeansArgs& a, const float* rowpart, const OffsetsArgs* fused, const P2PFused& fx, cudaStream_t s) {
     if (a.n_tasks <= 0) return;
     const int blocks = (a.n_tasks + 7) / 8;
     if (fused) {
         const size_t n = (size_t)fused->B * fused->F;
         const size_t smem = ((n * 24 + 15) & ~(size_t)15) + n * sizeof(DevRec) + (size_t)fused->term_start[fused->F] * sizeof(DevShiftTerm);
-        launch_k(task_fold_kernel<1>, dim3(blocks), dim3(256), smem, s, a, rowpart, *fused);
+        if (fx.p2p) {
+            static bool opted[64] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!opted[dev & 63]) { cudaFuncSetAttribute(task_fold_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); opted[dev & 63] = true; }
+            long long want = (fx.n_pix_send * fx.C + 255) / 256;
+            const int push = (int)(want > 32 ? 32 : want);
+            launch_k(task_fold_kernel<2>, dim3(blocks + push), dim3(256), smem, s, a, rowpart, *fused, fx, blocks);
+        } else {
+            static bool opted[64] = {};
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (!opted[dev & 63]) { cudaFuncSetAttribute(task_fold_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); opted[dev & 63] = true; }
+            launch_k(task_fold_kernel<1>, dim3(blocks), dim3(256), smem, s, a, rowpart, *fused, fx, blocks);
+        }
     }
-    else launch_k(task_fold_kernel<0>, dim3(blocks), dim3(256), 0, s, a, rowpart, OffsetsArgs{});
+    else launch_k(task_fold_kernel<0>, dim3(blocks), dim3(256), 0, s, a, rowpart, OffsetsArgs{}, fx, blocks);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -941,8 +1031,10 @@ __global__ void __launch_bounds__(1024) offsets_kernel(OffsetsArgs a) {
 void launch_offsets(const OffsetsArgs& a, cudaStream_t s) {
     const int n = a.B * a.F;
     const size_t smem = n <= kOffsetsSmemMax ? (size_t)n * 24 : 0;
-    static bool opted = false;
-    if (!opted) { cudaFuncSetAttribute(offsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOffsetsSmemMax * 24); opted = true; }
+    static bool opted[64] = {};                                                    // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!opted[dev & 63]) { cudaFuncSetAttribute(offsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOffsetsSmemMax * 24); opted[dev & 63] = true; }
     launch_k(offsets_kernel, dim3(1), dim3(1024), smem, s, a);
 }
 

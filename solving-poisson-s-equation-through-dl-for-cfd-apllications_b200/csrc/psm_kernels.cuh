@@ -63,10 +63,21 @@ struct P2PArgs {
     long long cell_send_ptr[kMaxPeers + 1], pix_send_ptr[kMaxPeers + 1];
     unsigned int pix_recv_mask;                  // peers this rank receives ghost pixels from
     Scalars* sc;
+    // fused flow (no separate push kernels, no assembled field): ghost pixels go straight from MY predicted blocks into the
+    // ghost region behind rank p's blocks array, laid out [chunk][C][S*S] so that the channels of a slot are S*S apart
+    float* blk_ghost[kMaxPeers];                 // rank p's ghost region (start)
+    long long pix_slot0[kMaxPeers];              // first ghost slot of MY pixels in rank p's region
 };
 void launch_p2p_push_cells(const P2PArgs* d_pa, const float2* uv, const int32_t* send_idx, long long nsend, cudaStream_t s);
 void launch_p2p_push_means(const P2PArgs* d_pa, const struct DevTask* tasks, int n_tasks, int world, const double* means, cudaStream_t s);
 void launch_p2p_push_pix(const P2PArgs* d_pa, const float* field, const int32_t* send_idx, int F, long long my_stride, long long nsend, cudaStream_t s);
+// fused multi-GPU flow: what the tails of prep / the fold kernel push
+struct P2PFused {
+    const P2PArgs* p2p;                          // NULL: single GPU / legacy flow
+    const int32_t* cell_send_idx;                // prep tail: owned cells that are ghost cells elsewhere
+    const float* blocks; const int32_t* pix_send_blk; int C, S2;   // fold kernel: ghost pixels from the predicted blocks (channel-0 offsets)
+    long long n_pix_send;
+};
 
 struct ScalarArgs {
     Scalars* sc;
@@ -86,6 +97,7 @@ struct PrepArgs {
     double* p_prev;       // [n] column 4
     double* u_prev;       // [n][2] (mode 2)
     Scalars* sc;
+    P2PFused fx;          // multi-GPU fused flow: the last CTA pushes maxima + ghost cells and raises the phase-0 flags
 };
 void launch_prep(const PrepArgs& a, cudaStream_t s);
 
@@ -97,6 +109,7 @@ struct PrepFieldsArgs {
     int stride; long long n;
     int mode;             // 0: field = U; 1: field = dU; 2: field = U - U_prev (resident)
     float2* uv; double* u_prev; Scalars* sc;
+    P2PFused fx;
 };
 void launch_prep_fields(const PrepFieldsArgs& a, cudaStream_t s);
 
@@ -281,7 +294,9 @@ void launch_offsets(const OffsetsArgs& a, cudaStream_t s);
 // `fused` != NULL (single GPU, B*F <= 1024): the last CTA of the means kernel also runs the offsets (no second launch)
 void launch_means(const MeansArgs& a, const OffsetsArgs* fused, cudaStream_t s);
 // K6a': the same means from the row partials the PCA-inverse epilogue left (StripRows): one warp per task, FP64, fixed order
-void launch_fold(const MeansArgs& a, const float* rowpart, const OffsetsArgs* fused, cudaStream_t s);
+// fx.p2p != NULL (multi-GPU fused flow, `fused` required): extra CTAs push the ghost pixels, the last CTA pushes this rank's
+// means, raises the phase-1 / phase-2 flags, waits for every peer's means and runs the offsets.
+void launch_fold(const MeansArgs& a, const float* rowpart, const OffsetsArgs* fused, const P2PFused& fx, cudaStream_t s);
 
 // K7: placement through the owner map.
 struct PlaceArgs {
@@ -318,6 +333,22 @@ struct BackArgs {
     int n_blocks; int block_plane;    // S*S: distance between the channels of one block
 };
 void launch_back(const BackArgs& a, cudaStream_t s);
+
+// U_to_gradP pressure recovery (psm_integrate.cu): GRAD:371-416 integrate_field on four quadrants + the stitch GRAD:585-628.
+struct IntegrateFix { int32_t n; int32_t pos[4]; int32_t prev[4]; };     // per block-local row: entries the reference's "reset" overwrites
+struct IntegrateArgs {
+    const float* dpdx; const float* dpdy;     // assembled gradient fields [H][W]
+    const uint8_t* mask;                      // [H][W] sdfunct != 0
+    const IntegrateFix* fix;                  // [max(cy, H - cy)]
+    int H, W, cx, cy;                         // centre column / row (GRAD:591-592)
+    double dx, dy;                            // np.diff(xl)[0], np.diff(yl)[0]
+    double* sdpx;                             // scratch [2][H][W]
+    double* anchor;                           // scratch [4][H]
+    double* corr;                             // scratch [2]
+    int* status;                              // [1]: 1 = the two stitch masks have different counts (numpy would raise)
+    double* out;                              // [H][W]
+};
+void launch_integrate(const IntegrateArgs& a, cudaStream_t s);
 
 // Static sparse exchange (multi-GPU): dst[i] = src[idx[i]] for the elements other ranks need.
 struct PackArgs { const float* src; const int32_t* idx; float* dst; long long n; int width; long long src_stride; };

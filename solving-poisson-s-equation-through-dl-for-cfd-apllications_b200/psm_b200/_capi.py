@@ -62,6 +62,11 @@ class PsmGeometry(C.Structure):
                 ('n_ghost_cells', C.c_int64), ('n_ghost_pix', C.c_int64)]
 
 
+class PsmIntegrateGeometry(C.Structure):
+    _fields_ = [('min_x', C.c_double), ('max_x', C.c_double), ('min_y', C.c_double), ('max_y', C.c_double),
+                ('x0_min', C.c_double), ('center_row', C.c_int32), ('reserved', C.c_int32)]
+
+
 class PsmShard(C.Structure):
     _fields_ = [('rank', C.c_int32), ('world', C.c_int32), ('grid_h', C.c_int32), ('grid_w', C.c_int32),
                 ('row0', C.c_int32), ('row1', C.c_int32), ('ext_rows', C.c_int32), ('send_rows', C.c_int32),
@@ -71,7 +76,8 @@ class PsmShard(C.Structure):
                 ('vert', c_int32_p), ('weights', c_double_p), ('sdfunct', c_double_p),
                 ('vert_back', c_int32_p), ('weights_back', c_double_p),
                 ('cell_send_ptr', c_int64_p), ('cell_send_idx', c_int32_p), ('cell_recv_ptr', c_int64_p),
-                ('pix_send_ptr', c_int64_p), ('pix_send_idx', c_int32_p), ('pix_recv_ptr', c_int64_p)]
+                ('pix_send_ptr', c_int64_p), ('pix_send_idx', c_int32_p), ('pix_recv_ptr', c_int64_p),
+                ('ghost_pix', c_int64_p)]
 
 
 # every symbol include/psm_b200.h declares: name -> (restype, argtypes)
@@ -102,6 +108,7 @@ SYMBOLS = {
     'psm_get_owner_map': (C.c_int, [C.c_void_p, c_int32_p]),
     'psm_get_forward_table': (C.c_int, [C.c_void_p, c_int32_p, c_float_p]),
     'psm_get_stage': (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64]),
+    'psm_integrate_gradp': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     'psm_get_timings': (C.c_int, [C.c_void_p, c_float_p, C.c_int32]),
     'psm_set_timings': (C.c_int, [C.c_void_p, C.c_int32]),
     'psm_get_launch_count': (C.c_int, [C.c_void_p]),

@@ -292,6 +292,8 @@ class PressureSurrogate:
         T.cell_send_ptr, T.cell_recv_ptr = arr('cell_send_ptr', np.int64, C.c_int64), arr('cell_recv_ptr', np.int64, C.c_int64)
         T.pix_send_ptr, T.pix_recv_ptr = arr('pix_send_ptr', np.int64, C.c_int64), arr('pix_recv_ptr', np.int64, C.c_int64)
         T.cell_send_idx, T.pix_send_idx = arr('cell_send_idx', np.int32, C.c_int32), arr('pix_send_idx', np.int32, C.c_int32)
+        if sh.get('ghost_pix') is not None and int(sh['n_ghost_pix']) > 0:
+            T.ghost_pix = arr('ghost_pix', np.int64, C.c_int64)
         self._check(self.lib.psm_init_sharded(self._h, C.byref(T)))
         self.n_cells, self.W = T.n_owned, T.grid_w
         self.H = T.row1 - T.row0
@@ -398,6 +400,17 @@ class PressureSurrogate:
         }[name]
         out = np.empty(spec[1], dtype=spec[2])
         self._check(self.lib.psm_get_stage(self._h, spec[0], out.ctypes.data, out.nbytes))
+        return out
+
+    def integrate_gradp(self, top, x0_min, center_row=200):
+        """U_to_gradP: pressure field [H, W] recovered from the gradient fields of the last step (GRAD:371-416, 585-628).
+        ``top``: the top/bottom boundary points whose bounding box the reference integrates over (GRAD:205);
+        ``x0_min``: x of the first grid column."""
+        top = np.asarray(top, dtype=np.float64)
+        g = capi.PsmIntegrateGeometry(min_x=float(top[:, 0].min()), max_x=float(top[:, 0].max()), min_y=float(top[:, 1].min()),
+                                      max_y=float(top[:, 1].max()), x0_min=float(x0_min), center_row=int(center_row))
+        out = np.empty((self.H, self.W), dtype=np.float64)
+        self._check(self.lib.psm_integrate_gradp(self._h, C.byref(g), out.ctypes.data))
         return out
 
     def timings(self):

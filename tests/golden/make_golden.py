@@ -347,6 +347,72 @@ def golden_grad(name, mesh_kw, seed, pc_in=24, pc_p=20):
 
 
 
+def golden_grad_integrate(name, mesh_kw, seed, pc_in=24, pc_p=20):
+    """Run the reference U_to_gradP ``timeStep`` to its END: the two assembled gradient fields, then the pressure recovery
+    (``integrate_field`` GRAD:371-416 on four quadrants + the stitch GRAD:585-628).  The recovered field is a local of
+    ``timeStep``; it is captured where the reference hands it to ``np.ma.array`` for plotting (GRAD:631).  Needs a grid whose
+    hard-coded centre row 200 (GRAD:592) crosses the obstacle.  Also records ``integrate_field`` called directly on a seeded
+    block (all four direction combinations)."""
+    sys.path.insert(0, os.path.join(REF, 'Improved_SM/U_to_gradP/evaluation'))
+    import Eval_dual_Dense_onlycil as GRAD
+    mesh = syn.make_mesh(seed=seed, **mesh_kw)
+    F = syn.make_fields(mesh, seed=seed)
+    P = syn.make_params(seed=seed, pc_in=pc_in, pc_p=pc_p, standardization='max_abs', n_out_channels=2,
+                        maxs=(1.0, 0.536, 0.999, 0.8, 0.7))
+    n = mesh['cells'].shape[0]
+    rng = np.random.default_rng(seed + 5)
+    lab = 0.01 * rng.standard_normal((n, 3))
+    cols = np.stack([F['Ux'], F['Uy'], F['p_prev'], mesh['cells'][:, 0], mesh['cells'][:, 1], lab[:, 0],
+                     lab[:, 1], lab[:, 2]], axis=1)
+    frame = (padded(cols), padded(mesh['top']), padded(mesh['obst']))
+    cwd = os.getcwd()
+    cap = {'fields': [], 'ma': []}
+    with tempfile.TemporaryDirectory() as tmp:
+        write_param_files(tmp, P, extra=8, var=0.95, model_name='model_1.h5')
+        os.chdir(tmp)
+        try:
+            ev = GRAD.Evaluation(5e-3, 128, 96, 0.95, 0.95, 'unused.hdf5', 'model_1.h5', 512)
+            ev.read_dataset = lambda path, sim, time: tuple(a.copy() for a in frame)
+            ev.computeOnlyOnce(0)
+            orig = ev.assemble_prediction
+
+            def wrapped(field, array, indices_list, n_x, n_y, *rest):
+                res = orig(field, array, indices_list, n_x, n_y, *rest)
+                cap['fields'].append((field, np.array(res[0, :, :, 0], copy=True)))
+                return res
+
+            ev.assemble_prediction = wrapped
+            GRAD.plt.subplots = lambda *a, **k: (mock.MagicMock(), mock.MagicMock())
+            ma_orig = np.ma.array
+
+            def ma_hook(data, *a, **k):
+                cap['ma'].append(np.array(data, copy=True))
+                return ma_orig(data, *a, **k)
+
+            np.ma.array = ma_hook
+            try:
+                ev.timeStep(0, 0, False, False, False, False)
+            finally:
+                np.ma.array = ma_orig
+            # integrate_field on its own: seeded block narrower and lower than the grid, every direction combination
+            r2 = np.random.default_rng(seed + 77)
+            blk = r2.standard_normal((150, 120, 2))
+            xl = np.linspace(ev.min_x, ev.max_x, ev.grid_shape_x)
+            yl = np.linspace(ev.min_y, ev.max_y, ev.grid_shape_y)
+            kat = [ev.integrate_field(blk.copy(), xl, yl, direction_x=dx_, direction_y=dy_) for dx_ in (1, -1) for dy_ in (1, -1)]
+        finally:
+            os.chdir(cwd)
+    (f0, r0), (f1, r1) = cap['fields'][0], cap['fields'][1]
+    assert (f0, f1) == ('dp_dx', 'dp_dy')
+    p_field = cap['ma'][0]                                     # GRAD:631: np.ma.array(field, mask=...)
+    out = dict(mesh_kw=np.array(repr(mesh_kw)), seed=seed, pc_in=pc_in, pc_p=pc_p,
+               grid_shape=np.array([ev.grid_shape_y, ev.grid_shape_x]), sdfunct=ev.sdfunct[:, :, 0].astype(np.float64),
+               bbox=np.array([ev.min_x, ev.max_x, ev.min_y, ev.max_y]), x0_min=np.array(ev.X0.min()),
+               dp_dx=r0, dp_dy=r1, p_field=p_field, kat_block_seed=seed + 77, kat=np.stack(kat))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, 'grid', out['grid_shape'], 'p_field', p_field.shape, 'nan', int(np.isnan(p_field).sum()))
+
+
 class sentinel_empty:
     """PMP:225 allocates ``indices`` with ``np.empty`` and its raster loop (PMP:233-243) writes only the valid rows, so the
     other rows are uninitialised memory.  While ``init_func`` runs, ``np.empty`` is wrapped to pre-fill integer-free float
@@ -444,6 +510,7 @@ GOLDEN_CASES = {
     'smc_small': ('smc', dict(H=240, W=330, nx=130, ny=90, R=0.1), 11),
     'smc_bigobst': ('smc', dict(H=240, W=330, nx=130, ny=90, R=0.35, center=(0.3575, -0.0375)), 12),      # empty strips -> NaN chains
     'grad_small': ('grad', dict(H=240, W=340, nx=130, ny=90, R=0.1), 13),
+    'grad_integrate': ('grad_integrate', dict(H=400, W=340, nx=130, ny=150, R=0.1), 16),   # row 200 (GRAD:592) crosses the cylinder
     'pmp_init_small': ('pmp_init', dict(H=240, W=340, nx=130, ny=90, R=0.1), 14),
     'pmp_step_small': ('pmp_step', dict(H=260, W=380, nx=150, ny=100, R=0.1), 15),
 }
@@ -460,6 +527,8 @@ def main():
             golden_smc(name, mesh_kw, seed)
         elif kind == 'grad':
             golden_grad(name, mesh_kw, seed)
+        elif kind == 'grad_integrate':
+            golden_grad_integrate(name, mesh_kw, seed)
         elif kind == 'pmp_step':
             golden_pmp_step(name, mesh_kw, seed)
         else:

@@ -406,3 +406,33 @@ def test_native_field_entry_matches_the_row_entry(deltas_case):
         sm5b.predict(prev)
         out_rows, _ = sm5b.predict(rows5)
     np.testing.assert_array_equal(out1, out_rows)
+
+
+def test_gradp_pressure_recovery_matches_reference():
+    """f.2: integrate_field on four quadrants + stitch (GRAD:371-416, 585-628) on the GPU.  (a) against the CPU restatement
+    applied to the GPU's own gradient fields: FP64 on both sides, only the scan order differs; (b) against the pressure
+    field the reference's timeStep itself produced (tests/golden/grad_integrate.npz), end to end within the 1e-3 bound."""
+    from oracle import integrate as ointeg
+    z, mesh_kw, seed = load_golden('grad_integrate')
+    mesh = syn.make_mesh(seed=seed, **mesh_kw)
+    F = syn.make_fields(mesh, seed=seed)
+    params = syn.make_params(seed=seed, pc_in=int(z['pc_in']), pc_p=int(z['pc_p']), standardization='max_abs',
+                             n_out_channels=2, maxs=(1.0, 0.536, 0.999, 0.8, 0.7))
+    rng = np.random.default_rng(seed + 5)
+    lab = 0.01 * rng.standard_normal((mesh['cells'].shape[0], 3))
+    bb = z['bbox']
+    with psm_b200.PressureSurrogate('U_to_gradP') as sm:
+        sm.load_params(params)
+        sm.init_from_mesh(mesh['cells'], mesh['top'], mesh['obst'], lab[:, 0])
+        sm.predict(syn.pack_cells(mesh, F, with_delta=False))
+        field = sm.stage('field')
+        p = sm.integrate_gradp(mesh['top'], float(z['x0_min']))
+        with pytest.raises(psm_b200.PsmError):                       # a centre row that misses the obstacle: the reference fails too
+            sm.integrate_gradp(mesh['top'], float(z['x0_min']), center_row=20)
+    assert [sm.H, sm.W] == list(z['grid_shape'])
+    sdf = z['sdfunct'][:, :, None]
+    ref_own, cx = ointeg.recover_pressure(field[0].astype(np.float64), field[1].astype(np.float64), sdf, bb[0], bb[1], bb[2], bb[3],
+                                          float(z['x0_min']), 5e-3)
+    np.testing.assert_allclose(p, ref_own, rtol=0, atol=1e-11 * np.abs(ref_own).max())
+    assert rel_l2(field[0], z['dp_dx']) < 1e-3 and rel_l2(field[1], z['dp_dy']) < 1e-3
+    assert rel_l2(p, z['p_field']) < 1e-3

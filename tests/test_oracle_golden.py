@@ -135,3 +135,24 @@ def test_thesis_oracle_matches_reference_py_func():
     assert np.array_equal(kept, kept_ref)
     scale = np.abs(z['p'] - F['p_prev']).max()
     np.testing.assert_allclose(r['p'], z['p'], rtol=0, atol=5e-6 * scale)
+
+
+def test_pressure_recovery_oracle_matches_reference_bit_for_bit():
+    """oracle/integrate.py against the unmodified reference: Evaluation.integrate_field called directly on a seeded block
+    (all four direction pairs) and the pressure field its timeStep produced after the quadrant stitch (GRAD:371-416, 585-628)."""
+    from oracle import integrate as ointeg
+    z, mesh_kw, seed = load_golden('grad_integrate')
+    sdf = z['sdfunct'][:, :, None]
+    bb = z['bbox']
+    H, W = z['grid_shape']
+    xl, yl = np.linspace(bb[0], bb[1], W), np.linspace(bb[2], bb[3], H)
+    blk = np.random.default_rng(int(z['kat_block_seed'])).standard_normal((150, 120, 2))
+    k = 0
+    for dx_ in (1, -1):
+        for dy_ in (1, -1):
+            np.testing.assert_array_equal(ointeg.integrate_field(blk.copy(), sdf, xl, yl, dx_, dy_), z['kat'][k])
+            k += 1
+    small = blk[:24, :40].copy()
+    np.testing.assert_array_equal(ointeg.integrate_field_literal(small.copy(), sdf, xl, yl, -1, 1), ointeg.integrate_field(small, sdf, xl, yl, -1, 1))
+    p, cx = ointeg.recover_pressure(z['dp_dx'], z['dp_dy'], sdf, bb[0], bb[1], bb[2], bb[3], float(z['x0_min']), 5e-3)
+    np.testing.assert_array_equal(p, z['p_field'])
