@@ -212,6 +212,37 @@ int psm_load_params_file(psm_handle* h, const char* path);
 int psm_save_tables(const psm_tables* tables, const char* path);
 int psm_save_params(const psm_params* params, int32_t shape, const char* path);
 
+/* init_func(array, top_boundary, obst_boundary) (PMP:172-247; SMC:89-180) for a C / C++ caller, without an interpreter.
+ * The library computes the rounded bounding box and the uniform grid (SMC:102-106, UTL:111-125), the flow mask and the distance
+ * field on the GPU (SMC:117-143), the index raster (SMC:161-178) and -- opt-in -- the grid -> cell tables in closed form.  The
+ * cells -> grid Delaunay tables stay with Qhull (the library the reference calls through SciPy): they are handed in as `vert` /
+ * `weights`, or come out of the table cache: with `cache_dir` set, the finished tables are stored under a hash of the mesh
+ * (psm_mesh_hash) and the next psm_init_mesh of the same mesh is one file read -- no Delaunay, no Python. */
+typedef struct psm_mesh {
+    int64_t n_cells;
+    const double* cells_xy;       /* cell centres: x at [i * xy_stride], y at [i * xy_stride + 1]; the solver's double[n][5] rows
+                                     (FOAM/PythonComm_init.H:53-75) are passed as (rows + 2, 5)                                  */
+    int32_t xy_stride;
+    int32_t back_closed_form;     /* 1: grid -> cell tables in closed form when vert_back is NULL (psm_b200/tables.py); 0: none  */
+    const double* top;  int64_t n_top;     /* "top" patch points  [n_top][2]   (FOAM/PythonComm_init.H:33-52)                   */
+    const double* obst; int64_t n_obst;    /* "obstacle" patch points [n_obst][2]                                               */
+    const double* probe;          /* [n_cells] field whose interpolation decides pixel validity (SMC:165: p; PMP:230: Ux), or NULL */
+    const int32_t* vert;          /* [H*W][3] Qhull simplex vertices (UTL:40), or NULL when the cache holds this mesh           */
+    const double*  weights;       /* [H*W][3]                                                                                    */
+    const int32_t* vert_back;     /* [n_cells][3] (PMP:211) or NULL                                                              */
+    const double*  weights_back;
+    const char* cache_dir;        /* directory of the table cache, or NULL                                                       */
+} psm_mesh;
+int psm_init_mesh(psm_handle* h, const psm_mesh* mesh);
+
+/* Host-only helpers of psm_init_mesh (no GPU needed; the CPU test-suite checks them against the NumPy shim). */
+int psm_mesh_hash(int32_t variant, double delta, const double* cells_xy, int32_t xy_stride, int64_t n_cells, const double* top,
+                  int64_t n_top, const double* obst, int64_t n_obst, const double* probe, char out[17]);
+int psm_mesh_grid(int32_t variant, double delta, const double* cells_xy, int32_t xy_stride, int64_t n_cells, double bbox[4],
+                  int32_t* grid_h, int32_t* grid_w);
+int psm_back_tables_closed_form(const double* cells_xy, int32_t xy_stride, int64_t n_cells, const double* X0_row, int32_t W,
+                                const double* Y0_col, int32_t H, int32_t* vert_back, double* weights_back);
+
 /* ---- multi-GPU: one process per GPU, block rows over ranks ------------- */
 
 #define PSM_UNIQUE_ID_BYTES 128

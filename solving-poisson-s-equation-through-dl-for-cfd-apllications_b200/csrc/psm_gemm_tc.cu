@@ -789,7 +789,9 @@ constexpr int I_NB = 128;                                // blocks per chunk = U
 constexpr int I_A_TILE = BM * BK * 4;                    // 16 KB
 constexpr int I_B_TILE = I_NB * BK * 4;                  // 16 KB
 constexpr int I_BSTAGES = 2;
-constexpr int I_SMEM = 2 * I_KB * I_A_TILE + I_BSTAGES * 2 * I_B_TILE + 1024 + 256;
+constexpr int I_TILE_LD = 129;                           // floats per parked block row (strip sums): odd pitch, conflict-free columns
+constexpr int I_TILE = 32 * I_TILE_LD * 4;
+constexpr int I_SMEM = 2 * I_KB * I_A_TILE + I_BSTAGES * 2 * I_B_TILE + 1024 + 256 + I_TILE;
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -820,6 +822,7 @@ pca_inverse_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     auto acc_full = [&](int b) { return bars + 16u + 8u * (2 * I_BSTAGES + b); };
     auto acc_empty = [&](int b) { return bars + 16u + 8u * (2 * I_BSTAGES + 4 + b); };
     const uint32_t tmem_slot = bars + 16u + 8u * (2 * I_BSTAGES + 8);
+    const uint32_t tile_off = bars + 256u;                       // [32][I_TILE_LD] floats: the strip-sum tile
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
     pdl_launch_dependents();
@@ -918,24 +921,18 @@ pca_inverse_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
         // ---- epilogue: thread <-> pixel (TMEM lane); 32 blocks per tcgen05.ld; coalesced 128 B rows per block ----
         const int q = warp & 3;
-        // strip sums (StripRows): this CTA's static entry list, 32 entries per batch (lane i holds entry e_base + i); the
-        // first batch is fetched before the wait
+        // strip sums (StripRows): the 32 blocks x 128 pixels just read from TMEM are parked in a shared-memory tile; the 128
+        // epilogue threads then split this pixel row's (entry, warp-quarter) pairs of those 32 blocks among themselves -- every
+        // pair is an independent masked sum of 32 tile values (fixed order: deterministic), so the sums run at full thread-level
+        // parallelism instead of one dependent shuffle chain per entry.
         const StripRows& sr = g.strips;
         const bool strips = sr.row_ptr != nullptr;
-        int e = 0, e_end = 0, e_base = 0;
-        int my_src = 0x7fffffff, my_slot = 0; uint32_t my_w = 0u;
-        auto load_batch = [&](int base) {
-            const int idx = base + lane;
-            my_src = 0x7fffffff;
-            if (idx < e_end) { my_src = __ldg(sr.src + idx); my_slot = __ldg(sr.slot + idx); my_w = __ldg(sr.w + (size_t)q * sr.n_ent + idx); }
-        };
-        if (strips) {
-            e = __ldg(sr.row_ptr + blockIdx.x); e_end = __ldg(sr.row_ptr + blockIdx.x + 1);
-            e_base = e;
-            load_batch(e_base);
-        }
+        float* tile = reinterpret_cast<float*>(gen_base + (tile_off - base));
+        const int n_c32 = (g.B + 31) / 32;
+        const int32_t* rp = strips ? sr.row_ptr + (size_t)blockIdx.x * (n_c32 + 1) : nullptr;
         pdl_wait();                                              // g.sc->out_scale belongs to this step
-        const int P = p0 + q * 32 + lane;                        // planar pixel index (c*S*S + ly*S + lx)
+        const int lx = q * 32 + lane;
+        const int P = p0 + lx;                                   // planar pixel index (c*S*S + ly*S + lx)
         const float pm = __ldg(g.pmean + P);
         const float o_scale = g.sc->out_scale;
         for (int c = 0; c < n_chunks; ++c) {
@@ -953,24 +950,28 @@ pca_inverse_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     if (b0 + j < g.B) {
                         const float o = (v[j] + pm) * o_scale;
                         dst[(size_t)j * g.block_stride] = o;
-                        if (strips) {
-                            // every entry of this pixel row whose source is block b0 + j (warp-uniform control flow)
-                            while (e < e_end) {
-                                const int k = e - e_base;
-                                if (__shfl_sync(0xffffffffu, my_src, k) != b0 + j) break;
-                                const uint32_t wq = __shfl_sync(0xffffffffu, my_w, k);
-                                if (wq) {
-                                    float val = ((wq >> lane) & 1u) ? o : 0.f;
+                        if (strips) tile[j * I_TILE_LD + lx] = o;
+                    }
+                }
+                if (strips) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");               // the tile of these 32 blocks is complete
+                    const int cc = b0 >> 5;
+                    const int e_lo = __ldg(rp + cc), n_pairs = (__ldg(rp + cc + 1) - e_lo) * 4;
+                    for (int pr = t; pr < n_pairs; pr += 128) {
+                        const int e = e_lo + (pr >> 2), qq = pr & 3;
+                        const uint32_t wq = __ldg(sr.w + (size_t)qq * sr.n_ent + e);
+                        if (wq) {
+                            const float* row = tile + (__ldg(sr.src + e) - b0) * I_TILE_LD + qq * 32;
+                            float acc = 0.f;
 #pragma unroll
-                                    for (int sh = 16; sh > 0; sh >>= 1) val += __shfl_xor_sync(0xffffffffu, val, sh);
-                                    const int sl = __shfl_sync(0xffffffffu, my_slot, k);
-                                    if (lane == 0) sr.rowpart[(size_t)sl * 4 + q] = val;
-                                }
-                                ++e;
-                                if (e - e_base == 32) { e_base = e; load_batch(e_base); }
+                            for (int i = 0; i < 32; ++i) {
+                                const int ii = (i + 8 * qq) & 31;               // rotated start: the four quarters of one entry hit different banks
+                                if ((wq >> ii) & 1u) acc += row[ii];
                             }
+                            sr.rowpart[(size_t)__ldg(sr.slot + e) * 4 + qq] = acc;
                         }
                     }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");               // the tile may be overwritten
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

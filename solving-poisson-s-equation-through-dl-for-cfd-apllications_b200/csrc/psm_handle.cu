@@ -223,6 +223,9 @@ static int upload(psm_handle* h, T** p, const std::vector<T>& v) {
 
 namespace psm {
 int handle_shape(const psm_handle* h) { return h ? h->S : 0; }
+int handle_variant(const psm_handle* h) { return h->cfg.variant; }
+int handle_device(const psm_handle* h) { return h->cfg.device; }
+double handle_delta(const psm_handle* h) { return h->cfg.delta; }
 int handle_fail(psm_handle* h, int code, const char* fmt, ...) {
     char b[512];
     va_list ap;
@@ -699,18 +702,23 @@ static int init_local(psm_handle* h, LocalInit& L) {
                         if (!mrow || mrow[lx]) e.w[lx >> 5] |= 1u << (lx & 31);
                     rows[(size_t)t.ch * S + ly].push_back(e);
                 }
-            std::vector<int32_t> rp((size_t)h->C * S + 1, 0), es, el;
+            const int n_c32 = (h->B + 31) / 32;
+            std::vector<int32_t> rp((size_t)h->C * S * (n_c32 + 1), 0), es, el;
             size_t n_ent = 0;
             for (auto& r : rows) n_ent += r.size();
             std::vector<uint32_t> ew(4 * (n_ent ? n_ent : 1), 0u);
             es.reserve(n_ent); el.reserve(n_ent);
             for (size_t r = 0; r < rows.size(); ++r) {
                 std::stable_sort(rows[r].begin(), rows[r].end(), [](const Ent& a, const Ent& b) { return a.src < b.src; });
+                int32_t* rpr = rp.data() + r * (n_c32 + 1);
+                int chunk = 0;
+                rpr[0] = (int32_t)es.size();
                 for (const Ent& e : rows[r]) {
+                    while (chunk < e.src / 32) rpr[++chunk] = (int32_t)es.size();
                     for (int q = 0; q < 4; ++q) ew[(size_t)q * n_ent + es.size()] = e.w[q];
                     es.push_back(e.src); el.push_back(e.slot);
                 }
-                rp[r + 1] = (int32_t)es.size();
+                while (chunk < n_c32) rpr[++chunk] = (int32_t)es.size();
             }
             h->sr_n_ent = (int)n_ent;
             if (es.empty()) { es.push_back(0); el.push_back(0); }

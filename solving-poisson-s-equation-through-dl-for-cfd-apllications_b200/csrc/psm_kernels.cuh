@@ -197,7 +197,8 @@ int launch_dense_cluster(const TcGemm& t, cudaStream_t s);
 // covers that row (SMC:233-316, GRAD:300-340, SMC:350) is one warp reduction away -- the blocks are not re-read.
 // Entries are static (built once per mesh), grouped by CTA row and sorted by source block.
 struct StripRows {
-    const int32_t* row_ptr;   // [C*S + 1] entries of pixel row r = c*S + ly; NULL: disabled
+    const int32_t* row_ptr;   // [C*S][ceil(B/32) + 1]: entries of pixel row r = c*S + ly whose source block lies in 32-block chunk k are
+                              // [row_ptr[r][k], row_ptr[r][k+1]); NULL: disabled
     const int32_t* src;       // [n_ent] local source block (ascending within a row)
     const int32_t* slot;      // [n_ent] row-partial slot
     const uint32_t* w;        // [4][n_ent] lane masks per warp quarter: bit l of w[q] <=> pixel lx = 32 q + l counts

@@ -62,6 +62,13 @@ class PsmGeometry(C.Structure):
                 ('n_ghost_cells', C.c_int64), ('n_ghost_pix', C.c_int64)]
 
 
+class PsmMesh(C.Structure):
+    _fields_ = [('n_cells', C.c_int64), ('cells_xy', c_double_p), ('xy_stride', C.c_int32), ('back_closed_form', C.c_int32),
+                ('top', c_double_p), ('n_top', C.c_int64), ('obst', c_double_p), ('n_obst', C.c_int64), ('probe', c_double_p),
+                ('vert', c_int32_p), ('weights', c_double_p), ('vert_back', c_int32_p), ('weights_back', c_double_p),
+                ('cache_dir', C.c_char_p)]
+
+
 class PsmIntegrateGeometry(C.Structure):
     _fields_ = [('min_x', C.c_double), ('max_x', C.c_double), ('min_y', C.c_double), ('max_y', C.c_double),
                 ('x0_min', C.c_double), ('center_row', C.c_int32), ('reserved', C.c_int32)]
@@ -87,6 +94,12 @@ SYMBOLS = {
     'psm_load_params': (C.c_int, [C.c_void_p, C.POINTER(PsmParams)]),
     'psm_init_with_tables': (C.c_int, [C.c_void_p, C.POINTER(PsmTables)]),
     'psm_init_sharded': (C.c_int, [C.c_void_p, C.POINTER(PsmShard)]),
+    'psm_init_mesh': (C.c_int, [C.c_void_p, C.POINTER(PsmMesh)]),
+    'psm_mesh_hash': (C.c_int, [C.c_int32, C.c_double, c_double_p, C.c_int32, C.c_int64, c_double_p, C.c_int64, c_double_p, C.c_int64,
+                                c_double_p, C.c_char_p]),
+    'psm_mesh_grid': (C.c_int, [C.c_int32, C.c_double, c_double_p, C.c_int32, C.c_int64, c_double_p, c_int32_p, c_int32_p]),
+    'psm_back_tables_closed_form': (C.c_int, [c_double_p, C.c_int32, C.c_int64, c_double_p, C.c_int32, c_double_p, C.c_int32, c_int32_p,
+                                              c_double_p]),
     'psm_comm_get_unique_id': (C.c_int, [C.c_void_p]),
     'psm_comm_init': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     'psm_init_from_file': (C.c_int, [C.c_void_p, C.c_char_p]),

@@ -46,6 +46,47 @@ def compile_plan(variant, H, W, mask, shape=128, overlap=32):
     return dict(origins=origins, indices_list=il, owner=owner, rec=rec, tasks=tasks, lines=lines, n_blocks=B, n_fields=F)
 
 
+def mesh_hash(variant, delta, cells_xy, top, obst, probe=None):
+    """Key of the table cache (``psm_mesh_hash``): 16 hex digits over variant, spacing, cell centres, boundary points, probe."""
+    cells_xy = np.ascontiguousarray(cells_xy, dtype=np.float64)
+    top = np.ascontiguousarray(top, dtype=np.float64)
+    obst = np.ascontiguousarray(obst, dtype=np.float64)
+    pr = None if probe is None else np.ascontiguousarray(probe, dtype=np.float64)
+    out = C.create_string_buffer(17)
+    rc = capi.load().psm_mesh_hash(_VARIANT_CODE[variant], float(delta), _ptr(cells_xy, C.c_double), 2, cells_xy.shape[0],
+                                   _ptr(top, C.c_double), top.shape[0], _ptr(obst, C.c_double), obst.shape[0],
+                                   None if pr is None else _ptr(pr, C.c_double), out)
+    if rc < 0:
+        raise capi.PsmError(rc, 'psm_mesh_hash failed')
+    return out.value.decode()
+
+
+def mesh_grid(variant, delta, cells_xy):
+    """Rounded bounding box and grid shape exactly as ``psm_init_mesh`` derives them: ((x_min, x_max, y_min, y_max), H, W)."""
+    cells_xy = np.ascontiguousarray(cells_xy, dtype=np.float64)
+    bbox = (C.c_double * 4)()
+    H, W = C.c_int32(), C.c_int32()
+    rc = capi.load().psm_mesh_grid(_VARIANT_CODE[variant], float(delta), _ptr(cells_xy, C.c_double), 2, cells_xy.shape[0], bbox,
+                                   C.byref(H), C.byref(W))
+    if rc < 0:
+        raise capi.PsmError(rc, 'psm_mesh_grid failed')
+    return tuple(bbox), H.value, W.value
+
+
+def back_tables_closed_form(cells_xy, X0_row, Y0_col):
+    """``psm_back_tables_closed_form`` (the C++ port of ``tables.regular_grid_back_tables``)."""
+    cells_xy = np.ascontiguousarray(cells_xy, dtype=np.float64)
+    X0_row = np.ascontiguousarray(X0_row, dtype=np.float64)
+    Y0_col = np.ascontiguousarray(Y0_col, dtype=np.float64)
+    n = cells_xy.shape[0]
+    vb, wb = np.empty((n, 3), np.int32), np.empty((n, 3), np.float64)
+    rc = capi.load().psm_back_tables_closed_form(_ptr(cells_xy, C.c_double), 2, n, _ptr(X0_row, C.c_double), X0_row.size,
+                                                 _ptr(Y0_col, C.c_double), Y0_col.size, _ptr(vb, C.c_int32), _ptr(wb, C.c_double))
+    if rc < 0:
+        raise capi.PsmError(rc, 'psm_back_tables_closed_form failed')
+    return vb, wb
+
+
 def register_host_buffer(a):
     """Page-lock a NumPy buffer that lives for the whole run (FOAM/PythonComm_init.H:53 allocates the solver's rows once),
     so that psm_predict copies it at full PCIe speed and the step stays one CUDA graph.  Returns True on success."""
@@ -306,6 +347,43 @@ class PressureSurrogate:
     def init_from_mesh(self, cells_xy, top, obst, probe_values, back=True):
         t = _tables.build_tables(cells_xy, top, obst, probe_values, variant=self.variant, delta=self.delta, back=back)
         return self.init_tables(t)
+
+    def init_mesh(self, cells_xy, top, obst, probe_values, back=True, cache_dir=None, tables=None):
+        """``psm_init_mesh``: bbox / grid / flow mask / distance field / raster inside the library (the distance field on the GPU);
+        only the cells -> grid Delaunay comes from here (SciPy's Qhull, like the reference) -- and not even that when the table
+        cache (``cache_dir``) already holds this mesh.  ``back``: True = Qhull grid -> cell tables (PMP:211), 'closed_form', or
+        False.  ``tables`` = (vert, weights) to reuse tables built elsewhere."""
+        cells_xy = np.ascontiguousarray(cells_xy, dtype=np.float64)
+        top = np.ascontiguousarray(top, dtype=np.float64)
+        obst = np.ascontiguousarray(obst, dtype=np.float64)
+        probe = np.ascontiguousarray(probe_values, dtype=np.float64)
+        M = capi.PsmMesh()
+        M.n_cells, M.cells_xy, M.xy_stride = cells_xy.shape[0], _ptr(cells_xy, C.c_double), 2
+        M.top, M.n_top, M.obst, M.n_obst, M.probe = _ptr(top, C.c_double), top.shape[0], _ptr(obst, C.c_double), obst.shape[0], _ptr(probe, C.c_double)
+        M.back_closed_form = int(back == 'closed_form')
+        keep = [cells_xy, top, obst, probe]
+        hit = False
+        if cache_dir is not None:
+            M.cache_dir = str(cache_dir).encode()
+            import os
+            hit = os.path.exists(os.path.join(str(cache_dir), 'psm_tables_%s_%s.bin' % (
+                mesh_hash(self.variant, self.delta, cells_xy, top, obst, probe), 'cf' if M.back_closed_form else 'qh')))
+        if not hit:
+            bbox, H, W = mesh_grid(self.variant, self.delta, cells_xy)
+            if tables is None:
+                X0, Y0 = _tables.uniform_grid(bbox[0], bbox[1], bbox[2], bbox[3], self.delta)
+                xy0 = np.stack([X0, Y0], axis=1)
+                vert, wts = _tables.barycentric_tables(cells_xy, xy0)                       # UTL:38-44 (Qhull)
+                if back is True:
+                    vb, wb = _tables.barycentric_tables(xy0, cells_xy)                      # PMP:211
+                    keep += [vb, wb]
+                    M.vert_back, M.weights_back = _ptr(vb, C.c_int32), _ptr(wb, C.c_double)
+            else:
+                vert, wts = np.ascontiguousarray(tables[0], dtype=np.int32), np.ascontiguousarray(tables[1], dtype=np.float64)
+            keep += [vert, wts]
+            M.vert, M.weights = _ptr(vert, C.c_int32), _ptr(wts, C.c_double)
+        self._check(self.lib.psm_init_mesh(self._h, C.byref(M)))
+        return self._after_init()
 
     # ------------------------------------------------------------------ per step
     def predict(self, cells, out=None):
