@@ -930,11 +930,42 @@ pca_inverse_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         float* tile = reinterpret_cast<float*>(gen_base + (tile_off - base));
         const int n_c32 = (g.B + 31) / 32;
         const int32_t* rp = strips ? sr.row_ptr + (size_t)blockIdx.x * (n_c32 + 1) : nullptr;
+        // the (entry, quarter) pairs of a 32-block chunk are static: each thread keeps the metadata of its (up to KP) pairs of the
+        // NEXT chunk in registers, requested one chunk ahead (the first one before the wait), so no L2 round trip sits between
+        // the two barriers of a chunk
+        constexpr int KP = 4;
+        uint32_t nw[KP]; int nsrc[KP], nslot[KP]; int n_pairs_next = 0, e_lo_next = 0;
+        auto prefetch = [&](int cc) {
+            n_pairs_next = 0;
+            if (cc >= n_c32) return;
+            e_lo_next = __ldg(rp + cc);
+            n_pairs_next = (__ldg(rp + cc + 1) - e_lo_next) * 4;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) {
+                const int pr = t + 128 * k;
+                nw[k] = 0u; nsrc[k] = 0; nslot[k] = 0;
+                if (pr < n_pairs_next) {
+                    const int e = e_lo_next + (pr >> 2);
+                    nw[k] = __ldg(sr.w + (size_t)(pr & 3) * sr.n_ent + e);
+                    nsrc[k] = __ldg(sr.src + e); nslot[k] = __ldg(sr.slot + e);
+                }
+            }
+        };
+        if (strips) prefetch(0);
         pdl_wait();                                              // g.sc->out_scale belongs to this step
         const int lx = q * 32 + lane;
         const int P = p0 + lx;                                   // planar pixel index (c*S*S + ly*S + lx)
         const float pm = __ldg(g.pmean + P);
         const float o_scale = g.sc->out_scale;
+        auto pair_sum = [&](uint32_t wq, const float* row, int qq) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int ii = (i + 8 * qq) & 31;               // rotated start: the four quarters of one entry hit different banks
+                if ((wq >> ii) & 1u) acc += row[ii];
+            }
+            return acc;
+        };
         for (int c = 0; c < n_chunks; ++c) {
             const int buf = c & 3;
             mbar_wait(acc_full(buf), (c >> 2) & 1);
@@ -954,22 +985,22 @@ pca_inverse_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                 }
                 if (strips) {
+                    // this chunk's pair metadata moves out of the prefetch registers, the next chunk's is requested
+                    uint32_t cw[KP]; int csrc[KP], cslot[KP];
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) { cw[k] = nw[k]; csrc[k] = nsrc[k]; cslot[k] = nslot[k]; }
+                    const int n_pairs = n_pairs_next, e_lo = e_lo_next;
+                    prefetch((b0 >> 5) + 1);
                     asm volatile("bar.sync 1, 128;" ::: "memory");               // the tile of these 32 blocks is complete
-                    const int cc = b0 >> 5;
-                    const int e_lo = __ldg(rp + cc), n_pairs = (__ldg(rp + cc + 1) - e_lo) * 4;
-                    for (int pr = t; pr < n_pairs; pr += 128) {
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        const int qq = (t + 128 * k) & 3;
+                        if (cw[k]) sr.rowpart[(size_t)cslot[k] * 4 + qq] = pair_sum(cw[k], tile + (csrc[k] - b0) * I_TILE_LD + qq * 32, qq);
+                    }
+                    for (int pr = t + 128 * KP; pr < n_pairs; pr += 128) {       // more than KP pairs per thread: plain loads
                         const int e = e_lo + (pr >> 2), qq = pr & 3;
                         const uint32_t wq = __ldg(sr.w + (size_t)qq * sr.n_ent + e);
-                        if (wq) {
-                            const float* row = tile + (__ldg(sr.src + e) - b0) * I_TILE_LD + qq * 32;
-                            float acc = 0.f;
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int ii = (i + 8 * qq) & 31;               // rotated start: the four quarters of one entry hit different banks
-                                if ((wq >> ii) & 1u) acc += row[ii];
-                            }
-                            sr.rowpart[(size_t)__ldg(sr.slot + e) * 4 + qq] = acc;
-                        }
+                        if (wq) sr.rowpart[(size_t)__ldg(sr.slot + e) * 4 + qq] = pair_sum(wq, tile + (__ldg(sr.src + e) - b0) * I_TILE_LD + qq * 32, qq);
                     }
                     asm volatile("bar.sync 1, 128;" ::: "memory");               // the tile may be overwritten
                 }

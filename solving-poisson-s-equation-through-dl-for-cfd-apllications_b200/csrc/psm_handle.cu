@@ -126,6 +126,7 @@ struct psm_handle {
     bool fuse_place = false; bool field_stale = false; bool no_fused_offsets = false;
     // multi-GPU fused flow: ghost pixels pushed from the owners' blocks into the region behind d_blocks
     bool mgpu_fused = false; long long ghost_base = 0; int32_t* d_pix_send_blk = nullptr;
+    std::vector<int32_t> host_cell_send_idx; SendRun* d_runs = nullptr; int n_runs = 0;
     int filter_radius = 0; float* d_gauss_w = nullptr; float* d_filter_tmp = nullptr;   // optional post-filter (SMC:353-356)
     std::vector<uint8_t> host_mask;   // [Hglob][W] flow mask (sdfunct != 0), host copy
     bool plan_mask_at(int y, int x) const { return host_mask[(size_t)y * W + x] != 0; }
@@ -512,6 +513,19 @@ static int setup_p2p(psm_handle* h) {
     for (int p = 0; p < Wd; ++p) ok = ok && flags[p];
     h->p2p = ok;
     h->mgpu_fused = ok && fused;
+    if (h->mgpu_fused) {
+        // the cell send list as runs of consecutive cells (see SendRun): pushed by the prep CTAs themselves when there are few
+        std::vector<SendRun> runs;
+        for (int p = 0; p < Wd; ++p)
+            for (long long e = h->cell_send_ptr[p]; e < h->cell_send_ptr[p + 1]; ++e) {
+                const int32_t c = h->host_cell_send_idx[e];
+                if (!runs.empty() && runs.back().peer == p && runs.back().end == c) { ++runs.back().end; continue; }
+                runs.push_back(SendRun{c, c + 1, p, 0, e - h->cell_send_ptr[p]});
+            }
+        h->n_runs = (runs.size() <= (size_t)kMaxRuns && !env_on("PSM_NO_SEND_RUNS")) ? (int)runs.size() : 0;
+        if (runs.empty()) runs.push_back(SendRun{0, 0, 0, 0, 0});
+        TRY(upload(h, &h->d_runs, runs));
+    }
     if (!h->mgpu_fused && h->fuse_place) h->fuse_place = false;      // legacy flow: the assembled field + ghost pixels of the field
     if (!ok) return PSM_OK;                       // NCCL exchange
     for (int p = 0; p <= Wd; ++p) { pa.cell_send_ptr[p] = h->cell_send_ptr[p]; pa.pix_send_ptr[p] = h->pix_send_ptr[p]; }
@@ -739,6 +753,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
         for (int32_t v : L.pix_send_idx) if (v < 0 || v >= G) PSM_FAIL(h, PSM_ERR_INVALID, "pix_send_idx out of range");
         if (h->cell_recv_ptr[L.world] != L.n_ghost || h->pix_recv_ptr[L.world] != L.n_ghost_pix) PSM_FAIL(h, PSM_ERR_INVALID, "recv lists do not match the ghost counts");
         TRY(upload(h, &h->d_cell_send_idx, L.cell_send_idx));
+        h->host_cell_send_idx = L.cell_send_idx;
         TRY(upload(h, &h->d_pix_send_idx, L.pix_send_idx));
         TRY(dalloc(h, &h->d_cell_send, (size_t)L.cell_send_idx.size() * 2));
         TRY(dalloc(h, &h->d_pix_send, (size_t)L.pix_send_idx.size() * h->F));
@@ -1090,7 +1105,7 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
     // fused multi-GPU flow: the exchanges ride in the tails of prep and of the fold kernel (no push launches, no assembled field)
     const bool mfused = p2p && h->mgpu_fused && d_out != nullptr;
     P2PFused fx{};
-    if (mfused) fx = P2PFused{h->d_p2p, h->d_cell_send_idx, h->d_blocks, h->d_pix_send_blk, h->C, S2, h->pix_send_ptr[h->world]};
+    if (mfused) fx = P2PFused{h->d_p2p, h->d_cell_send_idx, h->d_runs, h->n_runs, h->d_blocks, h->d_pix_send_blk, h->C, S2, h->pix_send_ptr[h->world]};
     if (fields) {
         PrepFieldsArgs pf{in.U, in.dU, in.u_stride, h->n_cells, mode, h->d_uv, h->d_uprev, h->d_sc, fx};
         launch_prep_fields(pf, s); ++nl;

@@ -173,10 +173,20 @@ __device__ __forceinline__ void publish_scalars(const ScalarArgs& sa, unsigned l
 // Multi-GPU fused flow: the LAST CTA of a prep kernel to finish pushes this rank's two running maxima and the cells that are
 // ghost cells elsewhere straight into the peers' buffers, fences at system scope and raises the phase-0 flags -- no separate
 // push launch.  Every CTA pays one device-scope fence + one atomic.
-__device__ __forceinline__ void prep_p2p_tail(const P2PFused& fx, const float2* uv, Scalars* sc) {
+__device__ __forceinline__ void prep_load_runs(const P2PFused& fx, SendRun* s_runs) {
+    if (fx.p2p && (int)threadIdx.x < fx.n_runs) s_runs[threadIdx.x] = fx.runs[threadIdx.x];      // static: before the wait
+}
+// cell i has just been converted by this thread: push it if a peer needs it as a ghost cell
+__device__ __forceinline__ void prep_push_cell(const P2PFused& fx, const SendRun* s_runs, long long i, float2 val, bool& pushed) {
+    for (int r = 0; r < fx.n_runs; ++r) {
+        const SendRun& R = s_runs[r];
+        if (i >= R.begin && i < R.end) { fx.p2p->uv_ghost[R.peer][R.dst + (i - R.begin)] = val; pushed = true; }
+    }
+}
+__device__ __forceinline__ void prep_p2p_tail(const P2PFused& fx, const float2* uv, Scalars* sc, bool pushed) {
     if (!fx.p2p) return;
     __shared__ bool s_last;
-    __syncthreads();
+    if (__syncthreads_or(pushed ? 1 : 0)) __threadfence_system();       // this CTA stored into peer memory: order it before the counter
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned int prev = atomicAdd(&sc->push_done[0], 1u);
@@ -187,14 +197,28 @@ __device__ __forceinline__ void prep_p2p_tail(const P2PFused& fx, const float2* 
     if (!s_last) return;
     const P2PArgs& P = *fx.p2p;
     const unsigned int step = P.sc->step + 1u;
-    const long long nsend = P.cell_send_ptr[P.world];
-    for (long long e = threadIdx.x; e < nsend; e += blockDim.x) {
-        int p = 0;
-        while (e >= P.cell_send_ptr[p + 1]) ++p;
-        P.uv_ghost[p][e - P.cell_send_ptr[p]] = __ldcg(uv + fx.cell_send_idx[e]);
+    if (fx.n_runs == 0) {
+        // fragmented send list: this one CTA moves it, eight independent index -> value chains per thread in flight
+        const long long nsend = P.cell_send_ptr[P.world];
+        for (long long e0 = threadIdx.x; e0 < nsend; e0 += (long long)blockDim.x * 8) {
+            int idx[8]; float2 val[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { const long long e = e0 + (long long)k * blockDim.x; idx[k] = (e < nsend) ? __ldg(fx.cell_send_idx + e) : 0; }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) val[k] = __ldcg(uv + idx[k]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const long long e = e0 + (long long)k * blockDim.x;
+                if (e < nsend) {
+                    int p = 0;
+                    while (e >= P.cell_send_ptr[p + 1]) ++p;
+                    P.uv_ghost[p][e - P.cell_send_ptr[p]] = val[k];
+                }
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
     }
-    __threadfence_system();
-    __syncthreads();
     if (threadIdx.x == 0) P.sc->step = step;
     if ((int)threadIdx.x < P.world) {
         const int p = threadIdx.x;
@@ -214,6 +238,10 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
     float2* __restrict__ uv = a.uv;
     double2* __restrict__ u_prev = reinterpret_cast<double2*>(a.u_prev);
     double m_u = 0.0, m_d = 0.0;
+    __shared__ SendRun s_runs[kMaxRuns];
+    bool pushed = false;
+    prep_load_runs(a.fx, s_runs);
+    if (a.fx.p2p) __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
         const double* row = cells + i * NCOL;
@@ -230,7 +258,9 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
         p_prev[i] = pp;
         m_u = fmax(m_u, __dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)));
         if (MODE != 0) m_d = fmax(m_d, __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)));
-        uv[i] = make_float2((float)fx, (float)fy);
+        const float2 val = make_float2((float)fx, (float)fy);
+        uv[i] = val;
+        if (a.fx.p2p) prep_push_cell(a.fx, s_runs, i, val, pushed);
     }
     m_u = warp_max(m_u);
     m_d = warp_max(m_d);
@@ -248,7 +278,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepArgs a) {
             atomicMax(&a.sc->dumax2_bits, (unsigned long long)__double_as_longlong(m_d));
         }
     }
-    prep_p2p_tail(a.fx, a.uv, a.sc);
+    prep_p2p_tail(a.fx, a.uv, a.sc, pushed);
 }
 
 // Bulk-copy variant (opt-in, see launch_prep): persistent CTAs stream 256-row tiles of the
@@ -301,6 +331,10 @@ __global__ void __launch_bounds__(kPrepRows) prep_bulk_kernel(PrepArgs a) {
     double* __restrict__ p_prev = a.p_prev;
     float2* __restrict__ uv = a.uv;
     double2* __restrict__ u_prev = reinterpret_cast<double2*>(a.u_prev);
+    __shared__ SendRun s_runs[kMaxRuns];
+    bool pushed = false;
+    prep_load_runs(a.fx, s_runs);
+    if (a.fx.p2p) __syncthreads();
     auto row_work = [&](long long i, double ux, double uy, double pp, double gx, double gy, double2 prev) {
         double fx, fy;
         if (MODE == 0) { fx = ux; fy = uy; }
@@ -309,7 +343,9 @@ __global__ void __launch_bounds__(kPrepRows) prep_bulk_kernel(PrepArgs a) {
         p_prev[i] = pp;
         m_u = fmax(m_u, __dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)));
         if (MODE != 0) m_d = fmax(m_d, __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)));
-        uv[i] = make_float2((float)fx, (float)fy);
+        const float2 val = make_float2((float)fx, (float)fy);
+        uv[i] = val;
+        if (a.fx.p2p) prep_push_cell(a.fx, s_runs, i, val, pushed);
     };
     int k = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
@@ -349,7 +385,7 @@ __global__ void __launch_bounds__(kPrepRows) prep_bulk_kernel(PrepArgs a) {
             atomicMax(&a.sc->dumax2_bits, (unsigned long long)__double_as_longlong(m_d));
         }
     }
-    prep_p2p_tail(a.fx, a.uv, a.sc);
+    prep_p2p_tail(a.fx, a.uv, a.sc, pushed);
 }
 template <int MODE, int NCOL>
 static void launch_prep_bulk(const PrepArgs& a, cudaStream_t s) {
@@ -394,6 +430,10 @@ __global__ void __launch_bounds__(256) prep_fields_kernel(PrepFieldsArgs a) {
     double2* __restrict__ u_prev = reinterpret_cast<double2*>(a.u_prev);
     const int st = a.stride;
     double m_u = 0.0, m_d = 0.0;
+    __shared__ SendRun s_runs[kMaxRuns];
+    bool pushed = false;
+    prep_load_runs(a.fx, s_runs);
+    if (a.fx.p2p) __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += stride) {
         const double ux = __ldcs(U + i * st), uy = __ldcs(U + i * st + 1);
@@ -407,7 +447,9 @@ __global__ void __launch_bounds__(256) prep_fields_kernel(PrepFieldsArgs a) {
         }
         m_u = fmax(m_u, __dadd_rn(__dmul_rn(ux, ux), __dmul_rn(uy, uy)));
         if (MODE != 0) m_d = fmax(m_d, __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)));
-        uv[i] = make_float2((float)fx, (float)fy);
+        const float2 val = make_float2((float)fx, (float)fy);
+        uv[i] = val;
+        if (a.fx.p2p) prep_push_cell(a.fx, s_runs, i, val, pushed);
     }
     m_u = warp_max(m_u);
     m_d = warp_max(m_d);
@@ -425,7 +467,7 @@ __global__ void __launch_bounds__(256) prep_fields_kernel(PrepFieldsArgs a) {
             atomicMax(&a.sc->dumax2_bits, (unsigned long long)__double_as_longlong(m_d));
         }
     }
-    prep_p2p_tail(a.fx, a.uv, a.sc);
+    prep_p2p_tail(a.fx, a.uv, a.sc, pushed);
 }
 void launch_prep_fields(const PrepFieldsArgs& a, cudaStream_t s) {
     long long want = (a.n + 255) / 256;
@@ -474,21 +516,31 @@ __device__ __forceinline__ PixTables load_tables(const GatherArgs& a, long long 
     t.q2 = __ldcs(reinterpret_cast<const float4*>(a.w2) + g);
     return t;
 }
-// four pixels: weighted gather (UTL:88-89), scaling (SMC:441-442), NaN -> 0 (SMC:438)
-__device__ __forceinline__ void gather4(const float2* __restrict__ uv, const PixTables& t, float s0, float s1, float4& ox, float4& oy) {
-    const int4 i0 = t.i0, i1 = t.i1, i2 = t.i2; const float4 q0 = t.q0, q1 = t.q1, q2 = t.q2;
-    float2 a0 = ldg_f2(uv + i0.x), b0 = ldg_f2(uv + i1.x), c0 = ldg_f2(uv + i2.x);
-    float2 a1 = ldg_f2(uv + i0.y), b1 = ldg_f2(uv + i1.y), c1 = ldg_f2(uv + i2.y);
-    float2 a2 = ldg_f2(uv + i0.z), b2 = ldg_f2(uv + i1.z), c2 = ldg_f2(uv + i2.z);
-    float2 a3 = ldg_f2(uv + i0.w), b3 = ldg_f2(uv + i1.w), c3 = ldg_f2(uv + i2.w);
-    ox.x = (a0.x * q0.x + b0.x * q1.x + c0.x * q2.x) * s0;  oy.x = (a0.y * q0.x + b0.y * q1.x + c0.y * q2.x) * s1;
-    ox.y = (a1.x * q0.y + b1.x * q1.y + c1.x * q2.y) * s0;  oy.y = (a1.y * q0.y + b1.y * q1.y + c1.y * q2.y) * s1;
-    ox.z = (a2.x * q0.z + b2.x * q1.z + c2.x * q2.z) * s0;  oy.z = (a2.y * q0.z + b2.y * q1.z + c2.y * q2.z) * s1;
-    ox.w = (a3.x * q0.w + b3.x * q1.w + c3.x * q2.w) * s0;  oy.w = (a3.y * q0.w + b3.y * q1.w + c3.y * q2.w) * s1;
+// four pixels: weighted gather (UTL:88-89), scaling (SMC:441-442), NaN -> 0 (SMC:438).  Split in two so that a kernel can
+// issue the twelve gathers BEFORE it touches the step's scalars (in-order issue: a stalled scalar load would hold them back).
+struct PixVals { float2 a0, b0, c0, a1, b1, c1, a2, b2, c2, a3, b3, c3; };
+__device__ __forceinline__ void gather4_load(const float2* __restrict__ uv, const PixTables& t, PixVals& v) {
+    const int4 i0 = t.i0, i1 = t.i1, i2 = t.i2;
+    v.a0 = ldg_f2(uv + i0.x); v.b0 = ldg_f2(uv + i1.x); v.c0 = ldg_f2(uv + i2.x);
+    v.a1 = ldg_f2(uv + i0.y); v.b1 = ldg_f2(uv + i1.y); v.c1 = ldg_f2(uv + i2.y);
+    v.a2 = ldg_f2(uv + i0.z); v.b2 = ldg_f2(uv + i1.z); v.c2 = ldg_f2(uv + i2.z);
+    v.a3 = ldg_f2(uv + i0.w); v.b3 = ldg_f2(uv + i1.w); v.c3 = ldg_f2(uv + i2.w);
+}
+__device__ __forceinline__ void gather4_combine(const PixVals& v, const PixTables& t, float s0, float s1, float4& ox, float4& oy) {
+    const float4 q0 = t.q0, q1 = t.q1, q2 = t.q2;
+    ox.x = (v.a0.x * q0.x + v.b0.x * q1.x + v.c0.x * q2.x) * s0;  oy.x = (v.a0.y * q0.x + v.b0.y * q1.x + v.c0.y * q2.x) * s1;
+    ox.y = (v.a1.x * q0.y + v.b1.x * q1.y + v.c1.x * q2.y) * s0;  oy.y = (v.a1.y * q0.y + v.b1.y * q1.y + v.c1.y * q2.y) * s1;
+    ox.z = (v.a2.x * q0.z + v.b2.x * q1.z + v.c2.x * q2.z) * s0;  oy.z = (v.a2.y * q0.z + v.b2.y * q1.z + v.c2.y * q2.z) * s1;
+    ox.w = (v.a3.x * q0.w + v.b3.x * q1.w + v.c3.x * q2.w) * s0;  oy.w = (v.a3.y * q0.w + v.b3.y * q1.w + v.c3.y * q2.w) * s1;
     ox.x = (ox.x != ox.x) ? 0.f : ox.x; ox.y = (ox.y != ox.y) ? 0.f : ox.y;
     ox.z = (ox.z != ox.z) ? 0.f : ox.z; ox.w = (ox.w != ox.w) ? 0.f : ox.w;
     oy.x = (oy.x != oy.x) ? 0.f : oy.x; oy.y = (oy.y != oy.y) ? 0.f : oy.y;
     oy.z = (oy.z != oy.z) ? 0.f : oy.z; oy.w = (oy.w != oy.w) ? 0.f : oy.w;
+}
+__device__ __forceinline__ void gather4(const float2* __restrict__ uv, const PixTables& t, float s0, float s1, float4& ox, float4& oy) {
+    PixVals v;
+    gather4_load(uv, t, v);
+    gather4_combine(v, t, s0, s1, ox, oy);
 }
 
 // The tables are static: every thread loads those of its first pixel group BEFORE waiting for the previous
@@ -562,13 +614,30 @@ __global__ void __launch_bounds__(256, U == 1 ? 4 : 3) gather_extract_kernel(Gat
     for (int u = 0; u < U; ++u)
         if (g + u * T < a.n_pix4) t[u] = load_tables(a, g + u * T);
     pdl_wait();
-    float s0, s1;
-    step_scales<READY>(a, s0, s1);
+    // The step's scalars: their LOADS are issued here, their first USE sits behind the first group's gathers (in-order issue:
+    // a warp parked on the scalar round trip would otherwise have no gather in flight).  With the peer-memory wait in front
+    // (multi-GPU) the ghost cells must land first, so the old order is kept there.
+    Scalars* sc = a.sa.sc;
+    float s0 = 0.f, s1 = 0.f;
+    unsigned long long um2 = 0ull, dm2 = 0ull;
+    bool have = false;
+    if (READY || a.p2p) { step_scales<READY>(a, s0, s1); have = true; }
+    else { um2 = sc->umax2_bits; dm2 = sc->dumax2_bits; }
     while (g < a.n_pix4) {
         float4 ox[U], oy[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
-            if (g + u * T < a.n_pix4) gather4(a.uv, t[u], s0, s1, ox[u], oy[u]);
+            if (g + u * T < a.n_pix4) {
+                PixVals pv;
+                gather4_load(a.uv, t[u], pv);
+                if (!have) {
+                    if (blockIdx.x == 0 && threadIdx.x == 0) publish_scalars(a.sa, um2, dm2, s0, s1);
+                    const double um = sqrt(__longlong_as_double((long long)um2));
+                    s0 = (float)(1.0 / (um * a.sa.max_abs_ux)); s1 = (float)(1.0 / (um * a.sa.max_abs_uy));
+                    have = true;
+                }
+                gather4_combine(pv, t[u], s0, s1, ox[u], oy[u]);
+            }
         const long long gn = g + (long long)U * T;
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -721,8 +790,13 @@ __global__ void __launch_bounds__(256) reduce_standardise_kernel(ReduceArgs a) {
     const long long i = (long long)blockIdx.x * 32 + ox;
     float sum = 0.f;
     if (i < total) {
-#pragma unroll 4
-        for (int sp = grp; sp < a.splits; sp += 8) sum += __ldcs(a.part + (long long)sp * total + i);
+        // up to 16 partials per thread, all loads in flight at once (the partials sit in L2: the kernel is latency-bound)
+        float pv[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { const int sp = grp + 8 * k; pv[k] = (sp < a.splits) ? __ldcs(a.part + (long long)sp * total + i) : 0.f; }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sum += pv[k];
+        for (int sp = grp + 128; sp < a.splits; sp += 8) sum += __ldcs(a.part + (long long)sp * total + i);
     }
     __shared__ float red[8][33];
     red[grp][ox] = sum;
@@ -893,10 +967,16 @@ __global__ void __launch_bounds__(256) task_fold_kernel(MeansArgs a, const float
         }
         __threadfence_system();
     } else if (ti < a.n_tasks) {
+        // <= 4 * 128 partials per task: 16 per lane, all loads in flight before the (fixed-order) FP64 adds
         const float* p = rowpart + (long long)t.part_base * 4;
         const int n = 4 * (t.y1 - t.y0);
+        float pv[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { const int i = lane + 32 * k; pv[k] = (i < n) ? __ldcg(p + i) : 0.f; }
         double acc = 0.0;
-        for (int i = lane; i < n; i += 32) acc += (double)__ldcg(p + i);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc += (double)pv[k];
+        for (int i = lane + 512; i < n; i += 32) acc += (double)__ldcg(p + i);
         acc = warp_sum(acc);
         const double val = (t.kind == 1) ? acc : ((t.count > 0) ? acc / (double)t.count : CUDART_NAN);
         if (lane == 0) a.means[t.out] = val;
@@ -1196,12 +1276,13 @@ __global__ void __launch_bounds__(256) back_kernel(BackArgs a) {
 template <bool FROM_BLOCKS>
 __device__ __forceinline__ double back_one(const BackArgs& a, const float* __restrict__ src, int i0, int i1, int i2, float q0, float q1, float q2,
                                            int b0, int b1, int b2, double pp, int skip) {
+    // the gathers depend on the tables only: they are issued whatever the step's skip word says (it is applied to the result)
     double out = pp;
-    if (i0 >= 0 && !skip) {
+    if (i0 >= 0) {
         float f0 = __ldg(src + i0), f1 = __ldg(src + i1), f2 = __ldg(src + i2);
         if (FROM_BLOCKS) { f0 -= __ldg(a.coff + b0); f1 -= __ldg(a.coff + b1); f2 -= __ldg(a.coff + b2); }   // SMC:243,350
         const float v = f0 * q0 + f1 * q1 + f2 * q2;
-        if (v == v) out = a.additive ? pp + (double)v : (double)v;
+        if (v == v && !skip) out = a.additive ? pp + (double)v : (double)v;
     }
     return out;
 }
@@ -1246,8 +1327,10 @@ __global__ void __launch_bounds__(256) back4_kernel(BackArgs a) {
     if (i < n4) load();
     pdl_wait();
     if (a.p2p) p2p_wait(a.p2p, 2, a.p2p->pix_recv_mask);   // ghost pixels pushed by their owners
-    const int skip = a.sc->skip;
+    const int* skip_p = &a.sc->skip;
     const float* __restrict__ src = a.field;               // the assembled field, or the predicted blocks
+    int skip = 0;
+    bool have_skip = false;
     while (i < n4) {
         const int bA[4] = {(int)(o0.x & 0xFFFFu), (int)(o0.x >> 16), (int)(o0.y & 0xFFFFu), (int)(o0.y >> 16)};
         const int bB[4] = {(int)(o1.x & 0xFFFFu), (int)(o1.x >> 16), (int)(o1.y & 0xFFFFu), (int)(o1.y >> 16)};
@@ -1258,9 +1341,26 @@ __global__ void __launch_bounds__(256) back4_kernel(BackArgs a) {
             const double2 pa = __ldcs(reinterpret_cast<const double2*>(a.p_prev) + 2 * i);
             const double2 pb = __ldcs(reinterpret_cast<const double2*>(a.p_prev) + 2 * i + 1);
             const double pp[4] = {pa.x, pa.y, pb.x, pb.y};
+            // gathers first (they depend on the static tables only) ...
+            float v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k] = CUDART_NAN_F;
+                if (iA[k] >= 0) {
+                    float f0 = __ldg(src + iA[k]), f1 = __ldg(src + iB[k]), f2 = __ldg(src + iC[k]);
+                    if (FROM_BLOCKS) { f0 -= __ldg(a.coff + bA[k]); f1 -= __ldg(a.coff + bB[k]); f2 -= __ldg(a.coff + bC[k]); }   // SMC:243,350
+                    v[k] = f0 * qA[k] + f1 * qB[k] + f2 * qC[k];
+                }
+            }
+            // ... then the step's skip word (once; a compiler barrier keeps its load behind the gathers: in-order issue would
+            // otherwise park the whole warp on this one L2 round trip before any gather is in flight)
+            if (!have_skip) {
+                asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(skip) : "l"(skip_p) : "memory");
+                have_skip = true;
+            }
             double r[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) r[k] = back_one<FROM_BLOCKS>(a, src, iA[k], iB[k], iC[k], qA[k], qB[k], qC[k], bA[k], bB[k], bC[k], pp[k], skip);
+            for (int k = 0; k < 4; ++k) r[k] = (v[k] == v[k] && !skip) ? (a.additive ? pp[k] + (double)v[k] : (double)v[k]) : pp[k];
             __stcs(reinterpret_cast<double2*>(a.out) + 2 * i, make_double2(r[0], r[1]));
             __stcs(reinterpret_cast<double2*>(a.out) + 2 * i + 1, make_double2(r[2], r[3]));
         } else {
@@ -1272,6 +1372,7 @@ __global__ void __launch_bounds__(256) back4_kernel(BackArgs a) {
         if (i < n4) load();
     }
     if (blockIdx.x == 0 && (long long)threadIdx.x < (a.n & 3)) {     // the last n % 4 cells
+        if (!have_skip) skip = *skip_p;
         const long long c = (n4 << 2) + threadIdx.x;
         const int i0 = a.v0[c], i1 = a.v1[c], i2 = a.v2[c];
         const float q0 = a.w0[c], q1 = a.w1[c], q2 = a.w2[c];

@@ -72,9 +72,15 @@ void launch_p2p_push_cells(const P2PArgs* d_pa, const float2* uv, const int32_t*
 void launch_p2p_push_means(const P2PArgs* d_pa, const struct DevTask* tasks, int n_tasks, int world, const double* means, cudaStream_t s);
 void launch_p2p_push_pix(const P2PArgs* d_pa, const float* field, const int32_t* send_idx, int F, long long my_stride, long long nsend, cudaStream_t s);
 // fused multi-GPU flow: what the tails of prep / the fold kernel push
+// A maximal run of consecutive owned cells [begin, end) that land consecutively in peer `peer`'s ghost-cell region from slot
+// `dst` on: the ghost cells of a block-row shard are (nearly) whole cell rows next to a rank boundary, so a mesh numbered row
+// by row has a handful of runs and every prep CTA can push the cells it has just converted itself (coalesced remote stores).
+struct SendRun { int32_t begin, end, peer, pad; long long dst; };
+constexpr int kMaxRuns = 32;
 struct P2PFused {
     const P2PArgs* p2p;                          // NULL: single GPU / legacy flow
-    const int32_t* cell_send_idx;                // prep tail: owned cells that are ghost cells elsewhere
+    const int32_t* cell_send_idx;                // owned cells that are ghost cells elsewhere (pushed by the last CTA when n_runs == 0)
+    const SendRun* runs; int n_runs;             // the same list as runs (n_runs <= kMaxRuns), or n_runs = 0: too fragmented
     const float* blocks; const int32_t* pix_send_blk; int C, S2;   // fold kernel: ghost pixels from the predicted blocks (channel-0 offsets)
     long long n_pix_send;
 };

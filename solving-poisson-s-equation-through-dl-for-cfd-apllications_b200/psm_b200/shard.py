@@ -67,6 +67,29 @@ def block_row_split(H, shape, overlap, world):
     return ranges, rows
 
 
+def _fill_ghost_gaps(ghost, cell_rank, max_gap=16, slack=0.25):
+    """The ghost cells a rank needs from one owner are (nearly) whole cell rows next to the rank boundary, minus the few cells
+    the forward table happens not to reference.  Closing the small holes (<= ``max_gap`` ids, at most ``slack`` more cells in
+    total) turns the list into a handful of runs of consecutive cell ids, which the owner's prep kernel pushes with coalesced
+    stores as it converts them (``SendRun`` in csrc/psm_kernels.cuh).  Far-away singles (the cells of the (0,0) raster quirk)
+    stay singles.  ``ghost`` must be sorted by (owner, id); returns the same ordering."""
+    if ghost.size == 0:
+        return ghost
+    out = []
+    owners = cell_rank[ghost]
+    for o in np.unique(owners):
+        g = ghost[owners == o]
+        d = np.diff(g)
+        holes = np.flatnonzero((d > 1) & (d <= max_gap + 1))
+        if holes.size == 0 or int((d[holes] - 1).sum()) > slack * g.size + 64:
+            out.append(g)
+            continue
+        extra = np.concatenate([np.arange(g[k] + 1, g[k + 1]) for k in holes])
+        extra = extra[cell_rank[extra] == o]
+        out.append(np.unique(np.concatenate([g, extra])))
+    return np.concatenate(out)
+
+
 def _csr(counts):
     p = np.zeros(len(counts) + 1, np.int64)
     p[1:] = np.cumsum(counts)
@@ -117,6 +140,7 @@ def partition(tables, cells_xy, world, variant='deltaU_to_deltaP', shape=128, ov
         need = np.unique(v[live])
         ghost = need[cell_rank[need] != g]
         ghost = ghost[np.lexsort((ghost, cell_rank[ghost]))]            # by owner rank, then global id
+        ghost = _fill_ghost_gaps(ghost, cell_rank)
         lut = np.zeros(N, np.int64)
         lut[owned[g]] = np.arange(owned[g].size)
         lut[ghost] = owned[g].size + np.arange(ghost.size)
@@ -264,6 +288,7 @@ def band_phase2(L, summaries):
     need = np.unique(L['fv'][live])
     ghost = need[L['cell_rank'][need] != rank]
     ghost = ghost[np.lexsort((ghost, L['cell_rank'][ghost]))]
+    ghost = _fill_ghost_gaps(ghost, L['cell_rank'])
     q0, q1 = L['row0'] * W, L['row1'] * W
     needp = np.unique(L['bv'][~L['keep']])
     gp = needp[(needp < q0) | (needp >= q1)]
