@@ -894,7 +894,10 @@ static int init_local(psm_handle* h, LocalInit& L) {
             it.args = InvTArgs{h->d_blocks, (long long)S2 * h->C, h->B, Bp, h->pc_p_pad, S2 * h->C, three, h->d_pmean, h->d_sc, StripRows{}};
             // the masked strip sums come out of this kernel's epilogue (the blocks are not read again): needs the CTA <-> pixel-row
             // match S == 128
-            h->strip_fuse = !env_on("PSM_NO_STRIP_FUSE") && S == 128 && h->n_tasks > 0;
+            // ... and one resident wave of CTAs (one per SM): with two output channels (256 CTAs) the longer epilogue sits on the
+            // critical path twice and the separate means kernel is faster (measured at configs[2]: 117 vs 61 us for this kernel)
+            h->strip_fuse = !env_on("PSM_NO_STRIP_FUSE") && S == 128 && h->n_tasks > 0 && (S2 * h->C) / 128 <= 148;
+            if (env_on("PSM_FORCE_STRIP_FUSE") && S == 128 && h->n_tasks > 0) h->strip_fuse = true;
             if (h->strip_fuse) it.args.strips = StripRows{h->d_sr_rowptr, h->d_sr_src, h->d_sr_slot, h->d_sr_w, h->sr_n_ent, h->d_rowpart};
         }
         // ---- the whole Dense stack as one persistent launch -------------------------------------------------

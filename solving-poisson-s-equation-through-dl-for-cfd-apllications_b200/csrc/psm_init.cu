@@ -126,7 +126,11 @@ extern "C" int psm_mesh_hash(int32_t variant, double delta, const double* cells_
     f.add("PSMMESH1", 8); f.add(&variant, 4); f.add(&delta, 8); f.add(&n_cells, 8); f.add(&n_top, 8); f.add(&n_obst, 8);
     for (int64_t i = 0; i < n_cells; ++i) f.add(cells_xy + i * xy_stride, 16);
     f.add(top, (size_t)n_top * 16); f.add(obst, (size_t)n_obst * 16);
-    if (probe) f.add(probe, (size_t)n_cells * 8);
+    // the probe field only decides validity where its interpolation is NaN (SMC:165-169): a finite probe leaves the tables
+    // untouched, so its VALUES (the solver's initial pressure, different from run to run) stay out of the key
+    bool probe_nan = false;
+    if (probe) for (int64_t i = 0; i < n_cells && !probe_nan; ++i) probe_nan = probe[i] != probe[i];
+    if (probe_nan) f.add(probe, (size_t)n_cells * 8);
     snprintf(out, 17, "%016llx", f.h);
     return PSM_OK;
 }

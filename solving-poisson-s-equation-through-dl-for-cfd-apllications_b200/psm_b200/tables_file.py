@@ -2,6 +2,11 @@
 
   python -m psm_b200.tables_file --cells cells.npy --top top.npy --obst obst.npy --out psm_tables.bin \
          [--variant deltaU_to_deltaP] [--delta 5e-3] [--back qhull|closed_form|none] [--params psm_params.npz --params-out psm_params.bin]
+         [--cache-dir psm_cache]
+
+With ``--cache-dir`` the table file is ALSO stored in the table cache under the hash of the mesh (``psm_mesh_hash``), where
+``psm_init_mesh`` of a C/C++ caller finds it: the solver then initialises from its raw arrays (cell centres, "top" and
+"obstacle" patch points) with no file name to agree on and no interpreter.
 
 ``cells`` is the solver's ``double[nCells][>=4]`` array ``{Ux,Uy,Cx,Cy,...}`` (FOAM/PythonComm_init.H:53-60) or just the
 ``[nCells][2]`` cell centres; ``top`` / ``obst`` are the boundary-face centres of the patches named "top" and "obstacle"
@@ -28,6 +33,7 @@ def main(argv=None):
     ap.add_argument('--back', default='qhull', choices=['qhull', 'closed_form', 'none'])
     ap.add_argument('--params', default=None, help='npz written by psm_b200.params.save_npz')
     ap.add_argument('--params-out', default=None)
+    ap.add_argument('--cache-dir', default=None)
     a = ap.parse_args(argv)
     cells = np.load(a.cells)
     xy = cells[:, 2:4] if cells.shape[1] >= 4 else cells[:, :2]
@@ -36,6 +42,14 @@ def main(argv=None):
                              back=None if a.back == 'none' else a.back)
     save_tables(t, a.out)
     print('%s: %d cells, grid %d x %d' % (a.out, t['n_cells'], t['H'], t['W']))
+    if a.cache_dir and a.back != 'none':
+        import os
+        from .surrogate import mesh_hash
+        os.makedirs(a.cache_dir, exist_ok=True)
+        key = mesh_hash(a.variant, a.delta, np.ascontiguousarray(xy), np.load(a.top), np.load(a.obst), probe)
+        path = os.path.join(a.cache_dir, 'psm_tables_%s_%s.bin' % (key, 'cf' if a.back == 'closed_form' else 'qh'))
+        save_tables(t, path)
+        print(path)
     if a.params:
         save_params(_params.load_npz(a.params), a.params_out or 'psm_params.bin')
         print(a.params_out or 'psm_params.bin')

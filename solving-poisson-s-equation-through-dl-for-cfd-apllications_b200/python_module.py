@@ -50,6 +50,13 @@ def init_func(array, top_boundary, obst_boundary, placeholder=None):
     sm = _surrogate()
     array = np.asarray(array, dtype=np.float64)
     probe = array[:, 4] if sm.variant == 'deltaU_to_deltaP' else array[:, 0]     # SMC:165 p ; PMP:230 ux
+    cache = os.environ.get('PSM_TABLE_CACHE')
+    if cache:
+        # psm_init_mesh: mask / distance / raster inside the library, Qhull only on a cache miss; the finished tables are stored
+        # under the hash of the mesh, where a later run (also a pure C caller, examples/openfoam/PsmComm_init.H) finds them
+        os.makedirs(cache, exist_ok=True)
+        sm.init_mesh(array[:, 2:4], top_boundary, obst_boundary, probe, back=True, cache_dir=cache)
+        return 0
     t = _tables.build_tables(array[:, 2:4], np.asarray(top_boundary, dtype=np.float64),
                              np.asarray(obst_boundary, dtype=np.float64), probe, variant=sm.variant, delta=sm.delta)
     sm.init_tables(t)

@@ -54,5 +54,8 @@ def test_mesh_hash_is_stable_and_sensitive():
               mesh_hash('U_to_gradP', 5e-3, mesh['cells'], mesh['top'], mesh['obst'], p),
               mesh_hash('deltaU_to_deltaP', 4e-3, mesh['cells'], mesh['top'], mesh['obst'], p),
               mesh_hash('deltaU_to_deltaP', 5e-3, mesh['cells'], mesh['top'][::-1], mesh['obst'], p),
-              mesh_hash('deltaU_to_deltaP', 5e-3, mesh['cells'], mesh['top'], mesh['obst'], None)}
+              mesh_hash('deltaU_to_deltaP', 5e-3, mesh['cells'], mesh['top'], mesh['obst'], np.where(p == 3, np.nan, p))}
     assert a not in others and len(others) == 5
+    # a finite probe decides nothing (SMC:165-169): its values stay out of the key
+    assert a == mesh_hash('deltaU_to_deltaP', 5e-3, mesh['cells'], mesh['top'], mesh['obst'], p + 1.0)
+    assert a == mesh_hash('deltaU_to_deltaP', 5e-3, mesh['cells'], mesh['top'], mesh['obst'], None)
