@@ -255,6 +255,22 @@ int psm_comm_init(psm_handle* h, const void* unique_id, int32_t rank, int32_t wo
  * collective calls: cells = this rank's n_owned rows, p_out = its n_owned pressures. */
 int psm_init_sharded(psm_handle* h, const psm_shard* shard);
 
+/* Cell routing: the solver's own domain decomposition need not be the block-row partition.  The reference takes ANY per-rank cell
+ * sets (scotch, system/decomposeParDict) by gathering every rank's rows to rank 0 and scattering the pressures back (PMP:179-185, 258,
+ * 501-511); here a rank describes once where each of its cells belongs and psm_predict_routed moves the rows to the owning GPU
+ * (grouped ncclSend / ncclRecv) and the pressures back.  dest_rank / dest_index come from the partitioner (psm_b200.shard.route):
+ * the rank whose block rows contain the cell, and the cell's position among that rank's owned cells. */
+typedef struct psm_route {
+    int64_t n_local;              /* cells this solver rank holds: any subset of the mesh, any order; every cell on exactly one rank */
+    const int32_t* dest_rank;     /* [n_local]                                                                                   */
+    const int32_t* dest_index;    /* [n_local] row of the cell in the owner's psm_predict input (0 .. its n_owned - 1)             */
+} psm_route;
+/* Collective over the ranks of psm_comm_init, after psm_init_sharded (also valid on a single-GPU handle: a pure permutation). */
+int psm_route_init(psm_handle* h, const psm_route* route);
+/* psm_predict_fields on the rank's OWN cells (host arrays, n_local rows, the order of psm_route); collective. */
+int psm_predict_routed(psm_handle* h, const double* U, int32_t u_stride, const double* dU, const double* p, int64_t n_local,
+                       double* out);
+
 /* Idempotent; NULL is accepted. */
 int psm_destroy(psm_handle* h);
 

@@ -173,6 +173,11 @@ struct psm_handle {
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_u = nullptr, ev_p = nullptr;
     bool pprev_zero = false;          // d_pprev currently holds zeros (psm_predict_fields without p)
     size_t cells_capacity = 0;        // doubles in d_cells
+    // cell routing (psm_route_init / psm_predict_routed): arbitrary per-rank cell sets -> block-row owners and back
+    bool routed = false; long long route_n = 0;
+    std::vector<long long> rt_send_ptr, rt_recv_ptr;   // [world + 1], in rows
+    int32_t *d_rt_perm = nullptr, *d_rt_recv_idx = nullptr;
+    double *d_rt_in = nullptr, *d_rt_send = nullptr, *d_rt_recv = nullptr, *d_rt_osend = nullptr, *d_rt_orecv = nullptr, *d_rt_out = nullptr;
 };
 
 // What the first kernel of a step reads (device pointers): the solver's packed rows, or its native field arrays.
@@ -1429,6 +1434,140 @@ extern "C" int psm_predict_device(psm_handle* h, const double* d_cells, int64_t 
     TRY(submit_device(h, in, d_p_out));
     if (sync) return finish(h);
     return PSM_OK;
+}
+
+// ---- cell routing -----------------------------------------------------------------------------------------------
+// The reference accepts any domain decomposition (scotch, system/decomposeParDict): every MPI rank hands its cells to rank 0,
+// which computes alone and scatters the pressures back (PMP:179-185, 258, 501-511).  Here every rank keeps a GPU and the block
+// rows of the plan decide who evaluates what, so a rank's cells are routed: rows go to the rank whose block rows contain the
+// cell (grouped ncclSend / ncclRecv over NVLink), the pressures come back the same way.  Static lists, built once.
+extern "C" int psm_route_init(psm_handle* h, const psm_route* r) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "psm_route_init before psm_init_sharded");
+    if (!r || r->n_local < 0 || (r->n_local > 0 && (!r->dest_rank || !r->dest_index))) PSM_FAIL(h, PSM_ERR_INVALID, "psm_route_init: bad route");
+    if (h->routed) PSM_FAIL(h, PSM_ERR_STATE, "a route is already installed");
+    if (h->world > 1 && !h->comm) PSM_FAIL(h, PSM_ERR_STATE, "psm_route_init needs the communicator of psm_comm_init");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const int Wd = h->world, me = h->rank;
+    const long long nl = r->n_local, no = h->n_cells;
+    // send side: local cells grouped by destination rank (stable: the order inside a group is the caller's order)
+    std::vector<long long> cnt(Wd, 0);
+    for (long long i = 0; i < nl; ++i) {
+        if (r->dest_rank[i] < 0 || r->dest_rank[i] >= Wd) PSM_FAIL(h, PSM_ERR_INVALID, "dest_rank[%lld] = %d is not a rank", i, r->dest_rank[i]);
+        ++cnt[r->dest_rank[i]];
+    }
+    h->rt_send_ptr.assign(Wd + 1, 0);
+    for (int p = 0; p < Wd; ++p) h->rt_send_ptr[p + 1] = h->rt_send_ptr[p] + cnt[p];
+    std::vector<int32_t> perm(nl > 0 ? nl : 1), sidx(nl > 0 ? nl : 1);
+    {
+        std::vector<long long> fill(h->rt_send_ptr.begin(), h->rt_send_ptr.end() - 1);
+        for (long long i = 0; i < nl; ++i) { const long long s = fill[r->dest_rank[i]]++; perm[s] = (int32_t)i; sidx[s] = r->dest_index[i]; }
+    }
+    // counts of every (source, destination) pair
+    std::vector<long long> all((size_t)Wd * Wd, 0);
+    for (int p = 0; p < Wd; ++p) all[(size_t)me * Wd + p] = cnt[p];
+    if (Wd > 1) {
+        long long* d_all = nullptr;
+        CU(h, cudaMalloc(&d_all, sizeof(long long) * Wd * Wd));
+        CU(h, cudaMemcpyAsync(d_all + (size_t)me * Wd, cnt.data(), sizeof(long long) * Wd, cudaMemcpyHostToDevice, h->stream));
+        NC(h, g_nccl.AllGather(d_all + (size_t)me * Wd, d_all, sizeof(long long) * Wd, ncclChar, h->comm, h->stream));
+        CU(h, cudaMemcpyAsync(all.data(), d_all, sizeof(long long) * Wd * Wd, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+        cudaFree(d_all);
+    }
+    h->rt_recv_ptr.assign(Wd + 1, 0);
+    for (int p = 0; p < Wd; ++p) h->rt_recv_ptr[p + 1] = h->rt_recv_ptr[p] + all[(size_t)p * Wd + me];
+    if (h->rt_recv_ptr[Wd] != no)
+        PSM_FAIL(h, PSM_ERR_INVALID, "the ranks route %lld cells to rank %d, its block rows own %lld", h->rt_recv_ptr[Wd], me, no);
+    // the receiver learns where every incoming row goes: exchange the dest_index lists along the same routes
+    TRY(upload(h, &h->d_rt_perm, perm));
+    int32_t* d_sidx = nullptr;
+    CU(h, cudaMalloc(&d_sidx, sizeof(int32_t) * (nl > 0 ? nl : 1)));
+    CU(h, cudaMemcpyAsync(d_sidx, sidx.data(), sizeof(int32_t) * nl, cudaMemcpyHostToDevice, h->stream));
+    TRY(dalloc(h, &h->d_rt_recv_idx, (size_t)(no > 0 ? no : 1)));
+    if (Wd > 1) {
+        NC(h, g_nccl.GroupStart());
+        for (int p = 0; p < Wd; ++p) {
+            if (p == me) continue;
+            const long long ns = cnt[p], nr = h->rt_recv_ptr[p + 1] - h->rt_recv_ptr[p];
+            if (ns > 0) NC(h, g_nccl.Send(d_sidx + h->rt_send_ptr[p], (size_t)ns, ncclInt32, p, h->comm, h->stream));
+            if (nr > 0) NC(h, g_nccl.Recv(h->d_rt_recv_idx + h->rt_recv_ptr[p], (size_t)nr, ncclInt32, p, h->comm, h->stream));
+        }
+        NC(h, g_nccl.GroupEnd());
+    }
+    CU(h, cudaMemcpyAsync(h->d_rt_recv_idx + h->rt_recv_ptr[me], d_sidx + h->rt_send_ptr[me], sizeof(int32_t) * cnt[me], cudaMemcpyDeviceToDevice, h->stream));
+    std::vector<int32_t> ridx(no > 0 ? no : 1);
+    CU(h, cudaMemcpyAsync(ridx.data(), h->d_rt_recv_idx, sizeof(int32_t) * no, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    cudaFree(d_sidx);
+    {   // every owned cell exactly once
+        std::vector<uint8_t> seen(no > 0 ? no : 1, 0);
+        for (long long k = 0; k < no; ++k) {
+            if (ridx[k] < 0 || ridx[k] >= no || seen[ridx[k]]) PSM_FAIL(h, PSM_ERR_INVALID, "routed rows do not cover the owned cells of rank %d exactly once (row %lld -> %d)", me, k, ridx[k]);
+            seen[ridx[k]] = 1;
+        }
+    }
+    const size_t nlz = (size_t)(nl > 0 ? nl : 1), noz = (size_t)(no > 0 ? no : 1);
+    TRY(dalloc(h, &h->d_rt_in, nlz * 7));                  // U (stride <= 3) + dU (stride <= 3) + p
+    TRY(dalloc(h, &h->d_rt_send, nlz * 5)); TRY(dalloc(h, &h->d_rt_recv, noz * 5));
+    TRY(dalloc(h, &h->d_rt_osend, noz * h->F)); TRY(dalloc(h, &h->d_rt_orecv, nlz * h->F)); TRY(dalloc(h, &h->d_rt_out, nlz * h->F));
+    CU(h, cudaStreamSynchronize(h->stream));
+    h->route_n = nl; h->routed = true;
+    return PSM_OK;
+}
+
+static int route_exchange(psm_handle* h, const double* send, const std::vector<long long>& sp, double* recv, const std::vector<long long>& rp, int k) {
+    const int Wd = h->world, me = h->rank;
+    if (Wd > 1) {
+        NC(h, g_nccl.GroupStart());
+        for (int p = 0; p < Wd; ++p) {
+            if (p == me) continue;
+            const long long ns = sp[p + 1] - sp[p], nr = rp[p + 1] - rp[p];
+            if (ns > 0) NC(h, g_nccl.Send(send + sp[p] * k, (size_t)ns * k, ncclDouble, p, h->comm, h->stream));
+            if (nr > 0) NC(h, g_nccl.Recv(recv + rp[p] * k, (size_t)nr * k, ncclDouble, p, h->comm, h->stream));
+        }
+        NC(h, g_nccl.GroupEnd());
+    }
+    const long long ns = sp[me + 1] - sp[me];
+    if (ns > 0) CU(h, cudaMemcpyAsync(recv + rp[me] * k, send + sp[me] * k, sizeof(double) * ns * k, cudaMemcpyDeviceToDevice, h->stream));
+    return PSM_OK;
+}
+
+extern "C" int psm_predict_routed(psm_handle* h, const double* U, int32_t u_stride, const double* dU, const double* p, int64_t n_local,
+                                  double* out) {
+    if (!h) return PSM_ERR_INVALID;
+    if (!h->initialised || !h->routed) PSM_FAIL(h, PSM_ERR_STATE, "psm_predict_routed before psm_route_init");
+    if (n_local != h->route_n) PSM_FAIL(h, PSM_ERR_INVALID, "n_local %lld does not match the installed route (%lld)", (long long)n_local, h->route_n);
+    if (n_local > 0 && (!U || !out)) PSM_FAIL(h, PSM_ERR_INVALID, "NULL buffer");
+    if (u_stride != 2 && u_stride != 3) PSM_FAIL(h, PSM_ERR_INVALID, "u_stride must be 3 (OpenFOAM vector) or 2");
+    if (dU && h->cfg.variant != PSM_DELTAU_TO_DELTAP) PSM_FAIL(h, PSM_ERR_INVALID, "dU is only meaningful for deltaU_to_deltaP");
+    if (!h->have_back) PSM_FAIL(h, PSM_ERR_STATE, "no grid->cell tables were given");
+    CU(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = h->stream;
+    const long long nl = n_local, no = h->n_cells;
+    const size_t nu = (size_t)nl * u_stride;
+    double* dUl = h->d_rt_in; double* ddUl = h->d_rt_in + nu; double* dpl = h->d_rt_in + 2 * nu;
+    if (nl > 0) {
+        CU(h, cudaMemcpyAsync(dUl, U, nu * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (dU) CU(h, cudaMemcpyAsync(ddUl, dU, nu * sizeof(double), cudaMemcpyHostToDevice, s));
+        if (p) CU(h, cudaMemcpyAsync(dpl, p, (size_t)nl * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    const int k = 3 + (dU ? 2 : 0);
+    launch_route_pack(RoutePackArgs{dUl, dU ? ddUl : nullptr, p ? dpl : nullptr, u_stride, h->d_rt_perm, nl, k, h->d_rt_send}, s);
+    TRY(route_exchange(h, h->d_rt_send, h->rt_send_ptr, h->d_rt_recv, h->rt_recv_ptr, k));
+    // the routed rows become the handle's native-field input: U as double[n_owned][2], dU behind it, p in the p_prev buffer
+    double* U2 = h->d_cells; double* dU2 = h->d_cells + 2 * (size_t)no;
+    launch_route_scatter(RouteScatterArgs{h->d_rt_recv, h->d_rt_recv_idx, no, k, dU ? 1 : 0, U2, dU2, h->d_pprev}, s);
+    h->pprev_zero = false;
+    h->last_host = true; h->field_stale = h->fuse_place;
+    StepInput in; in.U = U2; in.dU = dU ? dU2 : nullptr; in.u_stride = 2;
+    if (h->eager_steps > 0) --h->eager_steps;
+    TRY(run_step(h, in, h->d_out));
+    launch_route_back(RouteBackArgs{h->d_out, h->d_rt_recv_idx, no, h->F, h->d_rt_osend, 1}, s);
+    TRY(route_exchange(h, h->d_rt_osend, h->rt_recv_ptr, h->d_rt_orecv, h->rt_send_ptr, h->F));
+    launch_route_back(RouteBackArgs{h->d_rt_orecv, h->d_rt_perm, nl, h->F, h->d_rt_out, 0}, s);
+    if (nl > 0) CU(h, cudaMemcpyAsync(out, h->d_rt_out, (size_t)nl * h->F * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return finish(h);
 }
 
 extern "C" int psm_synchronize(psm_handle* h) {

@@ -1399,6 +1399,41 @@ void launch_back(const BackArgs& a, cudaStream_t s) {
     else launch_k(back_kernel<false>, dim3(blocks), dim3(256), 0, s, a);
 }
 
+// Cell routing kernels (see psm_kernels.cuh): plain permutations of 8-byte words, one row per thread.
+__global__ void __launch_bounds__(256) route_pack_kernel(RoutePackArgs a) {
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < a.n; s += (long long)gridDim.x * blockDim.x) {
+        const long long i = a.perm[s];
+        double* o = a.send + s * a.k;
+        int c = 0;
+        o[c++] = a.U[i * a.stride]; o[c++] = a.U[i * a.stride + 1];
+        if (a.dU) { o[c++] = a.dU[i * a.stride]; o[c++] = a.dU[i * a.stride + 1]; }
+        o[c] = a.p ? a.p[i] : 0.0;
+    }
+}
+__global__ void __launch_bounds__(256) route_scatter_kernel(RouteScatterArgs a) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (long long)gridDim.x * blockDim.x) {
+        const long long j = a.idx[r];
+        const double* in = a.recv + r * a.k;
+        int c = 0;
+        a.U2[2 * j] = in[c++]; a.U2[2 * j + 1] = in[c++];
+        if (a.has_du) { a.dU2[2 * j] = in[c++]; a.dU2[2 * j + 1] = in[c++]; }
+        a.p[j] = in[c];
+    }
+}
+__global__ void __launch_bounds__(256) route_back_kernel(RouteBackArgs a) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < a.n; r += (long long)gridDim.x * blockDim.x) {
+        const long long j = a.idx[r];
+        for (int f = 0; f < a.F; ++f) {
+            if (a.gather) a.dst[r * a.F + f] = a.src[j * a.F + f];
+            else a.dst[j * a.F + f] = a.src[r * a.F + f];
+        }
+    }
+}
+static int route_blocks(long long n) { long long w = (n + 255) / 256; return (int)(w < 1 ? 1 : (w > kSMs * 8 ? kSMs * 8 : w)); }
+void launch_route_pack(const RoutePackArgs& a, cudaStream_t s) { if (a.n > 0) route_pack_kernel<<<route_blocks(a.n), 256, 0, s>>>(a); }
+void launch_route_scatter(const RouteScatterArgs& a, cudaStream_t s) { if (a.n > 0) route_scatter_kernel<<<route_blocks(a.n), 256, 0, s>>>(a); }
+void launch_route_back(const RouteBackArgs& a, cudaStream_t s) { if (a.n > 0) route_back_kernel<<<route_blocks(a.n), 256, 0, s>>>(a); }
+
 // Static sparse exchange (multi-GPU): contiguous send buffer from an index list.
 __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
     pdl_enter();

@@ -357,6 +357,16 @@ struct IntegrateArgs {
 };
 void launch_integrate(const IntegrateArgs& a, cudaStream_t s);
 
+// Cell routing (psm_predict_routed): a solver rank holds an arbitrary subset of the cells; rows travel to the rank whose block rows
+// contain them and the pressures travel back.  pack: send[s][:] = {U[perm[s]].x, .y, (dU.x, .y,) p[perm[s]]}; scatter: the received
+// row r becomes cell idx[r] of the handle's native-field buffers; the two reverse kernels move the result.
+struct RoutePackArgs { const double* U; const double* dU; const double* p; int stride; const int32_t* perm; long long n; int k; double* send; };
+struct RouteScatterArgs { const double* recv; const int32_t* idx; long long n; int k; int has_du; double* U2; double* dU2; double* p; };
+struct RouteBackArgs { const double* src; const int32_t* idx; long long n; int F; double* dst; int gather; };   // gather: dst[r] = src[idx[r]]; else dst[idx[r]] = src[r]
+void launch_route_pack(const RoutePackArgs& a, cudaStream_t s);
+void launch_route_scatter(const RouteScatterArgs& a, cudaStream_t s);
+void launch_route_back(const RouteBackArgs& a, cudaStream_t s);
+
 // Static sparse exchange (multi-GPU): dst[i] = src[idx[i]] for the elements other ranks need.
 struct PackArgs { const float* src; const int32_t* idx; float* dst; long long n; int width; long long src_stride; };
 void launch_pack(const PackArgs& a, cudaStream_t s);

@@ -69,6 +69,10 @@ class PsmMesh(C.Structure):
                 ('cache_dir', C.c_char_p)]
 
 
+class PsmRoute(C.Structure):
+    _fields_ = [('n_local', C.c_int64), ('dest_rank', c_int32_p), ('dest_index', c_int32_p)]
+
+
 class PsmIntegrateGeometry(C.Structure):
     _fields_ = [('min_x', C.c_double), ('max_x', C.c_double), ('min_y', C.c_double), ('max_y', C.c_double),
                 ('x0_min', C.c_double), ('center_row', C.c_int32), ('reserved', C.c_int32)]
@@ -95,6 +99,8 @@ SYMBOLS = {
     'psm_init_with_tables': (C.c_int, [C.c_void_p, C.POINTER(PsmTables)]),
     'psm_init_sharded': (C.c_int, [C.c_void_p, C.POINTER(PsmShard)]),
     'psm_init_mesh': (C.c_int, [C.c_void_p, C.POINTER(PsmMesh)]),
+    'psm_route_init': (C.c_int, [C.c_void_p, C.POINTER(PsmRoute)]),
+    'psm_predict_routed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'psm_mesh_hash': (C.c_int, [C.c_int32, C.c_double, c_double_p, C.c_int32, C.c_int64, c_double_p, C.c_int64, c_double_p, C.c_int64,
                                 c_double_p, C.c_char_p]),
     'psm_mesh_grid': (C.c_int, [C.c_int32, C.c_double, c_double_p, C.c_int32, C.c_int64, c_double_p, c_int32_p, c_int32_p]),

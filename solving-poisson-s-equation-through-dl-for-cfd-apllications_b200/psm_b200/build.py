@@ -40,11 +40,15 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
-    cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT] + SOURCES
+    tmp = OUT + '.tmp%d' % os.getpid()                    # link next to the target, then rename: a reader never sees a half-written file
+    cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', tmp] + SOURCES
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError('nvcc failed building libpsm_b200.so')
+    os.replace(tmp, OUT)
     if verbose:
         sys.stderr.write(r.stderr)
     with open(STAMP, 'w') as fh:

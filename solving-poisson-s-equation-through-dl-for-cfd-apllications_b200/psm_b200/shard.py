@@ -90,6 +90,20 @@ def _fill_ghost_gaps(ghost, cell_rank, max_gap=16, slack=0.25):
     return np.concatenate(out)
 
 
+def route(cell_rank, my_cells):
+    """Where a solver rank's own cells go (``psm_route``).  ``cell_rank`` [N]: owner rank of every GLOBAL cell (the rank whose
+    pixel rows contain it -- ``partition`` / ``band_phase1`` compute it); ``my_cells``: global ids of the cells this solver rank
+    holds, in its own order.  Returns (dest_rank, dest_index): the owner and the cell's position among the owner's cells (which
+    are passed to ``psm_predict`` in ascending global id, ``owned_ids``)."""
+    cell_rank = np.asarray(cell_rank)
+    my_cells = np.asarray(my_cells, dtype=np.int64)
+    pos = np.empty(cell_rank.size, np.int64)
+    for g in np.unique(cell_rank):
+        sel = np.flatnonzero(cell_rank == g)
+        pos[sel] = np.arange(sel.size)
+    return cell_rank[my_cells].astype(np.int32), pos[my_cells].astype(np.int32)
+
+
 def _csr(counts):
     p = np.zeros(len(counts) + 1, np.int64)
     p[1:] = np.cumsum(counts)
@@ -145,7 +159,7 @@ def partition(tables, cells_xy, world, variant='deltaU_to_deltaP', shape=128, ov
         lut[owned[g]] = np.arange(owned[g].size)
         lut[ghost] = owned[g].size + np.arange(ghost.size)
         lv = np.where(live[:, None], lut[v], 0).astype(np.int32)
-        sh = dict(rank=g, world=world, H=H, W=W, row0=r0, row1=r1,
+        sh = dict(rank=g, world=world, H=H, W=W, row0=r0, row1=r1, cell_rank=cell_rank,
                   ext_rows=ext - lext, send_rows=0 if (g == 0 or halo == 'cells') else overlap, local_ext_rows=lext,
                   blk_row0=ranges[g][0], blk_row1=ranges[g][1], mask_global=mask,
                   owned_ids=owned[g], ghost_ids=ghost, n_owned=int(owned[g].size), n_ghost=int(ghost.size),
@@ -327,7 +341,7 @@ def band_phase3(L, ghost_lists):
         cs.append(owned_sorted_pos(mine)); cc.append(mine.size)
         pm = gl['ghost_pix'][(gl['ghost_pix'] >= q0) & (gl['ghost_pix'] < q1)]
         ps.append(pm - q0); pc.append(pm.size)
-    sh = dict(rank=rank, world=world, H=L['H'], W=W, row0=L['row0'], row1=L['row1'], ext_rows=L['ext_rows'],
+    sh = dict(rank=rank, world=world, H=L['H'], W=W, row0=L['row0'], row1=L['row1'], ext_rows=L['ext_rows'], cell_rank=L['cell_rank'],
               send_rows=L['send_rows'], local_ext_rows=L['local_ext_rows'], blk_row0=L['ranges'][rank][0], blk_row1=L['ranges'][rank][1],
               mask_global=L['mask_global'], owned_ids=owned, ghost_ids=ghost, n_owned=int(owned.size), n_ghost=int(ghost.size),
               vert=np.ascontiguousarray(lv), weights=np.ascontiguousarray(L['fw']), sdfunct=L['sdfunct'],

@@ -344,6 +344,29 @@ class PressureSurrogate:
         self.n_blocks = g['n_blocks']
         return self
 
+    def route_init(self, dest_rank, dest_index):
+        """Collective: install the cell route of this rank (``psm_b200.shard.route``): its cells may be any subset of the mesh."""
+        dr = np.ascontiguousarray(dest_rank, dtype=np.int32)
+        di = np.ascontiguousarray(dest_index, dtype=np.int32)
+        R = capi.PsmRoute(n_local=dr.size, dest_rank=_ptr(dr, C.c_int32), dest_index=_ptr(di, C.c_int32))
+        self._check(self.lib.psm_route_init(self._h, C.byref(R)))
+        self.n_routed = dr.size
+        return self
+
+    def predict_routed(self, U, p=None, dU=None, out=None):
+        """``predict_fields`` on this rank's own (routed) cells; collective.  Returns (out, status)."""
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        n = U.shape[0]
+        if dU is not None:
+            dU = np.ascontiguousarray(dU, dtype=np.float64)
+        if p is not None:
+            p = np.ascontiguousarray(p, dtype=np.float64)
+        if out is None:
+            out = np.empty(n if self.n_fields == 1 else (n, 2), dtype=np.float64)
+        rc = self._check(self.lib.psm_predict_routed(self._h, U.ctypes.data, U.shape[1], dU.ctypes.data if dU is not None else None,
+                                                     p.ctypes.data if p is not None else None, n, out.ctypes.data))
+        return out, rc
+
     def init_from_mesh(self, cells_xy, top, obst, probe_values, back=True):
         t = _tables.build_tables(cells_xy, top, obst, probe_values, variant=self.variant, delta=self.delta, back=back)
         return self.init_tables(t)

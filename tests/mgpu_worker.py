@@ -104,11 +104,27 @@ def main():
         dist.barrier()
         sm.predict_device(d_in.data_ptr(), own.size, d_o.data_ptr(), sync=True)
     fields_equal = fields_equal and bool(np.array_equal(d_o.cpu().numpy(), out, equal_nan=True))
+    # cell routing: a scotch-like decomposition -- every solver rank holds a random subset of the cells in a random order, the
+    # library moves the rows to the block-row owners and the pressures back (replaces the gather-to-root of PMP:258, 501-511)
+    n_all = mesh['cells'].shape[0]
+    rng = np.random.default_rng(123)
+    assign = rng.integers(0, world, size=n_all)
+    mine = rng.permutation(np.flatnonzero(assign == rank))
+    dr, di = pshard.route(sh['cell_rank'], mine)
+    sm.route_init(dr, di)
+    Ua = np.zeros((mine.size, 3))
+    Ua[:, 0], Ua[:, 1] = F['Ux'][mine], F['Uy'][mine]
+    dUa = None
+    if deltas:
+        dUa = np.zeros((mine.size, 3))
+        dUa[:, 0], dUa[:, 1] = F['dUx'][mine], F['dUy'][mine]
+    for _ in range(2):
+        out_routed, rc_routed = sm.predict_routed(Ua, p=F['p_prev'][mine], dU=dUa)
     offsets = sm.stage('offsets')
     field = sm.stage('field')
     geo = sm.geometry()
     gathered = [None] * world
-    dist.gather_object((sh['owned_ids'], out, offsets, field, (sh['row0'], sh['row1']), rc, fields_equal), gathered if rank == 0 else None, dst=0)
+    dist.gather_object((sh['owned_ids'], out, offsets, field, (sh['row0'], sh['row1']), rc, fields_equal, mine, out_routed), gathered if rank == 0 else None, dst=0)
     sm.close()
     ok = True
     if rank == 0:
@@ -123,9 +139,11 @@ def main():
         H, W = tables['H'], tables['W']
         fld = np.zeros((nf, H, W), np.float32)
         all_fields_equal = True
-        for (own, o_out, o_offs, o_field, (r0, r1), o_rc, o_feq) in gathered:
+        routed = np.full(n if deltas else (n, 2), np.nan)
+        for (own, o_out, o_offs, o_field, (r0, r1), o_rc, o_feq, o_mine, o_routed) in gathered:
             all_fields_equal = all_fields_equal and o_feq
             full[own] = o_out
+            routed[o_mine] = o_routed
             fld[:, r0:r1] = o_field
             assert np.array_equal(np.isnan(o_offs), np.isnan(gathered[0][2])) and np.allclose(o_offs, gathered[0][2], rtol=0, atol=0, equal_nan=True), \
                 'offsets differ between ranks'
@@ -152,7 +170,9 @@ def main():
         print('mgpu %s world=%d builder=%s: rel-L2 vs oracle cells %.2e field %.2e | vs single-GPU cells %.2e field %.2e | '
               'ghost cells/pix on rank0 %d/%d | fields/device entry bit-identical: %s' %
               (variant, world, args.builder, e_or, e_field, e_single, e_sf, geo['n_ghost_cells'], geo['n_ghost_pix'], all_fields_equal))
-        ok = e_or < 1e-3 and e_field < 1e-3 and e_single < 1e-5 and e_sf < 1e-5 and all_fields_equal
+        routed_equal = bool(np.array_equal(routed, full, equal_nan=True))
+        print('routed (random decomposition) == block-row owned rows, bit for bit: %s' % routed_equal)
+        ok = e_or < 1e-3 and e_field < 1e-3 and e_single < 1e-5 and e_sf < 1e-5 and all_fields_equal and routed_equal
         print('MGPU_PARITY_OK' if ok else 'MGPU_PARITY_FAIL')
     dist.barrier()
     dist.destroy_process_group()

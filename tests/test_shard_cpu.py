@@ -299,3 +299,25 @@ def test_band_local_shards_equal_partition_of_global_tables(variant, world):
         assert np.array_equal(live, np.any(wb != 0, axis=1))
         assert np.array_equal(va[live], vb[live])
         np.testing.assert_allclose(wa, wb, rtol=0, atol=1e-11)
+
+
+def test_route_sends_every_cell_to_its_block_row_owner():
+    """psm_b200.shard.route: for a random (scotch-like) decomposition every cell is routed to the rank whose pixel rows contain
+    it, at its position among that rank's owned cells (ascending global id) -- the order psm_predict takes them in."""
+    mesh = syn.make_mesh(seed=3, H=500, W=420, nx=220, ny=260, R=0.12)
+    F = syn.make_fields(mesh, seed=3)
+    t = ptables.build_tables(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'])
+    world = 3
+    shards = pshard.partition(t, mesh['cells'], world)
+    n = mesh['cells'].shape[0]
+    rng = np.random.default_rng(9)
+    assign = rng.integers(0, 5, size=n)                      # 5 solver ranks onto 3 GPU ranks
+    seen = np.zeros(n, bool)
+    for r in range(5):
+        mine = rng.permutation(np.flatnonzero(assign == r))
+        dr, di = pshard.route(shards[0]['cell_rank'], mine)
+        for g in range(world):
+            sel = dr == g
+            np.testing.assert_array_equal(shards[g]['owned_ids'][di[sel]], mine[sel])
+        seen[mine] = True
+    assert seen.all()
