@@ -897,12 +897,14 @@ static int init_local(psm_handle* h, LocalInit& L) {
                 make_kmajor_map(&it.mapBlo, h->d_r_lo, Bp, h->pc_p_pad, h->pc_p_pad, 128) != 0)
                 PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed (PCA inverse)");
             it.args = InvTArgs{h->d_blocks, (long long)S2 * h->C, h->B, Bp, h->pc_p_pad, S2 * h->C, three, h->d_pmean, h->d_sc, StripRows{}};
-            // the masked strip sums come out of this kernel's epilogue (the blocks are not read again): needs the CTA <-> pixel-row
-            // match S == 128
-            // ... and one resident wave of CTAs (one per SM): with two output channels (256 CTAs) the longer epilogue sits on the
-            // critical path twice and the separate means kernel is faster (measured at configs[2]: 117 vs 61 us for this kernel)
-            h->strip_fuse = !env_on("PSM_NO_STRIP_FUSE") && S == 128 && h->n_tasks > 0 && (S2 * h->C) / 128 <= 148;
-            if (env_on("PSM_FORCE_STRIP_FUSE") && S == 128 && h->n_tasks > 0) h->strip_fuse = true;
+            // The masked strip sums can come out of this kernel's epilogue (the blocks are not read again); needs the CTA <-> pixel-row
+            // match S == 128 and one resident wave of CTAs (with two output channels -- 256 CTAs -- the longer epilogue sits on the
+            // critical path twice: 117 vs 61 us at configs[2]).  Measured on one GPU (same box, c2 / c5): 99.1 / 267.4 us per step with
+            // the fused epilogue against 96.6 / 263.1 us with the separate task_means_kernel, whose 263 CTAs start under the previous
+            // kernel (PDL) -- so a single-GPU handle keeps the separate kernel.  A sharded handle takes the epilogue sums: the fold
+            // kernel that follows carries the whole exchange, 136 vs 151-161 us per step at two GPUs.
+            const bool want = (L.world > 1 || env_on("PSM_STRIP_FUSE")) && !env_on("PSM_NO_STRIP_FUSE");
+            h->strip_fuse = want && S == 128 && h->n_tasks > 0 && ((S2 * h->C) / 128 <= 148 || env_on("PSM_FORCE_STRIP_FUSE"));
             if (h->strip_fuse) it.args.strips = StripRows{h->d_sr_rowptr, h->d_sr_src, h->d_sr_slot, h->d_sr_w, h->sr_n_ent, h->d_rowpart};
         }
         // ---- the whole Dense stack as one persistent launch -------------------------------------------------

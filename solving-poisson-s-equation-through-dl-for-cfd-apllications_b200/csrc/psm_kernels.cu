@@ -657,10 +657,12 @@ __global__ void __launch_bounds__(256, U == 1 ? 4 : 3) gather_extract_kernel(Gat
     }
 }
 void launch_gather_extract(const GatherExtractArgs& a, cudaStream_t s) {
-    // two groups in flight per thread (3 CTAs / SM); a mesh too small to give every thread of one resident wave a group keeps U = 1
+    // One pixel group per thread and four CTAs per SM is the default.  Two groups in flight per thread (PSM_GATHER_U=2: twelve table
+    // loads before the wait, 3 CTAs / SM) measured equal at 1 M cells (99.1 vs 99.8 us per step) and slower at 4 M (gather 43.8 vs
+    // 38.7 us): at 80 registers the second group's tables spill.
     static const int force_u = [] { const char* v = getenv("PSM_GATHER_U"); return v ? atoi(v) : 0; }();
     const long long wave2 = (long long)kSMs * 3 * 256, wave1 = (long long)kSMs * 4 * 256;
-    const int U = force_u ? force_u : (a.g.n_pix4 > wave1 ? 2 : 1);
+    const int U = (force_u == 2) ? 2 : 1;
     long long want = (a.g.n_pix4 + 255) / 256;
     if (U == 2) {
         want = (a.g.n_pix4 + 511) / 512;

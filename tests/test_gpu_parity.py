@@ -436,3 +436,27 @@ def test_gradp_pressure_recovery_matches_reference():
     np.testing.assert_allclose(p, ref_own, rtol=0, atol=1e-11 * np.abs(ref_own).max())
     assert rel_l2(field[0], z['dp_dx']) < 1e-3 and rel_l2(field[1], z['dp_dy']) < 1e-3
     assert rel_l2(p, z['p_field']) < 1e-3
+
+
+def test_strip_sums_from_the_inverse_epilogue_match_the_means_kernel(deltas_case, monkeypatch):
+    """PSM_STRIP_FUSE=1: the masked strip means come out of the PCA-inverse epilogue (FP32 partials of 32 pixels, FP64 beyond)
+    instead of task_means_kernel (FP64 throughout) -- the path every sharded handle takes.  Same means to ~1e-6, same pressures."""
+    c = deltas_case
+    ref, _ = c.sm.predict(c.cells)
+    means_ref = c.sm.stage('means')
+    off_ref = c.sm.stage('offsets')
+    monkeypatch.setenv('PSM_STRIP_FUSE', '1')
+    with psm_b200.PressureSurrogate('deltaU_to_deltaP') as sm:
+        sm.load_params(c.params)
+        sm.init_tables(c.tables)
+        out, rc = sm.predict(c.cells)
+        out2, _ = sm.predict(c.cells)
+        means = sm.stage('means')
+        off = sm.stage('offsets')
+    assert rc == 0
+    np.testing.assert_array_equal(out, out2)
+    assert np.array_equal(np.isnan(means), np.isnan(means_ref))
+    ok = ~np.isnan(means_ref)
+    np.testing.assert_allclose(means[ok], means_ref[ok], rtol=0, atol=2e-6 * np.abs(means_ref[ok]).max())
+    np.testing.assert_allclose(off, off_ref, rtol=0, atol=1e-5 * np.abs(off_ref).max())
+    assert rel_l2(out - c.F['p_prev'], ref - c.F['p_prev']) < 1e-5
