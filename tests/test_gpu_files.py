@@ -158,3 +158,33 @@ def test_init_mesh_builds_the_shim_tables_and_serves_them_from_the_cache(variant
         M.cache_dir = str(tmp_path / 'nowhere').encode()
         rc = c.lib.psm_init_mesh(c._h, C.byref(M))
         assert rc == -4 and b'cache' in c.lib.psm_last_error(c._h)
+
+
+def test_plain_c_driver_initialises_from_raw_arrays_and_native_fields(case, tmp_path):
+    """The C program with no Python in the process: psm_init_mesh from the raw arrays (cell centres, "top" and "obstacle" points)
+    with the Delaunay tables served by the table cache, every step through psm_predict_fields on U double[n][3] + p double[n].
+    Same pressures as the Python-initialised handle fed the same (closed-form back) tables."""
+    d, cells, ref = case
+    mesh = syn.make_mesh(seed=6, **syn.CONFIGS['tiny'])
+    F = syn.make_fields(mesh, seed=6)
+    params = syn.make_params(seed=6, pc_in=40, pc_p=24)
+    cache = tmp_path / 'cache'
+    cache.mkdir()
+    with psm_b200.PressureSurrogate('deltaU_to_deltaP') as sm:            # first run of the case: fills the cache (Qhull once)
+        sm.load_params(params)
+        sm.init_mesh(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'], back='closed_form', cache_dir=cache)
+        expect, rc = sm.predict(cells)
+        assert rc == 0
+    exe = os.path.join(REPO, 'examples', 'c_driver', 'psm_driver')
+    r = subprocess.run(['make', '-C', os.path.dirname(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cells.astype(np.float64).tofile(tmp_path / 'cells.bin')
+    mesh['top'].astype(np.float64).tofile(tmp_path / 'top.bin')
+    mesh['obst'].astype(np.float64).tofile(tmp_path / 'obst.bin')
+    env = dict(os.environ, PSM_DRIVER_CACHE=str(cache), PSM_DRIVER_TOP=str(tmp_path / 'top.bin'), PSM_DRIVER_OBST=str(tmp_path / 'obst.bin'),
+               PSM_DRIVER_FIELDS='1')
+    r = subprocess.run([exe, str(d / 'params.bin'), 'unused', str(tmp_path / 'cells.bin'), str(cells.shape[0]), str(cells.shape[1]), '0', '4',
+                        str(tmp_path / 'p_out.bin')], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert 'status 0' in r.stdout, r.stdout
+    np.testing.assert_array_equal(np.fromfile(tmp_path / 'p_out.bin', dtype=np.float64), expect)
