@@ -255,6 +255,18 @@ int psm_comm_init(psm_handle* h, const void* unique_id, int32_t rank, int32_t wo
  * collective calls: cells = this rank's n_owned rows, p_out = its n_owned pressures. */
 int psm_init_sharded(psm_handle* h, const psm_shard* shard);
 
+/* The block-row partitioner for C / C++ callers (host only, no GPU): this rank's psm_shard from the GLOBAL tables -- the C++ twin of
+ * psm_b200/shard.py `partition` (halo in cell space), array for array.  y_min: rounded lower edge of the cell bounding box (bbox[2] of
+ * psm_mesh_grid).  The object owns the arrays psm_shard_view points into; free it after psm_init_sharded. */
+typedef struct psm_shard_owned psm_shard_owned;
+int psm_shard_build(const psm_tables* tables, const double* cells_xy, int32_t xy_stride, double y_min, double delta, int32_t variant,
+                    int32_t shape, int32_t overlap, double near_wall_sdf, int32_t rank, int32_t world, psm_shard_owned** out);
+const psm_shard* psm_shard_view(const psm_shard_owned* s);
+/* owned_ids int64[n_owned]: global ids of the cells this rank passes to psm_predict (ascending); cell_rank int32[n_cells]: owner of
+ * every global cell (input of the cell routing). */
+int psm_shard_cells(const psm_shard_owned* s, const int64_t** owned_ids, const int32_t** cell_rank);
+int psm_shard_free(psm_shard_owned* s);
+
 /* Cell routing: the solver's own domain decomposition need not be the block-row partition.  The reference takes ANY per-rank cell
  * sets (scotch, system/decomposeParDict) by gathering every rank's rows to rank 0 and scattering the pressures back (PMP:179-185, 258,
  * 501-511); here a rank describes once where each of its cells belongs and psm_predict_routed moves the rows to the owning GPU

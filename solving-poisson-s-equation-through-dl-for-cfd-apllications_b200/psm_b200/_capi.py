@@ -99,6 +99,11 @@ SYMBOLS = {
     'psm_init_with_tables': (C.c_int, [C.c_void_p, C.POINTER(PsmTables)]),
     'psm_init_sharded': (C.c_int, [C.c_void_p, C.POINTER(PsmShard)]),
     'psm_init_mesh': (C.c_int, [C.c_void_p, C.POINTER(PsmMesh)]),
+    'psm_shard_build': (C.c_int, [C.POINTER(PsmTables), c_double_p, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    'psm_shard_view': (C.POINTER(PsmShard), [C.c_void_p]),
+    'psm_shard_cells': (C.c_int, [C.c_void_p, C.POINTER(c_int64_p), C.POINTER(c_int32_p)]),
+    'psm_shard_free': (C.c_int, [C.c_void_p]),
     'psm_route_init': (C.c_int, [C.c_void_p, C.POINTER(PsmRoute)]),
     'psm_predict_routed': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'psm_mesh_hash': (C.c_int, [C.c_int32, C.c_double, c_double_p, C.c_int32, C.c_int64, c_double_p, C.c_int64, c_double_p, C.c_int64,

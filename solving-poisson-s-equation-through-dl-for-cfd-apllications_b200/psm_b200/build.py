@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), 'csrc')
 OUT = os.path.join(HERE, 'libpsm_b200.so')
-SOURCES = ['psm_plan.cpp', 'psm_files.cpp', 'psm_kernels.cu', 'psm_gemm_tc.cu', 'psm_integrate.cu', 'psm_init.cu', 'psm_handle.cu']
+SOURCES = ['psm_plan.cpp', 'psm_files.cpp', 'psm_partition.cpp', 'psm_kernels.cu', 'psm_gemm_tc.cu', 'psm_integrate.cu', 'psm_init.cu', 'psm_handle.cu']
 HEADERS = ['psm_plan.h', 'psm_kernels.cuh', 'psm_internal.h', os.path.join('..', '..', 'include', 'psm_b200.h')]
 STAMP = OUT + '.srchash'
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
