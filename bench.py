@@ -587,6 +587,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-c5', action='store_true', help='skip the roofline_c5 block (same kernels on the 4 M-cell mesh)')
     ap.add_argument('--no-parity', action='store_true', help='N > 1: skip the parity check after the timed runs')
+    ap.add_argument('--cold-host', action='store_true', help='also time the e2e call with the CPU caches swept between refill and call')
     ap.add_argument('--latency', action='store_true', help='configs[4]: per-step latency over --steps consecutive steps')
     ap.add_argument('--input-cols', type=int, default=5, choices=[5, 7],
                     help='5: rows {Ux,Uy,Cx,Cy,p} exactly as FOAM/PythonComm.H:2-9 fills them, the handle keeps U(t-1) resident '
@@ -622,7 +623,7 @@ def main():
         sm, dc, n, geo = res['sm'], res['dc'], res['n'], res['geo']
         e2e_each = dc.time_host('fields', args.steps)
         rows_each = dc.time_host('rows', max(10, args.steps // 2))
-        cold_each = dc.time_host('fields', max(10, args.steps // 2), cold=True)
+        cold_each = dc.time_host('fields', max(10, args.steps // 2), cold=True) if args.cold_host else None
         # deltaU_to_deltaP falls back to p_prev (always finite); U_to_gradP keeps NaN where the reference's grid->cell
         # interpolation is NaN (cells outside the grid hull, GRAD has no previous-gradient fallback)
         assert np.isfinite(dc.h_out.numpy()).mean() > (0.999 if variant == 'deltaU_to_deltaP' else 0.95)
@@ -656,17 +657,18 @@ def main():
                 'e2e': {'value': n / e2e_s, 'unit': 'cells/s', 'h2d_bytes_per_step': int(u_bytes + p_bytes),
                         'd2h_bytes_per_step': int(n * sm.n_fields * 8), 'ms_per_step': e2e_s * 1e3,
                         'entry_point': 'psm_predict_fields: pinned U double[n][3] (OpenFOAM vector layout) + p double[n] in, p out; '
-                                       'the copy of p overlaps the kernels',
+                                       'p goes up in chunks while the kernels run, the grid->cell gather and the copy of the pressures '
+                                       'down follow chunk by chunk (both directions of the link busy at once)',
                         'p50_ms': float(np.percentile(e2e_each, 50) * 1e3), 'p99_ms': float(np.percentile(e2e_each, 99) * 1e3),
-                        'device_events_ms': {'h2d_U': float(parts_f[0]), 'kernels_and_p_copy': float(parts_f[1]), 'd2h': float(parts_f[2])},
-                        'cold_host_cache': {'ms_per_step': float(np.mean(cold_each) * 1e3), 'value': n / float(np.mean(cold_each)),
-                                            'note': 'same call, but a 256 MiB host buffer is read between the refill of U and the timed call, so the '
-                                                    'DMA reads U from DRAM instead of lines still dirty in the CPU cache (the host-side twin of the L2 '
-                                                    'flush); the headline e2e keeps the hot refill'},
+                        'device_events_ms': {'h2d_U': float(parts_f[0]), 'kernels_p_copy_and_chunked_d2h': float(parts_f[1] + parts_f[2])},
+                        'cold_host_cache': None if cold_each is None else {
+                            'ms_per_step': float(np.mean(cold_each) * 1e3), 'value': n / float(np.mean(cold_each)),
+                            'note': '--cold-host: same call, but a 256 MiB host buffer is read between the refill of U and the timed call (the '
+                                    'refilled lines have left the CPU caches); a host-platform diagnostic, not the headline'},
                         'rows5': {'entry_point': 'psm_predict: pinned double[n][%d] rows (the reference layout, FOAM/PythonComm.H:2-9)' % ncol,
                                   'value': n / float(np.mean(rows_each)), 'ms_per_step': float(np.mean(rows_each) * 1e3),
                                   'h2d_bytes_per_step': int(n * ncol * 8), 'd2h_bytes_per_step': int(n * sm.n_fields * 8),
-                                  'device_events_ms': {'h2d': float(parts_r[0]), 'kernels': float(parts_r[1]), 'd2h': float(parts_r[2])}}},
+                                  'device_events_ms': {'h2d': float(parts_r[0]), 'kernels_and_chunked_d2h': float(parts_r[1] + parts_r[2])}}},
                 'gpu_launches': res['launches'], 'roofline': roof, 'gemm': gemm, 'cpu_baseline': cpu, 'stages': res['stages'],
                 'stage_event_overhead_ms': res['event_overhead_ms'],
                 'tables': "cells -> grid: SciPy Qhull (as the reference); grid -> cell: closed form (psm_b200.tables.regular_grid_back_tables, "
@@ -710,8 +712,17 @@ def main():
     dc.run_device(max(args.warmup, 3), False)
     dc.barrier()
     sampler.start()
-    ms_total, _, _ = dc.run_device(args.steps, False)
+    sm.wait_ns(reset=True)
+    ms_total, _, each_dev = dc.run_device(args.steps, False)
     assert sm.synchronize() == 0, 'the last timed step was short-cut by the skip rule'
+    # per-phase wait histogram of the timed steps: what CTA 0 of each consuming kernel spent waiting for its peers' pushes
+    wz = sm.wait_ns(reset=True)
+    mine = {'rank': rank, 'cells': int(n), 'ms_per_step': ms_total / args.steps, 'p50_ms': float(np.percentile(each_dev, 50)),
+            'max_ms': float(np.max(each_dev)),
+            'wait_us_per_step': {ph: (wz['ns'][i] / max(wz['count'][i], 1)) * 1e-3
+                                 for i, ph in enumerate(('ghost_cells_and_maxima', 'strip_means', 'ghost_pixels'))}}
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, mine)
     dc.barrier()
     launches = sm.launch_count() * args.steps
     sm.set_timings(True)
@@ -758,9 +769,11 @@ def main():
                 'e2e': {'value': n_total / (e2e_s / args.steps), 'unit': 'cells/s', 'h2d_bytes_per_step': int(n * 32 + (n * 24 if ncol == 7 else 0)),
                         'd2h_bytes_per_step': int(n * sm.n_fields * 8), 'ms_per_step': e2e_s / args.steps * 1e3,
                         'entry_point': 'psm_predict_fields on every rank (its own cells), pinned U double[n][3] + p double[n]; bytes are per rank',
-                        'device_events_ms': {'h2d_U': float(parts_f[0]), 'kernels_and_p_copy': float(parts_f[1]), 'd2h': float(parts_f[2])}},
+                        'device_events_ms': {'h2d_U': float(parts_f[0]), 'kernels_p_copy_and_chunked_d2h': float(parts_f[1] + parts_f[2])}},
                 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': None, 'stages': stages, 'stage_event_overhead_ms': ovh,
                 'parity': parity, 'parity_rel_l2': None if not parity else parity.get('vs_oracle', parity.get('vs_single_gpu')),
+                'per_rank': per_rank, 'limiting_phase': max(per_rank[0]['wait_us_per_step'],
+                                                            key=lambda ph: max(r['wait_us_per_step'][ph] for r in per_rank)),
                 'geometry': geo, 'init_tables_s': t_init, 'n_cells_total': n_total}
         print(json.dumps(line))
     sm.close()

@@ -366,6 +366,13 @@ int psm_set_timings(psm_handle* h, int32_t on);
 /* Number of kernels launched by the last psm_predict* call. */
 int psm_get_launch_count(const psm_handle* h);
 
+/* Multi-GPU wait histogram: nanoseconds the consuming kernels of THIS rank have spent waiting for their peers' pushes
+ * since the last reset, per exchange phase (0 = ghost cells + maxima, awaited by the gather; 1 = strip means, awaited
+ * by the fold kernel's last CTA; 2 = ghost pixels, awaited by the grid->cell gather), and the number of waits.
+ * One sample per kernel launch (its first CTA).  reset != 0 zeroes the counters after reading.  Synchronises the stream.
+ * The reference has no counterpart: its ranks block in MPI gather / scatter (PMP:258, 501-511). */
+int psm_get_wait_ns(psm_handle* h, uint64_t ns[3], uint32_t count[3], int32_t reset);
+
 /* ---- host-only plan compiler (no GPU needed; used by the CPU test-suite) ---------------- */
 
 /* Compile the static block/assembly plan for a grid and return its sizes.

@@ -15,8 +15,8 @@ for r in rows[1:]:
         pass
 mine = {k: v for k, v in d.items() if 'psm::' in k}
 tot = sum(sum(v) / len(v) * (len(v) / max(len(x) for x in mine.values()) if False else 1) for v in mine.values())
-steps = max(len(v) for k, v in mine.items() if 'gather_kernel' in k) if any('gather_kernel' in k for k in mine) else 1
-per_step = {k: sum(v) / steps for k, v in mine.items() if len(v) >= steps}
+steps = max(len(v) for k, v in mine.items() if 'gather' in k) if any('gather' in k for k in mine) else 1
+per_step = {k: sum(v) / steps for k, v in mine.items() if len(v) >= steps // 4}
 T = sum(per_step.values())
 print('%-72s %5s %10s %10s %7s' % ('kernel', 'n', 'mean_ns', 'ns/step', 'share'))
 for k, v in sorted(per_step.items(), key=lambda kv: -kv[1]):

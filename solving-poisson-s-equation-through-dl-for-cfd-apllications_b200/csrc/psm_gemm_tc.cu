@@ -98,6 +98,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // dynamic shared memory: STAGES x [A_hi | A_lo | B_hi | B_lo] after manual 1024 B alignment, then barriers
 template <int BN> struct Cfg {
     static constexpr int STAGES = (BN == 128) ? 3 : 4;
@@ -324,7 +340,8 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1)
-dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcGemmArgs g) {
+dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmAlo, const __grid_constant__ CUtensorMap tmBlo, TcGemmArgs g) {
     constexpr int BN = D_BN, STAGES = D_STAGES, A_BYTES = D_A_BYTES, B_BYTES = D_B_BYTES, STAGE = D_STAGE;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -363,10 +380,13 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     cluster_sync_all();                                          // every CTA of the cluster runs: its shared memory may be written remotely
     // the Dense kernels are static: their tiles of the first ring pass are requested before waiting for the previous layer
     const int n_pre = g.b_static ? min(nkb, STAGES) : 0;
+    const bool pre = g.presplit != 0;                            // lo halves come from global memory: no converter pass
+    const uint32_t tx = pre ? 2 * (A_BYTES + B_BYTES) : A_BYTES + B_BYTES;
     if (threadIdx.x == 0) {
         for (int it = 0; it < n_pre; ++it) {
-            mbar_expect_tx(full_bar(it), A_BYTES + B_BYTES);
+            mbar_expect_tx(full_bar(it), tx);
             tma_load_2d(base + it * STAGE + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(it));
+            if (pre) tma_load_2d(base + it * STAGE + 2 * A_BYTES + B_BYTES, &tmBlo, (kb0 + it) * BK, n0, full_bar(it));
         }
     }
     pdl_wait();                                                  // barriers + TMEM are set up while the previous kernel drains
@@ -379,10 +399,12 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const uint32_t st = base + s * STAGE;
                 if (it >= n_pre) {
                     mbar_wait(empty_bar(s), ph ^ 1);
-                    mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
+                    mbar_expect_tx(full_bar(s), tx);
                     tma_load_2d(st + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(s));
+                    if (pre) tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBlo, (kb0 + it) * BK, n0, full_bar(s));
                 }
                 tma_load_2d(st, &tmA, (kb0 + it) * BK, m0, full_bar(s));
+                if (pre) tma_load_2d(st + A_BYTES, &tmAlo, (kb0 + it) * BK, m0, full_bar(s));
             }
         }
         __syncwarp();
@@ -392,7 +414,7 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(g.three_pass ? conv_bar(s) : full_bar(s), ph);
+                mbar_wait((g.three_pass && !pre) ? conv_bar(s) : full_bar(s), ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t st = base + s * STAGE;
                 const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
@@ -413,7 +435,7 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else {
         const int t = threadIdx.x - 64;
         const bool keep_hi = g.three_pass != 2;
-        if (g.three_pass) {
+        if (g.three_pass && !pre) {
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -483,11 +505,11 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (m < g.M) {
                 const size_t off = (size_t)m * g.ldc + n;
                 *reinterpret_cast<float4*>(g.C + off) = o;
-                if (g.C_hi) {                                    // operand of the transposed PCA inverse, pre-split
+                if (g.C_lo) {                                    // pre-split operand of the next contraction (C_hi only for the PCA inverse)
                     float4 hi;
                     hi.x = __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u);
                     hi.z = __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u);
-                    *reinterpret_cast<float4*>(g.C_hi + off) = hi;
+                    if (g.C_hi) *reinterpret_cast<float4*>(g.C_hi + off) = hi;
                     *reinterpret_cast<float4*>(g.C_lo + off) = make_float4(o.x - hi.x, o.y - hi.y, o.z - hi.z, o.w - hi.w);
                 }
             }
@@ -518,7 +540,252 @@ int launch_dense_cluster(const TcGemm& t, cudaStream_t s) {
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(&t.mapA);
     const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(&t.mapB);
-    return cudaLaunchKernelEx(&cfg, dense_cluster_kernel, a, b, t.args) == cudaSuccess ? 0 : -1;
+    const CUtensorMap& al = *reinterpret_cast<const CUtensorMap*>(t.args.presplit ? &t.mapAlo : &t.mapA);
+    const CUtensorMap& bl = *reinterpret_cast<const CUtensorMap*>(t.args.presplit ? &t.mapBlo : &t.mapB);
+    return cudaLaunchKernelEx(&cfg, dense_cluster_kernel, a, b, al, bl, t.args) == cudaSuccess ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PCA projection (SMC:494) + standardisation (SMC:505-523) as ONE launch -- see ProjArgs in psm_kernels.cuh.
+// Main loop = tc_gemm_kernel<128> (TMA -> 3xTF32 split -> tcgen05.mma, 3-stage ring); the epilogue replaces the
+// [splits][M][N] partials in HBM + the reduce launch by two on-chip levels:
+//   1. after a cluster barrier (all main loops of the cluster are done: the ring memory is free) every CTA pushes row slab s of
+//      its 128 x 128 partial into CTA s's ring memory through distributed shared memory; CTA z then folds the ks slices of
+//      slab z in a fixed order and stores the cluster partial (L2-resident, ks times smaller than before);
+//   2. one counter per (tile, slab): the LAST cluster to store slab z folds the ncl cluster partials of that slab in a fixed
+//      order, adds zc, standardises and writes the Dense input.  No spinning anywhere; the result does not depend on which
+//      cluster arrives last (bit-identical replays).
+namespace {
+constexpr int P_BN = 128, P_STAGES = 3;
+constexpr int P_A_BYTES = BM * BK * 4, P_B_BYTES = P_BN * BK * 4, P_STAGE = 2 * (P_A_BYTES + P_B_BYTES);
+constexpr int P_PARK_LD = P_BN + 4;                                  // floats per parked row (conflict-free float4 rows)
+constexpr int P_SMEM = P_STAGES * P_STAGE + 1024 + 256;
+static_assert(BM * P_PARK_LD * 4 <= P_STAGES * P_STAGE, "the receive buffer re-uses the operand ring");
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+proj_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ProjArgs g) {
+    constexpr int BN = P_BN, STAGES = P_STAGES, A_BYTES = P_A_BYTES, B_BYTES = P_B_BYTES, STAGE = P_STAGE;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES * STAGE;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto conv_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (3 * STAGES);
+    const uint32_t tmem_slot = accum_bar + 8u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KS = g.ks;
+    const int z = blockIdx.z % KS, cl = blockIdx.z / KS, ncl = g.splits / KS;   // cluster = (1,1,KS): consecutive z
+    const int m0 = blockIdx.y * BM;
+    const int kb_total = g.K / BK;
+    const int kb_per = (kb_total + g.splits - 1) / g.splits;
+    const int kb0 = min(blockIdx.z * kb_per, kb_total);
+    const int kb1 = min(kb_total, kb0 + kb_per);
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+    // the PCA matrix is static: its tiles of the first ring pass are requested before waiting for the gather
+    const int n_pre = g.b_static ? min(nkb, STAGES) : 0;
+    if (threadIdx.x == 0) {
+        for (int it = 0; it < n_pre; ++it) {
+            mbar_expect_tx(full_bar(it), A_BYTES + B_BYTES);
+            tma_load_2d(base + it * STAGE + 2 * A_BYTES, &tmB, (kb0 + it) * BK, 0, full_bar(it));
+        }
+    }
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const uint32_t st = base + s * STAGE;
+                if (it >= n_pre) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), A_BYTES + B_BYTES);
+                    tma_load_2d(st + 2 * A_BYTES, &tmB, (kb0 + it) * BK, 0, full_bar(s));
+                }
+                tma_load_2d(st, &tmA, (kb0 + it) * BK, m0, full_bar(s));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(BM, BN);
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(g.three_pass ? conv_bar(s) : full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * STAGE;
+                const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t ko = k * UMMA_K * 4;
+                    umma_tf32(tmem_base, make_smem_desc(a_hi + ko), make_smem_desc(b_hi + ko), idesc, (it | k) != 0);
+                    if (g.three_pass) {
+                        umma_tf32(tmem_base, make_smem_desc(a_hi + ko), make_smem_desc(b_lo + ko), idesc, 1);
+                        umma_tf32(tmem_base, make_smem_desc(a_lo + ko), make_smem_desc(b_hi + ko), idesc, 1);
+                    }
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(accum_bar);
+        }
+        __syncwarp();
+    } else {
+        const int t = threadIdx.x - 64;
+        const bool keep_hi = g.three_pass != 2;
+        if (g.three_pass) {
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                uint8_t* st = gen_base + s * STAGE;
+                float4* a_hi = reinterpret_cast<float4*>(st);
+                float4* a_lo = reinterpret_cast<float4*>(st + A_BYTES);
+                float4* b_hi = reinterpret_cast<float4*>(st + 2 * A_BYTES);
+                float4* b_lo = reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES);
+                auto split4 = [](float4 v, float4& hi, float4& lo) {
+                    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+                    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+                };
+#pragma unroll 4
+                for (int j = t; j < A_BYTES / 16; j += 128) { float4 hi, lo; split4(a_hi[j], hi, lo); if (keep_hi) a_hi[j] = hi; a_lo[j] = lo; }
+#pragma unroll 4
+                for (int j = t; j < B_BYTES / 16; j += 128) { float4 hi, lo; split4(b_hi[j], hi, lo); if (keep_hi) b_hi[j] = hi; b_lo[j] = lo; }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(conv_bar(s));
+            }
+        }
+        if (nkb > 0) mbar_wait(accum_bar, 0);                    // my MMAs have retired: my ring memory is free
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                                          // every main loop of the cluster is done: ring memory may be written remotely
+    const int rows_per = BM / KS;
+    if (warp >= 2) {
+        // push: thread <-> row (TMEM lane); row r goes to slot [z][r % rows_per] of CTA r / rows_per
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t dst = base + (uint32_t)((z * rows_per + (row % rows_per)) * P_PARK_LD) * 4u;
+        const uint32_t owner = (uint32_t)(row / rows_per);
+#pragma unroll
+        for (int c = 0; c < BN; c += 32) {
+            float v[32];
+            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) st_dsmem_v4(dst + 4u * c + 16u * i, owner, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    cluster_sync_all();                                          // all KS slices of my slab have landed
+    {
+        const float* buf = reinterpret_cast<const float*>(gen_base);
+        const size_t slab = (size_t)(m0 + z * rows_per) * BN;    // first element of my slab inside one [M][N] partial
+        float* mine = g.part + (size_t)cl * g.M * BN + slab;
+        for (int e = threadIdx.x; e < rows_per * (BN / 4); e += kThreads) {
+            const int rl = e / (BN / 4), c4 = e % (BN / 4);
+            float4 acc = *reinterpret_cast<const float4*>(buf + rl * P_PARK_LD + c4 * 4);
+            for (int p = 1; p < KS; ++p) {
+                const float4 w = *reinterpret_cast<const float4*>(buf + (p * rows_per + rl) * P_PARK_LD + c4 * 4);
+                acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+            }
+            __stcg(reinterpret_cast<float4*>(mine + (size_t)rl * BN + c4 * 4), acc);
+        }
+        __shared__ bool s_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int* cnt = g.counters + blockIdx.y * KS + z;
+            const unsigned int prev = atomicAdd(cnt, 1u);
+            s_last = (prev == (unsigned int)(ncl - 1));
+            if (s_last) { *cnt = 0u; __threadfence(); }          // re-armed for the next step
+        }
+        __syncthreads();
+        if (s_last) {
+            for (int e = threadIdx.x; e < rows_per * (BN / 4); e += kThreads) {
+                const int rl = e / (BN / 4), c4 = e % (BN / 4);
+                const size_t off = slab + (size_t)rl * BN + c4 * 4;
+                float4 acc = __ldcg(reinterpret_cast<const float4*>(g.part + off));
+                for (int c = 1; c < ncl; ++c) {
+                    const float4 w = __ldcg(reinterpret_cast<const float4*>(g.part + (size_t)c * g.M * BN + off));
+                    acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+                }
+                const float4 zc = __ldg(reinterpret_cast<const float4*>(g.zc + off));
+                const float4 sa = __ldg(reinterpret_cast<const float4*>(g.a + c4 * 4));
+                const float4 sb = __ldg(reinterpret_cast<const float4*>(g.b + c4 * 4));
+                const float4 o = make_float4((acc.x + zc.x) * sa.x + sb.x, (acc.y + zc.y) * sa.y + sb.y,
+                                             (acc.z + zc.z) * sa.z + sb.z, (acc.w + zc.w) * sa.w + sb.w);
+                *reinterpret_cast<float4*>(g.x + off) = o;
+                if (g.x_lo) {                                    // pre-split operand of the first Dense layer
+                    float4 hi;
+                    hi.x = __uint_as_float(__float_as_uint(o.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(o.y) & 0xFFFFE000u);
+                    hi.z = __uint_as_float(__float_as_uint(o.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(o.w) & 0xFFFFE000u);
+                    *reinterpret_cast<float4*>(g.x_lo + off) = make_float4(o.x - hi.x, o.y - hi.y, o.z - hi.z, o.w - hi.w);
+                }
+            }
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+static void proj_launch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, int tiles, int splits, int ks, cudaStream_t s, bool pdl) {
+    cfg.gridDim = dim3(1, tiles, splits);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = P_SMEM;
+    cfg.stream = s;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = ks;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
+}
+
+// Largest number of ks-CTA clusters the device holds at once (the split is sized to one resident wave).
+int proj_cluster_prepare(int tiles, int ks, int* max_clusters) {
+    if (cudaFuncSetAttribute(proj_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM) != cudaSuccess) return -1;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[2];
+    proj_launch_cfg(cfg, at, tiles, ks * 64, ks, 0, false);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, proj_cluster_kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); return -1; }
+    *max_clusters = n;
+    return 0;
+}
+
+int launch_proj_cluster(const ProjGemm& t, cudaStream_t s) {
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[2];
+    proj_launch_cfg(cfg, at, t.args.M / BM, t.args.splits, t.args.ks, s, pdl_enabled());
+    const CUtensorMap& a = *reinterpret_cast<const CUtensorMap*>(&t.mapA);
+    const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(&t.mapB);
+    return cudaLaunchKernelEx(&cfg, proj_cluster_kernel, a, b, t.args) == cudaSuccess ? 0 : -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -792,21 +1059,6 @@ constexpr int I_BSTAGES = 2;
 constexpr int I_TILE_LD = 129;                           // floats per parked block row (strip sums): odd pitch, conflict-free columns
 constexpr int I_TILE = 32 * I_TILE_LD * 4;
 constexpr int I_SMEM = 2 * I_KB * I_A_TILE + I_BSTAGES * 2 * I_B_TILE + 1024 + 256 + I_TILE;
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
 }  // namespace
 
 __global__ void __launch_bounds__(kThreads, 1)

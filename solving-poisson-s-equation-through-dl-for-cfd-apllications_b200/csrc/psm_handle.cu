@@ -4,6 +4,7 @@
 #include <nccl.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
@@ -150,6 +151,8 @@ struct psm_handle {
     Scalars* d_sc = nullptr; Scalars* h_sc = nullptr;   // h_sc: mapped pinned host memory, only .skip is written by the device
     int* d_host_skip = nullptr;
     TcGemm tc_proj{}, tc_inv{}; std::vector<TcGemm> tc_dense; std::vector<int> dense_splits; int tc_splits = 1;
+    bool dense_presplit = false; float* d_xin_lo = nullptr;            // Dense layers read pre-split operands (no converter pass)
+    ProjGemm proj_cl{}; bool proj_cluster = false; float* d_proj_part = nullptr; unsigned int* d_proj_cnt = nullptr;   // one-launch projection
     float* d_dpart = nullptr;       // split-K partials of the Dense layers   // tcgen05 path (gemm_mode 0/1)
     bool dense_cluster = true;      // Dense layers: cluster split-K with on-chip reduction (one launch per layer)
     // whole Dense stack in one persistent launch (opt-in, PSM_DENSE_STACK=1: measured equal to the per-layer cluster
@@ -171,6 +174,15 @@ struct psm_handle {
     int eager_steps = 0;
     // host entry points: a second stream copies the caller's p array while the kernels already run (only the last kernel reads it)
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_u = nullptr, ev_p = nullptr;
+    // chunked tail of the host entry points: p goes up, the grid->cell gather runs and the pressures go down chunk by chunk, so the
+    // device->host copy of chunk k shares the (full-duplex) link with the host->device copy of p's chunk k+1
+    static constexpr int kTailMax = 8;
+    cudaStream_t d2h_stream = nullptr; cudaEvent_t ev_pc[kTailMax] = {}, ev_bc[kTailMax] = {}, ev_d2h = nullptr;
+    // one DMA stream reaches ~43 GB/s host->device on this platform, two concurrent ones ~53 GB/s (profiles/pcie_probe.py): the
+    // host entry points upload every array as two halves on two streams (the main stream and copy_stream), p's chunks alternate
+    // between copy_stream and copy_stream2
+    cudaStream_t copy_stream2 = nullptr; cudaEvent_t ev_um = nullptr; bool split_h2d = true;
+    int tail_chunks = 4;
     bool pprev_zero = false;          // d_pprev currently holds zeros (psm_predict_fields without p)
     size_t cells_capacity = 0;        // doubles in d_cells
     // cell routing (psm_route_init / psm_predict_routed): arbitrary per-rank cell sets -> block-row owners and back
@@ -186,6 +198,8 @@ struct StepInput {
     const double* U = nullptr; const double* dU = nullptr; int u_stride = 0;   // double[n][u_stride] (psm_predict_fields*)
     const double* p_dev = nullptr;                                  // fields: previous pressure read in place (NULL: h->d_pprev)
     bool wait_p = false;                                            // host fields path: the p copy runs on copy_stream
+    int tail_chunks = 1;                                            // host paths: chunks of the grid->cell gather (wait_p: h->ev_pc[k] per chunk)
+    double* host_out = nullptr;                                     // host paths: chunk k of d_out is copied here on d2h_stream behind its gather
 };
 
 #define PSM_FAIL(h, code, ...)                                    \
@@ -247,6 +261,40 @@ extern "C" int psm_api_version(void) { return PSM_API_VERSION; }
 
 extern "C" const char* psm_last_error(const psm_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+static bool make_tail(psm_handle* h) {
+    if (cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&h->ev_um, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (const char* e = getenv("PSM_NO_SPLIT_H2D")) h->split_h2d = !(e[0] == '1');
+    for (int k = 0; k < psm_handle::kTailMax; ++k)
+        if (cudaEventCreateWithFlags(&h->ev_pc[k], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&h->ev_bc[k], cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&h->ev_d2h, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (const char* e = getenv("PSM_TAIL_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= psm_handle::kTailMax) h->tail_chunks = v; }
+    return true;
+}
+// cells [c0, c1) of tail chunk k of nch (boundaries on multiples of 4 cells: the 128-bit table loads of the gather stay aligned)
+static inline void tail_range(long long n, int nch, int k, long long* c0, long long* c1) {
+    const long long per = (((n + nch - 1) / nch) + 3) & ~3ll;
+    *c0 = per * k < n ? per * k : n;
+    *c1 = (k == nch - 1 || per * (k + 1) > n) ? n : per * (k + 1);
+}
+// Host->device copy of `n` doubles as two halves on the main stream and copy_stream (two DMA streams in flight); the main stream
+// then waits for the second half.  Small arrays (or PSM_NO_SPLIT_H2D=1) go up in one piece.
+static int upload_split(psm_handle* h, double* dst, const double* src, size_t n) {
+    if (!h->split_h2d || n < (size_t)(1 << 18)) {
+        CU(h, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        return PSM_OK;
+    }
+    const size_t half = (n / 2 + 15) & ~(size_t)15;
+    CU(h, cudaMemcpyAsync(dst + half, src + half, (n - half) * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+    CU(h, cudaMemcpyAsync(dst, src, half * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaEventRecord(h->ev_u, h->copy_stream));
+    CU(h, cudaStreamWaitEvent(h->stream, h->ev_u, 0));
+    return PSM_OK;
+}
+static inline int tail_chunks_for(const psm_handle* h) { return h->n_cells >= (1 << 18) ? h->tail_chunks : 1; }
+
 extern "C" int psm_create(psm_handle** out, const psm_config* cfg) {
     if (!out || !cfg) { g_create_error = "psm_create: NULL argument"; return PSM_ERR_INVALID; }
     *out = nullptr;
@@ -280,7 +328,7 @@ extern "C" int psm_create(psm_handle** out, const psm_config* cfg) {
         g_create_error = cudaGetErrorString(e); delete h; return PSM_ERR_CUDA;
     }
     if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_u, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_p, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_p, cudaEventDisableTiming) != cudaSuccess || !make_tail(h)) {
         g_create_error = "cannot create the copy stream / events"; cudaStreamDestroy(h->stream); delete h; return PSM_ERR_CUDA;
     }
     if (cudaHostAlloc((void**)&h->h_sc, sizeof(Scalars), cudaHostAllocMapped) != cudaSuccess) { g_create_error = "cudaMallocHost failed"; cudaStreamDestroy(h->stream); delete h; return PSM_ERR_CUDA; }
@@ -299,6 +347,11 @@ extern "C" int psm_destroy(psm_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->d2h_stream) { cudaStreamSynchronize(h->d2h_stream); cudaStreamDestroy(h->d2h_stream); }
+    if (h->copy_stream2) { cudaStreamSynchronize(h->copy_stream2); cudaStreamDestroy(h->copy_stream2); }
+    if (h->ev_um) cudaEventDestroy(h->ev_um);
+    for (int k = 0; k < psm_handle::kTailMax; ++k) { if (h->ev_pc[k]) cudaEventDestroy(h->ev_pc[k]); if (h->ev_bc[k]) cudaEventDestroy(h->ev_bc[k]); }
+    if (h->ev_d2h) cudaEventDestroy(h->ev_d2h);
     if (h->ev_u) cudaEventDestroy(h->ev_u);
     if (h->ev_p) cudaEventDestroy(h->ev_p);
     for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -849,6 +902,39 @@ static int init_local(psm_handle* h, LocalInit& L) {
         };
         TRY(mk(h->tc_proj, h->d_xu, Bp, h->d_comp_u, h->pc_in_pad, 2 * S2, h->d_part, h->pc_in_pad, h->tc_splits, EPI_PARTIAL,
                nullptr, nullptr, nullptr, tc_gemm_bn(h->pc_in_pad)));
+        // ---- projection + standardisation in one launch (cluster fold, last-arrival fold per row slab) ----
+        if (h->pc_in_pad == 128 && !env_on("PSM_NO_PROJ_CLUSTER")) {
+            const int tiles = Bp / 128, kb_total = 2 * S2 / 32;
+            int best_ks = 0, best_ncl = 0;
+            for (int ks = 8; ks >= 1; ks >>= 1) {                 // most CTAs of one resident wave; on a tie the larger cluster
+                int max_cl = 0;
+                if (proj_cluster_prepare(tiles, ks, &max_cl) != 0) continue;
+                int ncl = std::min(max_cl, 148 / ks) / tiles;     // clusters per tile
+                ncl = std::min(ncl, kb_total / ks);
+                if (ncl < 1) continue;
+                if (ncl * ks > best_ncl * best_ks) { best_ks = ks; best_ncl = ncl; }
+            }
+            if (const char* e = getenv("PSM_PROJ_KS")) {           // A/B: force the cluster size
+                const int ks = atoi(e); int max_cl = 0;
+                if ((ks == 1 || ks == 2 || ks == 4 || ks == 8) && proj_cluster_prepare(tiles, ks, &max_cl) == 0) {
+                    const int ncl = std::min(std::min(max_cl, 148 / ks) / tiles, kb_total / ks);
+                    if (ncl >= 1) { best_ks = ks; best_ncl = ncl; }
+                }
+            }
+            if (best_ks > 0) {
+                const int per = (kb_total + best_ks * best_ncl - 1) / (best_ks * best_ncl);
+                int splits = (kb_total + per - 1) / per;
+                splits = (splits + best_ks - 1) / best_ks * best_ks;      // whole clusters; surplus splits are empty (zero partials)
+                TRY(dalloc(h, &h->d_proj_part, (size_t)(splits / best_ks) * Bp * 128));
+                TRY(dalloc(h, &h->d_proj_cnt, (size_t)tiles * 8));
+                ProjGemm& pg = h->proj_cl;
+                if (make_kmajor_map(&pg.mapA, h->d_xu, Bp, 2 * S2, 2 * S2, 128) != 0 || make_kmajor_map(&pg.mapB, h->d_comp_u, h->pc_in_pad, 2 * S2, 2 * S2, 128) != 0)
+                    PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed (projection)");
+                pg.args = ProjArgs{Bp, 128, 2 * S2, splits, best_ks, three, env_on("PSM_NO_PREFETCH") ? 0 : 1, h->d_proj_part, h->d_proj_cnt,
+                                   h->d_zc, h->d_in_a, h->d_in_b, h->d_xin};
+                h->proj_cluster = true;
+            }
+        }
         // Dense layers: the batch is only B blocks (one or a few 128-row tiles), so every layer is cut into
         // 64-column tiles x split-K partials (each CTA streams <= ~100 KB), folded by the reduce kernel.
         h->tc_dense.resize(h->n_dense);
@@ -856,7 +942,16 @@ static int init_local(psm_handle* h, LocalInit& L) {
         h->dense_cluster = !env_on("PSM_NO_DENSE_CLUSTER");
         if (h->dense_cluster && dense_cluster_prepare() != 0) PSM_FAIL(h, PSM_ERR_CUDA, "cannot opt in to the shared memory of the Dense cluster kernel");
         TRY(dalloc(h, &h->d_dpart, (size_t)8 * Bp * maxw));
+        // pre-split operands: every producer of a Dense input also stores x - tf32(x), the Dense kernels' lo halves are static, so
+        // a layer stages four tiles by TMA and issues its MMAs straight away (no in-kernel converter pass on the critical path)
+        h->dense_presplit = h->dense_cluster && three == 2 && !env_on("PSM_NO_DENSE_PRESPLIT");
+        if (h->dense_presplit) {
+            TRY(dalloc(h, &h->d_xin_lo, (size_t)Bp * h->pc_in_pad));
+            for (int i = 0; i < 2; ++i) if (!h->d_act_lo[i]) TRY(dalloc(h, &h->d_act_lo[i], (size_t)Bp * maxw));
+            h->proj_cl.args.x_lo = h->d_xin_lo;
+        }
         const float* in = h->d_xin;
+        const float* in_lo = h->d_xin_lo;
         for (int l = 0; l < h->n_dense; ++l) {
             const bool last = (l == h->n_dense - 1);
             float* outp = last ? h->d_r : h->d_act[l & 1];
@@ -869,6 +964,15 @@ static int init_local(psm_handle* h, LocalInit& L) {
                 h->dense_splits[l] = ks;
                 TRY(mk(h->tc_dense[l], in, Bp, h->d_W[l], h->dims_pad[l + 1], h->dims_pad[l], outp, h->dims_pad[l + 1], ks,
                        last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU, h->d_bias[l], h->d_out_s, h->d_out_m, 64));
+                if (h->dense_presplit) {
+                    TcGemm& g = h->tc_dense[l];
+                    if (make_kmajor_map(&g.mapAlo, in_lo, Bp, h->dims_pad[l], h->dims_pad[l], 128) != 0 ||
+                        make_kmajor_map(&g.mapBlo, h->d_Wlo[l], h->dims_pad[l + 1], h->dims_pad[l], h->dims_pad[l], 64) != 0)
+                        PSM_FAIL(h, PSM_ERR_CUDA, "cuTensorMapEncodeTiled failed (Dense lo operands)");
+                    g.args.presplit = 1;
+                    if (!last) g.args.C_lo = h->d_act_lo[l & 1];
+                    in_lo = h->d_act_lo[l & 1];
+                }
                 in = outp;
                 continue;
             }
@@ -1170,7 +1274,10 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
     tick();   // extract
     const bool tc = h->cfg.gemm_mode != PSM_GEMM_FP32_SIMT;
     {
-        if (tc) launch_tc_gemm(h->tc_proj, s);
+        const bool one_launch = tc && h->proj_cluster && !h->dense_stack;
+        if (one_launch) {
+            if (launch_proj_cluster(h->proj_cl, s) != 0) PSM_FAIL(h, PSM_ERR_CUDA, "projection launch: %s", cudaGetErrorString(cudaGetLastError()));
+        } else if (tc) launch_tc_gemm(h->tc_proj, s);
         else {
             GemmArgs g{};
             g.A = h->d_xu; g.B = h->d_comp_u; g.C = h->d_part; g.M = Bp; g.N = h->pc_in_pad; g.K = 2 * S2;
@@ -1181,7 +1288,8 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
         ReduceArgs r{h->d_part, tc ? h->tc_splits : h->splits, Bp, h->pc_in_pad, h->d_zc, h->d_in_a, h->d_in_b, h->d_xin,
                      RED_STANDARDISE, nullptr, nullptr, nullptr};
         if (tc && h->dense_stack) { r.x_hi = h->d_act_hi[0]; r.x_lo = h->d_act_lo[0]; }
-        launch_reduce_standardise(r, s); ++nl;
+        else if (tc && h->dense_presplit) r.x_lo = h->d_xin_lo;
+        if (!one_launch) { launch_reduce_standardise(r, s); ++nl; }
     }
     tick();   // pca_project
     if (tc && h->dense_stack) {
@@ -1277,14 +1385,37 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
                                     h->pix_recv_ptr, 1));
             NC(h, g_nccl.GroupEnd());
         }
-        if (in.wait_p) CU(h, cudaStreamWaitEvent(s, h->ev_p, 0));          // the caller's p array has landed in d_pprev
         BackArgs ba{h->d_bv[0], h->d_bv[1], h->d_bv[2], h->d_bw[0], h->d_bw[1], h->d_bw[2], h->d_field, h->n_cells,
                     h->field_stride, (fields && in.p_dev) ? in.p_dev : h->d_pprev, d_out, h->F, h->cfg.additive, h->d_sc, d_p2p, nullptr, nullptr, nullptr, nullptr, 0, 0};
         if (fuse_place) {
             ba.v0 = h->d_bb[0]; ba.v1 = h->d_bb[1]; ba.v2 = h->d_bb[2]; ba.o0 = h->d_bo[0]; ba.o1 = h->d_bo[1]; ba.o2 = h->d_bo[2];
             ba.field = h->d_blocks; ba.plane = S2; ba.coff = h->d_coff; ba.n_blocks = h->Bg; ba.block_plane = S2;
         }
-        launch_back(ba, s); ++nl;
+        const int nch = in.tail_chunks > 1 ? in.tail_chunks : 1;
+        if (nch == 1) {
+            if (in.wait_p) CU(h, cudaStreamWaitEvent(s, h->ev_p, 0));      // the caller's p array has landed in d_pprev
+            launch_back(ba, s); ++nl;
+            if (in.host_out) CU(h, cudaMemcpyAsync(in.host_out, d_out, (size_t)h->n_cells * h->F * sizeof(double), cudaMemcpyDeviceToHost, s));
+        } else {
+            // chunked tail (host entry points): gather chunk k as soon as chunk k of p has landed, copy it out on the second copy
+            // stream while chunk k+1 of p is still on its way up -- the two directions of the link work at the same time
+            for (int k = 0; k < nch; ++k) {
+                long long c0, c1; tail_range(h->n_cells, nch, k, &c0, &c1);
+                if (c1 <= c0) continue;
+                if (in.wait_p) CU(h, cudaStreamWaitEvent(s, h->ev_pc[k], 0));
+                BackArgs bk = ba;
+                bk.v0 += c0; bk.v1 += c0; bk.v2 += c0; bk.w0 += c0; bk.w1 += c0; bk.w2 += c0;
+                if (bk.o0) { bk.o0 += c0; bk.o1 += c0; bk.o2 += c0; }
+                bk.p_prev += c0; bk.out += c0 * h->F; bk.n = c1 - c0;
+                launch_back(bk, s); ++nl;
+                if (in.host_out) {
+                    CU(h, cudaEventRecord(h->ev_bc[k], s));
+                    CU(h, cudaStreamWaitEvent(h->d2h_stream, h->ev_bc[k], 0));
+                    CU(h, cudaMemcpyAsync(in.host_out + c0 * h->F, d_out + c0 * h->F, (size_t)(c1 - c0) * h->F * sizeof(double), cudaMemcpyDeviceToHost, h->d2h_stream));
+                }
+            }
+            if (in.host_out) { CU(h, cudaEventRecord(h->ev_d2h, h->d2h_stream)); CU(h, cudaStreamWaitEvent(s, h->ev_d2h, 0)); }
+        }
     }
     tick();   // back_gather
     h->launches = nl;
@@ -1354,12 +1485,12 @@ extern "C" int psm_predict(psm_handle* h, const double* cells, int64_t n_cells, 
     h->last_host = true;
     h->field_stale = h->fuse_place;
     if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
-    CU(h, cudaMemcpyAsync(h->d_cells, cells, (size_t)h->n_cells * h->cfg.input_cols * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    TRY(upload_split(h, h->d_cells, cells, (size_t)h->n_cells * h->cfg.input_cols));
     if (h->ev_valid) cudaEventRecord(h->ev[11], h->stream);
     StepInput in; in.rows = h->d_cells;
+    in.host_out = p_out; in.tail_chunks = tail_chunks_for(h);       // the pressures go down chunk by chunk behind their gather
     if (h->eager_steps > 0) --h->eager_steps;
     TRY(run_step(h, in, h->d_out));
-    CU(h, cudaMemcpyAsync(p_out, h->d_out, (size_t)h->n_cells * h->F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
     return finish(h);
 }
@@ -1384,26 +1515,37 @@ extern "C" int psm_predict_fields(psm_handle* h, const double* U, int32_t u_stri
     h->last_host = true;
     h->field_stale = h->fuse_place;
     if (h->ev_valid) cudaEventRecord(h->ev[0], h->stream);
-    CU(h, cudaMemcpyAsync(h->d_cells, U, nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (dU) CU(h, cudaMemcpyAsync(h->d_cells + nu, dU, nu * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    TRY(upload_split(h, h->d_cells, U, nu));
+    if (dU) TRY(upload_split(h, h->d_cells + nu, dU, nu));
     if (h->ev_valid) cudaEventRecord(h->ev[11], h->stream);
     StepInput in; in.U = h->d_cells; in.dU = dU ? h->d_cells + nu : nullptr; in.u_stride = u_stride;
     if (p) {
         // p is read by the LAST kernel only: its copy starts when U has landed (so the two do not share the link) and runs on
         // the copy stream while the kernels execute
-        CU(h, cudaEventRecord(h->ev_u, h->stream));
-        CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_u, 0));
-        CU(h, cudaMemcpyAsync(h->d_pprev, p, (size_t)h->n_cells * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
-        CU(h, cudaEventRecord(h->ev_p, h->copy_stream));
+        CU(h, cudaEventRecord(h->ev_um, h->stream));                // U (both halves) has landed
+        CU(h, cudaStreamWaitEvent(h->copy_stream, h->ev_um, 0));
+        CU(h, cudaStreamWaitEvent(h->copy_stream2, h->ev_um, 0));
+        const int nch = tail_chunks_for(h);
+        if (nch == 1) {
+            CU(h, cudaMemcpyAsync(h->d_pprev, p, (size_t)h->n_cells * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+            CU(h, cudaEventRecord(h->ev_p, h->copy_stream));
+        } else {
+            for (int k = 0; k < nch; ++k) {                          // chunks alternate between the two copy streams
+                cudaStream_t cs = (h->split_h2d && (k & 1)) ? h->copy_stream2 : h->copy_stream;
+                long long c0, c1; tail_range(h->n_cells, nch, k, &c0, &c1);
+                if (c1 > c0) CU(h, cudaMemcpyAsync(h->d_pprev + c0, p + c0, (size_t)(c1 - c0) * sizeof(double), cudaMemcpyHostToDevice, cs));
+                CU(h, cudaEventRecord(h->ev_pc[k], cs));
+            }
+        }
         in.wait_p = true;
         h->pprev_zero = false;
     } else if (!h->pprev_zero) {
         CU(h, cudaMemsetAsync(h->d_pprev, 0, (size_t)h->n_cells * sizeof(double), h->stream));
         h->pprev_zero = true;
     }
+    in.host_out = out; in.tail_chunks = tail_chunks_for(h);
     if (h->eager_steps > 0) --h->eager_steps;
     TRY(run_step(h, in, h->d_out));
-    CU(h, cudaMemcpyAsync(out, h->d_out, (size_t)h->n_cells * h->F * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (h->ev_valid) cudaEventRecord(h->ev[PSM_N_TIMINGS], h->stream);
     return finish(h);
 }
@@ -1814,6 +1956,21 @@ extern "C" int psm_set_timings(psm_handle* h, int32_t on) {
 }
 
 extern "C" int psm_get_launch_count(const psm_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int psm_get_wait_ns(psm_handle* h, uint64_t ns[3], uint32_t count[3], int32_t reset) {
+    if (!h || !ns || !count) return PSM_ERR_INVALID;
+    if (!h->initialised) PSM_FAIL(h, PSM_ERR_STATE, "not initialised");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    Scalars sc;
+    CU(h, cudaMemcpy(&sc, h->d_sc, sizeof(Scalars), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 3; ++i) { ns[i] = sc.wait_ns[i]; count[i] = sc.wait_n[i]; }
+    if (reset) {
+        CU(h, cudaMemset(reinterpret_cast<char*>(h->d_sc) + offsetof(Scalars, wait_ns), 0, sizeof(sc.wait_ns)));
+        CU(h, cudaMemset(reinterpret_cast<char*>(h->d_sc) + offsetof(Scalars, wait_n), 0, sizeof(sc.wait_n)));
+    }
+    return PSM_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 extern "C" int psm_debug_gemm(int32_t device, int32_t mode, int32_t M, int32_t N, int32_t K, const float* A, const float* B,

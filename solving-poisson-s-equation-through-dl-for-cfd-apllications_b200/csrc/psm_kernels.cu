@@ -41,17 +41,26 @@ __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) 
 }
 // Thread 0 of the CTA waits until every peer in `mask` has raised flag[phase] to the current step, then the
 // CTA proceeds.  Bounded: after ~2 s the step is marked failed (PSM_ERR_COMM) instead of hanging the GPU.
-__device__ __forceinline__ void p2p_wait(const P2PArgs* P, int phase, unsigned int mask) {
+__device__ __forceinline__ void p2p_wait(const P2PArgs* P, int phase, unsigned int mask, int sample = -1) {
+    const bool sampled = sample < 0 ? blockIdx.x == 0 : sample != 0;
     if (threadIdx.x == 0) {
         const unsigned int step = P->sc->step;
         const PeerMail* mine = P->mail[P->rank];
         const long long t0 = clock64();
+        unsigned long long g0 = 0;
+        if (sampled) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g0));
         for (int p = 0; p < P->world; ++p) {
             if (!((mask >> p) & 1u) || p == P->rank) continue;
             while ((int)(ld_acquire_sys(&mine->flag[phase][p]) - step) < 0) {
                 if (clock64() - t0 > 4000000000ll) { P->sc->comm_error = 1; break; }
                 __nanosleep(64);
             }
+        }
+        if (sampled) {               // one sample per kernel: the wait histogram
+            unsigned long long g1;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
+            atomicAdd(&P->sc->wait_ns[phase], g1 - g0);
+            atomicAdd(&P->sc->wait_n[phase], 1u);
         }
     }
     __syncthreads();
@@ -813,9 +822,10 @@ __global__ void __launch_bounds__(256) reduce_standardise_kernel(ReduceArgs a) {
         else if (a.kind == RED_BIAS_RELU) o = fmaxf(tot + a.bias[n], 0.f);
         else o = (tot + a.bias[n]) * a.a[n] + a.b[n];
         a.x[i] = o;
-        if (a.x_hi) {
+        if (a.x_lo) {
             const float hi = __uint_as_float(__float_as_uint(o) & 0xFFFFE000u);
-            a.x_hi[i] = hi; a.x_lo[i] = o - hi;
+            if (a.x_hi) a.x_hi[i] = hi;
+            a.x_lo[i] = o - hi;
         }
     }
 }
@@ -999,12 +1009,19 @@ __global__ void __launch_bounds__(256) task_fold_kernel(MeansArgs a, const float
             // pixels the other CTAs pushed (phase 2; their system-scope fences precede the counter), then wait for the peers
             const P2PArgs& P = *fx.p2p;
             const unsigned int step = P.sc->step;
-            const int total = a.n_tasks * P.world;
-            for (int e = threadIdx.x; e < total; e += blockDim.x) {
-                const int p = e / a.n_tasks, i = e - p * a.n_tasks;
-                if (p == P.rank) continue;
-                const int slot = a.tasks[i].out;
-                P.means[p][slot] = ld_cg_f64(a.means + slot);
+            // every local mean is read ONCE (four independent slot -> value chains per thread in flight) and stored to all peers:
+            // the serial tail of this CTA does not grow with the number of ranks
+            for (int i0 = threadIdx.x; i0 < a.n_tasks; i0 += blockDim.x * 4) {
+                int slot[4]; double v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const int i = i0 + k * (int)blockDim.x; slot[k] = (i < a.n_tasks) ? a.tasks[i].out : -1; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = slot[k] >= 0 ? ld_cg_f64(a.means + slot[k]) : 0.0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (slot[k] >= 0)
+                        for (int p = 0; p < P.world; ++p)
+                            if (p != P.rank) P.means[p][slot[k]] = v[k];
             }
             __threadfence_system();
             __syncthreads();
@@ -1013,7 +1030,7 @@ __global__ void __launch_bounds__(256) task_fold_kernel(MeansArgs a, const float
                 st_release_sys(&P.mail[p]->flag[1][P.rank], step);
                 if (P.pix_send_ptr[p + 1] > P.pix_send_ptr[p]) st_release_sys(&P.mail[p]->flag[2][P.rank], step);
             }
-            p2p_wait(fx.p2p, 1, 0xFFu);
+            p2p_wait(fx.p2p, 1, 0xFFu, 1);           // only the last CTA waits here: it is the sample
         }
         offsets_body(oa, s_rec, s_terms, mk_smem);
     }

@@ -41,6 +41,10 @@ struct Scalars {
     unsigned int push_done[3];       // multi-GPU: CTAs of a push kernel that have finished their stores
     unsigned int means_done;         // CTAs of task_means_kernel that have published their mean (the last one runs the offsets)
     unsigned int dense_barrier;      // grid barrier of dense_stack_kernel (arrivals of the current step; re-armed by offsets_kernel)
+    // multi-GPU: time CTA 0 of each consuming kernel spent in p2p_wait, per phase (0 ghost cells + maxima, 1 strip means,
+    // 2 ghost pixels), and the number of waits -- the per-phase wait histogram psm_get_wait_ns reports
+    unsigned long long wait_ns[3];
+    unsigned int wait_n[3];
 };
 
 // ---- multi-GPU exchanges over peer memory (NVLink P2P, cudaIpc-mapped buffers) ---------------------------
@@ -185,12 +189,33 @@ struct TcGemmArgs {
     float* C_hi; float* C_lo;  // dense_cluster_kernel: optional tf32 hi / lo split of the result (same layout as C)
     int b_static;              // 1: the B operand does not depend on earlier kernels of the step (weights): its first tiles are
                                //    requested BEFORE the programmatic-dependent-launch wait
+    int presplit;              // dense_cluster_kernel, three_pass == 2: the lo halves of both operands exist in global memory (the
+                               //    previous layer's epilogue / the parameter load wrote them): TMA stages them, no converter pass
 };
-struct TcGemm { TensorMap128 mapA, mapB; TcGemmArgs args; int bn; };   // bn: N tile (64 or 128) the B map was built for
+struct TcGemm { TensorMap128 mapA, mapB; TcGemmArgs args; int bn; TensorMap128 mapAlo, mapBlo; };   // bn: N tile (64 or 128) the B map was built for
 int make_kmajor_map(TensorMap128* out, const float* ptr, int rows, int cols, int ld, int box_rows);
 int tc_gemm_bn(int N);
 int tc_gemm_prepare();
 void launch_tc_gemm(const TcGemm& t, cudaStream_t s);
+
+// PCA projection in ONE launch (psm_gemm_tc.cu): split-K over about one wave of CTAs, the `ks` CTAs of a thread-block cluster fold
+// their partial accumulators through distributed shared memory (row slab z of the tile goes to CTA z), the folded cluster partial
+// goes to `part`, and for every row slab the LAST cluster to arrive (one counter per slab) adds the `ncl` cluster partials in a
+// fixed order, adds the static distance-channel term and standardises (SMC:494,505-523).  Replaces tc_gemm_kernel + the
+// reduce_standardise launch and their [splits][M][N] partials in HBM.  N == 128, M % 128 == 0, K % 32 == 0.
+struct ProjArgs {
+    int M, N, K;
+    int splits, ks;               // K splits (a multiple of ks) and the cluster size along z (1, 2, 4 or 8)
+    int three_pass, b_static;
+    float* part;                  // [splits / ks][M][N] cluster partials
+    unsigned int* counters;       // [M / 128][ks], zero between steps (re-armed by the last arrival)
+    const float* zc; const float* a; const float* b;   // x = (sum + zc[m][n]) * a[n] + b[n]
+    float* x;                     // [M][N]
+    float* x_lo;                  // optional: x - tf32(x) (pre-split operand of the first Dense layer)
+};
+struct ProjGemm { TensorMap128 mapA, mapB; ProjArgs args; };
+int proj_cluster_prepare(int tiles, int ks, int* max_clusters);
+int launch_proj_cluster(const ProjGemm& t, cudaStream_t s);
 
 // Dense layer in one launch: cluster split-K + distributed-shared-memory reduction + fused epilogue
 // (psm_gemm_tc.cu).  t.args.splits = cluster size along K (1, 2, 4 or 8); N % 64 == 0.

@@ -136,6 +136,7 @@ SYMBOLS = {
     'psm_get_timings': (C.c_int, [C.c_void_p, c_float_p, C.c_int32]),
     'psm_set_timings': (C.c_int, [C.c_void_p, C.c_int32]),
     'psm_get_launch_count': (C.c_int, [C.c_void_p]),
+    'psm_get_wait_ns': (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32), C.c_int32]),
     'psm_debug_gemm': (C.c_int, [C.c_int32] * 5 + [c_float_p, c_float_p, c_float_p, C.c_int32]),
     'psm_debug_dense_stack': (C.c_int, [C.c_int32] * 4 + [c_int32_p, C.POINTER(c_float_p), C.POINTER(c_float_p), c_float_p, c_float_p,
                                         C.c_int32]),

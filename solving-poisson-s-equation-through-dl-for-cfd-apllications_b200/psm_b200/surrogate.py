@@ -524,3 +524,9 @@ class PressureSurrogate:
 
     def launch_count(self):
         return int(self.lib.psm_get_launch_count(self._h))
+
+    def wait_ns(self, reset=True):
+        """Multi-GPU wait histogram (psm_get_wait_ns): {'ns': [3], 'count': [3]} per exchange phase since the last reset."""
+        ns, cnt = (C.c_uint64 * 3)(), (C.c_uint32 * 3)()
+        self._check(self.lib.psm_get_wait_ns(self._h, ns, cnt, int(bool(reset))))
+        return {'ns': [int(x) for x in ns], 'count': [int(x) for x in cnt]}
