@@ -350,21 +350,16 @@ class DeviceCase:
         each = [a.elapsed_time(b) for a, b in evs]
         return sum(each), tot, each
 
-    def host_step(self, mode, cold=False):
-        """One end-to-end step through a host entry point; the refill of the solver's buffer is outside the timed interval.
-        ``cold``: after the refill a 256 MiB host buffer is read, so that the refilled lines have left the CPU's last-level cache
-        (a DMA read of lines that are still dirty in the cache is slower than one from DRAM) -- the host-side twin of the L2
-        flush; reported separately, the headline figure keeps the hot refill."""
+    def host_step(self, mode):
+        """One end-to-end step through a host entry point; the refill of the solver's buffer is outside the timed interval (the
+        refilled lines are still dirty in the CPU caches when the DMA reads them, as in the solver: profiles/pcie_probe.py
+        measures 0.555 ms for U that way against 0.445 ms from DRAM)."""
         st, sm = self.state, self.sm
         st['i'] ^= 1
         if mode == 'fields':
             self.hU.copy_(self.hU_src[st['i']])
         else:
             self.h_in.copy_(self.h_src[st['i']])
-        if cold:
-            if not hasattr(self, 'llc_sweep'):
-                self.llc_sweep = np.ones(32 << 20, dtype=np.float64)
-            self.llc_sweep.sum()
         if self.world > 1:
             self.dist.barrier()                   # collective call: all ranks enter together, refills not timed
         t0 = time.perf_counter()
@@ -377,12 +372,12 @@ class DeviceCase:
         st['skipped'] += int(rc != 0)
         return dt
 
-    def time_host(self, mode, steps, cold=False):
+    def time_host(self, mode, steps):
         for _ in range(3):
-            self.host_step(mode, cold)
+            self.host_step(mode)
         self.state['skipped'] = 0
         self.barrier()
-        each = [self.host_step(mode, cold) for _ in range(steps)]
+        each = [self.host_step(mode) for _ in range(steps)]
         assert self.state['skipped'] == 0, 'a timed step was short-cut by the skip rule'
         return each
 
@@ -587,7 +582,6 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-c5', action='store_true', help='skip the roofline_c5 block (same kernels on the 4 M-cell mesh)')
     ap.add_argument('--no-parity', action='store_true', help='N > 1: skip the parity check after the timed runs')
-    ap.add_argument('--cold-host', action='store_true', help='also time the e2e call with the CPU caches swept between refill and call')
     ap.add_argument('--latency', action='store_true', help='configs[4]: per-step latency over --steps consecutive steps')
     ap.add_argument('--input-cols', type=int, default=5, choices=[5, 7],
                     help='5: rows {Ux,Uy,Cx,Cy,p} exactly as FOAM/PythonComm.H:2-9 fills them, the handle keeps U(t-1) resident '
@@ -623,7 +617,6 @@ def main():
         sm, dc, n, geo = res['sm'], res['dc'], res['n'], res['geo']
         e2e_each = dc.time_host('fields', args.steps)
         rows_each = dc.time_host('rows', max(10, args.steps // 2))
-        cold_each = dc.time_host('fields', max(10, args.steps // 2), cold=True) if args.cold_host else None
         # deltaU_to_deltaP falls back to p_prev (always finite); U_to_gradP keeps NaN where the reference's grid->cell
         # interpolation is NaN (cells outside the grid hull, GRAD has no previous-gradient fallback)
         assert np.isfinite(dc.h_out.numpy()).mean() > (0.999 if variant == 'deltaU_to_deltaP' else 0.95)
@@ -661,10 +654,6 @@ def main():
                                        'down follow chunk by chunk (both directions of the link busy at once)',
                         'p50_ms': float(np.percentile(e2e_each, 50) * 1e3), 'p99_ms': float(np.percentile(e2e_each, 99) * 1e3),
                         'device_events_ms': {'h2d_U': float(parts_f[0]), 'kernels_p_copy_and_chunked_d2h': float(parts_f[1] + parts_f[2])},
-                        'cold_host_cache': None if cold_each is None else {
-                            'ms_per_step': float(np.mean(cold_each) * 1e3), 'value': n / float(np.mean(cold_each)),
-                            'note': '--cold-host: same call, but a 256 MiB host buffer is read between the refill of U and the timed call (the '
-                                    'refilled lines have left the CPU caches); a host-platform diagnostic, not the headline'},
                         'rows5': {'entry_point': 'psm_predict: pinned double[n][%d] rows (the reference layout, FOAM/PythonComm.H:2-9)' % ncol,
                                   'value': n / float(np.mean(rows_each)), 'ms_per_step': float(np.mean(rows_each) * 1e3),
                                   'h2d_bytes_per_step': int(n * ncol * 8), 'd2h_bytes_per_step': int(n * sm.n_fields * 8),
@@ -721,6 +710,14 @@ def main():
             'max_ms': float(np.max(each_dev)),
             'wait_us_per_step': {ph: (wz['ns'][i] / max(wz['count'][i], 1)) * 1e-3
                                  for i, ph in enumerate(('ghost_cells_and_maxima', 'strip_means', 'ghost_pixels'))}}
+    # the same steps back to back without the L2 flush between them (what a solver loop does): the flush kernels of the ranks
+    # end at slightly different times, which the timed interval above pays for as waiting
+    dc.barrier()
+    ms_nf, _, _ = dc.run_device(args.steps, False, flush=False)
+    wz2 = sm.wait_ns(reset=True)
+    mine['ms_per_step_no_flush'] = ms_nf / args.steps
+    mine['wait_us_per_step_no_flush'] = {ph: (wz2['ns'][i] / max(wz2['count'][i], 1)) * 1e-3
+                                         for i, ph in enumerate(('ghost_cells_and_maxima', 'strip_means', 'ghost_pixels'))}
     per_rank = [None] * world
     dist.all_gather_object(per_rank, mine)
     dc.barrier()

@@ -178,11 +178,11 @@ struct psm_handle {
     // device->host copy of chunk k shares the (full-duplex) link with the host->device copy of p's chunk k+1
     static constexpr int kTailMax = 8;
     cudaStream_t d2h_stream = nullptr; cudaEvent_t ev_pc[kTailMax] = {}, ev_bc[kTailMax] = {}, ev_d2h = nullptr;
-    // one DMA stream reaches ~43 GB/s host->device on this platform, two concurrent ones ~53 GB/s (profiles/pcie_probe.py): the
-    // host entry points upload every array as two halves on two streams (the main stream and copy_stream), p's chunks alternate
-    // between copy_stream and copy_stream2
-    cudaStream_t copy_stream2 = nullptr; cudaEvent_t ev_um = nullptr; bool split_h2d = true;
-    int tail_chunks = 4;
+    // PSM_SPLIT_H2D=1: every array goes up as two halves on two streams, p's chunks alternate between copy_stream and
+    // copy_stream2.  Measured neutral on this platform (profiles/r2h_pcie_probe.txt: 23.5 MB in 0.445 ms on one stream, 0.560 ms
+    // on two; e2e 0.916 vs 0.908 ms), so one stream is the default
+    cudaStream_t copy_stream2 = nullptr; cudaEvent_t ev_um = nullptr; bool split_h2d = false;
+    int tail_chunks = 2;
     bool pprev_zero = false;          // d_pprev currently holds zeros (psm_predict_fields without p)
     size_t cells_capacity = 0;        // doubles in d_cells
     // cell routing (psm_route_init / psm_predict_routed): arbitrary per-rank cell sets -> block-row owners and back
@@ -265,7 +265,7 @@ static bool make_tail(psm_handle* h) {
     if (cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) return false;
     if (cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&h->ev_um, cudaEventDisableTiming) != cudaSuccess) return false;
-    if (const char* e = getenv("PSM_NO_SPLIT_H2D")) h->split_h2d = !(e[0] == '1');
+    if (const char* e = getenv("PSM_SPLIT_H2D")) h->split_h2d = (e[0] == '1');
     for (int k = 0; k < psm_handle::kTailMax; ++k)
         if (cudaEventCreateWithFlags(&h->ev_pc[k], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&h->ev_bc[k], cudaEventDisableTiming) != cudaSuccess) return false;
@@ -280,7 +280,7 @@ static inline void tail_range(long long n, int nch, int k, long long* c0, long l
     *c1 = (k == nch - 1 || per * (k + 1) > n) ? n : per * (k + 1);
 }
 // Host->device copy of `n` doubles as two halves on the main stream and copy_stream (two DMA streams in flight); the main stream
-// then waits for the second half.  Small arrays (or PSM_NO_SPLIT_H2D=1) go up in one piece.
+// then waits for the second half.  Opt-in (PSM_SPLIT_H2D=1); otherwise, and for small arrays, one copy on the main stream.
 static int upload_split(psm_handle* h, double* dst, const double* src, size_t n) {
     if (!h->split_h2d || n < (size_t)(1 << 18)) {
         CU(h, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -903,7 +903,10 @@ static int init_local(psm_handle* h, LocalInit& L) {
         TRY(mk(h->tc_proj, h->d_xu, Bp, h->d_comp_u, h->pc_in_pad, 2 * S2, h->d_part, h->pc_in_pad, h->tc_splits, EPI_PARTIAL,
                nullptr, nullptr, nullptr, tc_gemm_bn(h->pc_in_pad)));
         // ---- projection + standardisation in one launch (cluster fold, last-arrival fold per row slab) ----
-        if (h->pc_in_pad == 128 && !env_on("PSM_NO_PROJ_CLUSTER")) {
+        // Measured on c2 (one B200, profiles/README.md round 2): 58.9 us for this kernel against 23.0 us for tc_gemm_kernel + the
+        // reduce launch -- distributed shared memory moves ~17-21 B/clk per SM, so pushing a 64 KB partial per CTA costs more than
+        // leaving it in L2.  Opt-in (PSM_PROJ_CLUSTER=1); parity-tested like the default path.
+        if (h->pc_in_pad == 128 && env_on("PSM_PROJ_CLUSTER")) {
             const int tiles = Bp / 128, kb_total = 2 * S2 / 32;
             int best_ks = 0, best_ncl = 0;
             for (int ks = 8; ks >= 1; ks >>= 1) {                 // most CTAs of one resident wave; on a tie the larger cluster
