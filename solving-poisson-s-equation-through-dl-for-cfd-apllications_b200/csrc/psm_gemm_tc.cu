@@ -355,6 +355,14 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
 
     pdl_launch_dependents();
+    const int cta_lin = (blockIdx.y * gridDim.x + blockIdx.x) * gridDim.z + blockIdx.z;
+    auto stamp = [&](int i) {
+        if (g.trace && threadIdx.x == 64 && cta_lin < 64) {
+            unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            g.trace[cta_lin * 8 + i] = t;
+        }
+    };
+    stamp(0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KS = gridDim.z;                                    // cluster = (1,1,KS): rank in cluster = blockIdx.z
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -390,6 +398,7 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     }
     pdl_wait();                                                  // barriers + TMEM are set up while the previous kernel drains
+    stamp(1);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -460,10 +469,12 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
         // push the partial accumulator: thread <-> row (TMEM lane); row r goes to slot [z][r % rows_per] of CTA r / rows_per
+        if (g.trace && nkb > 0 && nkb <= STAGES) { mbar_wait(full_bar(0), 0); stamp(2); }     // first operand tiles have landed
         if (nkb > 0) {
             mbar_wait(accum_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        stamp(3);
         const int q = warp & 3;
         const int row = q * 32 + lane;
         float v[64];
@@ -477,9 +488,11 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t owner = (uint32_t)(row / rows_per);
 #pragma unroll
         for (int i = 0; i < 16; ++i) st_dsmem_v4(dst + 16u * i, owner, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+        stamp(4);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();                                          // all KS partials of my rows have landed in my buffer
+    stamp(5);
     {
         // CTA z folds rows [z*rows_per, ...) from its OWN shared memory (slices 0..KS-1 in a fixed order: deterministic),
         // applies bias + ReLU (or bias + de-standardisation, SMC:533) and stores 256-byte row segments
@@ -515,6 +528,8 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
         }
     }
+    __syncthreads();
+    stamp(6);
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");

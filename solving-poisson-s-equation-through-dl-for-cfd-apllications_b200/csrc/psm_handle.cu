@@ -151,6 +151,7 @@ struct psm_handle {
     Scalars* d_sc = nullptr; Scalars* h_sc = nullptr;   // h_sc: mapped pinned host memory, only .skip is written by the device
     int* d_host_skip = nullptr;
     TcGemm tc_proj{}, tc_inv{}; std::vector<TcGemm> tc_dense; std::vector<int> dense_splits; int tc_splits = 1;
+    unsigned long long* d_layer_trace = nullptr; int trace_steps = 0;  // PSM_TRACE_LAYERS=1: in-kernel timeline of the Dense layers
     bool dense_presplit = false; float* d_xin_lo = nullptr;            // Dense layers read pre-split operands (no converter pass)
     ProjGemm proj_cl{}; bool proj_cluster = false; float* d_proj_part = nullptr; unsigned int* d_proj_cnt = nullptr;   // one-launch projection
     float* d_dpart = nullptr;       // split-K partials of the Dense layers   // tcgen05 path (gemm_mode 0/1)
@@ -990,6 +991,10 @@ static int init_local(psm_handle* h, LocalInit& L) {
         }
         TRY(mk(h->tc_inv, h->d_r, Bp, h->d_comp_out_t, S2 * h->C, h->pc_p_pad, h->d_blocks, S2 * h->C, 1, EPI_PCA_INV,
                h->d_pmean, nullptr, nullptr, 128));
+        if (h->dense_cluster && env_on("PSM_TRACE_LAYERS")) {
+            TRY(dalloc(h, &h->d_layer_trace, (size_t)h->n_dense * 64 * 8));
+            for (int l = 0; l < h->n_dense; ++l) h->tc_dense[l].args.trace = h->d_layer_trace + (size_t)l * 64 * 8;
+        }
         // ---- transposed PCA inverse: needs the last Dense layer to deliver r pre-split (cluster or stack kernel) ----
         h->inv_t = !env_on("PSM_NO_INV_T") && h->dense_cluster && h->pc_p_pad <= pca_inverse_t_max_k() && (S2 * h->C) % 128 == 0 &&
                    pca_inverse_t_prepare() == 0;
@@ -1468,8 +1473,32 @@ static int submit_device(psm_handle* h, const StepInput& in, double* out) {
     return PSM_OK;
 }
 
+// PSM_TRACE_LAYERS=1: after the 30th step, the globaltimer stamps of the Dense layers (min / max over the CTAs of a layer, in
+// ns since the first layer's first CTA entered) go to stderr once
+static void dump_layer_trace(psm_handle* h) {
+    std::vector<unsigned long long> tr((size_t)h->n_dense * 64 * 8);
+    if (cudaMemcpy(tr.data(), h->d_layer_trace, tr.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    unsigned long long t0 = ~0ull;
+    for (size_t i = 0; i < 64; ++i) if (tr[i * 8]) t0 = std::min(t0, tr[i * 8]);
+    static const char* nm[7] = {"entry", "wait_done", "operands", "accum", "pushed", "cluster_bar", "stored"};
+    for (int l = 0; l < h->n_dense; ++l) {
+        fprintf(stderr, "dense layer %d:", l);
+        for (int k = 0; k < 7; ++k) {
+            unsigned long long lo = ~0ull, hi = 0;
+            for (int c = 0; c < 64; ++c) {
+                const unsigned long long v = tr[((size_t)l * 64 + c) * 8 + k];
+                if (!v) continue;
+                lo = std::min(lo, v); hi = std::max(hi, v);
+            }
+            if (hi) fprintf(stderr, "  %s %lld..%lld", nm[k], (long long)(lo - t0), (long long)(hi - t0));
+        }
+        fprintf(stderr, "\n");
+    }
+}
+
 static int finish(psm_handle* h) {
     CU(h, cudaStreamSynchronize(h->stream));
+    if (h->d_layer_trace && ++h->trace_steps == 30) dump_layer_trace(h);
     const int v = h->h_sc->skip;        // skip | comm_error << 8, written by offsets_kernel through mapped memory
     if (v >> 8) PSM_FAIL(h, PSM_ERR_COMM, "a device-side wait timed out (peer-memory exchange: ranks out of step? / Dense-stack grid barrier)");
     return (v & 1) ? PSM_SKIPPED : PSM_OK;

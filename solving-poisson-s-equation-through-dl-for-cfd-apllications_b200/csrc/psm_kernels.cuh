@@ -189,6 +189,8 @@ struct TcGemmArgs {
     float* C_hi; float* C_lo;  // dense_cluster_kernel: optional tf32 hi / lo split of the result (same layout as C)
     int b_static;              // 1: the B operand does not depend on earlier kernels of the step (weights): its first tiles are
                                //    requested BEFORE the programmatic-dependent-launch wait
+    unsigned long long* trace; // dense_cluster_kernel, PSM_TRACE_LAYERS=1: [<= 64 CTAs][8] globaltimer stamps (entry, after the wait,
+                               //    operands landed, accumulator ready, partial pushed, cluster barrier passed, stored)
     int presplit;              // dense_cluster_kernel, three_pass == 2: the lo halves of both operands exist in global memory (the
                                //    previous layer's epilogue / the parameter load wrote them): TMA stages them, no converter pass
 };
