@@ -293,6 +293,178 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// PCA projection with the A operand fetched from the grid planes (GridA in psm_kernels.cuh): tc_gemm_kernel<128> with another
+// producer.  Split-K partials only (EPI_PARTIAL); rows of a tile the segments do not cover hold stale shared memory -- every
+// accumulator row depends on its own A row only, and the reduce kernel never reads those rows.
+namespace {
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+        : "memory");
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_grid_kernel(const __grid_constant__ CUtensorMap tmRow, const __grid_constant__ CUtensorMap tmCol,
+                    const __grid_constant__ CUtensorMap tmOne, const __grid_constant__ CUtensorMap tmB, TcGemmArgs g, GridA ga) {
+    constexpr int BN = 128;
+    constexpr int STAGES = Cfg<BN>::STAGES;
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE = 2 * (A_BYTES + B_BYTES);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + STAGES * STAGE;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto conv_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto empty_bar = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (3 * STAGES);
+    const uint32_t tmem_slot = accum_bar + 8u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.y, m0 = tile * BM;
+    const int kb_total = g.K / BK;
+    const int kb_per = (kb_total + g.splits - 1) / g.splits;
+    const int kb0 = min((int)blockIdx.z * kb_per, kb_total);
+    const int kb1 = min(kb_total, kb0 + kb_per);
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(conv_bar(s), 128); mbar_init(empty_bar(s), 1); }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+    // static per tile: its segment list and the bytes it delivers per k-block (fetched before the wait)
+    const int seg0 = __ldg(ga.seg_ptr + tile), seg1 = __ldg(ga.seg_ptr + tile + 1);
+    const uint32_t a_bytes = (uint32_t)__ldg(ga.a_bytes + tile);
+    const int n_pre = g.b_static ? min(nkb, STAGES) : 0;
+    if (threadIdx.x == 0) {
+        for (int it = 0; it < n_pre; ++it) {
+            mbar_expect_tx(full_bar(it), a_bytes + B_BYTES);
+            tma_load_2d(base + it * STAGE + 2 * A_BYTES, &tmB, (kb0 + it) * BK, 0, full_bar(it));
+        }
+    }
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int per_ch = ga.S * ga.S / BK, per_row = ga.S / BK;
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const uint32_t st = base + s * STAGE;
+                if (it >= n_pre) {
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), a_bytes + B_BYTES);
+                    tma_load_2d(st + 2 * A_BYTES, &tmB, (kb0 + it) * BK, 0, full_bar(s));
+                }
+                const int kb = kb0 + it;
+                const int ch = kb / per_ch, r = (kb % per_ch) / per_row, xo = (kb % per_row) * BK;
+                for (int q = seg0; q < seg1; ++q) {
+                    const ASeg sg = ga.segs[q];
+                    const CUtensorMap* mp = sg.map == 0 ? &tmRow : (sg.map == 1 ? &tmCol : &tmOne);
+                    tma_load_5d(st + (uint32_t)sg.row * (BK * 4), mp, sg.x + xo, 0, sg.y + r, 0, ch, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(BM, BN);
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(g.three_pass ? conv_bar(s) : full_bar(s), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * STAGE;
+                const uint32_t a_hi = st, a_lo = st + A_BYTES, b_hi = st + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint32_t ko = k * UMMA_K * 4;
+                    umma_tf32(tmem_base, make_smem_desc(a_hi + ko), make_smem_desc(b_hi + ko), idesc, (it | k) != 0);
+                    if (g.three_pass) {
+                        umma_tf32(tmem_base, make_smem_desc(a_hi + ko), make_smem_desc(b_lo + ko), idesc, 1);
+                        umma_tf32(tmem_base, make_smem_desc(a_lo + ko), make_smem_desc(b_hi + ko), idesc, 1);
+                    }
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        const int t = threadIdx.x - 64;
+        const bool keep_hi = g.three_pass != 2;
+        if (g.three_pass) {
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(full_bar(s), ph);
+                uint8_t* st = gen_base + s * STAGE;
+                float4* a_hi = reinterpret_cast<float4*>(st);
+                float4* a_lo = reinterpret_cast<float4*>(st + A_BYTES);
+                float4* b_hi = reinterpret_cast<float4*>(st + 2 * A_BYTES);
+                float4* b_lo = reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES);
+                auto split4 = [](float4 v, float4& hi, float4& lo) {
+                    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+                    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+                };
+#pragma unroll 4
+                for (int i = t; i < A_BYTES / 16; i += 128) { float4 hi, lo; split4(a_hi[i], hi, lo); if (keep_hi) a_hi[i] = hi; a_lo[i] = lo; }
+#pragma unroll 4
+                for (int i = t; i < B_BYTES / 16; i += 128) { float4 hi, lo; split4(b_hi[i], hi, lo); if (keep_hi) b_hi[i] = hi; b_lo[i] = lo; }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(conv_bar(s));
+            }
+        }
+        if (nkb > 0) {
+            mbar_wait(accum_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        float* Cp = g.C + (size_t)blockIdx.z * g.M * g.ldc + (size_t)(m0 + row) * g.ldc;
+        for (int c = 0; c < BN; c += 16) {
+            float v[16];
+            if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(Cp + c + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+int tc_gemm_grid_prepare() {
+    return cudaFuncSetAttribute(tc_gemm_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM_TOTAL) == cudaSuccess ? 0 : -1;
+}
+void launch_tc_gemm_grid(const TcGemmGrid& t, cudaStream_t s) {
+    dim3 grid(1, t.tiles, t.args.splits);
+    const CUtensorMap& r = *reinterpret_cast<const CUtensorMap*>(&t.mapRow);
+    const CUtensorMap& c = *reinterpret_cast<const CUtensorMap*>(&t.mapCol);
+    const CUtensorMap& o = *reinterpret_cast<const CUtensorMap*>(&t.mapOne);
+    const CUtensorMap& b = *reinterpret_cast<const CUtensorMap*>(&t.mapB);
+    launch_k(tc_gemm_grid_kernel, grid, dim3(kThreads), Cfg<128>::SMEM_TOTAL, s, r, c, o, b, t.args, t.ga);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Dense layer (NNS:24-33) as ONE launch: cluster split-K with an on-chip reduction.
 // The batch is only B blocks (one or a few 128-row tiles), so a layer is latency-bound: it is cut into
 // 64-column tiles x KS K-slices, the KS CTAs of a tile form a thread-block cluster, every CTA runs the
@@ -1326,6 +1498,27 @@ int make_kmajor_map(TensorMap128* out, const float* ptr, int rows, int cols, int
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
+// 5-D maps over the two grid planes: dims (x, bx, y, by, channel), byte strides (4,) 4*stride, 4*W, 4*W*stride, 4*plane_stride --
+// overlapping windows: element (x, bx, y, by, c) is pixel (y + by*stride, x + bx*stride) of plane c.  Three boxes over the same
+// tensor: gx blocks along x, gy blocks along y, one block; each box row is 32 pixels = 128 B = one swizzle row.
+int make_grid_maps(TcGemmGrid* out, const float* planes, int W, int H, long long plane_stride, int stride_px, int gx, int gy) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return -1;
+    const int nb = gx > gy ? gx : gy;
+    cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)nb, (cuuint64_t)H, (cuuint64_t)nb, 2};
+    cuuint64_t strides[4] = {(cuuint64_t)stride_px * 4, (cuuint64_t)W * 4, (cuuint64_t)W * 4 * stride_px, (cuuint64_t)plane_stride * 4};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const cuuint32_t boxes[3][5] = {{(cuuint32_t)BK, (cuuint32_t)gx, 1, 1, 1}, {(cuuint32_t)BK, 1, 1, (cuuint32_t)gy, 1}, {(cuuint32_t)BK, 1, 1, 1, 1}};
+    TensorMap128* maps[3] = {&out->mapRow, &out->mapCol, &out->mapOne};
+    for (int i = 0; i < 3; ++i) {
+        CUresult r = enc(reinterpret_cast<CUtensorMap*>(maps[i]), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(planes), dims,
+                         strides, boxes[i], estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return -(int)r - 1000;
+    }
+    return 0;
 }
 
 int tc_gemm_bn(int N) { return (N % 128 == 0) ? 128 : 64; }

@@ -151,6 +151,9 @@ struct psm_handle {
     Scalars* d_sc = nullptr; Scalars* h_sc = nullptr;   // h_sc: mapped pinned host memory, only .skip is written by the device
     int* d_host_skip = nullptr;
     TcGemm tc_proj{}, tc_inv{}; std::vector<TcGemm> tc_dense; std::vector<int> dense_splits; int tc_splits = 1;
+    // projection A operand straight from the grid planes (GridA): x_array is not materialised
+    bool grid_a = false; TcGemmGrid tc_proj_grid{}; float* d_part_grid = nullptr; int32_t* d_row_src = nullptr; int grid_a_rows = 0;
+    ASeg* d_aseg = nullptr; int32_t* d_aseg_ptr = nullptr; int32_t* d_a_bytes = nullptr;
     unsigned long long* d_layer_trace = nullptr; int trace_steps = 0;  // PSM_TRACE_LAYERS=1: in-kernel timeline of the Dense layers
     bool dense_presplit = false; float* d_xin_lo = nullptr;            // Dense layers read pre-split operands (no converter pass)
     ProjGemm proj_cl{}; bool proj_cluster = false; float* d_proj_part = nullptr; unsigned int* d_proj_cnt = nullptr;   // one-launch projection
@@ -494,6 +497,94 @@ struct LocalInit {
     std::vector<int32_t> cell_send_idx, pix_send_idx;
     std::vector<long long> ghost_pix;          // global pixel id per ghost slot (empty: unknown -> legacy multi-GPU flow)
 };
+}  // namespace
+
+// Box plan of the grid-plane A operand (GridA): blocks whose origins are an arithmetic progression of `st` pixels along x (same
+// y0) are fetched gx at a time, the blocks left over (the clamped column, SMC:467-472 / GRAD:486-494) gy at a time along y, the
+// rest one by one; boxes are packed into 128-row tiles.  Returns false when the layout does not pay (no run of >= 4 blocks).
+namespace {
+struct GridAPlan { std::vector<ASeg> segs; std::vector<int32_t> seg_ptr, a_bytes, row_src; int tiles = 0, gx = 1, gy = 1; };
+static int best_box(int n) { for (int g = std::min(n, 16); g >= 2; --g) if (n % g == 0) return g; return 1; }
+static bool build_grid_a(int B, const std::vector<int32_t>& by0, const std::vector<int32_t>& bx0, int st, GridAPlan& P) {
+    struct Item { int map, x, y, len; std::vector<int> blk; };
+    std::vector<Item> items;
+    std::vector<int> order(B);
+    for (int b = 0; b < B; ++b) order[b] = b;
+    // chains along x
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return by0[a] != by0[b] ? by0[a] < by0[b] : bx0[a] < bx0[b]; });
+    std::vector<std::vector<int>> chains;
+    for (int i = 0; i < B; ++i) {
+        const int b = order[i];
+        if (!chains.empty()) { const int p = chains.back().back(); if (by0[p] == by0[b] && bx0[b] - bx0[p] == st) { chains.back().push_back(b); continue; } }
+        chains.push_back({b});
+    }
+    size_t nreg = 0;
+    for (auto& c : chains) nreg = std::max(nreg, c.size());
+    if (nreg < 4) return false;
+    P.gx = best_box((int)nreg);
+    if (P.gx < 4) return false;
+    std::vector<int> left;
+    for (auto& c : chains) {
+        size_t i = 0;
+        for (; i + P.gx <= c.size(); i += P.gx) items.push_back(Item{0, bx0[c[i]], by0[c[i]], P.gx, std::vector<int>(c.begin() + i, c.begin() + i + P.gx)});
+        for (; i < c.size(); ++i) left.push_back(c[i]);
+    }
+    // chains along y among the blocks left over
+    std::sort(left.begin(), left.end(), [&](int a, int b) { return bx0[a] != bx0[b] ? bx0[a] < bx0[b] : by0[a] < by0[b]; });
+    std::vector<std::vector<int>> cols;
+    for (int b : left) {
+        if (!cols.empty()) { const int p = cols.back().back(); if (bx0[p] == bx0[b] && by0[b] - by0[p] == st) { cols.back().push_back(b); continue; } }
+        cols.push_back({b});
+    }
+    size_t ncol = 0;
+    for (auto& c : cols) ncol = std::max(ncol, c.size());
+    P.gy = ncol >= 2 ? best_box((int)ncol) : 1;
+    std::vector<int> singles;
+    for (auto& c : cols) {
+        size_t i = 0;
+        if (P.gy >= 2)
+            for (; i + P.gy <= c.size(); i += P.gy) items.push_back(Item{1, bx0[c[i]], by0[c[i]], P.gy, std::vector<int>(c.begin() + i, c.begin() + i + P.gy)});
+        for (; i < c.size(); ++i) singles.push_back(c[i]);
+    }
+    for (int b : singles) items.push_back(Item{2, bx0[b], by0[b], 1, {b}});
+    // first fit into 128-row tiles (boxes arrive largest first, singles last: they fill the gaps)
+    std::vector<int> used;
+    std::vector<std::vector<ASeg>> per_tile;
+    P.row_src.assign(B, -1);
+    for (const Item& it : items) {
+        int t = -1;
+        for (size_t k = 0; k < used.size(); ++k) if (used[k] + it.len <= 128) { t = (int)k; break; }
+        if (t < 0) { used.push_back(0); per_tile.emplace_back(); t = (int)used.size() - 1; }
+        per_tile[t].push_back(ASeg{it.map, used[t], it.x, it.y});
+        for (int i = 0; i < it.len; ++i) P.row_src[it.blk[i]] = t * 128 + used[t] + i;
+        used[t] += it.len;
+    }
+    P.tiles = (int)used.size();
+    P.seg_ptr.assign(1, 0);
+    for (int t = 0; t < P.tiles; ++t) {
+        for (const ASeg& sg : per_tile[t]) P.segs.push_back(sg);
+        P.seg_ptr.push_back((int32_t)P.segs.size());
+        P.a_bytes.push_back(used[t] * 128);
+    }
+    // self-check: every block is fetched exactly once, from its own origin
+    std::vector<int> seen(B, 0);
+    for (int t = 0; t < P.tiles; ++t)
+        for (int q = P.seg_ptr[t]; q < P.seg_ptr[t + 1]; ++q) {
+            const ASeg& sg = P.segs[q];
+            const int len = sg.map == 0 ? P.gx : (sg.map == 1 ? P.gy : 1);
+            for (int i = 0; i < len; ++i) {
+                const int row = t * 128 + sg.row + i;
+                int b = -1;
+                for (int k = 0; k < B; ++k) if (P.row_src[k] == row) { b = k; break; }
+                if (b < 0) return false;
+                const int x = sg.x + (sg.map == 0 ? i * st : 0), y = sg.y + (sg.map == 1 ? i * st : 0);
+                if (bx0[b] != x || by0[b] != y) return false;
+                ++seen[b];
+            }
+        }
+    for (int b = 0; b < B; ++b) if (seen[b] != 1) return false;
+    return true;
+}
 }  // namespace
 
 // Map every peer's exchange buffers (cudaIpc over NVLink) and build the push tables.  Collective.  Falls back
@@ -903,6 +994,36 @@ static int init_local(psm_handle* h, LocalInit& L) {
         };
         TRY(mk(h->tc_proj, h->d_xu, Bp, h->d_comp_u, h->pc_in_pad, 2 * S2, h->d_part, h->pc_in_pad, h->tc_splits, EPI_PARTIAL,
                nullptr, nullptr, nullptr, tc_gemm_bn(h->pc_in_pad)));
+        // ---- projection A operand straight from the grid planes (TMA boxes over overlapping windows) ----
+        if (h->fused_extract && L.world == 1 && h->pc_in_pad == 128 && S % 32 == 0 && (S - h->cfg.overlap) % 4 == 0 && env_on("PSM_GRID_A") &&
+            tc_gemm_grid_prepare() == 0) {
+            GridAPlan gp;
+            std::vector<int32_t> hy(h->B), hx(h->B);
+            CU(h, cudaMemcpy(hy.data(), h->d_by0, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost));
+            CU(h, cudaMemcpy(hx.data(), h->d_bx0, sizeof(int32_t) * h->B, cudaMemcpyDeviceToHost));
+            const int st = S - h->cfg.overlap;
+            TcGemmGrid& tg = h->tc_proj_grid;
+            if (build_grid_a(h->B, hy, hx, st, gp) &&
+                make_grid_maps(&tg, h->d_grid, W, (int)(h->grid_stride / W), h->grid_stride, st, gp.gx, gp.gy) == 0 &&
+                make_kmajor_map(&tg.mapB, h->d_comp_u, h->pc_in_pad, 2 * S2, 2 * S2, 128) == 0) {
+                const int kb_total = 2 * S2 / 32;
+                int ts = (148 + gp.tiles - 1) / gp.tiles;
+                ts = std::max(1, std::min(ts, 128));
+                const int per = (kb_total + ts - 1) / ts;
+                const int splits = (kb_total + per - 1) / per;
+                h->grid_a_rows = gp.tiles * 128;
+                TRY(dalloc(h, &h->d_part_grid, (size_t)splits * h->grid_a_rows * 128));
+                std::vector<int32_t> rs(Bp, -1);
+                for (int b = 0; b < h->B; ++b) rs[b] = gp.row_src[b];
+                TRY(upload(h, &h->d_row_src, rs));
+                TRY(upload(h, &h->d_aseg, gp.segs)); TRY(upload(h, &h->d_aseg_ptr, gp.seg_ptr)); TRY(upload(h, &h->d_a_bytes, gp.a_bytes));
+                tg.args = TcGemmArgs{h->d_part_grid, h->grid_a_rows, 128, 2 * S2, 128, splits, EPI_PARTIAL, three, nullptr, nullptr, nullptr, h->d_sc,
+                                     nullptr, nullptr, env_on("PSM_NO_PREFETCH") ? 0 : 1};
+                tg.ga = GridA{h->d_aseg, h->d_aseg_ptr, h->d_a_bytes, S};
+                tg.tiles = gp.tiles;
+                h->grid_a = true;
+            }
+        }
         // ---- projection + standardisation in one launch (cluster fold, last-arrival fold per row slab) ----
         // Measured on c2 (one B200, profiles/README.md round 2): 58.9 us for this kernel against 23.0 us for tc_gemm_kernel + the
         // reduce launch -- distributed shared memory moves ~17-21 B/clk per SM, so pushing a 64 KB partial per CTA costs more than
@@ -964,7 +1085,8 @@ static int init_local(psm_handle* h, LocalInit& L) {
             if (h->dense_cluster) {
                 // K-slices per tile = cluster size: as many as keep the grid within ~2 waves, at most one k-block each
                 int ks = 8;
-                while (ks > 1 && (ks > kb || tiles * ks > 2 * 148)) ks >>= 1;
+                const int waves = env_on("PSM_DENSE_ONE_WAVE") ? 1 : 2;
+                while (ks > 1 && (ks > kb || tiles * ks > waves * 148)) ks >>= 1;
                 h->dense_splits[l] = ks;
                 TRY(mk(h->tc_dense[l], in, Bp, h->d_W[l], h->dims_pad[l + 1], h->dims_pad[l], outp, h->dims_pad[l + 1], ks,
                        last ? EPI_BIAS_AFFINE : EPI_BIAS_RELU, h->d_bias[l], h->d_out_s, h->d_out_m, 64));
@@ -1256,7 +1378,7 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
     GatherArgs ga{h->d_fv[0], h->d_fv[1], h->d_fv[2], h->d_fw[0], h->d_fw[1], h->d_fw[2], h->d_uv,
                   grid0, grid1, h->G_pad / 4, sa, 0, d_p2p};
     if (h->fused_extract) {
-        GatherExtractArgs ge{ga, h->d_rowcov, h->d_colcov, h->d_xu, h->W / 4, S, h->keep_grid ? 1 : 0};
+        GatherExtractArgs ge{ga, h->d_rowcov, h->d_colcov, h->d_xu, h->W / 4, S, (h->keep_grid || h->grid_a) ? 1 : 0, h->grid_a ? 1 : 0};
         launch_gather_extract(ge, s); ++nl;
     } else {
         launch_gather(ga, s); ++nl;
@@ -1282,8 +1404,10 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
     tick();   // extract
     const bool tc = h->cfg.gemm_mode != PSM_GEMM_FP32_SIMT;
     {
-        const bool one_launch = tc && h->proj_cluster && !h->dense_stack;
-        if (one_launch) {
+        const bool one_launch = tc && h->proj_cluster && !h->dense_stack && !h->grid_a;
+        const bool from_grid = tc && h->grid_a && !h->dense_stack;
+        if (from_grid) launch_tc_gemm_grid(h->tc_proj_grid, s);
+        else if (one_launch) {
             if (launch_proj_cluster(h->proj_cl, s) != 0) PSM_FAIL(h, PSM_ERR_CUDA, "projection launch: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (tc) launch_tc_gemm(h->tc_proj, s);
         else {
@@ -1297,6 +1421,7 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
                      RED_STANDARDISE, nullptr, nullptr, nullptr};
         if (tc && h->dense_stack) { r.x_hi = h->d_act_hi[0]; r.x_lo = h->d_act_lo[0]; }
         else if (tc && h->dense_presplit) r.x_lo = h->d_xin_lo;
+        if (from_grid) { r.part = h->d_part_grid; r.splits = h->tc_proj_grid.args.splits; r.row_src = h->d_row_src; r.part_rows = h->grid_a_rows; }
         if (!one_launch) { launch_reduce_standardise(r, s); ++nl; }
     }
     tick();   // pca_project
@@ -1829,7 +1954,7 @@ extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_
         case PSM_STAGE_GRID: {
             const int64_t gl = (int64_t)(h->H + h->local_ext + h->ext_rows) * h->W;
             TRY(need(2 * gl * 4));
-            if (h->fused_extract && !h->keep_grid) {
+            if (h->fused_extract && !h->keep_grid && !h->grid_a) {
                 // the fused gather writes only the block operand: rebuild the planes of the LAST step from the
                 // still-resident cell field and the scales that step published
                 ScalarArgs sa{h->d_sc, h->maxs[0], h->maxs[1], 1.0, 0, 0.0, 0, 1};
@@ -1880,6 +2005,11 @@ extern "C" int psm_get_stage(psm_handle* h, int32_t stage, void* out, int64_t n_
         }
         case PSM_STAGE_XU:
             TRY(need((int64_t)h->B * 2 * S2 * 4));
+            if (h->grid_a) {     // the projection read the grid planes itself: build the block operand of the last step on demand
+                ExtractArgs ea{h->d_grid, h->d_grid + h->grid_stride, h->d_by0, h->d_bx0, h->d_xu, h->B, h->W, h->S, 2};
+                launch_extract(ea, h->stream);
+                CU(h, cudaStreamSynchronize(h->stream));
+            }
             CU(h, cudaMemcpy(out, h->d_xu, (size_t)h->B * 2 * S2 * 4, cudaMemcpyDeviceToHost));
             return PSM_OK;
         case PSM_STAGE_MEANS:

@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(256, U == 1 ? 4 : 3) gather_extract_kernel(Gat
                     reinterpret_cast<float4*>(a.grid0)[gu] = ox[u];
                     reinterpret_cast<float4*>(a.grid1)[gu] = oy[u];
                 }
-                store_cover(e.xu, e.rowcov, e.colcov, (unsigned int)gu, (unsigned int)e.W4, S2, ox[u], oy[u]);
+                if (!e.skip_xu) store_cover(e.xu, e.rowcov, e.colcov, (unsigned int)gu, (unsigned int)e.W4, S2, ox[u], oy[u]);
             }
         }
         g = gn;
@@ -801,13 +801,22 @@ __global__ void __launch_bounds__(256) reduce_standardise_kernel(ReduceArgs a) {
     const long long i = (long long)blockIdx.x * 32 + ox;
     float sum = 0.f;
     if (i < total) {
+        // the partials may be in another row order (A operand fetched from the grid planes in box order)
+        long long ptotal = total, pi = i;
+        bool live = true;
+        if (a.row_src) {
+            const int m = (int)(i / a.N), src = a.row_src[m];
+            ptotal = (long long)a.part_rows * a.N;
+            live = src >= 0;
+            pi = (long long)(live ? src : 0) * a.N + (i - (long long)m * a.N);
+        }
         // up to 16 partials per thread, all loads in flight at once (the partials sit in L2: the kernel is latency-bound)
         float pv[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { const int sp = grp + 8 * k; pv[k] = (sp < a.splits) ? __ldcs(a.part + (long long)sp * total + i) : 0.f; }
+        for (int k = 0; k < 16; ++k) { const int sp = grp + 8 * k; pv[k] = (live && sp < a.splits) ? __ldcs(a.part + (long long)sp * ptotal + pi) : 0.f; }
 #pragma unroll
         for (int k = 0; k < 16; ++k) sum += pv[k];
-        for (int sp = grp + 128; sp < a.splits; sp += 8) sum += __ldcs(a.part + (long long)sp * total + i);
+        if (live) for (int sp = grp + 128; sp < a.splits; sp += 8) sum += __ldcs(a.part + (long long)sp * ptotal + pi);
     }
     __shared__ float red[8][33];
     red[grp][ox] = sum;

@@ -150,6 +150,7 @@ struct GatherExtractArgs {
     const CoverEntry* colcov;     // [W/4]
     float* xu; int W4; int S;
     int store_grid;               // 0: only the block operand is written (the grid planes are rebuilt on demand by psm_get_stage)
+    int skip_xu;                  // 1: the projection reads the grid planes itself (GridA): no block operand is written
 };
 void launch_gather_extract(const GatherExtractArgs& a, cudaStream_t s);
 
@@ -195,6 +196,22 @@ struct TcGemmArgs {
                                //    previous layer's epilogue / the parameter load wrote them): TMA stages them, no converter pass
 };
 struct TcGemm { TensorMap128 mapA, mapB; TcGemmArgs args; int bn; TensorMap128 mapAlo, mapBlo; };   // bn: N tile (64 or 128) the B map was built for
+
+// PCA projection with the A operand read straight from the interpolated grid planes (SMC:464-492): the block
+// extraction is a TMA address pattern, x_array is never materialised.  Blocks whose origins form an arithmetic progression (step =
+// stride pixels along x, or along y) are fetched as ONE box of a 5-D tensor map over the planes -- dims (x, bx, y, by, channel)
+// with byte strides (4, 4 stride, 4 W, 4 W stride, plane), i.e. overlapping windows -- so an A tile (128 block rows x 32 pixels of
+// one block-local pixel row) is a handful of boxes.  The rows of a tile are in "box order"; ReduceArgs::row_src maps block -> row.
+struct ASeg { int32_t map; int32_t row; int32_t x, y; };       // map: 0 row box, 1 column box, 2 single block; row: first tile row; origin
+struct GridA {
+    const ASeg* segs; const int32_t* seg_ptr;   // segments of tile t: [seg_ptr[t], seg_ptr[t+1])
+    const int32_t* a_bytes;                     // bytes the segments of tile t deliver per k-block
+    int S;                                      // block side (k-block kb <-> channel kb / (S*S/32), row (kb % (S*S/32)) / (S/32), chunk kb % (S/32))
+};
+struct TcGemmGrid { TensorMap128 mapRow, mapCol, mapOne, mapB; TcGemmArgs args; GridA ga; int tiles; };
+int make_grid_maps(TcGemmGrid* out, const float* planes, int W, int H, long long plane_stride, int stride_px, int gx, int gy);
+int tc_gemm_grid_prepare();
+void launch_tc_gemm_grid(const TcGemmGrid& t, cudaStream_t s);
 int make_kmajor_map(TensorMap128* out, const float* ptr, int rows, int cols, int ld, int box_rows);
 int tc_gemm_bn(int N);
 int tc_gemm_prepare();
@@ -289,6 +306,8 @@ struct ReduceArgs {
     int kind;
     const float* bias;    // RED_BIAS_*: [N]
     float* x_hi; float* x_lo;   // optional: the result split into tf32(x) and x - tf32(x) (operand of dense_stack_kernel)
+    const int32_t* row_src;     // optional: output row m sums partial row row_src[m] (< 0: nothing) of [splits][part_rows][N]
+    int part_rows;
 };
 void launch_reduce_standardise(const ReduceArgs& a, cudaStream_t s);
 
