@@ -318,6 +318,7 @@ class DeviceCase:
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
         self.flush_rd = torch.zeros(32 << 20, dtype=torch.int64, device='cuda')      # 256 MiB
         self.ext = torch.cuda.ExternalStream(sm.stream_ptr())
+        self.sync_t = torch.zeros(1, device='cuda')
         torch.cuda.synchronize()
 
     def barrier(self):
@@ -337,6 +338,11 @@ class DeviceCase:
                 if flush:
                     self.flush.zero_()       # evicts the previous step's lines (write 256 MiB) ...
                     self.flush_rd.sum()      # ... then a 256 MiB read pass leaves L2 full of CLEAN foreign lines, so the
+                if self.world > 1 and flush:
+                    # the ranks' flush kernels end at different times: a one-element all-reduce in stream order lines the ranks up
+                    # again before the timed interval opens (the barrier the timing contract brackets a step with), so a step is not
+                    # charged for its neighbours' flush
+                    self.dist.all_reduce(self.sync_t)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(self.ext)          # timed step does not also pay for writing the flush buffer back
                 sm.predict_device(self.d_in.data_ptr(), self.n, self.d_out.data_ptr(), sync=False)
@@ -769,6 +775,8 @@ def main():
                         'device_events_ms': {'h2d_U': float(parts_f[0]), 'kernels_p_copy_and_chunked_d2h': float(parts_f[1] + parts_f[2])}},
                 'gpu_launches': launches, 'roofline': roof, 'cpu_baseline': None, 'stages': stages, 'stage_event_overhead_ms': ovh,
                 'parity': parity, 'parity_rel_l2': None if not parity else parity.get('vs_oracle', parity.get('vs_single_gpu')),
+                'rank_alignment': 'a one-element NCCL all-reduce in stream order closes each L2 flush, so the ranks open their timed '
+                                  'interval together; per_rank[].ms_per_step_no_flush = the same steps back to back, no flush, no alignment',
                 'per_rank': per_rank, 'limiting_phase': max(per_rank[0]['wait_us_per_step'],
                                                             key=lambda ph: max(r['wait_us_per_step'][ph] for r in per_rank)),
                 'geometry': geo, 'init_tables_s': t_init, 'n_cells_total': n_total}

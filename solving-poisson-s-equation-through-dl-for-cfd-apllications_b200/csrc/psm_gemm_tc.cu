@@ -356,24 +356,31 @@ tc_gemm_grid_kernel(const __grid_constant__ CUtensorMap tmRow, const __grid_cons
     pdl_wait();
 
     if (warp == 0) {
-        if (lane == 0) {
-            const int per_ch = ga.S * ga.S / BK, per_row = ga.S / BK;
-            for (int it = 0; it < nkb; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                const uint32_t st = base + s * STAGE;
-                if (it >= n_pre) {
-                    mbar_wait(empty_bar(s), ph ^ 1);
+        // the whole warp produces: lane q issues box q of the tile (one instruction moves up to 32 boxes), lane 0 also the B tile
+        const int per_ch = ga.S * ga.S / BK, per_row = ga.S / BK;
+        const int q0 = seg0 + lane;
+        ASeg mine{};
+        const CUtensorMap* mp = &tmOne;
+        if (q0 < seg1) { mine = ga.segs[q0]; mp = mine.map == 0 ? &tmRow : (mine.map == 1 ? &tmCol : &tmOne); }
+        for (int it = 0; it < nkb; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            const uint32_t st = base + s * STAGE;
+            if (it >= n_pre) {
+                mbar_wait(empty_bar(s), ph ^ 1);
+                if (lane == 0) {
                     mbar_expect_tx(full_bar(s), a_bytes + B_BYTES);
                     tma_load_2d(st + 2 * A_BYTES, &tmB, (kb0 + it) * BK, 0, full_bar(s));
                 }
-                const int kb = kb0 + it;
-                const int ch = kb / per_ch, r = (kb % per_ch) / per_row, xo = (kb % per_row) * BK;
-                for (int q = seg0; q < seg1; ++q) {
-                    const ASeg sg = ga.segs[q];
-                    const CUtensorMap* mp = sg.map == 0 ? &tmRow : (sg.map == 1 ? &tmCol : &tmOne);
-                    tma_load_5d(st + (uint32_t)sg.row * (BK * 4), mp, sg.x + xo, 0, sg.y + r, 0, ch, full_bar(s));
-                }
+                __syncwarp();
+            }
+            const int kb = kb0 + it;
+            const int ch = kb / per_ch, r = (kb % per_ch) / per_row, xo = (kb % per_row) * BK;
+            if (q0 < seg1) tma_load_5d(st + (uint32_t)mine.row * (BK * 4), mp, mine.x + xo, 0, mine.y + r, 0, ch, full_bar(s));
+            for (int q = q0 + 32; q < seg1; q += 32) {           // more than 32 boxes per tile: plain loop
+                const ASeg sg = ga.segs[q];
+                const CUtensorMap* m2 = sg.map == 0 ? &tmRow : (sg.map == 1 ? &tmCol : &tmOne);
+                tma_load_5d(st + (uint32_t)sg.row * (BK * 4), m2, sg.x + xo, 0, sg.y + r, 0, ch, full_bar(s));
             }
         }
     } else if (warp == 1) {
@@ -474,6 +481,7 @@ void launch_tc_gemm_grid(const TcGemmGrid& t, cudaStream_t s) {
 // bias + de-standardisation, SMC:533) and stores coalesced rows.  No partials in HBM, no reduce kernel.
 namespace {
 constexpr int D_BN = 64;
+static_assert(kThreads % (D_BN / 4) == 0, "one epilogue column group per thread");
 constexpr int D_STAGES = 2;
 constexpr int D_A_BYTES = BM * BK * 4, D_B_BYTES = D_BN * BK * 4, D_STAGE = 2 * (D_A_BYTES + D_B_BYTES);
 constexpr int D_PARK_LD = D_BN + 4;                    // floats per received row (16-byte aligned, conflict-free float4 rows)
@@ -568,6 +576,15 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tma_load_2d(base + it * STAGE + 2 * A_BYTES, &tmB, (kb0 + it) * BK, n0, full_bar(it));
             if (pre) tma_load_2d(base + it * STAGE + 2 * A_BYTES + B_BYTES, &tmBlo, (kb0 + it) * BK, n0, full_bar(it));
         }
+    }
+    // the epilogue vectors of this thread's output columns are static too (every element this thread folds has the same c4):
+    // fetched before the wait instead of behind the cluster barrier
+    const int my_c4 = threadIdx.x % (BN / 4);
+    const float4 e_b = __ldg(reinterpret_cast<const float4*>(g.v0 + n0 + my_c4 * 4));
+    float4 e_sc = make_float4(1.f, 1.f, 1.f, 1.f), e_sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.epi != EPI_BIAS_RELU) {
+        e_sc = __ldg(reinterpret_cast<const float4*>(g.v1 + n0 + my_c4 * 4));
+        e_sh = __ldg(reinterpret_cast<const float4*>(g.v2 + n0 + my_c4 * 4));
     }
     pdl_wait();                                                  // barriers + TMEM are set up while the previous kernel drains
     stamp(1);
@@ -678,13 +695,12 @@ dense_cluster_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
             }
             const int n = n0 + c4 * 4, m = m0 + blockIdx.z * rows_per + rl;
-            const float4 b = __ldg(reinterpret_cast<const float4*>(g.v0 + n));
+            const float4 b = e_b;                                // kThreads % (BN / 4) == 0: c4 == my_c4 for every e of this thread
             float4 o;
             if (g.epi == EPI_BIAS_RELU) {
                 o = make_float4(fmaxf(acc.x + b.x, 0.f), fmaxf(acc.y + b.y, 0.f), fmaxf(acc.z + b.z, 0.f), fmaxf(acc.w + b.w, 0.f));
             } else {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(g.v1 + n));
-                const float4 sh = __ldg(reinterpret_cast<const float4*>(g.v2 + n));
+                const float4 sc = e_sc, sh = e_sh;
                 o = make_float4((acc.x + b.x) * sc.x + sh.x, (acc.y + b.y) * sc.y + sh.y, (acc.z + b.z) * sc.z + sh.z, (acc.w + b.w) * sc.w + sh.w);
             }
             if (m < g.M) {

@@ -1085,7 +1085,9 @@ static int init_local(psm_handle* h, LocalInit& L) {
             if (h->dense_cluster) {
                 // K-slices per tile = cluster size: as many as keep the grid within ~2 waves, at most one k-block each
                 int ks = 8;
-                const int waves = env_on("PSM_DENSE_ONE_WAVE") ? 1 : 2;
+                // one resident wave of CTAs: at c5 / c3 (4 / 7 row tiles) the Dense stack takes 34.8 / 40.2 us against 57.3 / 55.4 us
+                // with twice the K-slices over two waves (PSM_DENSE_TWO_WAVES=1); c2 (one tile) is the same either way
+                const int waves = env_on("PSM_DENSE_TWO_WAVES") ? 2 : 1;
                 while (ks > 1 && (ks > kb || tiles * ks > waves * 148)) ks >>= 1;
                 h->dense_splits[l] = ks;
                 TRY(mk(h->tc_dense[l], in, Bp, h->d_W[l], h->dims_pad[l + 1], h->dims_pad[l], outp, h->dims_pad[l + 1], ks,
