@@ -143,20 +143,24 @@ def build_sharded_case(world, rank, variant, dist, mesh_kw, seed=0):
     return mesh, F, params, sh, L, time.time() - t0
 
 
-def stage_bytes(n_cells, G, B, C, pc_in, pc_p, ncol, S=128, fused_extract=True, from_blocks=True):
+def stage_bytes(n_cells, G, B, C, pc_in, pc_p, ncol, S=128, fused_extract=True, from_blocks=True, grid_a=False):
     """Algorithmic bytes per step and stage (SURVEY.md section 8d / DESIGN.md): FP32 device storage,
     f64 only at the ABI.  Overlap re-reads and L2-resident intermediates are NOT counted twice.
     With the fused gather+extraction kernel (the default when W % 4 == 0) the block operand is written by the
-    gather itself: its bytes move from 'extract' to 'gather'; the grid planes are neither written nor re-read."""
+    gather itself: its bytes move from 'extract' to 'gather'; the grid planes are neither written nor re-read.
+    grid_a (single-GPU default): the gather writes the two grid planes and the projection fetches its A tiles from them by TMA --
+    no block operand exists; the projection's unique bytes are the planes, not B overlapping copies of them."""
     S2 = S * S
     xu = 4 * B * 2 * S2
+    if grid_a:
+        fused_extract = False
     return {
         # read rows, write float2 field + p_prev; 5-column mode also reads and rewrites the resident U(t-1)
         'prep': n_cells * (ncol * 8 + 8 + 8 + (32 if ncol == 5 else 0)),
         # tables + each cell value once + (fused: the block operand | else: the two grid planes)
         'gather': G * (12 + 12) + 8 * n_cells + (xu if fused_extract else 8 * G),
-        'extract': 0 if fused_extract else 8 * G + xu,        # grid read once, operand written
-        'pca_project': 4 * B * 2 * S2 + 4 * 2 * S2 * pc_in + 4 * B * pc_in,
+        'extract': 0 if (fused_extract or grid_a) else 8 * G + xu,        # grid read once, operand written
+        'pca_project': (8 * G if grid_a else 4 * B * 2 * S2) + 4 * 2 * S2 * pc_in + 4 * B * pc_in,
         'mlp': 4 * (pc_in * 512 + 2 * 512 * 512 + 512 * pc_p) + 8 * B * pc_p,
         'pca_inverse': 4 * pc_p * S2 * C + 4 * B * S2 * C,
         'strip_means': 0,                                      # row partials come out of the PCA-inverse epilogue
@@ -447,7 +451,8 @@ def single_gpu_measure(torch, psm_b200, args, name, mesh_kw, variant, ncol, loca
     res = dict(n=n, geo=geo, t_init=t_init, ms_step=ms_total / args.steps, launches=launches, sm=sm, dc=dc,
                mesh=mesh, F=F, params=params, tables=tables)
     fused = geo['grid_w'] % 4 == 0 and not os.environ.get('PSM_NO_FUSED_EXTRACT')
-    sb = stage_bytes(n, geo['grid_h'] * geo['grid_w'], geo['n_blocks'], sm.n_fields, sm.pc_in, sm.pc_p, ncol, fused_extract=fused)
+    grid_a = fused and not os.environ.get('PSM_NO_GRID_A') and sm.pc_in <= 128
+    sb = stage_bytes(n, geo['grid_h'] * geo['grid_w'], geo['n_blocks'], sm.n_fields, sm.pc_in, sm.pc_p, ncol, fused_extract=fused, grid_a=grid_a)
     stage_avg = dict(zip(psm_b200._capi.TIMING_NAMES, (stage_ms / args.steps).tolist()))
     res['stages'], res['event_overhead_ms'] = stage_report(sb, stage_avg)
     res['sb'] = sb
