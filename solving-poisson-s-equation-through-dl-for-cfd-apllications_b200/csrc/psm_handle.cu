@@ -128,6 +128,7 @@ struct psm_handle {
     // multi-GPU fused flow: ghost pixels pushed from the owners' blocks into the region behind d_blocks
     bool mgpu_fused = false; long long ghost_base = 0; int32_t* d_pix_send_blk = nullptr;
     std::vector<int32_t> host_cell_send_idx; SendRun* d_runs = nullptr; int n_runs = 0;
+    uint2* d_send_words = nullptr; int2* d_send_entries = nullptr;       // send map of the fused flow (P2PFused)
     int filter_radius = 0; float* d_gauss_w = nullptr; float* d_filter_tmp = nullptr;   // optional post-filter (SMC:353-356)
     std::vector<uint8_t> host_mask;   // [Hglob][W] flow mask (sdfunct != 0), host copy
     bool plan_mask_at(int y, int x) const { return host_mask[(size_t)y * W + x] != 0; }
@@ -675,6 +676,43 @@ static int setup_p2p(psm_handle* h) {
         h->n_runs = (runs.size() <= (size_t)kMaxRuns && !env_on("PSM_NO_SEND_RUNS")) ? (int)runs.size() : 0;
         if (runs.empty()) runs.push_back(SendRun{0, 0, 0, 0, 0});
         TRY(upload(h, &h->d_runs, runs));
+        // The send map: works for any cell numbering and any list length (a solver's cells are not numbered row by row, and even on
+        // the synthetic lattice a 4000-wide boundary is hundreds of runs: with the run list the LAST prep CTA then moved 130 k ghost
+        // cells alone, 180 us of the 470 us step at 4 GPUs on c4).  PSM_SEND_RUNS=1 keeps the run list.
+        if (!env_on("PSM_SEND_RUNS")) {
+            struct Ent { int32_t cell, peer; long long dst; };
+            std::vector<Ent> ent;
+            for (int p = 0; p < Wd; ++p)
+                for (long long e = h->cell_send_ptr[p]; e < h->cell_send_ptr[p + 1]; ++e)
+                    ent.push_back(Ent{h->host_cell_send_idx[e], p, e - h->cell_send_ptr[p]});
+            std::stable_sort(ent.begin(), ent.end(), [](const Ent& a, const Ent& b) { return a.cell < b.cell; });
+            const size_t nw = (size_t)(h->n_cells + 31) / 32 + 1;
+            std::vector<uint2> words(nw, make_uint2(0u, 0u));
+            // one main entry per marked cell (index = rank of the cell among the marked ones: bitmap prefix + popcount); a cell
+            // that goes to several peers chains its further entries behind the main ones (next index in the bits above 9)
+            size_t n_marked = 0;
+            for (size_t k = 0; k < ent.size(); ++k) if (k == 0 || ent[k].cell != ent[k - 1].cell) ++n_marked;
+            std::vector<int2> entries(ent.size() ? ent.size() : 1, make_int2(0, 0));
+            size_t main_i = 0, over_i = n_marked;
+            for (size_t k = 0; k < ent.size();) {
+                size_t k1 = k;
+                while (k1 < ent.size() && ent[k1].cell == ent[k].cell) ++k1;
+                words[(size_t)ent[k].cell >> 5].x |= 1u << (ent[k].cell & 31);
+                size_t at = main_i++;
+                for (size_t q = k; q < k1; ++q) {
+                    const bool more = q + 1 < k1;
+                    const size_t nxt = more ? over_i++ : 0;
+                    entries[at] = make_int2(ent[q].peer | (more ? 0x100 : 0) | (int)(nxt << 9), (int)ent[q].dst);
+                    at = nxt;
+                }
+                k = k1;
+            }
+            unsigned int run = 0;
+            for (size_t w = 0; w < nw; ++w) { words[w].y = run; run += (unsigned int)__builtin_popcount(words[w].x); }
+            TRY(upload(h, &h->d_send_words, words));
+            TRY(upload(h, &h->d_send_entries, entries));
+            h->n_runs = 0;
+        }
     }
     if (!h->mgpu_fused && h->fuse_place) h->fuse_place = false;      // legacy flow: the assembled field + ghost pixels of the field
     if (!ok) return PSM_OK;                       // NCCL exchange
@@ -1353,7 +1391,8 @@ static int run_step(psm_handle* h, const StepInput& in, double* d_out) {
     // fused multi-GPU flow: the exchanges ride in the tails of prep and of the fold kernel (no push launches, no assembled field)
     const bool mfused = p2p && h->mgpu_fused && d_out != nullptr;
     P2PFused fx{};
-    if (mfused) fx = P2PFused{h->d_p2p, h->d_cell_send_idx, h->d_runs, h->n_runs, h->d_blocks, h->d_pix_send_blk, h->C, S2, h->pix_send_ptr[h->world]};
+    if (mfused) fx = P2PFused{h->d_p2p, h->d_cell_send_idx, h->d_runs, h->n_runs, h->d_blocks, h->d_pix_send_blk, h->C, S2, h->pix_send_ptr[h->world],
+                             h->d_send_words, h->d_send_entries};
     if (fields) {
         PrepFieldsArgs pf{in.U, in.dU, in.u_stride, h->n_cells, mode, h->d_uv, h->d_uprev, h->d_sc, fx};
         launch_prep_fields(pf, s); ++nl;

@@ -187,6 +187,21 @@ __device__ __forceinline__ void prep_load_runs(const P2PFused& fx, SendRun* s_ru
 }
 // cell i has just been converted by this thread: push it if a peer needs it as a ghost cell
 __device__ __forceinline__ void prep_push_cell(const P2PFused& fx, const SendRun* s_runs, long long i, float2 val, bool& pushed) {
+    if (fx.send_words) {
+        const uint2 w = __ldg(fx.send_words + (i >> 5));
+        const unsigned int bit = 1u << (i & 31);
+        if (w.x & bit) {
+            int k = (int)w.y + __popc(w.x & (bit - 1u));
+            for (;;) {
+                const int2 e = __ldg(fx.send_entries + k);
+                fx.p2p->uv_ghost[e.x & 0xFF][e.y] = val;
+                if (!(e.x & 0x100)) break;
+                k = e.x >> 9;                                    // a cell that goes to several peers: its further entries are chained
+            }
+            pushed = true;
+        }
+        return;
+    }
     for (int r = 0; r < fx.n_runs; ++r) {
         const SendRun& R = s_runs[r];
         if (i >= R.begin && i < R.end) { fx.p2p->uv_ghost[R.peer][R.dst + (i - R.begin)] = val; pushed = true; }
@@ -206,8 +221,8 @@ __device__ __forceinline__ void prep_p2p_tail(const P2PFused& fx, const float2* 
     if (!s_last) return;
     const P2PArgs& P = *fx.p2p;
     const unsigned int step = P.sc->step + 1u;
-    if (fx.n_runs == 0) {
-        // fragmented send list: this one CTA moves it, eight independent index -> value chains per thread in flight
+    if (fx.n_runs == 0 && !fx.send_words) {
+        // fragmented send list, no send map: this one CTA moves it, eight independent index -> value chains per thread in flight
         const long long nsend = P.cell_send_ptr[P.world];
         for (long long e0 = threadIdx.x; e0 < nsend; e0 += (long long)blockDim.x * 8) {
             int idx[8]; float2 val[8];

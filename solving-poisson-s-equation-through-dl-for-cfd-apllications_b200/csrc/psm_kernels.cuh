@@ -87,6 +87,11 @@ struct P2PFused {
     const SendRun* runs; int n_runs;             // the same list as runs (n_runs <= kMaxRuns), or n_runs = 0: too fragmented
     const float* blocks; const int32_t* pix_send_blk; int C, S2;   // fold kernel: ghost pixels from the predicted blocks (channel-0 offsets)
     long long n_pix_send;
+    // send map (any cell order, any list length): word i/32 = {bit c set <=> owned cell 32*(i/32) + c is a ghost cell elsewhere,
+    // number of marked cells before this word}; entry k (k = rank of the cell among the marked ones) = {peer | 0x100 if the cell has
+    // a further entry | index of that entry << 9, slot in that peer's ghost region}.  Every prep thread looks its own cell up: one
+    // 8-byte broadcast load per warp, a popcount, then the stores.
+    const uint2* send_words; const int2* send_entries;
 };
 
 struct ScalarArgs {
