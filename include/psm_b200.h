@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define PSM_API_VERSION 4
+#define PSM_API_VERSION 5
 
 typedef struct psm_handle psm_handle;
 
@@ -392,6 +392,21 @@ int psm_plan_compile(int32_t variant, int32_t grid_h, int32_t grid_w, int32_t sh
  * `lines` may be NULL to query n_lines. */
 int psm_plan_shift_lines(int32_t variant, int32_t grid_h, int32_t grid_w, int32_t shape, int32_t overlap,
                          const uint8_t* mask, int32_t* n_lines, int32_t* lines);
+
+/* Box plan of the PCA projection's A operand when it is fetched from the grid planes (replaces the block
+ * extraction SMC:464-492 / GRAD:479-516): blocks whose origins (by0, bx0) form an arithmetic progression of `stride` pixels are one TMA
+ * box.  tiles = 128-row operand tiles (0: the layout does not pay and the handle keeps the extracted operand), gx / gy = blocks per
+ * row / column box, row_src int32[n_blocks] = operand row of every block, segs int32[n_segs][5] = (tile, kind 0 row box / 1 column
+ * box / 2 single block, first row inside the tile, x origin, y origin).  row_src / segs may be NULL. */
+int psm_grid_operand_plan(int32_t n_blocks, const int32_t* by0, const int32_t* bx0, int32_t stride, int32_t* tiles, int32_t* gx,
+                          int32_t* gy, int32_t* n_segs, int32_t* row_src, int32_t* segs, int32_t max_segs);
+
+/* Ghost-cell send map of a sharded handle (replaces the gather to rank 0 of PMP:258): send_idx[send_ptr[p] ..
+ * send_ptr[p+1]) are the owned cells rank p needs.  words uint32[(n_cells + 31) / 32 + 1][2] = (bitmap of the marked cells, marked
+ * cells before the word); entries int32[n_entries][2] = (peer | 0x100 if the cell has a further entry | its index << 9, slot in the
+ * peer's ghost region); entry k < number of marked cells belongs to the k-th marked cell.  words / entries may be NULL. */
+int psm_send_map_build(int64_t n_cells, int32_t world, const int64_t* send_ptr, const int32_t* send_idx, uint32_t* words,
+                       int32_t* entries, int64_t* n_entries);
 
 /* Unit-test entry for the GEMM kernels: C[splits][M][N] (host) = A[M][K] * B[N][K]^T (host), split-K
  * partials left unreduced.  mode = psm_gemm_mode_code.  M % 128 == 0, N % 64 == 0, K % 32 == 0. */

@@ -588,6 +588,40 @@ static bool build_grid_a(int B, const std::vector<int32_t>& by0, const std::vect
 }
 }  // namespace
 
+// Send map of the fused multi-GPU flow (P2PFused::send_words / send_entries): see psm_kernels.cuh.  send_idx[send_ptr[p] ..
+// send_ptr[p+1]) are the owned cells peer p needs, entry e of that list lands in slot e - send_ptr[p] of p's ghost region.
+static void build_send_map(long long n_cells, int world, const long long* send_ptr, const int32_t* send_idx,
+                           std::vector<uint2>& words, std::vector<int2>& entries) {
+    struct Ent { int32_t cell, peer; long long dst; };
+    std::vector<Ent> ent;
+    for (int p = 0; p < world; ++p)
+        for (long long e = send_ptr[p]; e < send_ptr[p + 1]; ++e) ent.push_back(Ent{send_idx[e], p, e - send_ptr[p]});
+    std::stable_sort(ent.begin(), ent.end(), [](const Ent& a, const Ent& b) { return a.cell < b.cell; });
+    const size_t nw = (size_t)(n_cells + 31) / 32 + 1;
+    words.assign(nw, make_uint2(0u, 0u));
+    // one main entry per marked cell (index = rank of the cell among the marked ones: bitmap prefix + popcount); a cell
+    // that goes to several peers chains its further entries behind the main ones (next index in the bits above 9)
+    size_t n_marked = 0;
+    for (size_t k = 0; k < ent.size(); ++k) if (k == 0 || ent[k].cell != ent[k - 1].cell) ++n_marked;
+    entries.assign(ent.size() ? ent.size() : 1, make_int2(0, 0));
+    size_t main_i = 0, over_i = n_marked;
+    for (size_t k = 0; k < ent.size();) {
+        size_t k1 = k;
+        while (k1 < ent.size() && ent[k1].cell == ent[k].cell) ++k1;
+        words[(size_t)ent[k].cell >> 5].x |= 1u << (ent[k].cell & 31);
+        size_t at = main_i++;
+        for (size_t q = k; q < k1; ++q) {
+            const bool more = q + 1 < k1;
+            const size_t nxt = more ? over_i++ : 0;
+            entries[at] = make_int2(ent[q].peer | (more ? 0x100 : 0) | (int)(nxt << 9), (int)ent[q].dst);
+            at = nxt;
+        }
+        k = k1;
+    }
+    unsigned int run = 0;
+    for (size_t w = 0; w < nw; ++w) { words[w].y = run; run += (unsigned int)__builtin_popcount(words[w].x); }
+}
+
 // Map every peer's exchange buffers (cudaIpc over NVLink) and build the push tables.  Collective.  Falls back
 // to the NCCL exchange when any rank cannot map a peer, when PSM_COMM=nccl, or in the grid-row halo mode.
 static int setup_p2p(psm_handle* h) {
@@ -680,35 +714,8 @@ static int setup_p2p(psm_handle* h) {
         // the synthetic lattice a 4000-wide boundary is hundreds of runs: with the run list the LAST prep CTA then moved 130 k ghost
         // cells alone, 180 us of the 470 us step at 4 GPUs on c4).  PSM_SEND_RUNS=1 keeps the run list.
         if (!env_on("PSM_SEND_RUNS")) {
-            struct Ent { int32_t cell, peer; long long dst; };
-            std::vector<Ent> ent;
-            for (int p = 0; p < Wd; ++p)
-                for (long long e = h->cell_send_ptr[p]; e < h->cell_send_ptr[p + 1]; ++e)
-                    ent.push_back(Ent{h->host_cell_send_idx[e], p, e - h->cell_send_ptr[p]});
-            std::stable_sort(ent.begin(), ent.end(), [](const Ent& a, const Ent& b) { return a.cell < b.cell; });
-            const size_t nw = (size_t)(h->n_cells + 31) / 32 + 1;
-            std::vector<uint2> words(nw, make_uint2(0u, 0u));
-            // one main entry per marked cell (index = rank of the cell among the marked ones: bitmap prefix + popcount); a cell
-            // that goes to several peers chains its further entries behind the main ones (next index in the bits above 9)
-            size_t n_marked = 0;
-            for (size_t k = 0; k < ent.size(); ++k) if (k == 0 || ent[k].cell != ent[k - 1].cell) ++n_marked;
-            std::vector<int2> entries(ent.size() ? ent.size() : 1, make_int2(0, 0));
-            size_t main_i = 0, over_i = n_marked;
-            for (size_t k = 0; k < ent.size();) {
-                size_t k1 = k;
-                while (k1 < ent.size() && ent[k1].cell == ent[k].cell) ++k1;
-                words[(size_t)ent[k].cell >> 5].x |= 1u << (ent[k].cell & 31);
-                size_t at = main_i++;
-                for (size_t q = k; q < k1; ++q) {
-                    const bool more = q + 1 < k1;
-                    const size_t nxt = more ? over_i++ : 0;
-                    entries[at] = make_int2(ent[q].peer | (more ? 0x100 : 0) | (int)(nxt << 9), (int)ent[q].dst);
-                    at = nxt;
-                }
-                k = k1;
-            }
-            unsigned int run = 0;
-            for (size_t w = 0; w < nw; ++w) { words[w].y = run; run += (unsigned int)__builtin_popcount(words[w].x); }
+            std::vector<uint2> words; std::vector<int2> entries;
+            build_send_map(h->n_cells, Wd, h->cell_send_ptr.data(), h->host_cell_send_idx.data(), words, entries);
             TRY(upload(h, &h->d_send_words, words));
             TRY(upload(h, &h->d_send_entries, entries));
             h->n_runs = 0;
@@ -2161,6 +2168,40 @@ extern "C" int psm_set_timings(psm_handle* h, int32_t on) {
 }
 
 extern "C" int psm_get_launch_count(const psm_handle* h) { return h ? h->launches : 0; }
+
+// ---- host-only test entries (no GPU): the box plan of the grid-plane A operand and the ghost-cell send map -------------------
+extern "C" int psm_grid_operand_plan(int32_t n_blocks, const int32_t* by0, const int32_t* bx0, int32_t stride, int32_t* tiles, int32_t* gx,
+                                     int32_t* gy, int32_t* n_segs, int32_t* row_src, int32_t* segs, int32_t max_segs) {
+    if (n_blocks < 1 || !by0 || !bx0 || stride < 1 || !tiles || !gx || !gy || !n_segs) return PSM_ERR_INVALID;
+    GridAPlan P;
+    std::vector<int32_t> y(by0, by0 + n_blocks), x(bx0, bx0 + n_blocks);
+    if (!build_grid_a(n_blocks, y, x, stride, P)) { *tiles = 0; *gx = *gy = 0; *n_segs = 0; return PSM_OK; }    // layout does not pay: 0 tiles
+    *tiles = P.tiles; *gx = P.gx; *gy = P.gy; *n_segs = (int32_t)P.segs.size();
+    if (row_src) for (int b = 0; b < n_blocks; ++b) row_src[b] = P.row_src[b];
+    if (segs) {
+        if ((int32_t)P.segs.size() > max_segs) return PSM_ERR_INVALID;
+        size_t t = 0;
+        for (size_t q = 0; q < P.segs.size(); ++q) {
+            while ((int32_t)q >= P.seg_ptr[t + 1]) ++t;
+            segs[5 * q + 0] = (int32_t)t; segs[5 * q + 1] = P.segs[q].map; segs[5 * q + 2] = P.segs[q].row;
+            segs[5 * q + 3] = P.segs[q].x; segs[5 * q + 4] = P.segs[q].y;
+        }
+    }
+    return PSM_OK;
+}
+
+extern "C" int psm_send_map_build(int64_t n_cells, int32_t world, const int64_t* send_ptr, const int32_t* send_idx, uint32_t* words,
+                                  int32_t* entries, int64_t* n_entries) {
+    if (n_cells < 0 || world < 1 || !send_ptr || !n_entries) return PSM_ERR_INVALID;
+    std::vector<long long> sp(send_ptr, send_ptr + world + 1);
+    for (long long e = 0; e < sp[world]; ++e) if (!send_idx || send_idx[e] < 0 || send_idx[e] >= n_cells) return PSM_ERR_INVALID;
+    std::vector<uint2> w; std::vector<int2> en;
+    build_send_map(n_cells, world, sp.data(), send_idx, w, en);
+    *n_entries = sp[world];
+    if (words) for (size_t i = 0; i < w.size(); ++i) { words[2 * i] = w[i].x; words[2 * i + 1] = w[i].y; }
+    if (entries) for (long long i = 0; i < sp[world]; ++i) { entries[2 * i] = en[i].x; entries[2 * i + 1] = en[i].y; }
+    return PSM_OK;
+}
 
 extern "C" int psm_get_wait_ns(psm_handle* h, uint64_t ns[3], uint32_t count[3], int32_t reset) {
     if (!h || !ns || !count) return PSM_ERR_INVALID;

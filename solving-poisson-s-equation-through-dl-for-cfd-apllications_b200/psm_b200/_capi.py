@@ -140,6 +140,10 @@ SYMBOLS = {
     'psm_debug_gemm': (C.c_int, [C.c_int32] * 5 + [c_float_p, c_float_p, c_float_p, C.c_int32]),
     'psm_debug_dense_stack': (C.c_int, [C.c_int32] * 4 + [c_int32_p, C.POINTER(c_float_p), C.POINTER(c_float_p), c_float_p, c_float_p,
                                         C.c_int32]),
+    'psm_grid_operand_plan': (C.c_int, [C.c_int32, c_int32_p, c_int32_p, C.c_int32, c_int32_p, c_int32_p, c_int32_p, c_int32_p, c_int32_p,
+                                        c_int32_p, C.c_int32]),
+    'psm_send_map_build': (C.c_int, [C.c_int64, C.c_int32, C.POINTER(C.c_int64), c_int32_p, C.POINTER(C.c_uint32), c_int32_p,
+                                     C.POINTER(C.c_int64)]),
     'psm_plan_sizes': (C.c_int, [C.c_int32] * 5 + [c_uint8_p, c_int32_p, c_int32_p, c_int32_p]),
     'psm_plan_compile': (C.c_int, [C.c_int32] * 5 + [c_uint8_p] + [c_int32_p] * 5),
     'psm_plan_shift_lines': (C.c_int, [C.c_int32] * 5 + [c_uint8_p, c_int32_p, c_int32_p]),

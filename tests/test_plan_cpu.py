@@ -158,7 +158,7 @@ def test_library_exports_every_declared_symbol():
     lib = _capi.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.psm_api_version() == 4
+    assert lib.psm_api_version() == 5
 
 
 @pytest.mark.parametrize("H,W", [(260, 380), (130, 250), (397, 998), (1000, 1000), (360, 360)])
