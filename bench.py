@@ -427,7 +427,7 @@ def roofline_block(sb, stages, peaks, peak_src, workload, live_traffic=True):
             'frac': ach / peaks['hbm_gbs'], 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src,
             'algorithmic_bytes_per_launch': sb[dom],
             'hbm_kernels': {k: {'GBps': stages[k]['GBps'], 'frac': stages[k]['GBps'] / peaks['hbm_gbs']}
-                            for k in HBM_STAGES if sb[k] > 0 and stages[k]['GBps']}}
+                            for k in HBM_STAGES if sb[k] > 0 and stages[k]['GBps'] and stages[k]['ms_net'] > 1e-3}}   # launched stages only
 
 
 def single_gpu_measure(torch, psm_b200, args, name, mesh_kw, variant, ncol, local_rank, cpu=True, latency=False):

@@ -977,7 +977,9 @@ static int init_local(psm_handle* h, LocalInit& L) {
         // tcgen05 path: one 128-row tile per CTA, split-K so that about one wave of CTAs streams the operands
         const int kb_total = 2 * S2 / 32;
         const int tc_tiles = (Bp / 128) * (h->pc_in_pad / tc_gemm_bn(h->pc_in_pad));
-        int ts = (148 + tc_tiles - 1) / tc_tiles;
+        // at most ONE resident wave (1 CTA per SM): 7 row tiles x 22 splits = 154 CTAs ran as two waves at c3 (ncu: 76 us, tensor
+        // pipe 50 %), so the split count is rounded down, not up
+        int ts = 148 / tc_tiles;
         if (ts > 128) ts = 128;
         if (ts < 1) ts = 1;
         const int per = (kb_total + ts - 1) / ts;
@@ -1054,7 +1056,7 @@ static int init_local(psm_handle* h, LocalInit& L) {
                 make_grid_maps(&tg, h->d_grid, W, (int)(h->grid_stride / W), h->grid_stride, st, gp.gx, gp.gy) == 0 &&
                 make_kmajor_map(&tg.mapB, h->d_comp_u, h->pc_in_pad, 2 * S2, 2 * S2, 128) == 0) {
                 const int kb_total = 2 * S2 / 32;
-                int ts = (148 + gp.tiles - 1) / gp.tiles;
+                int ts = 148 / gp.tiles;                           // one resident wave (see tc_splits above)
                 ts = std::max(1, std::min(ts, 128));
                 const int per = (kb_total + ts - 1) / ts;
                 const int splits = (kb_total + per - 1) / per;
