@@ -134,3 +134,34 @@ def test_send_map_empty_and_bad_input():
     bad = np.array([100], np.int32)
     ne = C.c_int64()
     assert lib.psm_send_map_build(100, 1, _p(ptr, C.c_int64), _p(bad, C.c_int32), None, None, C.byref(ne)) < 0     # cell id out of range
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_send_map_push_fills_every_ghost_region(world):
+    """The fused flow's first exchange on a real partition, in NumPy: every rank converts its cells and pushes, cell by cell
+    through the send map, into the consumers' ghost regions (slot = position in the consumer's ghost list from that owner) --
+    afterwards each rank's [owned | ghost] field equals the global field at its local-to-global ids (what NCCL send/recv or
+    the reference's gather to rank 0, PMP:258, would have delivered)."""
+    from psm_b200 import synthetic as syn, tables as ptables, shard as pshard
+    mesh = syn.make_mesh(seed=5, H=500, W=420, nx=160, ny=200, R=0.12)
+    F = syn.make_fields(mesh, seed=5)
+    t = ptables.build_tables(mesh['cells'], mesh['top'], mesh['obst'], F['p_prev'])
+    shards = pshard.partition(t, mesh['cells'], world)
+    field = np.stack([F['dUx'], F['dUy']], 1)                       # the global cell field
+    uv = [np.full((s['n_owned'] + s['n_ghost'], 2), np.nan) for s in shards]
+    for s in shards:
+        uv[s['rank']][:s['n_owned']] = field[s['owned_ids']]
+    pushed = 0
+    for s in shards:
+        r = s['rank']
+        words, entries = send_map(s['n_owned'], [s['cell_send_idx'][s['cell_send_ptr'][p]:s['cell_send_ptr'][p + 1]] for p in range(world)])
+        marked = np.flatnonzero([(int(words[i >> 5, 0]) >> (i & 31)) & 1 for i in range(s['n_owned'])])
+        for i in marked:
+            for peer, slot in lookup(words, entries, int(i)):
+                sp = shards[peer]
+                uv[peer][sp['n_owned'] + sp['cell_recv_ptr'][r] + slot] = uv[r][i]      # P2PArgs::uv_ghost[peer] + slot
+                pushed += 1
+    assert pushed == sum(s['n_ghost'] for s in shards) > 0
+    for s in shards:
+        l2g = np.concatenate([s['owned_ids'], s['ghost_ids']])
+        assert np.array_equal(uv[s['rank']], field[l2g])
