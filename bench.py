@@ -252,13 +252,13 @@ def time_oracle(o, variant, F, steps, warmup):
 
 def reference_sample_kw(name, mesh_kw, world):
     """Bounded sample of the workload for the CPU arm: the whole mesh up to ~1.2 M cells; for the larger domains a band of
-    1000 grid rows over the full width (what one rank of a 4-way split of c4 holds), or c2 for the weak c2xN domain."""
+    512 grid rows over the full width (what one rank of an 8-way split of c4 holds), or c2 for the weak c2xN domain."""
     cells = mesh_kw['nx'] * mesh_kw['ny']
     if cells <= 1_300_000:
         return dict(mesh_kw), 'the whole mesh'
     if name.startswith('c2x'):
         return dict(syn.CONFIGS['c2']), "one rank's share of the weak-scaling domain (the c2 mesh, ~1 M cells)"
-    H = 1000
+    H = 512      # ~2 M cells: table building (Qhull) + a few oracle steps stay within a few minutes on the box's host cores
     kw = dict(mesh_kw, H=H, ny=int(round(mesh_kw['ny'] * H / mesh_kw['H'])))
     return kw, 'a band of %d of the %d grid rows over the full width (%d x %d cell lattice)' % (H, mesh_kw['H'], kw['nx'], kw['ny'])
 
