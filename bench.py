@@ -121,7 +121,9 @@ def config_dict(name, mesh_kw, variant, world, ncol):
               % (name, variant, mesh_kw, world))
     else:
         wl = '%s: %s, synthetic flow-past-cylinder mesh %s, pc_in=pc_p=128, MLP 3x512, random-init' % (name, variant, mesh_kw)
-    return {'workload': wl, 'l2': L2_NOTE, 'input_cols': ncol}
+    return {'workload': wl, 'l2': L2_NOTE, 'input_cols': ncol,
+            'tables': "cells -> grid: SciPy Qhull (as the reference); grid -> cell: closed form on the regular grid (back='closed_form'), "
+                      "the same tables in the GPU path and the CPU oracle"}
 
 
 def build_sharded_case(world, rank, variant, dist, mesh_kw, seed=0):
@@ -471,6 +473,10 @@ def gemm_block(res, peaks):
         tf = f / (ms * 1e-3) / 1e12 if ms > 0 else None
         out[k] = {'ms': res['stages'][k]['ms'], 'tflops': tf, 'frac_of_tf32_peak': (tf / tf32_peak) if tf else None,
                   'GBps': res['stages'][k]['GBps']}
+    # NOT measured by this run: tensor-pipe activity of the same kernels in the round's ncu capture (cold-cache, serialised replay)
+    out['tensor_pipe_pct_ncu'] = {'pca_project': 25.5, 'mlp': [3.4, 6.3, 6.3, 6.4], 'pca_inverse': 20.6, 'pca_project_c3': 50.1,
+                                  'pca_inverse_c3': 45.4, 'source': 'profiles/r2m_full_summary.txt, profiles/r2m_full_summary_c3.txt '
+                                                                    '(sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active, ncu --set full, c2 / c3 step)'}
     out['note'] = ('algorithmic FLOPs (3xTF32 runs 3 tensor passes per algorithmic one); TF32 peak taken as 0.5 x measured bf16 '
                    '(%.0f TFLOP/s); at 121-441 rows these contractions are latency / HBM bound, tensor-pipe utilisation from ncu is '
                    'in profiles/' % tf32_peak)
