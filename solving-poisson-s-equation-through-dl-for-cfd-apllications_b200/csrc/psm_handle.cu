@@ -713,7 +713,7 @@ static int setup_p2p(psm_handle* h) {
         // The send map: works for any cell numbering and any list length (a solver's cells are not numbered row by row, and even on
         // the synthetic lattice a 4000-wide boundary is hundreds of runs: with the run list the LAST prep CTA then moved 130 k ghost
         // cells alone, 180 us of the 470 us step at 4 GPUs on c4).  PSM_SEND_RUNS=1 keeps the run list.
-        if (!env_on("PSM_SEND_RUNS")) {
+        if (!env_on("PSM_SEND_RUNS") && h->cell_send_ptr[Wd] < (1ll << 22)) {     // entry indices are packed into 22 bits
             std::vector<uint2> words; std::vector<int2> entries;
             build_send_map(h->n_cells, Wd, h->cell_send_ptr.data(), h->host_cell_send_idx.data(), words, entries);
             TRY(upload(h, &h->d_send_words, words));
@@ -2194,8 +2194,9 @@ extern "C" int psm_grid_operand_plan(int32_t n_blocks, const int32_t* by0, const
 
 extern "C" int psm_send_map_build(int64_t n_cells, int32_t world, const int64_t* send_ptr, const int32_t* send_idx, uint32_t* words,
                                   int32_t* entries, int64_t* n_entries) {
-    if (n_cells < 0 || world < 1 || !send_ptr || !n_entries) return PSM_ERR_INVALID;
+    if (n_cells < 0 || world < 1 || world > kMaxPeers || !send_ptr || !n_entries) return PSM_ERR_INVALID;
     std::vector<long long> sp(send_ptr, send_ptr + world + 1);
+    if (sp[world] >= (1ll << 22)) return PSM_ERR_INVALID;         // entry indices are packed into 22 bits (the handle then keeps the run list)
     for (long long e = 0; e < sp[world]; ++e) if (!send_idx || send_idx[e] < 0 || send_idx[e] >= n_cells) return PSM_ERR_INVALID;
     std::vector<uint2> w; std::vector<int2> en;
     build_send_map(n_cells, world, sp.data(), send_idx, w, en);
